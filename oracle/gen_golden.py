@@ -1,0 +1,311 @@
+"""Generate tests/golden/*.npz by importing the REAL reference from /root/reference.
+
+TEST INFRASTRUCTURE ONLY.  Run in the dev container (the reference tree does not travel
+to the GPU box):   python oracle/gen_golden.py
+
+What is executed is the reference's own code, unmodified:
+  * ``ms_deform_attn_core_pytorch`` (models/ops/functions/ms_deform_attn_func.py:41-61)
+    and autograd through it -- op-level vectors;
+  * the reference ``MSDeformAttn`` module (models/ops/modules/ms_deform_attn.py) and the
+    layer classes of models/deformable_transformer_single.py /
+    models/dformer_crossfusion_backbone.py, with ``MSDeformAttnFunction.apply`` replaced by
+    the reference oracle (the CUDA extension cannot be imported without a GPU build) --
+    module/layer-level vectors.
+Import shims: an empty ``MultiScaleDeformableAttention`` stub so
+func.py:18 imports; a bare ``models`` namespace package to bypass models/__init__.py
+(which pulls mmcv); torchvision.__version__ patched while util/misc.py:30 parses it.
+
+Everything is float64 unless the case says otherwise; inputs are drawn with the CPU
+generator in the order the reference test recipe uses (models/ops/test.py:28,33-36).
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("MSDA_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def import_reference():
+    sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
+    ops = os.path.join(REF, "models", "ops")
+    models_pkg = types.ModuleType("models")
+    models_pkg.__path__ = [os.path.join(REF, "models")]
+    sys.modules["models"] = models_pkg
+    ops_pkg = types.ModuleType("models.ops")
+    ops_pkg.__path__ = [ops]
+    sys.modules["models.ops"] = ops_pkg
+    sys.path.insert(0, REF)
+    func = importlib.import_module("models.ops.functions.ms_deform_attn_func")
+
+    class OracleFunction:  # stands in for the CUDA autograd.Function (func.py:21-38)
+        @staticmethod
+        def apply(value, shapes, lsi, loc, attn, im2col_step):
+            return func.ms_deform_attn_core_pytorch(value, shapes, loc, attn)
+
+    func.MSDeformAttnFunction = OracleFunction
+    sys.modules["models.ops.functions"].MSDeformAttnFunction = OracleFunction
+    mod = importlib.import_module("models.ops.modules.ms_deform_attn")
+    mod.MSDeformAttnFunction = OracleFunction
+    import torchvision
+    real_version = torchvision.__version__
+    torchvision.__version__ = "0.9.0"
+    try:
+        importlib.import_module("util.misc")
+    finally:
+        torchvision.__version__ = real_version
+    single = importlib.import_module("models.deformable_transformer_single")
+    backbone_cf = importlib.import_module("models.dformer_crossfusion_backbone")
+    return func, mod, single, backbone_cf
+
+
+def lsi_of(shapes):
+    return torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+
+
+def op_case(func, name, shapes, n, m, d, lq, p, seed, loc_range=(0.0, 1.0), dtype=torch.float64):
+    """The recipe of models/ops/test.py:33-36 (fp32 CPU draws, then cast)."""
+    torch.manual_seed(seed)
+    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
+    nl = len(shapes)
+    s = int(shapes_t.prod(1).sum())
+    f32 = torch.float32
+    value = torch.rand(n, s, m, d, dtype=f32) * 0.01
+    loc = torch.rand(n, lq, m, nl, p, 2, dtype=f32)
+    attn = torch.rand(n, lq, m, nl, p, dtype=f32) + 1e-5
+    attn /= attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    grad_out = torch.rand(n, lq, m * d, dtype=f32) - 0.5
+    lo, hi = loc_range
+    loc = loc * (hi - lo) + lo
+    value, loc, attn, grad_out = (t.to(dtype) for t in (value, loc, attn, grad_out))
+    v = value.clone().requires_grad_(True)
+    lc = loc.clone().requires_grad_(True)
+    aw = attn.clone().requires_grad_(True)
+    out = func.ms_deform_attn_core_pytorch(v, shapes_t, lc, aw)
+    gv, gl, ga = torch.autograd.grad(out, (v, lc, aw), grad_out)
+    np.savez_compressed(
+        os.path.join(OUT, f"op_{name}.npz"),
+        shapes=shapes_t.numpy(), level_start_index=lsi_of(shapes_t).numpy(),
+        value=value.numpy(), loc=loc.numpy(), attn=attn.numpy(), grad_out=grad_out.numpy(),
+        out=out.detach().numpy(), grad_value=gv.numpy(), grad_loc=gl.numpy(), grad_attn=ga.numpy())
+    print(f"op_{name}: out {tuple(out.shape)} |out|max {out.abs().max():.3e}")
+    return out
+
+
+def state_np(module):
+    return {k: v.detach().numpy() for k, v in module.state_dict().items()}
+
+
+def perturb(module, seed, std=0.05):
+    """Default init makes offsets query-independent and attention uniform
+    (ms_deform_attn.py:60-76); perturb so every parameter matters."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for prm in module.parameters():
+            prm.add_(torch.randn(prm.shape, generator=g, dtype=prm.dtype) * std)
+
+
+def grid_reference_points(single, shapes_t, n, dtype):
+    vr = torch.ones(n, shapes_t.shape[0], 2, dtype=dtype)
+    ref = single.DeformableTransformerEncoder.get_reference_points(
+        [(int(h), int(w)) for h, w in shapes_t], vr, device="cpu")
+    return ref.to(dtype)
+
+
+def save_module_case(name, module, inputs, call, wrt):
+    """Run ``call(module, **inputs)``, save inputs/state/output and the gradients of
+    sum(output * gout) w.r.t. the tensors named in ``wrt`` and every parameter."""
+    tensors = {k: (v.clone().requires_grad_(True) if k in wrt else v) for k, v in inputs.items()}
+    out = call(module, tensors)
+    g = torch.Generator().manual_seed(1234)
+    gout = torch.randn(out.shape, generator=g, dtype=out.dtype)
+    params = list(module.parameters())
+    grads = torch.autograd.grad(out, [tensors[k] for k in wrt] + params, gout, allow_unused=True)
+    blob = {f"in.{k}": (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in inputs.items()}
+    blob.update({f"state.{k}": v for k, v in state_np(module).items()})
+    blob["out"] = out.detach().numpy()
+    blob["gout"] = gout.numpy()
+    for k, gr in zip(wrt, grads[:len(wrt)]):
+        blob[f"grad_in.{k}"] = gr.numpy()
+    for (pname, _), gr in zip(module.named_parameters(), grads[len(wrt):]):
+        blob[f"grad_param.{pname}"] = (gr if gr is not None else torch.zeros(())).numpy()
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **blob)
+    print(f"{name}: out {tuple(out.shape)} |out|max {out.abs().max():.3e}")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_default_dtype(torch.float64)
+    func, mod, single, backbone_cf = import_reference()
+
+    # ---------------- op-level ------------------------------------------------
+    # (1) the reference test's own configuration and seed (test.py:21-28)
+    out = op_case(func, "toy_seed3", [(6, 4), (3, 2)], n=1, m=2, d=2, lq=2, p=2, seed=3)
+    known = [0.001899378416, 0.004602827533, 0.004671175247, 0.004384399819,
+             0.003795097174, 0.002512764199, 0.001844426151, 0.003634679248]
+    assert np.allclose(out.detach().numpy().ravel(), known, rtol=0, atol=1e-11), "RNG stream differs from survey"
+    # (2) locations outside [0,1): exercises the zero padding and the in-range test (cuh:288)
+    op_case(func, "oob", [(5, 7), (3, 4), (2, 2)], n=2, m=3, d=8, lq=5, p=3, seed=11, loc_range=(-0.3, 1.3))
+    # (3) production head width D=32, M=8, one level (shipped configs use 1 level)
+    op_case(func, "d32_l1", [(7, 9)], n=2, m=8, d=32, lq=6, p=4, seed=12, loc_range=(-0.1, 1.1))
+    # (4) four levels, D=32, M=8, P=4 (the COCO-scale head layout, tiny maps)
+    op_case(func, "d32_l4", [(10, 13), (5, 7), (3, 4), (2, 2)], n=1, m=8, d=32, lq=9, p=4, seed=13,
+            loc_range=(-0.05, 1.05))
+    # (5) odd channel count as in the reference gradcheck list (test.py:85 uses 30, 71)
+    op_case(func, "d30", [(6, 4), (3, 2)], n=1, m=2, d=30, lq=3, p=2, seed=14)
+    # (6) fp32 evaluation of case 3 (reference float check, test.py:47-60)
+    op_case(func, "d32_l1_f32", [(7, 9)], n=2, m=8, d=32, lq=6, p=4, seed=12, loc_range=(-0.1, 1.1),
+            dtype=torch.float32)
+
+    # ---------------- MSDeformAttn module (ms_deform_attn.py:31-117) ----------
+    shapes_t = torch.as_tensor([(6, 5), (3, 3)], dtype=torch.long)
+    lsi = lsi_of(shapes_t)
+    s = int(shapes_t.prod(1).sum())
+    n, c, heads, pts = 2, 32, 4, 3
+    torch.manual_seed(21)
+    attn_mod = mod.MSDeformAttn(c, 2, heads, pts).double()
+    perturb(attn_mod, 22)
+    query = torch.randn(n, s, c)
+    feat = torch.randn(n, s, c)
+    mask = torch.zeros(n, s, dtype=torch.bool)
+    mask[1, -4:] = True
+    ref2 = grid_reference_points(single, shapes_t, n, torch.float64)
+    save_module_case(
+        "module_msda_ref2", attn_mod,
+        dict(query=query, reference_points=ref2, input_flatten=feat, spatial_shapes=shapes_t,
+             level_start_index=lsi, padding_mask=mask),
+        lambda m_, t: m_(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"],
+                        t["level_start_index"], t["padding_mask"]),
+        wrt=["query", "reference_points", "input_flatten"])
+    # 4-d reference boxes (decoder with box refinement, ms_deform_attn.py:108-110), Lq != S
+    torch.manual_seed(23)
+    q7 = torch.randn(n, 7, c)
+    ref4 = torch.rand(n, 7, 2, 4) * 0.6 + 0.2
+    save_module_case(
+        "module_msda_ref4", attn_mod,
+        dict(query=q7, reference_points=ref4, input_flatten=feat, spatial_shapes=shapes_t,
+             level_start_index=lsi),
+        lambda m_, t: m_(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"],
+                        t["level_start_index"], None),
+        wrt=["query", "reference_points", "input_flatten"])
+
+    # ---------------- layer classes (deformable_transformer_single.py) --------
+    torch.manual_seed(31)
+    pos = torch.randn(n, s, c)
+    enc_layer = single.DeformableTransformerEncoderLayer(c, 64, 0.0, "relu", 2, heads, pts).double()
+    perturb(enc_layer, 32)
+    save_module_case(
+        "layer_encoder", enc_layer,
+        dict(src=feat, pos=pos, reference_points=ref2, spatial_shapes=shapes_t, level_start_index=lsi,
+             padding_mask=mask),
+        lambda m_, t: m_(t["src"], t["pos"], t["reference_points"], t["spatial_shapes"],
+                        t["level_start_index"], t["padding_mask"]),
+        wrt=["src", "pos"])
+
+    # Encoder Cross Fusion layer (:406-461): RGB queries over a depth pyramid of its own shapes
+    dshapes = torch.as_tensor([(4, 6)], dtype=torch.long)
+    dlsi = lsi_of(dshapes)
+    sd = int(dshapes.prod(1).sum())
+    torch.manual_seed(33)
+    depth = torch.randn(n, sd, c)
+    dmask = torch.zeros(n, sd, dtype=torch.bool)
+    dmask[0, -3:] = True
+    ref_d1 = ref2[:, :, :1].contiguous()             # one depth level
+    fusion = single.DeformableTransformerFusionLayerV2(c, 64, 0.0, "gelu", 1, heads, pts).double()
+    perturb(fusion, 34)
+    save_module_case(
+        "layer_fusion_v2", fusion,
+        dict(tgt=feat, query_pos=pos, reference_points=ref_d1, src=depth, src_spatial_shapes=dshapes,
+             level_start_index=dlsi, src_padding_mask=dmask),
+        lambda m_, t: m_(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                        t["level_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"])
+
+    # Late Fusion layer (:341-402)
+    late = single.DepthDeformableTransformerEncoderLayer(c, 64, 0.0, "relu", 1, heads, pts, True, True, True).double()
+    perturb(late, 35)
+    save_module_case(
+        "layer_late_fusion", late,
+        dict(tgt=feat, query_pos=pos, reference_points=ref_d1, src=depth, src_spatial_shapes=dshapes,
+             frame_start_index=dlsi, src_padding_mask=dmask),
+        lambda m_, t: m_(t["tgt"], t["query_pos"], None, None, t["reference_points"], None, t["src"],
+                        t["src_spatial_shapes"], t["frame_start_index"], None, t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"])
+
+    # decoder layer (:596-648), 4-d refs
+    torch.manual_seed(36)
+    tgt7 = torch.randn(n, 7, c)
+    qpos7 = torch.randn(n, 7, c)
+    dec = single.DeformableTransformerDecoderLayer(c, 64, 0.0, "relu", 2, heads, pts).double()
+    perturb(dec, 37)
+    save_module_case(
+        "layer_decoder", dec,
+        dict(tgt=tgt7, query_pos=qpos7, reference_points=ref4, src=feat, src_spatial_shapes=shapes_t,
+             level_start_index=lsi, src_padding_mask=mask),
+        lambda m_, t: m_(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                        t["level_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "src"])
+
+    # Encoder-CF encoder (:465-518): 3 encoder layers, 2 fusion layers after layers 0 and 1.
+    # One RGB level so that the fusion output (RGB length) can serve as the next fusion's
+    # value with the depth shapes -- the only way the shipped model runs.
+    one = torch.as_tensor([(4, 6)], dtype=torch.long)
+    one_lsi = lsi_of(one)
+    torch.manual_seed(38)
+    src1 = torch.randn(n, sd, c)
+    pos1 = torch.randn(n, sd, c)
+    enc1 = single.DeformableTransformerEncoderLayer(c, 64, 0.0, "relu", 1, heads, pts).double()
+    fus1 = single.DeformableTransformerFusionLayerV2(c, 64, 0.0, "gelu", 1, heads, pts).double()
+    rgbd = single.RGBDDeformableTransformerEncoderV2(enc1, fus1, 3, 2, 2, [0, 1]).double()
+    perturb(rgbd, 39)
+    vr = torch.ones(n, 1, 2)
+    vr[1, 0, 0] = 0.75
+    save_module_case(
+        "encoder_rgbd_v2", rgbd,
+        dict(src=src1, spatial_shapes=one, level_start_index=one_lsi, valid_ratios=vr, pos=pos1,
+             padding_mask=dmask, depth_src=depth, depth_spatial_shapes=dshapes, depth_level_start_index=dlsi),
+        lambda m_, t: m_(t["src"], t["spatial_shapes"], t["level_start_index"], t["valid_ratios"], t["pos"],
+                        t["padding_mask"], None, t["depth_src"], t["depth_spatial_shapes"],
+                        t["depth_level_start_index"], None, None, None),
+        wrt=["src", "depth_src"])
+
+    # plain encoder (:551-593), 2 levels, 2 layers
+    enc2 = single.DeformableTransformerEncoder(
+        single.DeformableTransformerEncoderLayer(c, 64, 0.0, "relu", 2, heads, pts), 2).double()
+    perturb(enc2, 40)
+    vr2 = torch.ones(n, 2, 2)
+    vr2[0, :, 1] = 0.8
+    save_module_case(
+        "encoder_plain", enc2,
+        dict(src=feat, spatial_shapes=shapes_t, level_start_index=lsi, valid_ratios=vr2, pos=pos,
+             padding_mask=mask),
+        lambda m_, t: m_(t["src"], t["spatial_shapes"], t["level_start_index"], t["valid_ratios"], t["pos"],
+                        t["padding_mask"]),
+        wrt=["src"])
+
+    # Backbone Cross Fusion U-DF: fuse_layers + its layer (dformer_crossfusion_backbone.py:387-428,120-181)
+    torch.manual_seed(41)
+    udf = backbone_cf.DepthDeformableTransformerEncoderLayer(c, 64, 0.0, "relu", 1, heads, pts).double()
+    perturb(udf, 42)
+    rgb_map = torch.randn(n, c, 3, 4)
+    dep_map = torch.randn(n, c, 6, 8)
+    pos_rgb = torch.randn(n, c, 3, 4)
+    pos_dep = torch.randn(n, c, 6, 8)
+    m_rgb = torch.zeros(n, 3, 4, dtype=torch.bool)
+    m_dep = torch.zeros(n, 6, 8, dtype=torch.bool)
+    m_dep[1, :, -2:] = True
+    m_rgb[1, :, -1:] = True
+    save_module_case(
+        "backbone_udf_fuse", udf,
+        dict(src=rgb_map, target=dep_map, pos_src=pos_rgb, pos_target=pos_dep, mask_src=m_rgb, mask_target=m_dep),
+        lambda m_, t: backbone_cf.FusionBackboneBase.fuse_layers(
+            t["src"], t["target"], t["pos_src"], t["pos_target"], t["mask_src"], t["mask_target"], m_),
+        wrt=["src", "target"])
+
+
+if __name__ == "__main__":
+    main()
