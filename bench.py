@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the MSDeformAttn hot path (BASELINE.json metric: "MSDeformAttn fwd+bwd
+queries/sec & HBM GB/s vs roofline").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                  [--dtype f32|bf16] [--dist grid|random] [--batch B]
+
+One "step" = one forward + one backward of the drop-in op
+``MSDeformAttnFunction`` (C ABI msda_forward + msda_backward) over one batch of B=8 frames of
+the COCO-scale 4-level pyramid of an 800x1333 input (S = Lq = 22223 tokens per frame, M=8
+heads, D=32, L=4, P=4): the encoder self-attention shape of BASELINE.json configs[1].
+Inputs of one step are 637 MB (fp32) > the 126 MB L2, so no explicit L2 flush is needed.
+N>1: one process per GPU (torchrun), every rank runs its own batch (frames shard across GPUs,
+no data-path collective) -> weak scaling; time = max over ranks.
+
+``--impl reference`` times the reference's CPU implementation of the same path -- the in-repo
+restatement of ms_deform_attn_core_pytorch (oracle/msda_oracle.py; the original cannot be
+imported on the GPU box, /root/reference does not travel) -- fwd + autograd bwd, all host
+threads, on a bounded sample (1 frame per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+COCO_SHAPES = [(100, 167), (50, 84), (25, 42), (13, 21)]
+M, D, P = 8, 32, 4
+METRIC = "msda_fwd_bwd_queries_per_sec"
+UNIT = "queries/s"
+
+
+def level_start(shapes):
+    out, acc = [], 0
+    for h, w in shapes:
+        out.append(acc)
+        acc += h * w
+    return out, acc
+
+
+def make_inputs(torch, n, seed, dist):
+    """CPU generator (identical bits for the CPU arm and the GPU arm)."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    lsi, s = level_start(COCO_SHAPES)
+    nl, lq = len(COCO_SHAPES), s
+    value = torch.randn(n, s, M, D, generator=g)
+    attn = torch.softmax(torch.randn(n, lq, M, nl * P, generator=g), -1).view(n, lq, M, nl, P)
+    if dist == "random":                       # reference test recipe: loc ~ U[0,1)  (models/ops/test.py:34)
+        loc = torch.rand(n, lq, M, nl, P, 2, generator=g)
+    else:                                      # encoder geometry: pixel-centre grid + init compass offsets + N(0,1) px
+        ref = []
+        for h, w in COCO_SHAPES:
+            ys = (torch.arange(h, dtype=torch.float32) + 0.5) / h
+            xs = (torch.arange(w, dtype=torch.float32) + 0.5) / w
+            yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+            ref.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+        ref = torch.cat(ref, 0)
+        ang = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
+        comp = torch.stack([ang.cos(), ang.sin()], -1)
+        comp = comp / comp.abs().max(-1, keepdim=True)[0]
+        steps = torch.arange(1, P + 1, dtype=torch.float32)
+        off = comp[:, None, None, :] * steps[None, None, :, None]
+        off = off.expand(M, nl, P, 2) + torch.randn(n, lq, M, nl, P, 2, generator=g)
+        norm = torch.tensor([[w, h] for h, w in COCO_SHAPES], dtype=torch.float32)
+        loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
+    grad_out = torch.randn(n, lq, M * D, generator=g)
+    return value.contiguous(), loc.contiguous(), attn.contiguous(), grad_out.contiguous()
+
+
+def algorithmic_bytes(n, e_v):
+    """every operand of the drop-in op counted once.  e_v = bytes per element of
+    value / output / grad_output / grad_value; locations and attention weights are fp32."""
+    _, s = level_start(COCO_SHAPES)
+    lq, c, nl = s, M * D, len(COCO_SHAPES)
+    side = lq * M * nl * P * (2 * 4 + 4)
+    fwd = n * (s * c * e_v + side + lq * c * e_v)
+    bwd = n * (s * c * e_v + side + lq * c * e_v + s * c * e_v + side)
+    return fwd, bwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                power.append(float(r[3]))
+                for name, flag in zip(names, r[4:8]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile(kind):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            return json.load(f).get(kind, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's ms_deform_attn_core_pytorch (restated), fwd + autograd bwd
+# ----------------------------------------------------------------------------------------------
+def time_cpu_reference(torch, steps, warmup, dist, seed=0):
+    from oracle import msda_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    value, loc, attn, gout = make_inputs(torch, 1, seed, dist)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        msda_oracle.core_pytorch_fwd_bwd(value, COCO_SHAPES, loc, attn, gout)
+        times.append(time.perf_counter() - t0)
+    timed = times[warmup:]
+    total = sum(timed)
+    q = value.shape[1] * len(timed)
+    return {"value": q / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(timed)} x (1 frame, {value.shape[1]} queries) fwd+bwd, fp32, "
+                      f"oracle.core_pytorch (= reference ms_deform_attn_core_pytorch) + autograd, "
+                      f"os.cpu_count()={os.cpu_count()}",
+            "ms_per_step": 1e3 * total / len(timed)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cb = time_cpu_reference(torch, args.steps, max(args.warmup, 1), args.dist)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "msda_core_op_fwd_bwd_coco_pyramid_800x1333", "levels": COCO_SHAPES,
+                       "queries_per_frame": level_start(COCO_SHAPES)[1], "heads": M, "head_dim": D,
+                       "points": P, "frames_per_step": 1, "loc_distribution": args.dist,
+                       "note": "bounded sample: 1 frame per step on host cores"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from dfvod_b200 import MultiScaleDeformableAttention as MSDA
+
+    tdtype = {"f32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
+    e_v = 4 if args.dtype == "f32" else 2
+    n = args.batch
+    lsi, s = level_start(COCO_SHAPES)
+    value_h, loc_h, attn_h, gout_h = make_inputs(torch, n, 1000 + rank, args.dist)
+    value_h, gout_h = value_h.to(tdtype), gout_h.to(tdtype)
+    host = [t.pin_memory() for t in (value_h, loc_h, attn_h, gout_h)]
+    value, loc, attn, gout = (t.to(dev) for t in host)
+    st = torch.as_tensor(COCO_SHAPES, dtype=torch.long, device=dev)
+    ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
+
+    def step():
+        out = MSDA.ms_deform_attn_forward(value, st, ls, loc, attn, 64)
+        return out, MSDA.ms_deform_attn_backward(value, st, ls, loc, attn, gout, 64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: device-resident inputs ------------------------------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for k in range(args.steps):
+            ev[k][0].record()
+            out = MSDA.ms_deform_attn_forward(value, st, ls, loc, attn, 64)
+            ev[k][1].record()
+            grads = MSDA.ms_deform_attn_backward(value, st, ls, loc, attn, gout, 64)
+            ev[k][2].record()
+        t_end.record()
+        barrier()
+        if args.steps * 1.0 < 1:      # keep the sampler alive long enough to see the load
+            pass
+    elapsed_ms = t_start.elapsed_time(t_end)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    total_queries = n * s * world * args.steps
+    value_qps = total_queries / (elapsed_ms * 1e-3)
+
+    # ---- end to end: host buffers in, host buffers out, copies inside the timed region ---------
+    pinned_out = [torch.empty((n, s, M * D), dtype=tdtype).pin_memory(),
+                  torch.empty_like(value_h).pin_memory(), torch.empty_like(loc_h).pin_memory(),
+                  torch.empty_like(attn_h).pin_memory()]
+
+    def e2e_step():
+        v, l, a, g = (t.to(dev, non_blocking=True) for t in host)
+        o = MSDA.ms_deform_attn_forward(v, st, ls, l, a, 64)
+        gv, gl, ga = MSDA.ms_deform_attn_backward(v, st, ls, l, a, g, 64)
+        for dst, src in zip(pinned_out, (o, gv, gl, ga)):
+            dst.copy_(src, non_blocking=True)
+
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_qps = n * s * world * e2e_steps / (float(t.item()) * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = sum(t.numel() * t.element_size() for t in pinned_out)
+
+    # ---- roofline of the dominant kernel (the backward) ----------------------------------------
+    peak, peak_src = peaks()
+    fwd_bytes, bwd_bytes = algorithmic_bytes(n, e_v)
+    achieved_bwd = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+    achieved_fwd = fwd_bytes / (fwd_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "msda_bwd_fast_kernel (+ its grad_value zero-fill"
+                                          + (" and bf16 cast" if e_v == 2 else "") + ")",
+                "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
+                "traffic": traffic_from_profile("backward"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": bwd_ms}
+    roofline_fwd = {"bound": "hbm", "kernel": "msda_fwd_fast_kernel", "achieved": achieved_fwd, "peak": peak,
+                    "unit": "GB/s", "frac": achieved_fwd / peak, "traffic": traffic_from_profile("forward"),
+                    "algorithmic_bytes_per_launch": fwd_bytes, "ms_per_launch": fwd_ms}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = time_cpu_reference(torch, 3, 1, args.dist)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {"metric": METRIC, "value": value_qps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "msda_core_op_fwd_bwd_coco_pyramid_800x1333", "levels": COCO_SHAPES,
+                       "queries_per_frame": s, "heads": M, "head_dim": D, "points": P,
+                       "frames_per_step_per_gpu": n, "loc_distribution": args.dist,
+                       "l2": "inputs (%d MB per step) larger than L2" % ((fwd_bytes + bwd_bytes) // (2 << 20)),
+                       "parallelism": f"dp{world} (frames sharded, no data-path collective)"},
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": args.steps * (2 if e_v == 4 else 3),
+            "clocks": clocks.summary(),
+            "roofline": roofline, "roofline_fwd": roofline_fwd,
+            "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+            "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--dist", default="grid", choices=["grid", "random"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

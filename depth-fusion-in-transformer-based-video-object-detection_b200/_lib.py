@@ -1,0 +1,53 @@
+"""ctypes binding of libmsda_b200.so (C ABI declared in include/msda_b200.h).
+
+The library is built in-tree by ``make`` in this directory (see ``__graft_entry__.build``).
+There is no fallback: if the shared object is missing the import of the op fails loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmsda_b200.so")
+
+ABI_VERSION = 1
+DTYPE_F32, DTYPE_F64, DTYPE_BF16, DTYPE_F16 = 0, 1, 2, 3
+FLAG_FORCE_GENERIC = 1
+
+_lib = None
+
+
+class MSDAError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once and declare the prototypes of include/msda_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MSDAError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make` in the package "
+            "directory). There is no CPU or PyTorch fallback for this op.")
+    lib = ctypes.CDLL(LIB_PATH)
+    c_int, c_vp = ctypes.c_int, ctypes.c_void_p
+    lib.msda_abi_version.restype = c_int
+    lib.msda_abi_version.argtypes = []
+    lib.msda_error_string.restype = ctypes.c_char_p
+    lib.msda_error_string.argtypes = [c_int]
+    lib.msda_forward.restype = c_int
+    lib.msda_forward.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp, c_int, c_vp]
+    lib.msda_backward.restype = c_int
+    lib.msda_backward.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 7 + \
+                                 [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]
+    if lib.msda_abi_version() != ABI_VERSION:
+        raise MSDAError(f"libmsda_b200.so ABI {lib.msda_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().msda_error_string(code).decode()
+        raise MSDAError(f"{what} failed: CUDA error {code} ({msg})")

@@ -1,0 +1,59 @@
+// C-ABI entry points of libmsda_b200.so (declared in include/msda_b200.h).
+#include "../../include/msda_b200.h"
+#include "msda_launch.h"
+
+static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
+{
+    return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
+}
+
+extern "C" int msda_abi_version(void) { return 1; }
+
+extern "C" const char* msda_error_string(int code)
+{
+    return cudaGetErrorString((cudaError_t)code);
+}
+
+extern "C" int msda_forward(int dtype, const void* value, const int64_t* spatial_shapes,
+                            const int64_t* level_start_index, const void* sampling_loc,
+                            const void* attn_weight, int batch, int spatial_size, int num_heads,
+                            int channels, int num_levels, int num_query, int num_point, void* output,
+                            int flags, void* stream)
+{
+    if (dtype < 0 || dtype > 3 || bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
+        return (int)cudaErrorInvalidValue;
+    msda::FwdArgs a;
+    a.dtype = dtype;
+    a.value = value; a.shapes = spatial_shapes; a.lsi = level_start_index;
+    a.loc = sampling_loc; a.attn = attn_weight; a.out = output;
+    a.N = batch; a.S = spatial_size; a.M = num_heads; a.D = channels;
+    a.L = num_levels; a.Lq = num_query; a.P = num_point;
+    a.force_generic = (flags & MSDA_FLAG_FORCE_GENERIC) ? 1 : 0;
+    if (num_levels == 0 || num_point == 0) {   // empty sum: output is all zeros
+        const size_t esz = dtype == MSDA_DTYPE_F64 ? 8 : (dtype == MSDA_DTYPE_F32 ? 4 : 2);
+        return (int)cudaMemsetAsync(output, 0, (size_t)batch * num_query * num_heads * channels * esz,
+                                    (cudaStream_t)stream);
+    }
+    return (int)msda::forward(a, (cudaStream_t)stream);
+}
+
+extern "C" int msda_backward(int dtype, const void* grad_output, const void* value,
+                             const int64_t* spatial_shapes, const int64_t* level_start_index,
+                             const void* sampling_loc, const void* attn_weight, int batch,
+                             int spatial_size, int num_heads, int channels, int num_levels,
+                             int num_query, int num_point, void* grad_value, void* grad_sampling_loc,
+                             void* grad_attn_weight, void* grad_value_accum_f32, int flags, void* stream)
+{
+    if (dtype < 0 || dtype > 3 || bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
+        return (int)cudaErrorInvalidValue;
+    msda::BwdArgs a;
+    a.dtype = dtype;
+    a.grad_out = grad_output; a.value = value; a.shapes = spatial_shapes; a.lsi = level_start_index;
+    a.loc = sampling_loc; a.attn = attn_weight;
+    a.grad_value = grad_value; a.grad_loc = grad_sampling_loc; a.grad_attn = grad_attn_weight;
+    a.grad_value_accum = (float*)grad_value_accum_f32;
+    a.N = batch; a.S = spatial_size; a.M = num_heads; a.D = channels;
+    a.L = num_levels; a.Lq = num_query; a.P = num_point;
+    a.force_generic = (flags & MSDA_FLAG_FORCE_GENERIC) ? 1 : 0;
+    return (int)msda::backward(a, (cudaStream_t)stream);
+}

@@ -1,0 +1,403 @@
+// Backward multi-scale deformable attention for sm_100a.
+//
+//   grad_value[n, pix, m, :] += w_corner * A * g            (scatter over the 4 corners)
+//   grad_attn [n,q,m,l,p]     = sum_c g_c * bilinear_c
+//   grad_loc  [n,q,m,l,p]     = ( W * A * sum_c g_c * d bilinear_c / dx ,
+//                                 H * A * sum_c g_c * d bilinear_c / dy )
+//
+// Replaces the reference's six col2im kernels + switch(channels) (cuda/ms_deform_im2col_cuda.cuh:
+// 301-920, 956-1327; helper :87-159).  The production reference kernel for D=32 runs one
+// 32-thread block per (n,q,m), issues 4 scalar atomicAdd per channel per sample, and reduces
+// grad_loc / grad_attn through shared memory with thread 0 summing serially between two
+// __syncthreads per sample (:376-394).
+//
+// Fast kernel (same lane mapping as the forward: a group of G lanes owns a pair, each lane a
+// 16-byte channel slice):
+//   * footprints are computed once per sample by one lane and shared through smem;
+//   * grad_value uses ONE 16-byte vector reduction (red.global.add.v4.f32 -> REDG.E.ADD.F32x4)
+//     per lane per corner instead of 4 scalar atomics, always into an fp32 buffer;
+//   * the three per-sample dot products stay in registers; after a 16-sample chunk the 48
+//     partials per lane are combined across the group with a shuffle reduce-scatter
+//     (24+12+6 shuffles for G=8 instead of 144 for a per-value butterfly) that leaves every
+//     lane holding the finished gradients of its own samples, which it stores directly.
+//     No shared-memory reduction, no block barrier;
+//   * grad_loc / grad_attn are written for every sample (zeros for samples outside the map),
+//     so they need no zero-fill pass; only grad_value is memset.
+// Generic kernel: any D / dtype (fp64 for gradcheck): one warp per pair, lanes stride channels.
+#include "msda_common.cuh"
+#include "msda_launch.h"
+
+namespace msda {
+
+template <int PAIRS> struct BwdWarps { static constexpr int value = PAIRS >= 16 ? 2 : (PAIRS >= 8 ? 4 : 8); };
+
+// After the call lane `sub` of each G-lane group holds, in v[0 .. N*2*OFF/G... ) -- precisely
+// v[0 .. N/(2*OFF)) -- the group-wide sums of original elements [sub*len, (sub+1)*len).
+template <int N, int OFF>
+__device__ __forceinline__ void reduce_scatter(float* v, int sub)
+{
+    if constexpr (OFF >= 1) {
+        const bool upper = (sub & OFF) != 0;
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float send = upper ? v[i] : v[i + N / 2];
+            const float keep = upper ? v[i + N / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        reduce_scatter<N / 2, OFF / 2>(v, sub);
+    }
+}
+
+template <typename VT, int D>
+__global__ void __launch_bounds__(BwdWarps<32 / (D / Traits<VT>::kEpl)>::value * 32)
+msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
+                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
+                     const float* __restrict__ loc, const float* __restrict__ attn,
+                     float* __restrict__ gv_accum, float* __restrict__ grad_loc,
+                     float* __restrict__ grad_attn,
+                     int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs)
+{
+    constexpr int EPL = Traits<VT>::kEpl;
+    constexpr int G = D / EPL;
+    constexpr int PAIRS = 32 / G;
+    constexpr int WARPS = BwdWarps<PAIRS>::value;
+    constexpr int SPL = kChunk / G;              // finished samples per lane after the reduce-scatter
+    static_assert(G >= 1 && G <= 16 && (G & (G - 1)) == 0, "fast backward needs 1..16 lanes per head");
+
+    __shared__ int s_meta[3 * kMaxLevelsFast];
+    __shared__ __align__(16) int4   s_geo[WARPS][PAIRS][kChunk];   // pix00, rowstep, ok, -
+    __shared__ __align__(16) float4 s_frac[WARPS][PAIRS][kChunk];  // lw, lh, a, -
+
+    if (threadIdx.x < L) {
+        s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
+        s_meta[3 * threadIdx.x + 1] = (int)shapes[2 * threadIdx.x + 1];
+        s_meta[3 * threadIdx.x + 2] = (int)lsi[threadIdx.x];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, sub = lane % G;
+    const long long pair_raw = ((long long)blockIdx.x * WARPS + warp) * PAIRS + grp;
+    const bool active = pair_raw < total_pairs;
+    const long long pair = active ? pair_raw : total_pairs - 1;
+    const int m = (int)(pair % M);
+    const long long n = (pair / M) / Lq;
+    const int LP = L * P;
+    const int MD = M * D;
+    const long long head_off = (n * S * M + m) * (long long)D + sub * EPL;
+    const VT* vbase = value + head_off;
+    float* gbase = gv_accum + head_off;
+    const float* lp = loc + pair * LP * 2;
+    const float* ap = attn + pair * LP;
+
+    float g[EPL];
+    unpack<VT>(ldg_stream_v4(grad_out + pair * D + sub * EPL), g);
+    if (!active) {
+#pragma unroll
+        for (int c = 0; c < EPL; ++c) g[c] = 0.f;     // clamped duplicate pair contributes nothing
+    }
+
+    for (int s0 = 0; s0 < LP; s0 += kChunk) {
+        const int cnt = min(kChunk, LP - s0);
+        const int cnt2 = (cnt + 1) & ~1;
+        // ---- phase 1: footprints --------------------------------------------------------------
+        for (int j = sub; j < cnt2; j += G) {
+            int4 geo = make_int4(0, 0, 0, 0);
+            float4 fr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < cnt) {
+                const int s = s0 + j;
+                const int l = div_by_points(s, p_magic);
+                const float2 xy = ldg_stream_f32x2(lp + 2 * s);
+                const float a = ldg_stream_f32(ap + s);
+                const Footprint f = footprint<float>(xy.x, xy.y, s_meta[3 * l], s_meta[3 * l + 1], s_meta[3 * l + 2]);
+                geo = make_int4(f.pix00, f.rowstep, (int)f.ok, 0);
+                fr = make_float4(f.lw, f.lh, a, 0.f);
+            }
+            s_geo[warp][grp][j] = geo;
+            s_frac[warp][grp][j] = fr;
+        }
+        __syncwarp();
+
+        // ---- phase 2: per-sample gather, dot products, vector reductions into grad_value -----
+        float part[3 * kChunk];
+#pragma unroll
+        for (int i = 0; i < 3 * kChunk; ++i) part[i] = 0.f;
+
+#pragma unroll
+        for (int j0 = 0; j0 < kChunk; j0 += 2) {
+            if (j0 < cnt2) {
+                int4 geo[2];
+                float4 fr[2];
+                uint4 raw[2][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    geo[u] = s_geo[warp][grp][j0 + u];
+                    fr[u] = s_frac[warp][grp][j0 + u];
+                    const VT* p00 = vbase + (long long)geo[u].x * MD;
+                    const long long row = (long long)geo[u].y * MD;
+                    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                    raw[u][0] = (geo[u].z & 1) ? ldg_v4(p00) : zero;
+                    raw[u][1] = (geo[u].z & 2) ? ldg_v4(p00 + MD) : zero;
+                    raw[u][2] = (geo[u].z & 4) ? ldg_v4(p00 + row) : zero;
+                    raw[u][3] = (geo[u].z & 8) ? ldg_v4(p00 + row + MD) : zero;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float lw = fr[u].x, lh = fr[u].y, a = fr[u].z;
+                    const float hw = 1.f - lw, hh = 1.f - lh;
+                    const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+                    float v1[EPL], v2[EPL], v3[EPL], v4[EPL], tg[EPL];
+                    unpack<VT>(raw[u][0], v1);
+                    unpack<VT>(raw[u][1], v2);
+                    unpack<VT>(raw[u][2], v3);
+                    unpack<VT>(raw[u][3], v4);
+                    float px = 0.f, py = 0.f, pa = 0.f;
+#pragma unroll
+                    for (int c = 0; c < EPL; ++c) {
+                        tg[c] = a * g[c];                                        // cuh:113
+                        const float val = w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c];
+                        const float dx = hh * (v2[c] - v1[c]) + lh * (v4[c] - v3[c]);   // cuh:119-151 (grad_w_weight)
+                        const float dy = hw * (v3[c] - v1[c]) + lw * (v4[c] - v2[c]);   // (grad_h_weight)
+                        pa = fmaf(g[c], val, pa);
+                        px = fmaf(tg[c], dx, px);
+                        py = fmaf(tg[c], dy, py);
+                    }
+                    part[3 * (j0 + u) + 0] = px;
+                    part[3 * (j0 + u) + 1] = py;
+                    part[3 * (j0 + u) + 2] = pa;
+                    float* q00 = gbase + (long long)geo[u].x * MD;
+                    const long long row = (long long)geo[u].y * MD;
+                    const float wk[4] = {w1, w2, w3, w4};
+                    float* const qk[4] = {q00, q00 + MD, q00 + row, q00 + row + MD};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (geo[u].z & (1 << k)) {
+#pragma unroll
+                            for (int c = 0; c < EPL; c += 4)
+                                red_add_f32x4(qk[k] + c, wk[k] * tg[c], wk[k] * tg[c + 1],
+                                              wk[k] * tg[c + 2], wk[k] * tg[c + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 3: combine the group's partials; each lane finishes SPL samples -----------
+        reduce_scatter<3 * kChunk, G / 2>(part, sub);
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+                const int j = sub * SPL + i;
+                if (j < cnt) {
+                    const int s = s0 + j;
+                    const int l = div_by_points(s, p_magic);
+                    const float Hf = (float)s_meta[3 * l], Wf = (float)s_meta[3 * l + 1];
+                    float2 gl = make_float2(Wf * part[3 * i + 0], Hf * part[3 * i + 1]);   // cuh:157-158
+                    *reinterpret_cast<float2*>(grad_loc + (pair * LP + s) * 2) = gl;
+                    grad_attn[pair * LP + s] = part[3 * i + 2];                            // cuh:156
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic path: one warp per pair, lanes stride the channels, scalar atomics.
+// ------------------------------------------------------------------------------------------
+template <typename VT> struct ScalarLoad {
+    using acc_t = typename Traits<VT>::acc_t;
+    static __device__ __forceinline__ acc_t load(const VT* p) { return (acc_t)to_f32<VT>(*p); }
+};
+template <> struct ScalarLoad<double> {
+    using acc_t = double;
+    static __device__ __forceinline__ double load(const double* p) { return *p; }
+};
+
+template <typename VT>
+__global__ void __launch_bounds__(256)
+msda_bwd_generic_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
+                        const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
+                        const typename Traits<VT>::loc_t* __restrict__ loc,
+                        const typename Traits<VT>::loc_t* __restrict__ attn,
+                        typename Traits<VT>::acc_t* __restrict__ gv_accum,
+                        typename Traits<VT>::loc_t* __restrict__ grad_loc,
+                        typename Traits<VT>::loc_t* __restrict__ grad_attn,
+                        int S, int M, int D, int L, int Lq, int P, long long total_pairs)
+{
+    using acc_t = typename Traits<VT>::acc_t;
+    using loc_t = typename Traits<VT>::loc_t;
+    const int lane = threadIdx.x & 31;
+    const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long MD = (long long)M * D;
+    for (long long pair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pair < total_pairs;
+         pair += warps_total) {
+        const int m = (int)(pair % M);
+        const long long n = (pair / M) / Lq;
+        const long long head_off = (n * S * M + m) * (long long)D;
+        const VT* go = grad_out + pair * D;
+        const loc_t* lp = loc + pair * L * P * 2;
+        const loc_t* ap = attn + pair * L * P;
+        for (int l = 0; l < L; ++l) {
+            const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1], start = (int)lsi[l];
+            for (int p = 0; p < P; ++p) {
+                const int s = l * P + p;
+                const loc_t x = lp[2 * s], y = lp[2 * s + 1];
+                const acc_t a = (acc_t)ap[s];
+                const Footprint f = footprint<loc_t>(x, y, H, W, start);
+                acc_t px = 0, py = 0, pa = 0;
+                if (f.ok) {
+                    const loc_t w_im = x * (loc_t)W - (loc_t)0.5, h_im = y * (loc_t)H - (loc_t)0.5;
+                    const acc_t lw = (acc_t)(w_im - floor(w_im)), lh = (acc_t)(h_im - floor(h_im));
+                    const acc_t hw = 1 - lw, hh = 1 - lh;
+                    const acc_t w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+                    const long long o00 = head_off + (long long)f.pix00 * MD;
+                    const long long row = (long long)f.rowstep * MD;
+                    for (int c = lane; c < D; c += 32) {
+                        const acc_t gc = ScalarLoad<VT>::load(go + c);
+                        const acc_t tg = a * gc;
+                        acc_t v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+                        if (f.ok & 1u) { v1 = ScalarLoad<VT>::load(value + o00 + c);            atomicAdd(gv_accum + o00 + c, w1 * tg); }
+                        if (f.ok & 2u) { v2 = ScalarLoad<VT>::load(value + o00 + MD + c);       atomicAdd(gv_accum + o00 + MD + c, w2 * tg); }
+                        if (f.ok & 4u) { v3 = ScalarLoad<VT>::load(value + o00 + row + c);      atomicAdd(gv_accum + o00 + row + c, w3 * tg); }
+                        if (f.ok & 8u) { v4 = ScalarLoad<VT>::load(value + o00 + row + MD + c); atomicAdd(gv_accum + o00 + row + MD + c, w4 * tg); }
+                        pa += gc * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
+                        px += tg * (hh * (v2 - v1) + lh * (v4 - v3));
+                        py += tg * (hw * (v3 - v1) + lw * (v4 - v2));
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    px += __shfl_xor_sync(0xffffffffu, px, off);
+                    py += __shfl_xor_sync(0xffffffffu, py, off);
+                    pa += __shfl_xor_sync(0xffffffffu, pa, off);
+                }
+                if (lane == 0) {
+                    grad_loc[(pair * L * P + s) * 2] = (loc_t)((acc_t)W * px);
+                    grad_loc[(pair * L * P + s) * 2 + 1] = (loc_t)((acc_t)H * py);
+                    grad_attn[pair * L * P + s] = (loc_t)pa;
+                }
+            }
+        }
+    }
+}
+
+// fp32 accumulation buffer -> 16-bit grad_value
+template <typename VT>
+__global__ void __launch_bounds__(256)
+msda_cast_accum_kernel(const float* __restrict__ src, VT* __restrict__ dst, long long count)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long vec = count / 8;
+    for (long long i = i0; i < vec; i += stride) {
+        float f[8];
+        const uint4 a = ldg_stream_v4(src + i * 8), b = ldg_stream_v4(src + i * 8 + 4);
+        unpack<float>(a, f);
+        unpack<float>(b, f + 4);
+        stg_stream_v4(dst + i * 8, pack<VT>(f));
+    }
+    for (long long i = vec * 8 + i0; i < count; i += stride) dst[i] = from_f32<VT>(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+template <typename VT, int D>
+static cudaError_t launch_bwd_fast(const BwdArgs& a, float* accum, cudaStream_t stream)
+{
+    constexpr int G = D / Traits<VT>::kEpl;
+    constexpr int PAIRS = 32 / G;
+    constexpr int WARPS = BwdWarps<PAIRS>::value;
+    const long long total_pairs = (long long)a.N * a.Lq * a.M;
+    const long long blocks = (total_pairs + WARPS * PAIRS - 1) / (WARPS * PAIRS);
+    const int p_magic = (65536 + a.P - 1) / a.P;
+    msda_bwd_fast_kernel<VT, D><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
+        (const VT*)a.grad_out, (const VT*)a.value, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn,
+        accum, (float*)a.grad_loc, (float*)a.grad_attn, a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+    return cudaGetLastError();
+}
+
+template <typename VT>
+static cudaError_t launch_bwd_generic(const BwdArgs& a, typename Traits<VT>::acc_t* accum, cudaStream_t stream)
+{
+    using loc_t = typename Traits<VT>::loc_t;
+    const long long total_pairs = (long long)a.N * a.Lq * a.M;
+    long long blocks = (total_pairs + 7) / 8;
+    if (blocks > (1ll << 30)) blocks = 1ll << 30;
+    msda_bwd_generic_kernel<VT><<<(unsigned)blocks, 256, 0, stream>>>(
+        (const VT*)a.grad_out, (const VT*)a.value, a.shapes, a.lsi, (const loc_t*)a.loc, (const loc_t*)a.attn,
+        accum, (loc_t*)a.grad_loc, (loc_t*)a.grad_attn, a.S, a.M, a.D, a.L, a.Lq, a.P, total_pairs);
+    return cudaGetLastError();
+}
+
+static bool fast_shape_ok(const BwdArgs& a)
+{
+    return !a.force_generic && a.L <= kMaxLevelsFast && a.P <= 64 && (long long)a.L * a.P * a.P < 65536 &&
+           (long long)a.S * a.M * a.D < (1ll << 31);
+}
+
+template <typename VT>
+static cudaError_t run_bwd_16or32(const BwdArgs& a, cudaStream_t stream)
+{
+    constexpr bool k16 = sizeof(VT) == 2;
+    const size_t count = (size_t)a.N * a.S * a.M * a.D;
+    float* accum = k16 ? a.grad_value_accum : (float*)a.grad_value;
+    if (k16 && accum == nullptr) return cudaErrorInvalidValue;
+    cudaError_t err = cudaMemsetAsync(accum, 0, count * sizeof(float), stream);
+    if (err != cudaSuccess) return err;
+    const long long total_pairs = (long long)a.N * a.Lq * a.M;
+    if (total_pairs > 0 && a.D > 0) {
+        bool done = false;
+        if (fast_shape_ok(a)) {
+            done = true;
+            if constexpr (k16) {
+                switch (a.D) {   // 16-bit: G = D/8 must be <= 16
+                    case 8:   err = launch_bwd_fast<VT, 8>(a, accum, stream); break;
+                    case 16:  err = launch_bwd_fast<VT, 16>(a, accum, stream); break;
+                    case 32:  err = launch_bwd_fast<VT, 32>(a, accum, stream); break;
+                    case 64:  err = launch_bwd_fast<VT, 64>(a, accum, stream); break;
+                    case 128: err = launch_bwd_fast<VT, 128>(a, accum, stream); break;
+                    default: done = false;
+                }
+            } else {
+                switch (a.D) {   // fp32: G = D/4 must be <= 16
+                    case 8:   err = launch_bwd_fast<VT, 8>(a, accum, stream); break;
+                    case 16:  err = launch_bwd_fast<VT, 16>(a, accum, stream); break;
+                    case 32:  err = launch_bwd_fast<VT, 32>(a, accum, stream); break;
+                    case 64:  err = launch_bwd_fast<VT, 64>(a, accum, stream); break;
+                    default: done = false;
+                }
+            }
+        }
+        if (!done) err = launch_bwd_generic<VT>(a, accum, stream);
+        if (err != cudaSuccess) return err;
+    }
+    if (k16 && count > 0) {
+        long long blocks = (long long)((count / 8 + 255) / 256);
+        if (blocks < 1) blocks = 1;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        msda_cast_accum_kernel<VT><<<(unsigned)blocks, 256, 0, stream>>>(accum, (VT*)a.grad_value, (long long)count);
+        err = cudaGetLastError();
+    }
+    return err;
+}
+
+cudaError_t backward(const BwdArgs& a, cudaStream_t stream)
+{
+    switch (a.dtype) {
+        case kF32:  return run_bwd_16or32<float>(a, stream);
+        case kBF16: return run_bwd_16or32<__nv_bfloat16>(a, stream);
+        case kF16:  return run_bwd_16or32<__half>(a, stream);
+        case kF64: {
+            const size_t count = (size_t)a.N * a.S * a.M * a.D;
+            cudaError_t err = cudaMemsetAsync(a.grad_value, 0, count * sizeof(double), stream);
+            if (err != cudaSuccess) return err;
+            if ((long long)a.N * a.Lq * a.M == 0 || a.D == 0) return cudaSuccess;
+            return launch_bwd_generic<double>(a, (double*)a.grad_value, stream);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace msda

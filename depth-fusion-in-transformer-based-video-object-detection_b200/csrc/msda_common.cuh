@@ -1,0 +1,159 @@
+// Shared device helpers for the sm_100a multi-scale deformable attention kernels.
+//
+// Data layout in HBM (the reference's, unchanged so the op stays a drop-in):
+//   value        [N, S, M, D]        pixel-major, one pixel record = M*D contiguous elements
+//   sampling_loc [N, Lq, M, L, P, 2] (x, y) normalised to [0,1]
+//   attn_weight  [N, Lq, M, L, P]
+//   output       [N, Lq, M, D]
+//   spatial_shapes [L,2] (H,W) int64 and level_start_index [L] int64, both ON DEVICE
+// A "pair" is one (n, q, m) triple; pairs are numbered flat, pair = (n*Lq + q)*M + m, so that
+// the loc / attn / output blocks of consecutive pairs are contiguous in memory.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msda {
+
+constexpr int kMaxLevelsFast = 32;   // level metadata staged in shared memory by the fast kernels
+constexpr int kChunk = 16;           // samples (level x point) processed per pass by the fast kernels
+
+// ----------------------------------------------------------------------------------------
+// dtype traits: storage type of value/output, arithmetic type, and the 16-byte vector shape
+// ----------------------------------------------------------------------------------------
+template <typename VT> struct Traits;
+template <> struct Traits<float>         { using acc_t = float;  using loc_t = float;  static constexpr int kEpl = 4; };
+template <> struct Traits<double>        { using acc_t = double; using loc_t = double; static constexpr int kEpl = 2; };
+template <> struct Traits<__nv_bfloat16> { using acc_t = float;  using loc_t = float;  static constexpr int kEpl = 8; };
+template <> struct Traits<__half>        { using acc_t = float;  using loc_t = float;  static constexpr int kEpl = 8; };
+
+template <typename VT> __device__ __forceinline__ float to_f32(VT v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename VT> __device__ __forceinline__ VT from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// ----------------------------------------------------------------------------------------
+// 128-bit global accesses.  Value rows are re-read by neighbouring queries, so they go through
+// the read-only path and are allowed to allocate in L1; loc/attn/grad streams are read once.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_v4(const void* p)
+{
+    uint4 r;
+    asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p)
+{
+    uint4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_v4(void* p, uint4 v)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float ldg_stream_f32(const float* p)
+{
+    float r;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ldg_stream_f32x2(const float* p)
+{
+    float2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+// one 16-byte vector reduction into global memory (sm_90+): REDG.E.ADD.F32x4
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// unpack one 16-byte vector of VT into kEpl floats
+template <typename VT> __device__ __forceinline__ void unpack(const uint4& raw, float* f);
+template <> __device__ __forceinline__ void unpack<float>(const uint4& raw, float* f)
+{
+    f[0] = __uint_as_float(raw.x); f[1] = __uint_as_float(raw.y);
+    f[2] = __uint_as_float(raw.z); f[3] = __uint_as_float(raw.w);
+}
+template <> __device__ __forceinline__ void unpack<__nv_bfloat16>(const uint4& raw, float* f)
+{
+    // bf16 -> f32 is a 16-bit shift
+    f[0] = __uint_as_float(raw.x << 16); f[1] = __uint_as_float(raw.x & 0xffff0000u);
+    f[2] = __uint_as_float(raw.y << 16); f[3] = __uint_as_float(raw.y & 0xffff0000u);
+    f[4] = __uint_as_float(raw.z << 16); f[5] = __uint_as_float(raw.z & 0xffff0000u);
+    f[6] = __uint_as_float(raw.w << 16); f[7] = __uint_as_float(raw.w & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack<__half>(const uint4& raw, float* f)
+{
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+template <typename VT> __device__ __forceinline__ uint4 pack(const float* f);
+template <> __device__ __forceinline__ uint4 pack<float>(const float* f)
+{
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+}
+template <> __device__ __forceinline__ uint4 pack<__nv_bfloat16>(const float* f)
+{
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return r;
+}
+template <> __device__ __forceinline__ uint4 pack<__half>(const float* f)
+{
+    uint4 r;
+    __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    return r;
+}
+
+// ----------------------------------------------------------------------------------------
+// Bilinear footprint of one sample (the arithmetic of ms_deform_attn_im2col_bilinear,
+// reference cuda/ms_deform_im2col_cuda.cuh:33-84, with the caller's range test :288 folded in).
+// ----------------------------------------------------------------------------------------
+struct Footprint {
+    int   pix00;     // level_start + y0*W + x0 (pixel index inside one batch element; may be
+                     // out of range when a corner is invalid -- never dereferenced then)
+    int   rowstep;   // W
+    unsigned ok;     // bit0..3: corner (y0,x0) (y0,x1) (y1,x0) (y1,x1) lies inside the map
+    float lw, lh;    // fractional parts
+};
+
+template <typename T>
+__device__ __forceinline__ Footprint footprint(T loc_x, T loc_y, int H, int W, int start)
+{
+    // pixel convention of align_corners=False: x = loc_x * W - 0.5   (cuh:285-286)
+    const T w_im = loc_x * (T)W - (T)0.5;
+    const T h_im = loc_y * (T)H - (T)0.5;
+    Footprint f;
+    const bool inside = (h_im > (T)-1) && (w_im > (T)-1) && (h_im < (T)H) && (w_im < (T)W);
+    const T hf = floor(h_im), wf = floor(w_im);
+    const int y0 = (int)hf, x0 = (int)wf;
+    f.lh = (float)(h_im - hf);
+    f.lw = (float)(w_im - wf);
+    const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= W - 1;
+    f.ok = inside ? ((y0ok && x0ok ? 1u : 0u) | (y0ok && x1ok ? 2u : 0u) |
+                     (y1ok && x0ok ? 4u : 0u) | (y1ok && x1ok ? 8u : 0u)) : 0u;
+    f.pix00 = start + y0 * W + x0;
+    f.rowstep = W;
+    return f;
+}
+
+// exact s / P for 0 <= s < 65536 / P  (magic = ceil(65536 / P), computed on the host)
+__device__ __forceinline__ int div_by_points(int s, int magic) { return (s * magic) >> 16; }
+
+}  // namespace msda

@@ -1,0 +1,250 @@
+// Forward multi-scale deformable attention for sm_100a.
+//
+//   out[n,q,m,:] = sum_{l,p} A[n,q,m,l,p] * bilinear(value_l[n,:,m,:], loc[n,q,m,l,p])
+//
+// Replaces the reference's ms_deformable_im2col_gpu_kernel (cuda/ms_deform_im2col_cuda.cuh:237-299,
+// one thread per output scalar, 4-byte loads, per-thread address arithmetic).
+//
+// Fast kernel (D*sizeof(VT) a power-of-two multiple of 16 B):
+//   * a group of G = D*sizeof(VT)/16 lanes owns one pair (n,q,m); a warp owns 32/G consecutive
+//     pairs, so loc / attn / out accesses of a warp are one contiguous block;
+//   * phase 1 (setup): the lanes of a group split the L*P samples between them; each computes
+//     one sample's bilinear footprint ONCE (4 clamped pixel indices + 4 weights already
+//     multiplied by the attention weight and zeroed for out-of-map corners) and parks it in
+//     shared memory - 32 B per sample.  No per-channel address arithmetic is left;
+//   * phase 2 (gather): every lane walks the samples, reads the 32-byte record with two
+//     broadcast LDS.128 and issues four independent 128-bit loads (one per corner) of its
+//     16-byte slice of the head's channel vector; 4 samples are unrolled so 16 loads are in
+//     flight per lane.  Accumulation is fp32 in registers; one 128-bit store per lane.
+// Generic kernel: any D, any dtype (fp64 for gradcheck), one thread per output scalar.
+#include "msda_common.cuh"
+#include "msda_launch.h"
+
+namespace msda {
+
+template <int PAIRS> struct FwdWarps { static constexpr int value = PAIRS >= 16 ? 2 : (PAIRS >= 8 ? 4 : 8); };
+
+template <typename VT, int D>
+__global__ void __launch_bounds__(FwdWarps<32 / (D / Traits<VT>::kEpl)>::value * 32)
+msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                     const float* __restrict__ attn, VT* __restrict__ out,
+                     int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs)
+{
+    constexpr int EPL = Traits<VT>::kEpl;
+    constexpr int G = D / EPL;
+    constexpr int PAIRS = 32 / G;
+    constexpr int WARPS = FwdWarps<PAIRS>::value;
+    static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "head width must map to a power-of-two lane group");
+
+    __shared__ int s_meta[3 * kMaxLevelsFast];
+    __shared__ __align__(16) int4   s_pix[WARPS][PAIRS][kChunk];
+    __shared__ __align__(16) float4 s_wgt[WARPS][PAIRS][kChunk];
+
+    if (threadIdx.x < L) {
+        s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
+        s_meta[3 * threadIdx.x + 1] = (int)shapes[2 * threadIdx.x + 1];
+        s_meta[3 * threadIdx.x + 2] = (int)lsi[threadIdx.x];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, sub = lane % G;
+    const long long pair_raw = ((long long)blockIdx.x * WARPS + warp) * PAIRS + grp;
+    const bool active = pair_raw < total_pairs;
+    const long long pair = active ? pair_raw : total_pairs - 1;   // clamp: loads stay in bounds
+    const int m = (int)(pair % M);
+    const long long n = (pair / M) / Lq;
+    const int LP = L * P;
+    const int MD = M * D;
+    const VT* vbase = value + (n * S * M + m) * (long long)D + sub * EPL;
+    const float* lp = loc + pair * LP * 2;
+    const float* ap = attn + pair * LP;
+
+    float acc[EPL];
+#pragma unroll
+    for (int c = 0; c < EPL; ++c) acc[c] = 0.f;
+
+    for (int s0 = 0; s0 < LP; s0 += kChunk) {
+        const int cnt = min(kChunk, LP - s0);
+        const int cnt4 = (cnt + 3) & ~3;
+        // ---- phase 1: footprints, one sample per lane of the group -------------------------
+        for (int j = sub; j < cnt4; j += G) {
+            int4 px = make_int4(0, 0, 0, 0);
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < cnt) {
+                const int s = s0 + j;
+                const int l = div_by_points(s, p_magic);
+                const float2 xy = ldg_stream_f32x2(lp + 2 * s);
+                const float a = ldg_stream_f32(ap + s);
+                const Footprint f = footprint<float>(xy.x, xy.y, s_meta[3 * l], s_meta[3 * l + 1], s_meta[3 * l + 2]);
+                const float hw = 1.f - f.lw, hh = 1.f - f.lh;
+                // invalid corners: weight 0 and a harmless in-range address (pixel 0)
+                px.x = (f.ok & 1u) ? f.pix00 : 0;
+                px.y = (f.ok & 2u) ? f.pix00 + 1 : 0;
+                px.z = (f.ok & 4u) ? f.pix00 + f.rowstep : 0;
+                px.w = (f.ok & 8u) ? f.pix00 + f.rowstep + 1 : 0;
+                w.x = (f.ok & 1u) ? hh * hw * a : 0.f;
+                w.y = (f.ok & 2u) ? hh * f.lw * a : 0.f;
+                w.z = (f.ok & 4u) ? f.lh * hw * a : 0.f;
+                w.w = (f.ok & 8u) ? f.lh * f.lw * a : 0.f;
+            }
+            s_pix[warp][grp][j] = px;
+            s_wgt[warp][grp][j] = w;
+        }
+        __syncwarp();
+        // ---- phase 2: gather, 4 samples x 4 corners in flight ------------------------------
+        for (int j0 = 0; j0 < cnt4; j0 += 4) {
+            uint4 raw[4][4];
+            float4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int4 px = s_pix[warp][grp][j0 + u];
+                w[u] = s_wgt[warp][grp][j0 + u];
+                raw[u][0] = ldg_v4(vbase + (long long)px.x * MD);
+                raw[u][1] = ldg_v4(vbase + (long long)px.y * MD);
+                raw[u][2] = ldg_v4(vbase + (long long)px.z * MD);
+                raw[u][3] = ldg_v4(vbase + (long long)px.w * MD);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float wk[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float v[EPL];
+                    unpack<VT>(raw[u][k], v);
+#pragma unroll
+                    for (int c = 0; c < EPL; ++c) acc[c] = fmaf(wk[k], v[c], acc[c]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (active) stg_stream_v4(out + pair * D + sub * EPL, pack<VT>(acc));
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic path: any channel count, any dtype.  One thread per output scalar; metadata from
+// global memory (no level limit).  Accumulates in acc_t (fp32 for 16-bit storage).
+// ------------------------------------------------------------------------------------------
+template <typename VT> struct Scalar {
+    using acc_t = typename Traits<VT>::acc_t;
+    static __device__ __forceinline__ acc_t load(const VT* p) { return (acc_t)to_f32<VT>(*p); }
+    static __device__ __forceinline__ VT store(acc_t v) { return from_f32<VT>((float)v); }
+};
+template <> struct Scalar<double> {
+    using acc_t = double;
+    static __device__ __forceinline__ double load(const double* p) { return *p; }
+    static __device__ __forceinline__ double store(double v) { return v; }
+};
+
+template <typename VT>
+__global__ void __launch_bounds__(256)
+msda_fwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ lsi, const typename Traits<VT>::loc_t* __restrict__ loc,
+                        const typename Traits<VT>::loc_t* __restrict__ attn, VT* __restrict__ out,
+                        int S, int M, int D, int L, int Lq, int P, long long total)
+{
+    using acc_t = typename Traits<VT>::acc_t;
+    using loc_t = typename Traits<VT>::loc_t;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % D);
+        const long long pair = idx / D;
+        const int m = (int)(pair % M);
+        const long long n = (pair / M) / Lq;
+        const VT* vbase = value + (n * S * M + m) * (long long)D + c;
+        const loc_t* lp = loc + pair * L * P * 2;
+        const loc_t* ap = attn + pair * L * P;
+        const long long MD = (long long)M * D;
+        acc_t acc = 0;
+        for (int l = 0; l < L; ++l) {
+            const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1], start = (int)lsi[l];
+            for (int p = 0; p < P; ++p) {
+                const loc_t x = lp[(l * P + p) * 2], y = lp[(l * P + p) * 2 + 1];
+                const acc_t a = (acc_t)ap[l * P + p];
+                const Footprint f = footprint<loc_t>(x, y, H, W, start);
+                if (!f.ok) continue;
+                // recompute the fractions in acc_t so that fp64 keeps fp64 weights
+                const loc_t w_im = x * (loc_t)W - (loc_t)0.5, h_im = y * (loc_t)H - (loc_t)0.5;
+                const acc_t lw = (acc_t)(w_im - floor(w_im)), lh = (acc_t)(h_im - floor(h_im));
+                const acc_t hw = 1 - lw, hh = 1 - lh;
+                const VT* p00 = vbase + (long long)f.pix00 * MD;
+                acc_t v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+                if (f.ok & 1u) v1 = Scalar<VT>::load(p00);
+                if (f.ok & 2u) v2 = Scalar<VT>::load(p00 + MD);
+                if (f.ok & 4u) v3 = Scalar<VT>::load(p00 + (long long)f.rowstep * MD);
+                if (f.ok & 8u) v4 = Scalar<VT>::load(p00 + (long long)f.rowstep * MD + MD);
+                acc += (hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4) * a;
+            }
+        }
+        out[idx] = Scalar<VT>::store(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+template <typename VT, int D>
+static cudaError_t launch_fwd_fast(const FwdArgs& a, cudaStream_t stream)
+{
+    constexpr int G = D / Traits<VT>::kEpl;
+    constexpr int PAIRS = 32 / G;
+    constexpr int WARPS = FwdWarps<PAIRS>::value;
+    const long long total_pairs = (long long)a.N * a.Lq * a.M;
+    const long long blocks = (total_pairs + WARPS * PAIRS - 1) / (WARPS * PAIRS);
+    const int p_magic = (65536 + a.P - 1) / a.P;
+    msda_fwd_fast_kernel<VT, D><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
+        (const VT*)a.value, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn, (VT*)a.out,
+        a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+    return cudaGetLastError();
+}
+
+template <typename VT>
+static cudaError_t launch_fwd_generic(const FwdArgs& a, cudaStream_t stream)
+{
+    using loc_t = typename Traits<VT>::loc_t;
+    const long long total = (long long)a.N * a.Lq * a.M * a.D;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (1ll << 30)) blocks = 1ll << 30;
+    msda_fwd_generic_kernel<VT><<<(unsigned)blocks, 256, 0, stream>>>(
+        (const VT*)a.value, a.shapes, a.lsi, (const loc_t*)a.loc, (const loc_t*)a.attn, (VT*)a.out,
+        a.S, a.M, a.D, a.L, a.Lq, a.P, total);
+    return cudaGetLastError();
+}
+
+static bool fast_shape_ok(const FwdArgs& a)
+{
+    return !a.force_generic && a.L <= kMaxLevelsFast && a.P <= 64 && (long long)a.L * a.P * a.P < 65536 &&
+           (long long)a.S * a.M * a.D < (1ll << 31);
+}
+
+template <typename VT>
+static cudaError_t dispatch_fwd_16or32(const FwdArgs& a, cudaStream_t stream)
+{
+    if (fast_shape_ok(a)) {
+        switch (a.D) {
+            case 8:   return launch_fwd_fast<VT, 8>(a, stream);
+            case 16:  return launch_fwd_fast<VT, 16>(a, stream);
+            case 32:  return launch_fwd_fast<VT, 32>(a, stream);
+            case 64:  return launch_fwd_fast<VT, 64>(a, stream);
+            case 128: return launch_fwd_fast<VT, 128>(a, stream);
+            default: break;
+        }
+    }
+    return launch_fwd_generic<VT>(a, stream);
+}
+
+cudaError_t forward(const FwdArgs& a, cudaStream_t stream)
+{
+    if ((long long)a.N * a.Lq * a.M * a.D == 0) return cudaSuccess;
+    switch (a.dtype) {
+        case kF32:  return dispatch_fwd_16or32<float>(a, stream);
+        case kBF16: return dispatch_fwd_16or32<__nv_bfloat16>(a, stream);
+        case kF16:  return dispatch_fwd_16or32<__half>(a, stream);
+        case kF64:  return launch_fwd_generic<double>(a, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace msda

@@ -1,0 +1,140 @@
+"""``MSDeformAttn`` -- multi-scale deformable attention module, B200 build.
+
+Drop-in for /root/reference/models/ops/modules/ms_deform_attn.py:31-117: same constructor
+``MSDeformAttn(d_model=256, n_levels=4, n_heads=8, n_points=4)``, same forward signature, same
+parameter names (``sampling_offsets``, ``attention_weights``, ``value_proj``, ``output_proj`` --
+reference checkpoints load unchanged), same initialisation (``_reset_parameters`` is called by the
+reference transformers, deformable_transformer_single.py:96-98) and same ``im2col_step`` attribute.
+
+What differs is underneath: the gather runs in the hand-written sm_100a kernels of
+libmsda_b200.so; the four projections stay library GEMMs (tensor cores) around it.
+The reference's per-call device->host sync (``assert ... .sum() == Len_in``, :92) is paid once
+per distinct ``input_spatial_shapes`` tensor instead of once per layer call.
+"""
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn.init import constant_, xavier_uniform_
+
+from ..functions import MSDeformAttnFunction
+
+
+def _is_power_of_2(n):
+    if (not isinstance(n, int)) or (n < 0):
+        raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
+    return (n & (n - 1) == 0) and n != 0
+
+
+# host copies of spatial_shapes tensors already validated: (data_ptr, version, numel) -> total pixels
+_SHAPE_CACHE = {}
+_SHAPE_CACHE_MAX = 64
+
+
+def _total_pixels(spatial_shapes):
+    """sum_l H_l*W_l, read back from the device at most once per tensor (reference :92 syncs
+    on every call)."""
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.numel(), spatial_shapes.device)
+    hit = _SHAPE_CACHE.get(key)
+    if hit is None:
+        if len(_SHAPE_CACHE) >= _SHAPE_CACHE_MAX:
+            _SHAPE_CACHE.clear()
+        hit = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum())
+        _SHAPE_CACHE[key] = hit
+    return hit
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
+        """
+        :param d_model   hidden dimension
+        :param n_levels  number of feature levels
+        :param n_heads   number of attention heads
+        :param n_points  number of sampling points per attention head per feature level
+        """
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError('d_model must be divisible by n_heads, but got {} and {}'.format(d_model, n_heads))
+        head_dim = d_model // n_heads
+        # the vectorised sm_100a kernels need head_dim*itemsize to be a power-of-two multiple of
+        # 16 bytes; anything else runs through the (slower) shape-generic kernels
+        if not _is_power_of_2(head_dim):
+            warnings.warn("You'd better set d_model in MSDeformAttn to make the dimension of each attention head "
+                          "a power of 2 which is more efficient in our CUDA implementation.")
+
+        self.im2col_step = 64
+
+        self.d_model = d_model
+        self.n_levels = n_levels
+        self.n_heads = n_heads
+        self.n_points = n_points
+
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        """Reference :60-76 -- offsets start as a fixed compass pattern (head h looks along
+        direction 2*pi*h/n_heads, point i at i+1 pixels), attention starts uniform."""
+        constant_(self.sampling_offsets.weight.data, 0.)
+        angles = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+        compass = torch.stack([angles.cos(), angles.sin()], -1)
+        compass = compass / compass.abs().max(-1, keepdim=True)[0]
+        steps = torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, self.n_points, 1)
+        bias = compass.view(self.n_heads, 1, 1, 2).repeat(1, self.n_levels, self.n_points, 1) * steps
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(bias.reshape(-1))
+        constant_(self.attention_weights.weight.data, 0.)
+        constant_(self.attention_weights.bias.data, 0.)
+        xavier_uniform_(self.value_proj.weight.data)
+        constant_(self.value_proj.bias.data, 0.)
+        xavier_uniform_(self.output_proj.weight.data)
+        constant_(self.output_proj.bias.data, 0.)
+
+    def _sampling_locations(self, reference_points, offsets, input_spatial_shapes):
+        """Reference :102-113.  offsets [N,Lq,M,L,P,2] in pixels of each level (2-d refs) or in
+        units of half a box (4-d refs)."""
+        if reference_points.shape[-1] == 2:
+            normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
+            return reference_points[:, :, None, :, None, :] + offsets / normalizer[None, None, None, :, None, :]
+        if reference_points.shape[-1] == 4:
+            return reference_points[:, :, None, :, None, :2] \
+                + offsets / self.n_points * reference_points[:, :, None, :, None, 2:] * 0.5
+        raise ValueError(
+            'Last dim of reference_points must be 2 or 4, but get {} instead.'.format(reference_points.shape[-1]))
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None):
+        """
+        :param query                    (N, Length_{query}, C)
+        :param reference_points         (N, Length_{query}, n_levels, 2), range in [0, 1], top-left (0,0),
+                                        bottom-right (1, 1), including padding area
+                                        or (N, Length_{query}, n_levels, 4), add additional (w, h) to form boxes
+        :param input_flatten            (N, sum_l H_l*W_l, C)
+        :param input_spatial_shapes     (n_levels, 2), [(H_0, W_0), ..., (H_{L-1}, W_{L-1})]
+        :param input_level_start_index  (n_levels, ), [0, H_0*W_0, H_0*W_0+H_1*W_1, ...]
+        :param input_padding_mask       (N, sum_l H_l*W_l), True for padding elements
+
+        :return output                  (N, Length_{query}, C)
+        """
+        N, Len_q, _ = query.shape
+        N, Len_in, _ = input_flatten.shape
+        assert _total_pixels(input_spatial_shapes) == Len_in
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
+        attention = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
+        attention = F.softmax(attention, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
+        sampling_locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
+        output = MSDeformAttnFunction.apply(
+            value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
+            attention.contiguous(), self.im2col_step)
+        return self.output_proj(output)

@@ -1,0 +1,82 @@
+/* msda_b200.h - C ABI of libmsda_b200.so: multi-scale deformable attention for NVIDIA B200
+ * (sm_100a).
+ *
+ * This is the drop-in boundary for the reference's native extension
+ * `MultiScaleDeformableAttention` (pybind module, /root/reference/models/ops/src/vision.cpp:13-16).
+ * Each entry point replaces one reference host launcher; argument order and meaning follow it:
+ *
+ *   msda_forward    <- ms_deformable_im2col_cuda   (models/ops/src/cuda/ms_deform_im2col_cuda.cuh:923-954)
+ *                      as called by ms_deform_attn_cuda_forward (cuda/ms_deform_attn_cuda.cu:61-75)
+ *   msda_backward   <- ms_deformable_col2im_cuda   (cuda/ms_deform_im2col_cuda.cuh:956-1327)
+ *                      as called by ms_deform_attn_cuda_backward (cuda/ms_deform_attn_cuda.cu:131-148)
+ *
+ * Conventions (all pointers are DEVICE pointers, contiguous, on the current device):
+ *   value        [N, S, M, D]         `dtype`
+ *   spatial_shapes [L, 2]  int64 (H, W);  level_start_index [L] int64   (read on the device,
+ *                                      exactly as the reference does, cuda/ms_deform_attn_cuda.cu:67-68)
+ *   sampling_loc [N, Lq, M, L, P, 2]  (x, y) normalised to [0,1];  fp32, or fp64 when dtype is F64
+ *   attn_weight  [N, Lq, M, L, P]     same type as sampling_loc
+ *   output / grad_output [N, Lq, M, D] `dtype`
+ * For the 16-bit dtypes (new behaviour - the reference op is fp32/fp64 only,
+ * cuda/ms_deform_attn_cuda.cu:64) value/output/grad_output/grad_value are 16-bit while
+ * locations, attention weights and their gradients stay fp32, and all arithmetic is fp32.
+ *
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ * asynchronous, re-entrant, keep no global state and never synchronise.
+ * Unlike the reference (which only printf's launch failures, cuh:948-952,1321-1325) every entry
+ * point returns the cudaError_t of its launches as an int: 0 on success.
+ * There is NO CPU implementation behind these symbols.
+ */
+#ifndef MSDA_B200_H
+#define MSDA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MSDA_DTYPE_F32 = 0,
+    MSDA_DTYPE_F64 = 1,
+    MSDA_DTYPE_BF16 = 2,
+    MSDA_DTYPE_F16 = 3
+} msda_dtype;
+
+/* flags */
+#define MSDA_FLAG_FORCE_GENERIC 1   /* route through the shape-generic kernels (testing) */
+
+/* ABI version of this header (bumped on any signature change). */
+int msda_abi_version(void);
+
+/* Human-readable text for a return code of the functions below. */
+const char* msda_error_string(int code);
+
+/* out[n,q,m,:] = sum_{l,p} attn[n,q,m,l,p] * bilinear(value_l[n,:,m,:], loc[n,q,m,l,p]).
+ * Writes every element of `output` (no zero-fill needed). */
+int msda_forward(int dtype,
+                 const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                 const void* sampling_loc, const void* attn_weight,
+                 int batch, int spatial_size, int num_heads, int channels,
+                 int num_levels, int num_query, int num_point,
+                 void* output, int flags, void* stream);
+
+/* Gradients of msda_forward.  grad_value is zero-filled by the call and then accumulated
+ * into; grad_sampling_loc and grad_attn_weight are fully overwritten (zeros for samples that
+ * fall outside the map), so none of the three needs initialising by the caller.
+ * grad_value_accum_f32: for 16-bit dtypes an fp32 scratch buffer of batch*spatial_size*
+ * num_heads*channels elements the vector atomics accumulate into before the cast to
+ * grad_value; ignored (may be NULL) for F32 / F64. */
+int msda_backward(int dtype,
+                  const void* grad_output,
+                  const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                  const void* sampling_loc, const void* attn_weight,
+                  int batch, int spatial_size, int num_heads, int channels,
+                  int num_levels, int num_query, int num_point,
+                  void* grad_value, void* grad_sampling_loc, void* grad_attn_weight,
+                  void* grad_value_accum_f32, int flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H */

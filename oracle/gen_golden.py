@@ -162,6 +162,10 @@ def main():
             dtype=torch.float32)
 
     # ---------------- MSDeformAttn module (ms_deform_attn.py:31-117) ----------
+    init_mod = mod.MSDeformAttn(32, 2, 4, 3)            # default initialisation (:60-76)
+    np.savez_compressed(os.path.join(OUT, "module_init.npz"),
+                        **{k: v.detach().numpy() for k, v in init_mod.state_dict().items()
+                           if k.startswith("sampling_offsets") or k.startswith("attention_weights")})
     shapes_t = torch.as_tensor([(6, 5), (3, 3)], dtype=torch.long)
     lsi = lsi_of(shapes_t)
     s = int(shapes_t.prod(1).sum())

@@ -1,0 +1,93 @@
+"""How each golden module/layer case (oracle/gen_golden.py) is rebuilt from this repo's classes.
+Shared by the CPU host-logic tests (oracle patched in) and the GPU tests (real kernels)."""
+import torch
+
+from dfvod_b200 import backbone_fusion, transformer_layers as tl
+from dfvod_b200.ops.modules import MSDeformAttn
+
+C, HEADS, PTS = 32, 4, 3
+
+
+def _enc(levels):
+    return tl.DeformableTransformerEncoderLayer(C, 64, 0.0, "relu", levels, HEADS, PTS)
+
+
+CASES = {
+    "module_msda_ref2": dict(
+        build=lambda: MSDeformAttn(C, 2, HEADS, PTS),
+        call=lambda m, t: m(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"],
+                            t["level_start_index"], t["padding_mask"]),
+        wrt=["query", "reference_points", "input_flatten"]),
+    "module_msda_ref4": dict(
+        build=lambda: MSDeformAttn(C, 2, HEADS, PTS),
+        call=lambda m, t: m(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"],
+                            t["level_start_index"], None),
+        wrt=["query", "reference_points", "input_flatten"]),
+    "layer_encoder": dict(
+        build=lambda: _enc(2),
+        call=lambda m, t: m(t["src"], t["pos"], t["reference_points"], t["spatial_shapes"],
+                            t["level_start_index"], t["padding_mask"]),
+        wrt=["src", "pos"]),
+    "layer_fusion_v2": dict(
+        build=lambda: tl.DeformableTransformerFusionLayerV2(C, 64, 0.0, "gelu", 1, HEADS, PTS),
+        call=lambda m, t: m(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                            t["level_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"]),
+    "layer_late_fusion": dict(
+        build=lambda: tl.DepthDeformableTransformerEncoderLayer(C, 64, 0.0, "relu", 1, HEADS, PTS, True, True, True),
+        call=lambda m, t: m(t["tgt"], t["query_pos"], None, None, t["reference_points"], None, t["src"],
+                            t["src_spatial_shapes"], t["frame_start_index"], None, t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"]),
+    "layer_decoder": dict(
+        build=lambda: tl.DeformableTransformerDecoderLayer(C, 64, 0.0, "relu", 2, HEADS, PTS),
+        call=lambda m, t: m(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                            t["level_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "src"]),
+    "encoder_rgbd_v2": dict(
+        build=lambda: tl.RGBDDeformableTransformerEncoderV2(
+            _enc(1), tl.DeformableTransformerFusionLayerV2(C, 64, 0.0, "gelu", 1, HEADS, PTS), 3, 2, 2, [0, 1]),
+        call=lambda m, t: m(t["src"], t["spatial_shapes"], t["level_start_index"], t["valid_ratios"], t["pos"],
+                            t["padding_mask"], None, t["depth_src"], t["depth_spatial_shapes"],
+                            t["depth_level_start_index"], None, None, None),
+        wrt=["src", "depth_src"]),
+    "encoder_plain": dict(
+        build=lambda: tl.DeformableTransformerEncoder(_enc(2), 2),
+        call=lambda m, t: m(t["src"], t["spatial_shapes"], t["level_start_index"], t["valid_ratios"], t["pos"],
+                            t["padding_mask"]),
+        wrt=["src"]),
+    "backbone_udf_fuse": dict(
+        build=lambda: backbone_fusion.DepthDeformableTransformerEncoderLayer(C, 64, 0.0, "relu", 1, HEADS, PTS),
+        call=lambda m, t: backbone_fusion.fuse_layers(t["src"], t["target"], t["pos_src"], t["pos_target"],
+                                                      t["mask_src"], t["mask_target"], m),
+        wrt=["src", "target"]),
+}
+
+
+def run_case(name, gold, device, dtype=torch.float64):
+    """Instantiate, load the reference state_dict (strict), run forward + backward.
+    Returns (out, {input grads}, {param grads}) as CPU float64 numpy."""
+    case = CASES[name]
+    module = case["build"]().to(dtype)
+    state = {k[len("state."):]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("state.")}
+    module.load_state_dict(state, strict=True)          # checkpoint-key compatibility with the reference
+    module = module.to(device).eval()
+    tensors = {}
+    for k, v in gold.items():
+        if not k.startswith("in."):
+            continue
+        t = torch.from_numpy(v).to(device)
+        if t.is_floating_point():
+            t = t.to(dtype) if t.dtype == torch.float64 else t     # fp32 inputs (valid ratios) stay fp32
+        name_in = k[len("in."):]
+        if name_in in case["wrt"]:
+            t = t.requires_grad_(True)
+        tensors[name_in] = t
+    out = case["call"](module, tensors)
+    gout = torch.from_numpy(gold["gout"]).to(device=device, dtype=out.dtype)
+    params = dict(module.named_parameters())
+    grads = torch.autograd.grad(out, [tensors[k] for k in case["wrt"]] + list(params.values()), gout,
+                                allow_unused=True)
+    gin = {k: g.detach().double().cpu().numpy() for k, g in zip(case["wrt"], grads)}
+    gpar = {k: (g.detach().double().cpu().numpy() if g is not None else None)
+            for k, g in zip(params.keys(), grads[len(case["wrt"]):])}
+    return out.detach().double().cpu().numpy(), gin, gpar

@@ -1,0 +1,289 @@
+"""GPU: the sm_100a op, called through the reference-facing boundary
+(MultiScaleDeformableAttention.ms_deform_attn_forward/backward -> C ABI -> kernels), against
+  (a) golden vectors produced by the real reference (tests/golden/op_*.npz),
+  (b) the CPU oracle in fp64 on seeded inputs (random, out-of-range, grid-like locations),
+  (c) the reference's own CUDA kernels recompiled for sm_100a (oracle/_ref), at COCO scale,
+  (d) the reference test-suite's own checks (models/ops/test.py: double/float forward, gradcheck).
+Tolerances: fp32 -> normalised max error and rel-L2 <= 1e-5 against the fp64
+oracle on the same fp32 inputs; bf16 -> normalised max <= 2^-7, rel-L2 <= 4e-3; fp64 -> 1e-9."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, msda_oracle
+from tests import util
+from tests.util import nerr
+
+pytestmark = pytest.mark.gpu
+
+import dfvod_b200
+from dfvod_b200 import MultiScaleDeformableAttention as MSDA
+from dfvod_b200 import MSDeformAttnFunction
+
+DEV = "cuda"
+F32_TOL = 1e-5
+BF16_MAX, BF16_L2 = 2.0 ** -7, 4e-3
+
+OP_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(util.GOLD, "op_*.npz")))
+
+
+def run_op(value, shapes, loc, attn, grad_out, generic=False):
+    """forward + backward through the boundary; returns CPU float64 numpy arrays."""
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v, l, a, g = (t.to(DEV).contiguous() for t in (value, loc, attn, grad_out))
+    MSDA._FORCE_GENERIC = generic
+    try:
+        out = MSDA.ms_deform_attn_forward(v, st, ls, l, a, 64)
+        gv, gl, ga = MSDA.ms_deform_attn_backward(v, st, ls, l, a, g, 64)
+    finally:
+        MSDA._FORCE_GENERIC = False
+    torch.cuda.synchronize()
+    return tuple(t.double().cpu().numpy() for t in (out, gv, gl, ga))
+
+
+def oracle64(value, shapes, loc, attn, grad_out):
+    args = (value.double().numpy(), shapes, util.lsi_of(shapes), loc.double().numpy(), attn.double().numpy())
+    out = c_oracle.forward(*args)
+    gv, gl, ga = c_oracle.backward(*args, grad_out.double().numpy())
+    return out, gv, gl, ga
+
+
+def assert_close(got, ref, max_tol, l2_tol, what):
+    for name, x, r in zip(("out", "grad_value", "grad_loc", "grad_attn"), got, ref):
+        emax, el2 = nerr(x.reshape(r.shape), r)
+        assert emax <= max_tol and el2 <= l2_tol, f"{what}/{name}: max {emax:.3e} l2 {el2:.3e}"
+
+
+# ------------------------------------------------------------------ (a) golden vectors
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("name", OP_CASES)
+def test_golden_vectors(name, generic):
+    g = util.load_golden(name)
+    t = {k: torch.from_numpy(v) for k, v in g.items()}
+    shapes = [tuple(x) for x in g["shapes"].tolist()]
+    got = run_op(t["value"], shapes, t["loc"], t["attn"], t["grad_out"], generic)
+    ref = (g["out"], g["grad_value"], g["grad_loc"], g["grad_attn"])
+    if g["value"].dtype == np.float64:
+        assert_close(got, ref, 1e-9, 1e-9, name)
+    else:
+        ref64 = oracle64(t["value"], shapes, t["loc"], t["attn"], t["grad_out"])
+        assert_close(got, ref64, F32_TOL, F32_TOL, name)
+
+
+@pytest.mark.parametrize("name", [n for n in OP_CASES if not n.endswith("_f32")])
+def test_golden_vectors_fp32_eval(name):
+    """fp64 golden inputs rounded to fp32 and run through the vectorised fp32 kernels."""
+    g = util.load_golden(name)
+    t = {k: torch.from_numpy(v).float() if v.dtype == np.float64 else torch.from_numpy(v) for k, v in g.items()}
+    shapes = [tuple(x) for x in g["shapes"].tolist()]
+    got = run_op(t["value"], shapes, t["loc"], t["attn"], t["grad_out"])
+    ref64 = oracle64(t["value"], shapes, t["loc"], t["attn"], t["grad_out"])
+    assert_close(got, ref64, F32_TOL, F32_TOL, name)
+
+
+# ------------------------------------------------------------------ (b) seeded inputs vs CPU oracle
+RANDOM_CASES = [
+    # shapes, N, M, D, Lq, P, loc_range
+    ([(6, 4), (3, 2)], 1, 2, 2, 2, 2, (0.0, 1.0)),                  # reference test config (generic path)
+    ([(20, 30), (10, 15), (5, 8), (3, 4)], 2, 8, 32, 257, 4, (-0.2, 1.2)),   # production head layout + OOB
+    ([(50, 84)], 2, 8, 32, 300, 4, (0.0, 1.0)),                     # shipped 1-level config, decoder-like Lq
+    ([(13, 21), (7, 11)], 3, 4, 64, 65, 4, (-0.1, 1.1)),            # D=64
+    ([(9, 9)], 1, 16, 16, 33, 8, (-0.5, 1.5)),                      # D=16, P=8
+    ([(8, 8), (4, 4), (2, 2)], 1, 5, 8, 31, 3, (0.0, 1.0)),         # D=8, odd P, odd M
+    ([(7, 5)], 2, 2, 128, 17, 2, (0.0, 1.0)),                       # D=128: fast fwd, generic bwd (fp32)
+    ([(6, 6), (3, 3)], 1, 3, 30, 10, 2, (-0.1, 1.1)),               # D=30: generic both ways
+    ([(5, 5)] * 5, 1, 2, 32, 9, 4, (0.0, 1.0)),                     # L*P = 20 > one 16-sample chunk
+    ([(1, 1), (1, 7), (7, 1)], 1, 2, 32, 11, 4, (-0.3, 1.3)),       # degenerate 1-pixel-wide maps
+]
+
+
+@pytest.mark.parametrize("case", RANDOM_CASES, ids=lambda c: f"L{len(c[0])}_N{c[1]}_M{c[2]}_D{c[3]}_Lq{c[4]}_P{c[5]}")
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16", "f64"])
+def test_seeded_vs_cpu_oracle(case, dtype):
+    shapes, n, m, d, lq, p, rng = case
+    value, loc, attn, gout = util.make_inputs(shapes, n, m, d, lq, p, seed=100 + d + lq, loc_range=rng)
+    if dtype == "f64":
+        value, loc, attn, gout = (t.double() for t in (value, loc, attn, gout))
+        got = run_op(value, shapes, loc, attn, gout)
+        assert_close(got, oracle64(value, shapes, loc, attn, gout), 1e-9, 1e-9, "f64")
+    elif dtype == "f32":
+        got = run_op(value, shapes, loc, attn, gout)
+        assert_close(got, oracle64(value, shapes, loc, attn, gout), F32_TOL, F32_TOL, "f32")
+    else:
+        td = torch.bfloat16 if dtype == "bf16" else torch.float16
+        v16, g16 = value.to(td), gout.to(td)
+        got = run_op(v16, shapes, loc, attn, g16)
+        # oracle on the 16-bit-rounded inputs, fp64 arithmetic
+        ref = oracle64(v16.float(), shapes, loc, attn, g16.float())
+        mx, l2 = (BF16_MAX, BF16_L2) if dtype == "bf16" else (2.0 ** -10, 5e-4)
+        assert_close(got, ref, mx, l2, dtype)
+
+
+def test_grid_locations_encoder_like():
+    """Encoder self-attention geometry (queries = pixels, offsets = init compass pattern + noise)."""
+    shapes = [(24, 40), (12, 20), (6, 10), (3, 5)]
+    s = sum(h * w for h, w in shapes)
+    value, loc, attn, gout = util.make_inputs(shapes, 2, 8, 32, s, 4, seed=5, dist="grid")
+    got = run_op(value, shapes, loc, attn, gout)
+    assert_close(got, oracle64(value, shapes, loc, attn, gout), F32_TOL, F32_TOL, "grid")
+
+
+# ------------------------------------------------------------------ (c) the reference's CUDA kernels, COCO scale
+@pytest.mark.parametrize("dist", ["random", "grid"])
+def test_coco_scale_vs_reference_cuda_kernels(dist):
+    if util.ref_cuda_lib() is None:
+        pytest.skip("oracle/_ref/libmsda_ref_cuda.so not built (reference tree absent at build time)")
+    shapes = util.COCO_SHAPES
+    s = sum(h * w for h, w in shapes)
+    value, loc, attn, gout = util.make_inputs(shapes, 2, 8, 32, s, 4, seed=0, dist=dist, loc_range=(-0.1, 1.1))
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v, l, a, g = (t.to(DEV) for t in (value, loc, attn, gout))
+    out = MSDA.ms_deform_attn_forward(v, st, ls, l, a, 64)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(v, st, ls, l, a, g, 64)
+    r_out = util.ref_cuda_forward(v, st, ls, l, a)
+    r_gv, r_gl, r_ga = util.ref_cuda_backward(v, st, ls, l, a, g)
+    torch.cuda.synchronize()
+    for name, x, r in (("out", out, r_out), ("grad_value", gv, r_gv), ("grad_loc", gl, r_gl), ("grad_attn", ga, r_ga)):
+        emax, el2 = nerr(x.double().cpu().numpy().reshape(r.shape), r.double().cpu().numpy())
+        # both sides are fp32 with different summation orders: 2x the one-sided bound
+        assert emax <= 2e-5 and el2 <= 2e-5, f"{dist}/{name}: max {emax:.3e} l2 {el2:.3e}"
+
+
+def test_coco_scale_vs_cpu_oracle_fp64():
+    """Config 1 of BASELINE.json at full size (N=1, S=Lq=22223) against the C oracle in fp64."""
+    shapes = util.COCO_SHAPES
+    s = sum(h * w for h, w in shapes)
+    value, loc, attn, gout = util.make_inputs(shapes, 1, 8, 32, s, 4, seed=0, dist="grid")
+    got = run_op(value, shapes, loc, attn, gout)
+    assert_close(got, oracle64(value, shapes, loc, attn, gout), F32_TOL, F32_TOL, "coco")
+    v16, g16 = value.bfloat16(), gout.bfloat16()
+    got16 = run_op(v16, shapes, loc, attn, g16)
+    assert_close(got16, oracle64(v16.float(), shapes, loc, attn, g16.float()), BF16_MAX, BF16_L2, "coco-bf16")
+
+
+# ------------------------------------------------------------------ (d) the reference's own test-suite
+def _reference_recipe(channels=2, dtype=torch.float64):
+    n, m, lq, nl, p = 1, 2, 2, 2, 2
+    shapes = [(6, 4), (3, 2)]
+    s = 30
+    value = torch.rand(n, s, m, channels) * 0.01
+    loc = torch.rand(n, lq, m, nl, p, 2)
+    attn = torch.rand(n, lq, m, nl, p) + 1e-5
+    attn /= attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    return shapes, value.to(dtype), loc.to(dtype), attn.to(dtype)
+
+
+def test_reference_check_forward_double_and_float():
+    """models/ops/test.py:31-60."""
+    torch.manual_seed(3)
+    shapes, value, loc, attn = _reference_recipe()
+    st, ls = util.shapes_tensors(shapes, DEV)
+    out = MSDeformAttnFunction.apply(value.to(DEV), st, ls, loc.to(DEV), attn.to(DEV), 2).cpu()
+    ref = msda_oracle.core_pytorch(value, shapes, loc, attn)
+    assert torch.allclose(out, ref)                                   # test.py:40 (rtol 1e-5, atol 1e-8)
+    shapes, value, loc, attn = _reference_recipe(dtype=torch.float32)
+    out = MSDeformAttnFunction.apply(value.to(DEV), st, ls, loc.to(DEV), attn.to(DEV), 2).cpu()
+    ref = msda_oracle.core_pytorch(value, shapes, loc, attn)
+    assert torch.allclose(out, ref, rtol=1e-2, atol=1e-3)             # test.py:56
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025])
+def test_reference_gradcheck(channels):
+    """models/ops/test.py:63-78 (fp64 gradcheck on all three differentiable inputs).  The
+    reference list also has 2048 and 3096, which only exercise its D>1024 kernel variants."""
+    torch.manual_seed(3)
+    shapes, value, loc, attn = _reference_recipe(channels)
+    st, ls = util.shapes_tensors(shapes, DEV)
+    value, loc, attn = (t.to(DEV).requires_grad_(True) for t in (value, loc, attn))
+    assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, st, ls, loc, attn, 2))
+
+
+# ------------------------------------------------------------------ boundary behaviour
+def test_boundary_validation_errors():
+    shapes = [(4, 4)]
+    value, loc, attn, gout = util.make_inputs(shapes, 2, 2, 32, 5, 4, seed=1)
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v, l, a = value.to(DEV), loc.to(DEV), attn.to(DEV)
+    with pytest.raises(RuntimeError, match="value tensor has to be contiguous"):
+        MSDA.ms_deform_attn_forward(v.transpose(2, 3), st, ls, l, a, 64)
+    with pytest.raises(RuntimeError, match="spatial_shapes must be a CUDA tensor"):
+        MSDA.ms_deform_attn_forward(v, st.cpu(), ls, l, a, 64)
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        MSDA.ms_deform_attn_forward(torch.cat([v, v[:1]]), st, ls, torch.cat([l, l[:1]]), torch.cat([a, a[:1]]), 2)
+    # level-count mismatch: silently mis-indexed by the reference -- raises here
+    l2 = torch.cat([l, l], dim=3).contiguous()
+    with pytest.raises(RuntimeError, match="sampling_loc shape"):
+        MSDA.ms_deform_attn_forward(v, st, ls, l2, a, 64)
+    with pytest.raises(RuntimeError, match="not implemented for"):
+        MSDA.ms_deform_attn_forward(v.to(torch.int32), st, ls, l, a, 64)
+
+
+def test_empty_and_tiny_inputs():
+    shapes = [(3, 3)]
+    st, ls = util.shapes_tensors(shapes, DEV)
+    # zero queries
+    out = MSDA.ms_deform_attn_forward(torch.randn(1, 9, 2, 32, device=DEV), st, ls,
+                                      torch.zeros(1, 0, 2, 1, 4, 2, device=DEV), torch.zeros(1, 0, 2, 1, 4, device=DEV), 64)
+    assert out.shape == (1, 0, 64)
+    # zero batch
+    out = MSDA.ms_deform_attn_forward(torch.randn(0, 9, 2, 32, device=DEV), st, ls,
+                                      torch.zeros(0, 3, 2, 1, 4, 2, device=DEV), torch.zeros(0, 3, 2, 1, 4, device=DEV), 64)
+    assert out.shape == (0, 3, 64)
+    # backward with zero queries still zero-fills grad_value
+    v = torch.randn(1, 9, 2, 32, device=DEV)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(v, st, ls, torch.zeros(1, 0, 2, 1, 4, 2, device=DEV),
+                                              torch.zeros(1, 0, 2, 1, 4, device=DEV), torch.zeros(1, 0, 64, device=DEV), 64)
+    assert gv.shape == v.shape and not gv.any()
+
+
+def test_all_samples_outside_give_zeros():
+    shapes = [(5, 6), (2, 3)]
+    value, loc, attn, gout = util.make_inputs(shapes, 1, 8, 32, 7, 4, seed=2, loc_range=(1.5, 3.0))
+    got = run_op(value, shapes, loc, attn, gout)
+    for x in got:
+        assert not np.any(x)
+
+
+def test_properties_at_full_size():
+    """Size-independent properties on the bench workload shape (COCO pyramid, batch 2):
+    linearity in value, and <out, g> == <value, grad_value> (adjointness of the gather/scatter)."""
+    shapes = util.COCO_SHAPES
+    s = sum(h * w for h, w in shapes)
+    value, loc, attn, gout = util.make_inputs(shapes, 2, 8, 32, s, 4, seed=9, dist="grid")
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v, l, a, g = (t.to(DEV) for t in (value, loc, attn, gout))
+    f = lambda x: MSDA.ms_deform_attn_forward(x, st, ls, l, a, 64)
+    out = f(v)
+    v2 = torch.randn_like(v)
+    lin = f(2.0 * v + v2) - (2.0 * out + f(v2))
+    assert float(lin.abs().max()) <= 1e-4 * float(out.abs().max())
+    gv, gl, ga = MSDA.ms_deform_attn_backward(v, st, ls, l, a, g, 64)
+    lhs = float((out.double() * g.double()).sum())
+    rhs = float((v.double() * gv.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0) + 1e-3
+    # d<out,g>/d attn = grad_attn: check through a directional derivative
+    da = torch.randn_like(a) * 1e-3
+    num = float(((MSDA.ms_deform_attn_forward(v, st, ls, l, a + da, 64).double() - out.double()) * g.double()).sum())
+    ana = float((ga.double() * da.double()).sum())
+    assert abs(num - ana) <= 1e-3 * max(abs(ana), 1.0)
+
+
+def test_autograd_function_contract():
+    """func.py:21-38: grads for args 0,3,4 only; usable under torch.autograd with non-default stream."""
+    shapes = [(6, 7)]
+    value, loc, attn, gout = util.make_inputs(shapes, 2, 8, 32, 11, 4, seed=4)
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v, l, a = (t.to(DEV).requires_grad_(True) for t in (value, loc, attn))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        out = MSDeformAttnFunction.apply(v, st, ls, l, a, 64)
+        (out * gout.to(DEV)).sum().backward()
+    side.synchronize()
+    ref = oracle64(value, shapes, loc, attn, gout)
+    got = (out.detach(), v.grad, l.grad, a.grad)
+    assert_close(tuple(t.double().cpu().numpy() for t in got), ref, F32_TOL, F32_TOL, "autograd")
+    assert st.grad is None and ls.grad is None

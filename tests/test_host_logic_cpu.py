@@ -1,0 +1,83 @@
+"""CPU: the host-side mirror (MSDeformAttn, the fusion / encoder / decoder layer classes,
+fuse_layers) reproduces the REAL reference classes' outputs and gradients
+(tests/golden/{module,layer,encoder,backbone}_*.npz, made by oracle/gen_golden.py) when the CUDA
+op is replaced by the oracle -- i.e. everything around the kernel is parity-checked without a
+GPU.  (The product never does this substitution; it happens here, in tests/, only.)"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import msda_oracle
+from tests import module_cases
+from tests.util import load_golden
+
+import dfvod_b200.ops.modules.ms_deform_attn as msda_module
+
+
+class _OracleFunction:
+    @staticmethod
+    def apply(value, shapes, lsi, loc, attn, im2col_step):
+        return msda_oracle.core_pytorch(value, shapes.tolist(), loc, attn)
+
+
+@pytest.fixture()
+def oracle_op(monkeypatch):
+    monkeypatch.setattr(msda_module, "MSDeformAttnFunction", _OracleFunction)
+
+
+@pytest.mark.parametrize("name", sorted(module_cases.CASES))
+def test_module_matches_reference_class(name, oracle_op):
+    gold = load_golden(name)
+    out, gin, gpar = module_cases.run_case(name, gold, "cpu")
+    np.testing.assert_allclose(out, gold["out"], rtol=1e-9, atol=1e-11)
+    for k, g in gin.items():
+        np.testing.assert_allclose(g, gold["grad_in." + k], rtol=1e-8, atol=1e-10, err_msg=k)
+    for k, g in gpar.items():
+        ref = gold["grad_param." + k]
+        if ref.shape == ():          # unused parameter in the reference
+            assert g is None or not np.any(g)
+            continue
+        np.testing.assert_allclose(g, ref, rtol=1e-8, atol=1e-10, err_msg=k)
+
+
+def test_state_dict_keys_and_init_match_reference():
+    """Parameter names are the checkpoint contract; init follows
+    ms_deform_attn.py:60-76."""
+    m = msda_module.MSDeformAttn(256, 4, 8, 4)
+    assert sorted(m.state_dict()) == sorted(
+        f"{n}.{p}" for n in ("sampling_offsets", "attention_weights", "value_proj", "output_proj")
+        for p in ("weight", "bias"))
+    assert sum(p.numel() for p in m.parameters()) == 230272
+    assert m.im2col_step == 64
+    assert not m.sampling_offsets.weight.any() and not m.attention_weights.weight.any()
+    assert not m.attention_weights.bias.any() and not m.value_proj.bias.any() and not m.output_proj.bias.any()
+    bias = m.sampling_offsets.bias.view(8, 4, 4, 2)
+    # head 0 looks along +x, head 2 along +y; point i sits at i+1 pixels; same on every level
+    np.testing.assert_allclose(bias[0, :, :, 0].detach().numpy(), np.tile([1., 2., 3., 4.], (4, 1)), atol=1e-6)
+    np.testing.assert_allclose(bias[0, :, :, 1].detach().numpy(), 0, atol=1e-6)
+    np.testing.assert_allclose(bias[2, :, :, 1].detach().numpy(), np.tile([1., 2., 3., 4.], (4, 1)), atol=1e-6)
+    np.testing.assert_allclose(bias[1, 0, 0].detach().numpy(), [1., 1.], atol=1e-6)     # 45 deg normalised by max
+    gold = load_golden("module_init")
+    ref = msda_module.MSDeformAttn(32, 2, 4, 3)
+    np.testing.assert_allclose(ref.sampling_offsets.bias.detach().numpy(), gold["sampling_offsets.bias"], atol=1e-7)
+
+
+def test_bad_reference_point_width_raises(oracle_op):
+    m = msda_module.MSDeformAttn(32, 1, 4, 2)
+    shapes = torch.tensor([[2, 3]])
+    with pytest.raises(ValueError, match="Last dim of reference_points must be 2 or 4"):
+        m(torch.zeros(1, 6, 32), torch.zeros(1, 6, 1, 3), torch.zeros(1, 6, 32), shapes, torch.tensor([0]))
+
+
+def test_length_mismatch_asserts(oracle_op):
+    m = msda_module.MSDeformAttn(32, 1, 4, 2)
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 6, 32), torch.zeros(1, 6, 1, 2), torch.zeros(1, 7, 32), torch.tensor([[2, 3]]),
+          torch.tensor([0]))
+
+
+def test_constructor_validation():
+    with pytest.raises(ValueError, match="d_model must be divisible by n_heads"):
+        msda_module.MSDeformAttn(30, 1, 4, 2)
+    with pytest.warns(UserWarning, match="power of 2"):
+        msda_module.MSDeformAttn(24, 1, 2, 2)
