@@ -86,55 +86,80 @@ def algorithmic_bytes(n, e_v):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  Uses NVML
+    in-process (a polling `nvidia-smi -lms` child was measured to stall individual launches by
+    10-30 ms on this box); falls back to one nvidia-smi query per sample if pynvml is missing."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.05):
+        self.index, self.period, self.rows = index, period_s, []
+        self._stop = threading.Event()
+        self.thread = None
+        self.nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        return self.index
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self.nvml = None
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
         return self
 
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+            return float(sm), float(self.max_sm), power, [name for name, bit in self.REASONS if mask & bit]
+        out = subprocess.run(
+            ["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-i", str(self._physical_index())],
+            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout
+        r = [x.strip() for x in out.strip().split(",")]
+        return float(r[0]), float(r[1]), float(r[2]), [name for (name, _), flag in zip(self.REASONS, r[3:7])
+                                                      if flag.lower().startswith("active")]
+
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        while not self._stop.is_set():
+            try:
+                self.rows.append(self._sample())
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def __exit__(self, *exc):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=5)
 
     def summary(self):
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                power.append(float(r[3]))
-                for name, flag in zip(names, r[4:8]):
-                    if flag.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({name for r in self.rows for name in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in self.rows), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(r[2] for r in self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def peaks():
@@ -228,39 +253,43 @@ def run_b200(args):
     st = torch.as_tensor(COCO_SHAPES, dtype=torch.long, device=dev)
     ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
 
-    def step():
-        out = MSDA.ms_deform_attn_forward(value, st, ls, loc, attn, 64)
-        return out, MSDA.ms_deform_attn_backward(value, st, ls, loc, attn, gout, 64)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def run_steps(k):
+        """k steps, each fwd + bwd through the public boundary; CUDA events around every launch.
+        Warm-up and the timed region run this same function, so the caching allocator is in
+        steady state (no cudaMalloc inside the timed region)."""
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(k)]
+        keep = None
+        for i in range(k):
+            ev[i][0].record()
+            out = MSDA.ms_deform_attn_forward(value, st, ls, loc, attn, 64)
+            ev[i][1].record()
+            grads = MSDA.ms_deform_attn_backward(value, st, ls, loc, attn, gout, 64)
+            ev[i][2].record()
+            keep = (out, grads)
+        return ev, keep
+
+    run_steps(max(args.warmup, 3))
     barrier()
 
     # ---- timed region: device-resident inputs ------------------------------------------------
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     with ClockSampler(local) as clocks:
         barrier()
         t_start = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
         t_start.record()
-        for k in range(args.steps):
-            ev[k][0].record()
-            out = MSDA.ms_deform_attn_forward(value, st, ls, loc, attn, 64)
-            ev[k][1].record()
-            grads = MSDA.ms_deform_attn_backward(value, st, ls, loc, attn, gout, 64)
-            ev[k][2].record()
+        ev, _ = run_steps(args.steps)
         t_end.record()
         barrier()
-        if args.steps * 1.0 < 1:      # keep the sampler alive long enough to see the load
-            pass
     elapsed_ms = t_start.elapsed_time(t_end)
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    fwd_all = sorted(e[0].elapsed_time(e[1]) for e in ev)
+    bwd_all = sorted(e[1].elapsed_time(e[2]) for e in ev)
+    fwd_ms, bwd_ms = sum(fwd_all) / args.steps, sum(bwd_all) / args.steps
+    fwd_med, bwd_med = fwd_all[len(fwd_all) // 2], bwd_all[len(bwd_all) // 2]
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -336,6 +365,8 @@ def run_b200(args):
             "clocks": clocks.summary(),
             "roofline": roofline, "roofline_fwd": roofline_fwd,
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+            "per_step_ms": {"fwd_median": fwd_med, "bwd_median": bwd_med, "fwd_min": fwd_all[0],
+                            "bwd_min": bwd_all[0], "fwd_max": fwd_all[-1], "bwd_max": bwd_all[-1]},
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -346,7 +377,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])

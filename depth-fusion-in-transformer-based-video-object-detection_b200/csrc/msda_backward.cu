@@ -15,7 +15,11 @@
 // 16-byte channel slice):
 //   * footprints are computed once per sample by one lane and shared through smem;
 //   * grad_value uses ONE 16-byte vector reduction (red.global.add.v4.f32 -> REDG.E.ADD.F32x4)
-//     per lane per corner instead of 4 scalar atomics, always into an fp32 buffer;
+//     per lane per corner instead of 4 scalar atomics, always into an fp32 buffer.  A lane
+//     always owns 4 channels here (16-bit values are read with 8-byte loads) so that the 8 lanes
+//     of a group cover one whole 128-byte fp32 row per instruction: measured on B200, the
+//     SM->L2 reduction path costs ~5.5 cycles per (instruction, row) whether the row is written
+//     whole or in halves (tools/microbench_red.cu), and it is what bounds this kernel;
 //   * the three per-sample dot products stay in registers; after a 16-sample chunk the 48
 //     partials per lane are combined across the group with a shuffle reduce-scatter
 //     (24+12+6 shuffles for G=8 instead of 144 for a per-value butterfly) that leaves every
@@ -30,6 +34,13 @@
 namespace msda {
 
 template <int PAIRS> struct BwdWarps { static constexpr int value = PAIRS >= 16 ? 2 : (PAIRS >= 8 ? 4 : 8); };
+
+#ifndef MSDA_BWD_MINBLOCKS
+#define MSDA_BWD_MINBLOCKS 2
+#endif
+#ifndef MSDA_CTA_PER_HEAD      // see msda_forward.cu
+#define MSDA_CTA_PER_HEAD 1
+#endif
 
 // After the call lane `sub` of each G-lane group holds, in v[0 .. N*2*OFF/G... ) -- precisely
 // v[0 .. N/(2*OFF)) -- the group-wide sums of original elements [sub*len, (sub+1)*len).
@@ -49,7 +60,7 @@ __device__ __forceinline__ void reduce_scatter(float* v, int sub)
 }
 
 template <typename VT, int D>
-__global__ void __launch_bounds__(BwdWarps<32 / (D / Traits<VT>::kEpl)>::value * 32)
+__global__ void __launch_bounds__(BwdWarps<32 / (D / 4)>::value * 32, MSDA_BWD_MINBLOCKS)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ attn,
@@ -57,7 +68,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                      float* __restrict__ grad_attn,
                      int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs)
 {
-    constexpr int EPL = Traits<VT>::kEpl;
+    constexpr int EPL = 4;                       // channels per lane: one red.v4.f32 per corner
+    using SliceT = Slice<VT, EPL>;
     constexpr int G = D / EPL;
     constexpr int PAIRS = 32 / G;
     constexpr int WARPS = BwdWarps<PAIRS>::value;
@@ -65,8 +77,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     static_assert(G >= 1 && G <= 16 && (G & (G - 1)) == 0, "fast backward needs 1..16 lanes per head");
 
     __shared__ int s_meta[3 * kMaxLevelsFast];
-    __shared__ __align__(16) int4   s_geo[WARPS][PAIRS][kChunk];   // pix00, rowstep, ok, -
-    __shared__ __align__(16) float4 s_frac[WARPS][PAIRS][kChunk];  // lw, lh, a, -
+    __shared__ __align__(16) int4   s_geo[WARPS][PAIRS][kChunk + 1];   // pix00, rowstep, ok, -
+    __shared__ __align__(16) float4 s_frac[WARPS][PAIRS][kChunk + 1];  // lw, lh, a, -
 
     if (threadIdx.x < L) {
         s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
@@ -77,11 +89,21 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, sub = lane % G;
+#if MSDA_CTA_PER_HEAD
+    const int m = (int)(blockIdx.x % M);
+    const long long nq_total = total_pairs / M;
+    const long long nq_raw = ((long long)(blockIdx.x / M) * WARPS + warp) * PAIRS + grp;
+    const bool active = nq_raw < nq_total;
+    const long long nq = active ? nq_raw : nq_total - 1;
+    const long long pair = nq * M + m;
+    const long long n = nq / Lq;
+#else
     const long long pair_raw = ((long long)blockIdx.x * WARPS + warp) * PAIRS + grp;
     const bool active = pair_raw < total_pairs;
     const long long pair = active ? pair_raw : total_pairs - 1;
     const int m = (int)(pair % M);
     const long long n = (pair / M) / Lq;
+#endif
     const int LP = L * P;
     const int MD = M * D;
     const long long head_off = (n * S * M + m) * (long long)D + sub * EPL;
@@ -91,7 +113,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     const float* ap = attn + pair * LP;
 
     float g[EPL];
-    unpack<VT>(ldg_stream_v4(grad_out + pair * D + sub * EPL), g);
+    SliceT::unpack(SliceT::load_stream(grad_out + pair * D + sub * EPL), g);
     if (!active) {
 #pragma unroll
         for (int c = 0; c < EPL; ++c) g[c] = 0.f;     // clamped duplicate pair contributes nothing
@@ -128,18 +150,17 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             if (j0 < cnt2) {
                 int4 geo[2];
                 float4 fr[2];
-                uint4 raw[2][4];
+                typename SliceT::raw_t raw[2][4];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     geo[u] = s_geo[warp][grp][j0 + u];
                     fr[u] = s_frac[warp][grp][j0 + u];
                     const VT* p00 = vbase + (long long)geo[u].x * MD;
                     const long long row = (long long)geo[u].y * MD;
-                    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-                    raw[u][0] = (geo[u].z & 1) ? ldg_v4(p00) : zero;
-                    raw[u][1] = (geo[u].z & 2) ? ldg_v4(p00 + MD) : zero;
-                    raw[u][2] = (geo[u].z & 4) ? ldg_v4(p00 + row) : zero;
-                    raw[u][3] = (geo[u].z & 8) ? ldg_v4(p00 + row + MD) : zero;
+                    raw[u][0] = (geo[u].z & 1) ? SliceT::load(p00) : SliceT::zero();
+                    raw[u][1] = (geo[u].z & 2) ? SliceT::load(p00 + MD) : SliceT::zero();
+                    raw[u][2] = (geo[u].z & 4) ? SliceT::load(p00 + row) : SliceT::zero();
+                    raw[u][3] = (geo[u].z & 8) ? SliceT::load(p00 + row + MD) : SliceT::zero();
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -147,10 +168,10 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     const float hw = 1.f - lw, hh = 1.f - lh;
                     const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
                     float v1[EPL], v2[EPL], v3[EPL], v4[EPL], tg[EPL];
-                    unpack<VT>(raw[u][0], v1);
-                    unpack<VT>(raw[u][1], v2);
-                    unpack<VT>(raw[u][2], v3);
-                    unpack<VT>(raw[u][3], v4);
+                    SliceT::unpack(raw[u][0], v1);
+                    SliceT::unpack(raw[u][1], v2);
+                    SliceT::unpack(raw[u][2], v3);
+                    SliceT::unpack(raw[u][3], v4);
                     float px = 0.f, py = 0.f, pa = 0.f;
 #pragma unroll
                     for (int c = 0; c < EPL; ++c) {
@@ -171,12 +192,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     float* const qk[4] = {q00, q00 + MD, q00 + row, q00 + row + MD};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (geo[u].z & (1 << k)) {
-#pragma unroll
-                            for (int c = 0; c < EPL; c += 4)
-                                red_add_f32x4(qk[k] + c, wk[k] * tg[c], wk[k] * tg[c + 1],
-                                              wk[k] * tg[c + 2], wk[k] * tg[c + 3]);
-                        }
+                        if (geo[u].z & (1 << k))
+                            red_add_f32x4(qk[k], wk[k] * tg[0], wk[k] * tg[1], wk[k] * tg[2], wk[k] * tg[3]);
                     }
                 }
             }
@@ -306,11 +323,17 @@ msda_cast_accum_kernel(const float* __restrict__ src, VT* __restrict__ dst, long
 template <typename VT, int D>
 static cudaError_t launch_bwd_fast(const BwdArgs& a, float* accum, cudaStream_t stream)
 {
-    constexpr int G = D / Traits<VT>::kEpl;
+    constexpr int G = D / 4;
     constexpr int PAIRS = 32 / G;
     constexpr int WARPS = BwdWarps<PAIRS>::value;
     const long long total_pairs = (long long)a.N * a.Lq * a.M;
+#if MSDA_CTA_PER_HEAD
+    const long long nq_total = (long long)a.N * a.Lq;
+    const long long blocks = ((nq_total + WARPS * PAIRS - 1) / (WARPS * PAIRS)) * a.M;
+#else
     const long long blocks = (total_pairs + WARPS * PAIRS - 1) / (WARPS * PAIRS);
+#endif
+    if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
     const int p_magic = (65536 + a.P - 1) / a.P;
     msda_bwd_fast_kernel<VT, D><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
         (const VT*)a.grad_out, (const VT*)a.value, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn,
@@ -351,23 +374,13 @@ static cudaError_t run_bwd_16or32(const BwdArgs& a, cudaStream_t stream)
         bool done = false;
         if (fast_shape_ok(a)) {
             done = true;
-            if constexpr (k16) {
-                switch (a.D) {   // 16-bit: G = D/8 must be <= 16
-                    case 8:   err = launch_bwd_fast<VT, 8>(a, accum, stream); break;
-                    case 16:  err = launch_bwd_fast<VT, 16>(a, accum, stream); break;
-                    case 32:  err = launch_bwd_fast<VT, 32>(a, accum, stream); break;
-                    case 64:  err = launch_bwd_fast<VT, 64>(a, accum, stream); break;
-                    case 128: err = launch_bwd_fast<VT, 128>(a, accum, stream); break;
-                    default: done = false;
-                }
-            } else {
-                switch (a.D) {   // fp32: G = D/4 must be <= 16
-                    case 8:   err = launch_bwd_fast<VT, 8>(a, accum, stream); break;
-                    case 16:  err = launch_bwd_fast<VT, 16>(a, accum, stream); break;
-                    case 32:  err = launch_bwd_fast<VT, 32>(a, accum, stream); break;
-                    case 64:  err = launch_bwd_fast<VT, 64>(a, accum, stream); break;
-                    default: done = false;
-                }
+            switch (a.D) {   // G = D/4 lanes per head must be a power of two <= 16
+                case 4:   err = launch_bwd_fast<VT, 4>(a, accum, stream); break;
+                case 8:   err = launch_bwd_fast<VT, 8>(a, accum, stream); break;
+                case 16:  err = launch_bwd_fast<VT, 16>(a, accum, stream); break;
+                case 32:  err = launch_bwd_fast<VT, 32>(a, accum, stream); break;
+                case 64:  err = launch_bwd_fast<VT, 64>(a, accum, stream); break;
+                default: done = false;
             }
         }
         if (!done) err = launch_bwd_generic<VT>(a, accum, stream);

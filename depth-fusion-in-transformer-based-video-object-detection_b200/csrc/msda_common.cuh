@@ -78,6 +78,19 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ uint2 ldg_v2(const void* p)
+{
+    uint2 r;
+    asm("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_v2(const void* p)
+{
+    uint2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
 // unpack one 16-byte vector of VT into kEpl floats
 template <typename VT> __device__ __forceinline__ void unpack(const uint4& raw, float* f);
 template <> __device__ __forceinline__ void unpack<float>(const uint4& raw, float* f)
@@ -120,6 +133,41 @@ template <> __device__ __forceinline__ uint4 pack<__half>(const float* f)
     for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
     return r;
 }
+
+// A lane's channel slice: EPL consecutive elements of VT, moved with ONE load of EPL*sizeof(VT)
+// bytes (16 B, or 8 B for the 16-bit backward where 4 channels per lane keep the fp32 vector
+// reductions row-complete).  `zero` slices stand in for out-of-map corners.
+template <typename VT, int EPL> struct Slice;
+template <typename VT> struct Slice<VT, 16 / (int)sizeof(VT)> {
+    using raw_t = uint4;
+    static __device__ __forceinline__ raw_t zero() { return make_uint4(0u, 0u, 0u, 0u); }
+    static __device__ __forceinline__ raw_t load(const VT* p) { return ldg_v4(p); }
+    static __device__ __forceinline__ raw_t load_stream(const VT* p) { return ldg_stream_v4(p); }
+    static __device__ __forceinline__ void unpack(const raw_t& r, float* f) { msda::unpack<VT>(r, f); }
+};
+template <> struct Slice<__nv_bfloat16, 4> {
+    using raw_t = uint2;
+    static __device__ __forceinline__ raw_t zero() { return make_uint2(0u, 0u); }
+    static __device__ __forceinline__ raw_t load(const __nv_bfloat16* p) { return ldg_v2(p); }
+    static __device__ __forceinline__ raw_t load_stream(const __nv_bfloat16* p) { return ldg_stream_v2(p); }
+    static __device__ __forceinline__ void unpack(const raw_t& r, float* f)
+    {
+        f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+        f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+};
+template <> struct Slice<__half, 4> {
+    using raw_t = uint2;
+    static __device__ __forceinline__ raw_t zero() { return make_uint2(0u, 0u); }
+    static __device__ __forceinline__ raw_t load(const __half* p) { return ldg_v2(p); }
+    static __device__ __forceinline__ raw_t load_stream(const __half* p) { return ldg_stream_v2(p); }
+    static __device__ __forceinline__ void unpack(const raw_t& r, float* f)
+    {
+        const __half2* h = reinterpret_cast<const __half2*>(&r);
+        const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    }
+};
 
 // ----------------------------------------------------------------------------------------
 // Bilinear footprint of one sample (the arithmetic of ms_deform_attn_im2col_bilinear,

@@ -24,8 +24,21 @@ namespace msda {
 
 template <int PAIRS> struct FwdWarps { static constexpr int value = PAIRS >= 16 ? 2 : (PAIRS >= 8 ? 4 : 8); };
 
+// ptxas only keeps the 16 gather loads of a 4-sample batch in flight together when it is told the
+// occupancy target (otherwise it minimises registers and sinks each load next to its FMAs):
+// measured best on B200 (tools/ab_variants.sh): 5 CTAs x 8 warps, <= 48 registers.
+#ifndef MSDA_FWD_MINBLOCKS
+#define MSDA_FWD_MINBLOCKS 5
+#endif
+// CTA -> work mapping.  1: a CTA owns WARPS*PAIRS consecutive queries of ONE head (neighbouring
+// queries of a head sample overlapping pixels -> L1 reuse); 0: consecutive pairs (all heads of a
+// few queries).
+#ifndef MSDA_CTA_PER_HEAD
+#define MSDA_CTA_PER_HEAD 1
+#endif
+
 template <typename VT, int D>
-__global__ void __launch_bounds__(FwdWarps<32 / (D / Traits<VT>::kEpl)>::value * 32)
+__global__ void __launch_bounds__(FwdWarps<32 / (D / Traits<VT>::kEpl)>::value * 32, MSDA_FWD_MINBLOCKS)
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ attn, VT* __restrict__ out,
@@ -38,8 +51,8 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "head width must map to a power-of-two lane group");
 
     __shared__ int s_meta[3 * kMaxLevelsFast];
-    __shared__ __align__(16) int4   s_pix[WARPS][PAIRS][kChunk];
-    __shared__ __align__(16) float4 s_wgt[WARPS][PAIRS][kChunk];
+    __shared__ __align__(16) int4   s_pix[WARPS][PAIRS][kChunk + 1];   // +1 record: group stride 272 B, so the groups of a warp hit distinct banks
+    __shared__ __align__(16) float4 s_wgt[WARPS][PAIRS][kChunk + 1];
 
     if (threadIdx.x < L) {
         s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
@@ -50,11 +63,21 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, sub = lane % G;
+#if MSDA_CTA_PER_HEAD
+    const int m = (int)(blockIdx.x % M);
+    const long long nq_total = total_pairs / M;
+    const long long nq_raw = ((long long)(blockIdx.x / M) * WARPS + warp) * PAIRS + grp;
+    const bool active = nq_raw < nq_total;
+    const long long nq = active ? nq_raw : nq_total - 1;          // clamp: loads stay in bounds
+    const long long pair = nq * M + m;
+    const long long n = nq / Lq;
+#else
     const long long pair_raw = ((long long)blockIdx.x * WARPS + warp) * PAIRS + grp;
     const bool active = pair_raw < total_pairs;
     const long long pair = active ? pair_raw : total_pairs - 1;   // clamp: loads stay in bounds
     const int m = (int)(pair % M);
     const long long n = (pair / M) / Lq;
+#endif
     const int LP = L * P;
     const int MD = M * D;
     const VT* vbase = value + (n * S * M + m) * (long long)D + sub * EPL;
@@ -192,7 +215,13 @@ static cudaError_t launch_fwd_fast(const FwdArgs& a, cudaStream_t stream)
     constexpr int PAIRS = 32 / G;
     constexpr int WARPS = FwdWarps<PAIRS>::value;
     const long long total_pairs = (long long)a.N * a.Lq * a.M;
+#if MSDA_CTA_PER_HEAD
+    const long long nq_total = (long long)a.N * a.Lq;
+    const long long blocks = ((nq_total + WARPS * PAIRS - 1) / (WARPS * PAIRS)) * a.M;
+#else
     const long long blocks = (total_pairs + WARPS * PAIRS - 1) / (WARPS * PAIRS);
+#endif
+    if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
     const int p_magic = (65536 + a.P - 1) / a.P;
     msda_fwd_fast_kernel<VT, D><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
         (const VT*)a.value, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn, (VT*)a.out,

@@ -23,6 +23,21 @@ def lsi_of(shapes):
     return out
 
 
+def nudge_off_pixel_boundaries(loc, shapes, eps=2e-3):
+    """grad_loc is discontinuous where a sample crosses a pixel boundary (and where it enters the
+    map), so an fp32 evaluation and the fp64 oracle may legitimately pick different cells for a
+    sample that sits within rounding distance of an integer pixel coordinate.  Move such samples
+    `eps` pixels away so both sides differentiate the same bilinear cell."""
+    loc = loc.clone().double()
+    for lvl, (h, w) in enumerate(shapes):
+        for axis, size in ((0, w), (1, h)):
+            px = loc[:, :, :, lvl, :, axis] * size - 0.5
+            near = (px - px.round()).abs() < eps
+            loc[:, :, :, lvl, :, axis] = torch.where(near, (px.round() + 2 * eps + 0.5) / size,
+                                                     loc[:, :, :, lvl, :, axis])
+    return loc.float()
+
+
 def make_inputs(shapes, n, m, d, lq, p, seed, dist="random", loc_range=(0.0, 1.0), dtype=torch.float32):
     """CPU-generated (so CPU oracle and GPU op see identical bits) op-level inputs.
     dist="random": loc ~ U[loc_range) as in the reference test (models/ops/test.py:34).
@@ -54,6 +69,7 @@ def make_inputs(shapes, n, m, d, lq, p, seed, dist="random", loc_range=(0.0, 1.0
         norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)   # [L,2]
         loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
     grad_out = torch.randn(n, lq, m * d, generator=g)
+    loc = nudge_off_pixel_boundaries(loc, shapes)
     return (value.to(dtype).contiguous(), loc.to(dtype).contiguous(), attn.to(dtype).contiguous(),
             grad_out.to(dtype).contiguous())
 
