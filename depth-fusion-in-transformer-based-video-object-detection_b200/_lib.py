@@ -42,6 +42,14 @@ def load():
     lib.msda_backward.restype = c_int
     lib.msda_backward.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 7 + \
                                  [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]
+    c_i64, c_fp = ctypes.c_int64, ctypes.c_void_p
+    lib.msda_fused_supported.restype = c_int
+    lib.msda_fused_supported.argtypes = [c_int] * 8
+    fused_common = [c_vp, c_vp, c_vp, c_fp, c_int, c_vp, c_i64, c_vp, c_i64] + [c_int] * 7
+    lib.msda_fused_forward.restype = c_int
+    lib.msda_fused_forward.argtypes = [c_int, c_int] + fused_common + [c_vp, c_vp]
+    lib.msda_fused_backward.restype = c_int
+    lib.msda_fused_backward.argtypes = [c_int, c_int, c_vp] + fused_common + [c_vp, c_vp, c_vp, c_fp, c_vp, c_vp]
     if lib.msda_abi_version() != ABI_VERSION:
         raise MSDAError(f"libmsda_b200.so ABI {lib.msda_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     _lib = lib

@@ -57,3 +57,62 @@ extern "C" int msda_backward(int dtype, const void* grad_output, const void* val
     a.force_generic = (flags & MSDA_FLAG_FORCE_GENERIC) ? 1 : 0;
     return (int)msda::backward(a, (cudaStream_t)stream);
 }
+
+static msda::FusedArgs make_fused(int dtype, int raw_dtype, const void* value, const int64_t* shapes,
+                                  const int64_t* lsi, const float* ref, int ref_dim, const void* offsets,
+                                  int64_t off_stride, const void* logits, int64_t logit_stride, int N, int S,
+                                  int M, int D, int L, int Lq, int P)
+{
+    msda::FusedArgs a = {};
+    a.dtype = dtype; a.raw_dtype = raw_dtype;
+    a.value = value; a.shapes = shapes; a.lsi = lsi; a.ref = ref; a.ref_dim = ref_dim;
+    a.offsets = offsets; a.off_stride = off_stride; a.logits = logits; a.logit_stride = logit_stride;
+    a.N = N; a.S = S; a.M = M; a.D = D; a.L = L; a.Lq = Lq; a.P = P;
+    return a;
+}
+
+extern "C" int msda_fused_supported(int dtype, int raw_dtype, int ref_dim, int spatial_size, int num_heads,
+                                    int channels, int num_levels, int num_point)
+{
+    msda::FusedArgs a = make_fused(dtype, raw_dtype, nullptr, nullptr, nullptr, nullptr, ref_dim, nullptr, 0,
+                                   nullptr, 0, 1, spatial_size, num_heads, channels, num_levels, 1, num_point);
+    return msda::fused_supported(a) ? 1 : 0;
+}
+
+extern "C" int msda_fused_forward(int dtype, int raw_dtype, const void* value, const int64_t* spatial_shapes,
+                                  const int64_t* level_start_index, const float* reference_points, int ref_dim,
+                                  const void* sampling_offsets_raw, int64_t offsets_query_stride,
+                                  const void* attention_logits_raw, int64_t logits_query_stride, int batch,
+                                  int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                                  int num_point, void* output, void* stream)
+{
+    if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
+        return (int)cudaErrorInvalidValue;
+    msda::FusedArgs a = make_fused(dtype, raw_dtype, value, spatial_shapes, level_start_index, reference_points,
+                                   ref_dim, sampling_offsets_raw, offsets_query_stride, attention_logits_raw,
+                                   logits_query_stride, batch, spatial_size, num_heads, channels, num_levels,
+                                   num_query, num_point);
+    a.out = output;
+    return (int)msda::fused_forward(a, (cudaStream_t)stream);
+}
+
+extern "C" int msda_fused_backward(int dtype, int raw_dtype, const void* grad_output, const void* value,
+                                   const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                   const float* reference_points, int ref_dim, const void* sampling_offsets_raw,
+                                   int64_t offsets_query_stride, const void* attention_logits_raw,
+                                   int64_t logits_query_stride, int batch, int spatial_size, int num_heads,
+                                   int channels, int num_levels, int num_query, int num_point, void* grad_value,
+                                   void* grad_offsets_raw, void* grad_logits_raw, float* grad_reference_points,
+                                   void* grad_value_accum_f32, void* stream)
+{
+    if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
+        return (int)cudaErrorInvalidValue;
+    msda::FusedArgs a = make_fused(dtype, raw_dtype, value, spatial_shapes, level_start_index, reference_points,
+                                   ref_dim, sampling_offsets_raw, offsets_query_stride, attention_logits_raw,
+                                   logits_query_stride, batch, spatial_size, num_heads, channels, num_levels,
+                                   num_query, num_point);
+    a.grad_out = grad_output;
+    a.grad_value = grad_value; a.grad_offsets = grad_offsets_raw; a.grad_logits = grad_logits_raw;
+    a.grad_ref = grad_reference_points; a.grad_value_accum = (float*)grad_value_accum_f32;
+    return (int)msda::fused_backward(a, (cudaStream_t)stream);
+}

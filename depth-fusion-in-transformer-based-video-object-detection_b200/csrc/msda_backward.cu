@@ -59,13 +59,25 @@ __device__ __forceinline__ void reduce_scatter(float* v, int sub)
     }
 }
 
-template <typename VT, int D>
+// Where the per-sample gradients go.  Plain: grad_sampling_loc / grad_attn_weight.  Fused:
+// gradients w.r.t. the raw projection outputs (through the location arithmetic and the softmax)
+// and, optionally, w.r.t. the reference points.
+struct GradDst {
+    void* loc;        // plain: grad_loc [pairs,LP,2] fp32 ; fused: grad_offsets (addressing of SampleSrc)
+    void* attn;       // plain: grad_attn [pairs,LP] fp32  ; fused: grad_logits
+    float* ref;       // fused: grad_ref [N*Lq, L, ref_dim] or nullptr
+};
+
+// FUSED: see msda_forward.cu.  Backward of the fused layer op additionally applies
+//   d loc / d offset  (1/W, 1/H  or  0.5*wh/P)           reference modules/ms_deform_attn.py:102-110
+//   softmax backward   g_logit = a * (g_a - sum_j a_j g_a_j)                      :99-100
+// to the finished per-sample gradients in phase 3, so neither the locations / weights nor their
+// gradients ever exist in HBM.
+template <typename VT, int D, bool FUSED, typename RT>
 __global__ void __launch_bounds__(BwdWarps<32 / (D / 4)>::value * 32, MSDA_BWD_MINBLOCKS)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
-                     const float* __restrict__ loc, const float* __restrict__ attn,
-                     float* __restrict__ gv_accum, float* __restrict__ grad_loc,
-                     float* __restrict__ grad_attn,
+                     const SampleSrc src, float* __restrict__ gv_accum, const GradDst dst,
                      int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs)
 {
     constexpr int EPL = 4;                       // channels per lane: one red.v4.f32 per corner
@@ -96,21 +108,30 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     const bool active = nq_raw < nq_total;
     const long long nq = active ? nq_raw : nq_total - 1;
     const long long pair = nq * M + m;
-    const long long n = nq / Lq;
 #else
     const long long pair_raw = ((long long)blockIdx.x * WARPS + warp) * PAIRS + grp;
     const bool active = pair_raw < total_pairs;
     const long long pair = active ? pair_raw : total_pairs - 1;
     const int m = (int)(pair % M);
-    const long long n = (pair / M) / Lq;
+    const long long nq = pair / M;
 #endif
+    const long long n = nq / Lq;
     const int LP = L * P;
     const int MD = M * D;
     const long long head_off = (n * S * M + m) * (long long)D + sub * EPL;
     const VT* vbase = value + head_off;
     float* gbase = gv_accum + head_off;
-    const float* lp = loc + pair * LP * 2;
-    const float* ap = attn + pair * LP;
+    const float* lp = nullptr;
+    const float* ap = nullptr;
+    const RT* op = nullptr;
+    const RT* gp = nullptr;
+    if constexpr (FUSED) {
+        op = static_cast<const RT*>(src.loc) + nq * src.loc_stride + (long long)m * LP * 2;
+        gp = static_cast<const RT*>(src.attn) + nq * src.attn_stride + (long long)m * LP;
+    } else {
+        lp = static_cast<const float*>(src.loc) + pair * LP * 2;
+        ap = static_cast<const float*>(src.attn) + pair * LP;
+    }
 
     float g[EPL];
     SliceT::unpack(SliceT::load_stream(grad_out + pair * D + sub * EPL), g);
@@ -123,14 +144,45 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         const int cnt = min(kChunk, LP - s0);
         const int cnt2 = (cnt + 1) & ~1;
         // ---- phase 1: footprints --------------------------------------------------------------
-        for (int j = sub; j < cnt2; j += G) {
+        constexpr int K = (kChunk + G - 1) / G;
+        float prob[K];
+        float inv_sum = 1.f;
+        if constexpr (FUSED) {                           // L*P <= kChunk: a single chunk
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int j = sub + k * G;
+                prob[k] = j < cnt ? load_raw1<RT>(gp + j) : -INFINITY;
+                mx = fmaxf(mx, prob[k]);
+            }
+            mx = group_max<G>(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                prob[k] = (sub + k * G) < cnt ? expf(prob[k] - mx) : 0.f;
+                sum += prob[k];
+            }
+            inv_sum = group_sum<G>(sum);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = sub + k * G;
+            if (j >= cnt2) break;
             int4 geo = make_int4(0, 0, 0, 0);
             float4 fr = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < cnt) {
                 const int s = s0 + j;
                 const int l = div_by_points(s, p_magic);
-                const float2 xy = ldg_stream_f32x2(lp + 2 * s);
-                const float a = ldg_stream_f32(ap + s);
+                float2 xy;
+                float a;
+                if constexpr (FUSED) {
+                    xy = fused_location(load_raw2<RT>(op + 2 * s), src.ref + (nq * L + l) * src.ref_dim, src.ref_dim,
+                                        s_meta[3 * l], s_meta[3 * l + 1], P);
+                    a = prob[k] / inv_sum;
+                } else {
+                    xy = ldg_stream_f32x2(lp + 2 * s);
+                    a = ldg_stream_f32(ap + s);
+                }
                 const Footprint f = footprint<float>(xy.x, xy.y, s_meta[3 * l], s_meta[3 * l + 1], s_meta[3 * l + 2]);
                 geo = make_int4(f.pix00, f.rowstep, (int)f.ok, 0);
                 fr = make_float4(f.lw, f.lh, a, 0.f);
@@ -202,18 +254,78 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 
         // ---- phase 3: combine the group's partials; each lane finishes SPL samples -----------
         reduce_scatter<3 * kChunk, G / 2>(part, sub);
-        if (active) {
+        if constexpr (!FUSED) {
+            float* grad_loc = static_cast<float*>(dst.loc);
+            float* grad_attn = static_cast<float*>(dst.attn);
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) {
+                    const int j = sub * SPL + i;
+                    if (j < cnt) {
+                        const int s = s0 + j;
+                        const int l = div_by_points(s, p_magic);
+                        const float Hf = (float)s_meta[3 * l], Wf = (float)s_meta[3 * l + 1];
+                        float2 gl = make_float2(Wf * part[3 * i + 0], Hf * part[3 * i + 1]);   // cuh:157-158
+                        *reinterpret_cast<float2*>(grad_loc + (pair * LP + s) * 2) = gl;
+                        grad_attn[pair * LP + s] = part[3 * i + 2];                            // cuh:156
+                    }
+                }
+            }
+        } else {
+            // softmax backward needs sum_j a_j * g_a_j over the pair's samples
+            float dot = 0.f;
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
                 const int j = sub * SPL + i;
-                if (j < cnt) {
-                    const int s = s0 + j;
-                    const int l = div_by_points(s, p_magic);
-                    const float Hf = (float)s_meta[3 * l], Wf = (float)s_meta[3 * l + 1];
-                    float2 gl = make_float2(Wf * part[3 * i + 0], Hf * part[3 * i + 1]);   // cuh:157-158
-                    *reinterpret_cast<float2*>(grad_loc + (pair * LP + s) * 2) = gl;
-                    grad_attn[pair * LP + s] = part[3 * i + 2];                            // cuh:156
+                if (j < cnt) dot = fmaf(s_frac[warp][grp][j].z, part[3 * i + 2], dot);
+            }
+            dot = group_sum<G>(dot);
+            if (active) {
+                RT* gop = static_cast<RT*>(dst.loc) + nq * src.loc_stride + (long long)m * LP * 2;
+                RT* ggp = static_cast<RT*>(dst.attn) + nq * src.attn_stride + (long long)m * LP;
+                int run_l = -1;                       // lane-local run of samples on one level -> one grad_ref update
+                float rx = 0.f, ry = 0.f, rw = 0.f, rh = 0.f;
+                auto flush_ref = [&]() {
+                    if (dst.ref != nullptr && run_l >= 0) {
+                        float* gr = dst.ref + (nq * L + run_l) * src.ref_dim;
+                        atomicAdd(gr, rx);
+                        atomicAdd(gr + 1, ry);
+                        if (src.ref_dim == 4) { atomicAdd(gr + 2, rw); atomicAdd(gr + 3, rh); }
+                    }
+                };
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) {
+                    const int j = sub * SPL + i;
+                    if (j < cnt) {
+                        const int s = s0 + j;
+                        const int l = div_by_points(s, p_magic);
+                        const float Hf = (float)s_meta[3 * l], Wf = (float)s_meta[3 * l + 1];
+                        const float glx = Wf * part[3 * i + 0], gly = Hf * part[3 * i + 1];   // d/d loc
+                        const float a = s_frac[warp][grp][j].z;
+                        const float glogit = a * (part[3 * i + 2] - dot);
+                        float gox, goy, gwx = 0.f, gwy = 0.f;
+                        if (src.ref_dim == 2) {
+                            gox = glx / Wf;
+                            goy = gly / Hf;
+                        } else {
+                            const float4 r = *reinterpret_cast<const float4*>(src.ref + (nq * L + l) * 4);
+                            gox = glx * (r.z * 0.5f / (float)P);
+                            goy = gly * (r.w * 0.5f / (float)P);
+                            if (dst.ref != nullptr) {
+                                const float2 off = load_raw2<RT>(op + 2 * s);
+                                gwx = glx * (off.x / (float)P * 0.5f);
+                                gwy = gly * (off.y / (float)P * 0.5f);
+                            }
+                        }
+                        store_raw2<RT>(gop + 2 * s, gox, goy);
+                        ggp[s] = from_f32<RT>(glogit);
+                        if (dst.ref != nullptr) {
+                            if (l != run_l) { flush_ref(); run_l = l; rx = ry = rw = rh = 0.f; }
+                            rx += glx; ry += gly; rw += gwx; rh += gwy;
+                        }
+                    }
                 }
+                flush_ref();
             }
         }
     }
@@ -335,9 +447,39 @@ static cudaError_t launch_bwd_fast(const BwdArgs& a, float* accum, cudaStream_t 
 #endif
     if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
     const int p_magic = (65536 + a.P - 1) / a.P;
-    msda_bwd_fast_kernel<VT, D><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
-        (const VT*)a.grad_out, (const VT*)a.value, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn,
-        accum, (float*)a.grad_loc, (float*)a.grad_attn, a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+    SampleSrc src;
+    src.loc = a.loc; src.attn = a.attn; src.ref = nullptr; src.loc_stride = 0; src.attn_stride = 0; src.ref_dim = 0;
+    GradDst dst;
+    dst.loc = a.grad_loc; dst.attn = a.grad_attn; dst.ref = nullptr;
+    msda_bwd_fast_kernel<VT, D, false, float><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
+        (const VT*)a.grad_out, (const VT*)a.value, a.shapes, a.lsi, src, accum, dst,
+        a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+    return cudaGetLastError();
+}
+
+template <typename VT, int D, typename RT>
+static cudaError_t launch_bwd_fused(const FusedArgs& a, float* accum, cudaStream_t stream)
+{
+    constexpr int G = D / 4;
+    constexpr int PAIRS = 32 / G;
+    constexpr int WARPS = BwdWarps<PAIRS>::value;
+    const long long total_pairs = (long long)a.N * a.Lq * a.M;
+#if MSDA_CTA_PER_HEAD
+    const long long nq_total = (long long)a.N * a.Lq;
+    const long long blocks = ((nq_total + WARPS * PAIRS - 1) / (WARPS * PAIRS)) * a.M;
+#else
+    const long long blocks = (total_pairs + WARPS * PAIRS - 1) / (WARPS * PAIRS);
+#endif
+    if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
+    const int p_magic = (65536 + a.P - 1) / a.P;
+    SampleSrc src;
+    src.loc = a.offsets; src.attn = a.logits; src.ref = a.ref;
+    src.loc_stride = a.off_stride; src.attn_stride = a.logit_stride; src.ref_dim = a.ref_dim;
+    GradDst dst;
+    dst.loc = a.grad_offsets; dst.attn = a.grad_logits; dst.ref = a.grad_ref;
+    msda_bwd_fast_kernel<VT, D, true, RT><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
+        (const VT*)a.grad_out, (const VT*)a.value, a.shapes, a.lsi, src, accum, dst,
+        a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
     return cudaGetLastError();
 }
 
@@ -394,6 +536,42 @@ static cudaError_t run_bwd_16or32(const BwdArgs& a, cudaStream_t stream)
         err = cudaGetLastError();
     }
     return err;
+}
+
+template <typename VT, typename RT>
+static cudaError_t run_bwd_fused(const FusedArgs& a, cudaStream_t stream)
+{
+    constexpr bool k16 = sizeof(VT) == 2;
+    const size_t count = (size_t)a.N * a.S * a.M * a.D;
+    float* accum = k16 ? a.grad_value_accum : (float*)a.grad_value;
+    if (k16 && accum == nullptr) return cudaErrorInvalidValue;
+    cudaError_t err = cudaMemsetAsync(accum, 0, count * sizeof(float), stream);
+    if (err != cudaSuccess) return err;
+    if ((long long)a.N * a.Lq * a.M > 0) {
+        switch (a.D) {
+            case 16: err = launch_bwd_fused<VT, 16, RT>(a, accum, stream); break;
+            case 32: err = launch_bwd_fused<VT, 32, RT>(a, accum, stream); break;
+            case 64: err = launch_bwd_fused<VT, 64, RT>(a, accum, stream); break;
+            default: err = cudaErrorInvalidValue;
+        }
+        if (err != cudaSuccess) return err;
+    }
+    if (k16 && count > 0) {
+        long long blocks = (long long)((count / 8 + 255) / 256);
+        if (blocks < 1) blocks = 1;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        msda_cast_accum_kernel<VT><<<(unsigned)blocks, 256, 0, stream>>>(accum, (VT*)a.grad_value, (long long)count);
+        err = cudaGetLastError();
+    }
+    return err;
+}
+
+cudaError_t fused_backward(const FusedArgs& a, cudaStream_t stream)
+{
+    if (!fused_supported(a)) return cudaErrorInvalidValue;
+    if (a.dtype == kF32) return run_bwd_fused<float, float>(a, stream);
+    if (a.raw_dtype == kF32) return run_bwd_fused<__nv_bfloat16, float>(a, stream);
+    return run_bwd_fused<__nv_bfloat16, __nv_bfloat16>(a, stream);
 }
 
 cudaError_t backward(const BwdArgs& a, cudaStream_t stream)

@@ -201,6 +201,76 @@ __device__ __forceinline__ Footprint footprint(T loc_x, T loc_y, int H, int W, i
     return f;
 }
 
+// ----------------------------------------------------------------------------------------
+// Where a pair's samples come from.  Plain: materialised sampling_loc / attn_weight (the drop-in
+// op).  Fused: raw projection outputs + reference points.
+// ----------------------------------------------------------------------------------------
+struct SampleSrc {
+    const void* loc;          // plain: sampling_loc base ; fused: offsets base
+    const void* attn;         // plain: attn_weight base  ; fused: logits base
+    const float* ref;         // fused only
+    long long loc_stride;     // fused: elements between consecutive queries
+    long long attn_stride;
+    int ref_dim;              // fused: 2 or 4
+};
+
+template <typename RT> __device__ __forceinline__ float2 load_raw2(const RT* p);
+template <> __device__ __forceinline__ float2 load_raw2<float>(const float* p) { return ldg_stream_f32x2(p); }
+template <> __device__ __forceinline__ float2 load_raw2<__nv_bfloat16>(const __nv_bfloat16* p)
+{
+    unsigned r;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 load_raw2<__half>(const __half* p)
+{
+    unsigned r;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return __half22float2(*reinterpret_cast<const __half2*>(&r));
+}
+template <typename RT> __device__ __forceinline__ float load_raw1(const RT* p) { return to_f32<RT>(*p); }
+template <> __device__ __forceinline__ float load_raw1<float>(const float* p) { return ldg_stream_f32(p); }
+
+template <typename RT> __device__ __forceinline__ void store_raw2(RT* p, float a, float b);
+template <> __device__ __forceinline__ void store_raw2<float>(float* p, float a, float b)
+{
+    *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+template <> __device__ __forceinline__ void store_raw2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b)
+{
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+template <> __device__ __forceinline__ void store_raw2<__half>(__half* p, float a, float b)
+{
+    *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b);
+}
+
+template <int G> __device__ __forceinline__ float group_max(float v)
+{
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+template <int G> __device__ __forceinline__ float group_sum(float v)
+{
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Sampling location of one sample from its raw offset and reference point
+// (reference modules/ms_deform_attn.py:102-110).
+__device__ __forceinline__ float2 fused_location(float2 off, const float* __restrict__ ref_l, int ref_dim,
+                                                 int H, int W, int P)
+{
+    if (ref_dim == 2) {
+        const float2 r = *reinterpret_cast<const float2*>(ref_l);
+        return make_float2(r.x + off.x / (float)W, r.y + off.y / (float)H);
+    }
+    const float4 r = *reinterpret_cast<const float4*>(ref_l);
+    return make_float2(r.x + off.x / (float)P * r.z * 0.5f, r.y + off.y / (float)P * r.w * 0.5f);
+}
+
 // exact s / P for 0 <= s < 65536 / P  (magic = ceil(65536 / P), computed on the host)
 __device__ __forceinline__ int div_by_points(int s, int magic) { return (s * magic) >> 16; }
 

@@ -37,11 +37,14 @@ template <int PAIRS> struct FwdWarps { static constexpr int value = PAIRS >= 16 
 #define MSDA_CTA_PER_HEAD 1
 #endif
 
-template <typename VT, int D>
+// FUSED = false: the drop-in op (sampling_loc / attn_weight materialised, fp32).
+// FUSED = true : the layer kernel - reads the raw sampling_offsets / attention_weights projection
+//                outputs (type RT) and the reference points; softmax over the L*P logits of the
+//                pair (group shuffles) and the offset -> location arithmetic happen in phase 1.
+template <typename VT, int D, bool FUSED, typename RT>
 __global__ void __launch_bounds__(FwdWarps<32 / (D / Traits<VT>::kEpl)>::value * 32, MSDA_FWD_MINBLOCKS)
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
-                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                     const float* __restrict__ attn, VT* __restrict__ out,
+                     const int64_t* __restrict__ lsi, const SampleSrc src, VT* __restrict__ out,
                      int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs)
 {
     constexpr int EPL = Traits<VT>::kEpl;
@@ -70,19 +73,28 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     const bool active = nq_raw < nq_total;
     const long long nq = active ? nq_raw : nq_total - 1;          // clamp: loads stay in bounds
     const long long pair = nq * M + m;
-    const long long n = nq / Lq;
 #else
     const long long pair_raw = ((long long)blockIdx.x * WARPS + warp) * PAIRS + grp;
     const bool active = pair_raw < total_pairs;
     const long long pair = active ? pair_raw : total_pairs - 1;   // clamp: loads stay in bounds
     const int m = (int)(pair % M);
-    const long long n = (pair / M) / Lq;
+    const long long nq = pair / M;
 #endif
+    const long long n = nq / Lq;
     const int LP = L * P;
     const int MD = M * D;
     const VT* vbase = value + (n * S * M + m) * (long long)D + sub * EPL;
-    const float* lp = loc + pair * LP * 2;
-    const float* ap = attn + pair * LP;
+    const float* lp = nullptr;
+    const float* ap = nullptr;
+    const RT* op = nullptr;
+    const RT* gp = nullptr;
+    if constexpr (FUSED) {
+        op = static_cast<const RT*>(src.loc) + nq * src.loc_stride + (long long)m * LP * 2;
+        gp = static_cast<const RT*>(src.attn) + nq * src.attn_stride + (long long)m * LP;
+    } else {
+        lp = static_cast<const float*>(src.loc) + pair * LP * 2;
+        ap = static_cast<const float*>(src.attn) + pair * LP;
+    }
 
     float acc[EPL];
 #pragma unroll
@@ -92,14 +104,45 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
         const int cnt = min(kChunk, LP - s0);
         const int cnt4 = (cnt + 3) & ~3;
         // ---- phase 1: footprints, one sample per lane of the group -------------------------
-        for (int j = sub; j < cnt4; j += G) {
+        constexpr int K = (kChunk + G - 1) / G;          // samples per lane per chunk
+        float prob[K];                                   // fused: softmax numerators, then weights
+        float inv_sum = 1.f;
+        if constexpr (FUSED) {                           // host guarantees L*P <= kChunk: one chunk
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int j = sub + k * G;
+                prob[k] = j < cnt ? load_raw1<RT>(gp + j) : -INFINITY;
+                mx = fmaxf(mx, prob[k]);
+            }
+            mx = group_max<G>(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                prob[k] = (sub + k * G) < cnt ? expf(prob[k] - mx) : 0.f;
+                sum += prob[k];
+            }
+            inv_sum = group_sum<G>(sum);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int j = sub + k * G;
+            if (j >= cnt4) break;
             int4 px = make_int4(0, 0, 0, 0);
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < cnt) {
                 const int s = s0 + j;
                 const int l = div_by_points(s, p_magic);
-                const float2 xy = ldg_stream_f32x2(lp + 2 * s);
-                const float a = ldg_stream_f32(ap + s);
+                float2 xy;
+                float a;
+                if constexpr (FUSED) {
+                    xy = fused_location(load_raw2<RT>(op + 2 * s), src.ref + (nq * L + l) * src.ref_dim, src.ref_dim,
+                                        s_meta[3 * l], s_meta[3 * l + 1], P);
+                    a = prob[k] / inv_sum;               // softmax: exp(x - max) / sum
+                } else {
+                    xy = ldg_stream_f32x2(lp + 2 * s);
+                    a = ldg_stream_f32(ap + s);
+                }
                 const Footprint f = footprint<float>(xy.x, xy.y, s_meta[3 * l], s_meta[3 * l + 1], s_meta[3 * l + 2]);
                 const float hw = 1.f - f.lw, hh = 1.f - f.lh;
                 // invalid corners: weight 0 and a harmless in-range address (pixel 0)
@@ -223,9 +266,33 @@ static cudaError_t launch_fwd_fast(const FwdArgs& a, cudaStream_t stream)
 #endif
     if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
     const int p_magic = (65536 + a.P - 1) / a.P;
-    msda_fwd_fast_kernel<VT, D><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
-        (const VT*)a.value, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn, (VT*)a.out,
-        a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+    SampleSrc src;
+    src.loc = a.loc; src.attn = a.attn; src.ref = nullptr; src.loc_stride = 0; src.attn_stride = 0; src.ref_dim = 0;
+    msda_fwd_fast_kernel<VT, D, false, float><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
+        (const VT*)a.value, a.shapes, a.lsi, src, (VT*)a.out, a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+    return cudaGetLastError();
+}
+
+template <typename VT, int D, typename RT>
+static cudaError_t launch_fwd_fused(const FusedArgs& a, cudaStream_t stream)
+{
+    constexpr int G = D / Traits<VT>::kEpl;
+    constexpr int PAIRS = 32 / G;
+    constexpr int WARPS = FwdWarps<PAIRS>::value;
+    const long long total_pairs = (long long)a.N * a.Lq * a.M;
+#if MSDA_CTA_PER_HEAD
+    const long long nq_total = (long long)a.N * a.Lq;
+    const long long blocks = ((nq_total + WARPS * PAIRS - 1) / (WARPS * PAIRS)) * a.M;
+#else
+    const long long blocks = (total_pairs + WARPS * PAIRS - 1) / (WARPS * PAIRS);
+#endif
+    if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
+    const int p_magic = (65536 + a.P - 1) / a.P;
+    SampleSrc src;
+    src.loc = a.offsets; src.attn = a.logits; src.ref = a.ref;
+    src.loc_stride = a.off_stride; src.attn_stride = a.logit_stride; src.ref_dim = a.ref_dim;
+    msda_fwd_fast_kernel<VT, D, true, RT><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
+        (const VT*)a.value, a.shapes, a.lsi, src, (VT*)a.out, a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
     return cudaGetLastError();
 }
 
@@ -262,6 +329,35 @@ static cudaError_t dispatch_fwd_16or32(const FwdArgs& a, cudaStream_t stream)
         }
     }
     return launch_fwd_generic<VT>(a, stream);
+}
+
+bool fused_supported(const FusedArgs& a)
+{
+    const bool dtype_ok = (a.dtype == kF32 && a.raw_dtype == kF32) ||
+                          (a.dtype == kBF16 && (a.raw_dtype == kF32 || a.raw_dtype == kBF16));
+    return dtype_ok && (a.D == 16 || a.D == 32 || a.D == 64) && a.L >= 1 && a.P >= 1 && a.L * a.P <= kChunk &&
+           a.L <= kMaxLevelsFast && (a.ref_dim == 2 || a.ref_dim == 4) &&
+           (long long)a.S * a.M * a.D < (1ll << 31) && (a.P % 2 == 0 || a.raw_dtype == kF32);
+}
+
+template <typename VT, typename RT>
+static cudaError_t dispatch_fwd_fused(const FusedArgs& a, cudaStream_t stream)
+{
+    switch (a.D) {
+        case 16: return launch_fwd_fused<VT, 16, RT>(a, stream);
+        case 32: return launch_fwd_fused<VT, 32, RT>(a, stream);
+        case 64: return launch_fwd_fused<VT, 64, RT>(a, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t fused_forward(const FusedArgs& a, cudaStream_t stream)
+{
+    if (!fused_supported(a)) return cudaErrorInvalidValue;
+    if ((long long)a.N * a.Lq * a.M * a.D == 0) return cudaSuccess;
+    if (a.dtype == kF32) return dispatch_fwd_fused<float, float>(a, stream);
+    if (a.raw_dtype == kF32) return dispatch_fwd_fused<__nv_bfloat16, float>(a, stream);
+    return dispatch_fwd_fused<__nv_bfloat16, __nv_bfloat16>(a, stream);
 }
 
 cudaError_t forward(const FwdArgs& a, cudaStream_t stream)

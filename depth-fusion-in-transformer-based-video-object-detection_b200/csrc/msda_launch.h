@@ -35,6 +35,37 @@ struct BwdArgs {
     int force_generic;
 };
 
+// Fused layer op: sampling locations and attention weights are NOT materialised.  The kernels
+// read the raw outputs of the sampling_offsets / attention_weights projections and the
+// reference points, and do softmax + location arithmetic (modules/ms_deform_attn.py:98-110 of the
+// reference) in registers.
+struct FusedArgs {
+    int dtype;                // value / out / grad_out / grad_value dtype (kF32, kBF16, kF16)
+    int raw_dtype;            // offsets / logits dtype (kF32 or kBF16/kF16 matching dtype)
+    const void* value;
+    const int64_t* shapes;
+    const int64_t* lsi;
+    const float* ref;         // [N*Lq, L, ref_dim] fp32
+    int ref_dim;              // 2 or 4
+    const void* offsets;      // element (nq, m, l, p, xy) at offsets[nq*off_stride + ((m*L + l)*P + p)*2 + xy]
+    long long off_stride;
+    const void* logits;       // element (nq, m, l, p)     at logits[nq*logit_stride + (m*L + l)*P + p]
+    long long logit_stride;
+    void* out;                // forward: [N,Lq,M,D]
+    // backward only
+    const void* grad_out;
+    void* grad_value;         // [N,S,M,D] dtype
+    float* grad_value_accum;  // 16-bit dtypes: fp32 scratch
+    void* grad_offsets;       // same addressing as offsets (raw dtype), fully written
+    void* grad_logits;        // same addressing as logits, fully written
+    float* grad_ref;          // [N*Lq, L, ref_dim] fp32, accumulated with atomics (caller zero-fills); may be null
+    int N, S, M, D, L, Lq, P;
+};
+
+bool fused_supported(const FusedArgs& a);
+cudaError_t fused_forward(const FusedArgs& a, cudaStream_t stream);
+cudaError_t fused_backward(const FusedArgs& a, cudaStream_t stream);
+
 cudaError_t forward(const FwdArgs& a, cudaStream_t stream);
 cudaError_t backward(const BwdArgs& a, cudaStream_t stream);
 

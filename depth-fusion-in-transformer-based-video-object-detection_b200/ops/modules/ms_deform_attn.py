@@ -10,6 +10,13 @@ What differs is underneath: the gather runs in the hand-written sm_100a kernels 
 libmsda_b200.so; the four projections stay library GEMMs (tensor cores) around it.
 The reference's per-call device->host sync (``assert ... .sum() == Len_in``, :92) is paid once
 per distinct ``input_spatial_shapes`` tensor instead of once per layer call.
+
+Fused path (default, ``self.fused``): the sampling-offset and attention-weight projections run as
+ONE GEMM and a single kernel per direction does softmax, offset -> location arithmetic, the
+multi-level bilinear gather and the weighted head reduction (ops/functions/
+ms_deform_attn_fused_func.py); locations and attention weights never reach HBM.  Shapes the fused
+kernels do not cover (head width not 16/32/64, more than 16 samples per head, fp64) take the
+reference's unfused sequence around the drop-in op -- still on the GPU, never on the CPU.
 """
 import math
 import warnings
@@ -19,7 +26,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported
 
 
 def _is_power_of_2(n):
@@ -65,6 +72,7 @@ class MSDeformAttn(nn.Module):
                           "a power of 2 which is more efficient in our CUDA implementation.")
 
         self.im2col_step = 64
+        self.fused = True          # one-kernel layer path when the shape allows it
 
         self.d_model = d_model
         self.n_levels = n_levels
@@ -130,6 +138,31 @@ class MSDeformAttn(nn.Module):
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError(
+                'Last dim of reference_points must be 2 or 4, but get {} instead.'.format(reference_points.shape[-1]))
+
+        if self.fused and value.is_cuda:
+            # [ offsets | logits ] from one GEMM; parameters stay separate for checkpoint compatibility
+            weight = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
+            bias = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+            raw = F.linear(query, weight, bias)
+            if raw.dtype != value.dtype and value.dtype == torch.float32:
+                raw = raw.float()
+            if fused_supported(value, raw, reference_points.shape[-1], self.n_levels, self.n_points):
+                output = MSDeformAttnFusedFunction.apply(
+                    value, input_spatial_shapes, input_level_start_index, reference_points, raw, self.n_points)
+                return self.output_proj(output)
+            split = self.n_heads * self.n_levels * self.n_points * 2
+            offsets = raw[..., :split].reshape(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
+            attention = raw[..., split:].reshape(N, Len_q, self.n_heads, self.n_levels * self.n_points)
+            attention = F.softmax(attention, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
+            sampling_locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
+            output = MSDeformAttnFunction.apply(
+                value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
+                attention.contiguous(), self.im2col_step)
+            return self.output_proj(output)
+
         offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         attention = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
         attention = F.softmax(attention, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)

@@ -76,6 +76,47 @@ int msda_backward(int dtype,
                   void* grad_value, void* grad_sampling_loc, void* grad_attn_weight,
                   void* grad_value_accum_f32, int flags, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused layer op (no counterpart symbol in the reference: it replaces the chain
+ * softmax -> offset/normaliser arithmetic -> MSDeformAttnFunction of MSDeformAttn.forward,
+ * /root/reference/models/ops/modules/ms_deform_attn.py:98-115, with ONE kernel per direction;
+ * sampling locations and attention weights never exist in HBM).
+ *
+ *   reference_points      [N*Lq, L, ref_dim] fp32, ref_dim 2 (points) or 4 (boxes cx,cy,w,h)
+ *   sampling_offsets_raw  output of the sampling_offsets projection, element (nq, m, l, p, xy) at
+ *                         base[nq*offsets_query_stride + ((m*L + l)*P + p)*2 + xy]
+ *   attention_logits_raw  output of the attention_weights projection (pre-softmax), element
+ *                         (nq, m, l, p) at base[nq*logits_query_stride + (m*L + l)*P + p]
+ *   raw_dtype             F32, or BF16 when dtype is BF16
+ * The two raw tensors may be slices of one [N*Lq, 3*M*L*P] GEMM output (both strides 3*M*L*P).
+ * Supported: dtype F32 / BF16, channels 16 / 32 / 64, num_levels*num_point <= 16
+ * (msda_fused_supported); everything else goes through msda_forward / msda_backward.
+ * Backward: grad_offsets_raw / grad_logits_raw use the addressing of their inputs and are fully
+ * written; grad_reference_points (may be NULL) is accumulated into with atomics - zero it first.
+ */
+int msda_fused_supported(int dtype, int raw_dtype, int ref_dim, int spatial_size, int num_heads,
+                         int channels, int num_levels, int num_point);
+
+int msda_fused_forward(int dtype, int raw_dtype,
+                       const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                       const float* reference_points, int ref_dim,
+                       const void* sampling_offsets_raw, int64_t offsets_query_stride,
+                       const void* attention_logits_raw, int64_t logits_query_stride,
+                       int batch, int spatial_size, int num_heads, int channels,
+                       int num_levels, int num_query, int num_point,
+                       void* output, void* stream);
+
+int msda_fused_backward(int dtype, int raw_dtype,
+                        const void* grad_output,
+                        const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                        const float* reference_points, int ref_dim,
+                        const void* sampling_offsets_raw, int64_t offsets_query_stride,
+                        const void* attention_logits_raw, int64_t logits_query_stride,
+                        int batch, int spatial_size, int num_heads, int channels,
+                        int num_levels, int num_query, int num_point,
+                        void* grad_value, void* grad_offsets_raw, void* grad_logits_raw,
+                        float* grad_reference_points, void* grad_value_accum_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

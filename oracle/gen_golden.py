@@ -197,6 +197,29 @@ def main():
                         t["level_start_index"], None),
         wrt=["query", "reference_points", "input_flatten"])
 
+    # head width 16 (d_model 64 / 4 heads): the shapes the FUSED sm_100a layer kernels cover
+    torch.manual_seed(24)
+    c16 = 64
+    attn16 = mod.MSDeformAttn(c16, 2, heads, 4).double()
+    perturb(attn16, 25)
+    query16 = torch.randn(n, s, c16)
+    feat16 = torch.randn(n, s, c16)
+    save_module_case(
+        "module_msda_ref2_d16", attn16,
+        dict(query=query16, reference_points=ref2, input_flatten=feat16, spatial_shapes=shapes_t,
+             level_start_index=lsi, padding_mask=mask),
+        lambda m_, t: m_(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"],
+                        t["level_start_index"], t["padding_mask"]),
+        wrt=["query", "reference_points", "input_flatten"])
+    q7_16 = torch.randn(n, 7, c16)
+    save_module_case(
+        "module_msda_ref4_d16", attn16,
+        dict(query=q7_16, reference_points=ref4, input_flatten=feat16, spatial_shapes=shapes_t,
+             level_start_index=lsi),
+        lambda m_, t: m_(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"],
+                        t["level_start_index"], None),
+        wrt=["query", "reference_points", "input_flatten"])
+
     # ---------------- layer classes (deformable_transformer_single.py) --------
     torch.manual_seed(31)
     pos = torch.randn(n, s, c)
@@ -224,6 +247,19 @@ def main():
     save_module_case(
         "layer_fusion_v2", fusion,
         dict(tgt=feat, query_pos=pos, reference_points=ref_d1, src=depth, src_spatial_shapes=dshapes,
+             level_start_index=dlsi, src_padding_mask=dmask),
+        lambda m_, t: m_(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                        t["level_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"])
+
+    fusion16 = single.DeformableTransformerFusionLayerV2(c16, 64, 0.0, "gelu", 1, heads, 4).double()
+    perturb(fusion16, 44)
+    torch.manual_seed(45)
+    pos16 = torch.randn(n, s, c16)
+    depth16 = torch.randn(n, sd, c16)
+    save_module_case(
+        "layer_fusion_v2_d16", fusion16,
+        dict(tgt=feat16, query_pos=pos16, reference_points=ref_d1, src=depth16, src_spatial_shapes=dshapes,
              level_start_index=dlsi, src_padding_mask=dmask),
         lambda m_, t: m_(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
                         t["level_start_index"], t["src_padding_mask"]),

@@ -23,6 +23,21 @@ CASES = {
         call=lambda m, t: m(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"],
                             t["level_start_index"], None),
         wrt=["query", "reference_points", "input_flatten"]),
+    "module_msda_ref2_d16": dict(
+        build=lambda: MSDeformAttn(64, 2, HEADS, 4),
+        call=lambda m, t: m(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"],
+                            t["level_start_index"], t["padding_mask"]),
+        wrt=["query", "reference_points", "input_flatten"]),
+    "module_msda_ref4_d16": dict(
+        build=lambda: MSDeformAttn(64, 2, HEADS, 4),
+        call=lambda m, t: m(t["query"], t["reference_points"], t["input_flatten"], t["spatial_shapes"],
+                            t["level_start_index"], None),
+        wrt=["query", "reference_points", "input_flatten"]),
+    "layer_fusion_v2_d16": dict(
+        build=lambda: tl.DeformableTransformerFusionLayerV2(64, 64, 0.0, "gelu", 1, HEADS, 4),
+        call=lambda m, t: m(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                            t["level_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"]),
     "layer_encoder": dict(
         build=lambda: _enc(2),
         call=lambda m, t: m(t["src"], t["pos"], t["reference_points"], t["spatial_shapes"],

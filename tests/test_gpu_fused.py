@@ -1,0 +1,145 @@
+"""GPU: the fused layer kernels (C ABI msda_fused_forward / msda_fused_backward) against
+  * the oracle composition  softmax -> offset/normaliser arithmetic -> oracle op, in fp64 on CPU,
+    written exactly as the reference module does it (models/ops/modules/ms_deform_attn.py:98-114);
+  * the unfused drop-in op fed with the same softmax / locations computed by PyTorch on the GPU.
+Outputs and the gradients w.r.t. value, the raw projection output and the reference points."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import msda_oracle
+from tests import util
+from tests.util import nerr
+
+pytestmark = pytest.mark.gpu
+
+from dfvod_b200.ops.functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported
+
+DEV = "cuda"
+
+
+def reference_composition(value, shapes, ref, raw, m, nl, p, op):
+    """modules/ms_deform_attn.py:98-114 on whatever device/dtype the inputs have."""
+    n, lq = raw.shape[:2]
+    mlp = m * nl * p
+    offsets = raw[..., :2 * mlp].reshape(n, lq, m, nl, p, 2)
+    attn = F.softmax(raw[..., 2 * mlp:].reshape(n, lq, m, nl * p), -1).view(n, lq, m, nl, p)
+    if ref.shape[-1] == 2:
+        normalizer = torch.tensor([[w, h] for h, w in shapes], dtype=raw.dtype, device=raw.device)
+        loc = ref[:, :, None, :, None, :] + offsets / normalizer[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + offsets / p * ref[:, :, None, :, None, 2:] * 0.5
+    return op(value, loc, attn)
+
+
+def make_case(shapes, n, m, d, lq, p, ref_dim, seed):
+    g = torch.Generator().manual_seed(seed)
+    nl = len(shapes)
+    s = sum(h * w for h, w in shapes)
+    value = torch.randn(n, s, m, d, generator=g)
+    raw = torch.randn(n, lq, 3 * m * nl * p, generator=g)
+    raw[..., :2 * m * nl * p] *= 2.0                       # offsets of a few pixels
+    if ref_dim == 2:
+        ref = torch.rand(n, lq, nl, 2, generator=g)
+    else:
+        ref = torch.cat([torch.rand(n, lq, nl, 2, generator=g), torch.rand(n, lq, nl, 2, generator=g) * 0.5 + 0.05], -1)
+    gout = torch.randn(n, lq, m * d, generator=g)
+    return value, raw, ref, gout
+
+
+def run_fused(value, shapes, ref, raw, gout, p, vdtype=torch.float32, rdtype=torch.float32):
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v = value.to(DEV, vdtype).requires_grad_(True)
+    r = raw.to(DEV, rdtype).requires_grad_(True)
+    rf = ref.to(DEV).requires_grad_(True)
+    out = MSDeformAttnFusedFunction.apply(v, st, ls, rf, r, p)
+    out.backward(gout.to(DEV, vdtype))
+    torch.cuda.synchronize()
+    return [t.detach().double().cpu().numpy() for t in (out, v.grad, r.grad, rf.grad)]
+
+
+def run_oracle64(value, shapes, ref, raw, gout, m, nl, p):
+    v = value.double().requires_grad_(True)
+    r = raw.double().requires_grad_(True)
+    rf = ref.double().requires_grad_(True)
+    out = reference_composition(v, shapes, rf, r, m, nl, p,
+                                lambda vv, loc, attn: msda_oracle.core_pytorch(vv, shapes, loc, attn))
+    out.backward(gout.double())
+    return [t.detach().numpy() for t in (out, v.grad, r.grad, rf.grad)]
+
+
+CASES = [
+    # shapes, N, M, D, Lq, P, ref_dim
+    ([(20, 30), (10, 15), (5, 8), (3, 4)], 2, 8, 32, 131, 4, 2),      # production layout, L*P = 16
+    ([(20, 30), (10, 15), (5, 8), (3, 4)], 1, 8, 32, 50, 4, 4),       # decoder with box refinement
+    ([(50, 84)], 2, 8, 32, 77, 4, 2),                                 # shipped 1-level config
+    ([(12, 9), (6, 5)], 2, 4, 16, 39, 3, 2),                          # D=16, odd P
+    ([(12, 9), (6, 5)], 1, 4, 64, 21, 4, 4),                          # D=64
+    ([(7, 7)] * 4, 1, 2, 32, 9, 2, 2),                                # frames-as-levels style
+]
+IDS = [f"L{len(c[0])}_M{c[2]}_D{c[3]}_P{c[5]}_ref{c[6]}" for c in CASES]
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_fused_fp32_vs_oracle_composition(case):
+    shapes, n, m, d, lq, p, ref_dim = case
+    nl = len(shapes)
+    value, raw, ref, gout = make_case(shapes, n, m, d, lq, p, ref_dim, seed=7 + d + p)
+    assert fused_supported(value.to(DEV), raw.to(DEV), ref_dim, nl, p)
+    got = run_fused(value, shapes, ref, raw, gout, p)
+    want = run_oracle64(value, shapes, ref, raw, gout, m, nl, p)
+    for name, x, r in zip(("out", "grad_value", "grad_raw", "grad_ref"), got, want):
+        emax, el2 = nerr(x, r)
+        # grad_raw / grad_ref inherit the pixel-boundary sensitivity of grad_loc: seeds are fixed and
+        # the bound is the fp32 one of BASELINE.md with 2x slack for the extra softmax/division steps
+        assert emax <= 2e-5 and el2 <= 2e-5, f"{name}: max {emax:.3e} l2 {el2:.3e}"
+
+
+@pytest.mark.parametrize("case", CASES[:3], ids=IDS[:3])
+def test_fused_matches_unfused_op_on_gpu(case):
+    shapes, n, m, d, lq, p, ref_dim = case
+    nl = len(shapes)
+    value, raw, ref, gout = make_case(shapes, n, m, d, lq, p, ref_dim, seed=99)
+    got = run_fused(value, shapes, ref, raw, gout, p)
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v = value.to(DEV).requires_grad_(True)
+    r = raw.to(DEV).requires_grad_(True)
+    rf = ref.to(DEV).requires_grad_(True)
+    out = reference_composition(
+        v, shapes, rf, r, m, nl, p,
+        lambda vv, loc, attn: MSDeformAttnFunction.apply(vv, st, ls, loc.contiguous(), attn.contiguous(), 64))
+    out.backward(gout.to(DEV))
+    want = [t.detach().double().cpu().numpy() for t in (out, v.grad, r.grad, rf.grad)]
+    for name, x, w in zip(("out", "grad_value", "grad_raw", "grad_ref"), got, want):
+        emax, el2 = nerr(x, w)
+        assert emax <= 2e-5 and el2 <= 2e-5, f"{name}: max {emax:.3e} l2 {el2:.3e}"
+
+
+@pytest.mark.parametrize("rdtype", [torch.float32, torch.bfloat16])
+def test_fused_bf16(rdtype):
+    shapes, n, m, d, lq, p, ref_dim = CASES[0]
+    nl = len(shapes)
+    value, raw, ref, gout = make_case(shapes, n, m, d, lq, p, ref_dim, seed=5)
+    v16, g16 = value.bfloat16(), gout.bfloat16()
+    r_in = raw.to(rdtype)
+    got = run_fused(v16, shapes, ref, r_in, g16, p, torch.bfloat16, rdtype)
+    want = run_oracle64(v16.float(), shapes, ref, r_in.float(), g16.float(), m, nl, p)
+    for name, x, w in zip(("out", "grad_value", "grad_raw", "grad_ref"), got, want):
+        emax, el2 = nerr(x, w)
+        assert emax <= 2.0 ** -7 and el2 <= 4e-3, f"{name}: max {emax:.3e} l2 {el2:.3e}"
+
+
+def test_fused_no_ref_grad_and_unsupported_shapes():
+    shapes, n, m, d, lq, p, ref_dim = CASES[2]
+    value, raw, ref, gout = make_case(shapes, n, m, d, lq, p, ref_dim, seed=3)
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v = value.to(DEV).requires_grad_(True)
+    r = raw.to(DEV).requires_grad_(True)
+    rf = ref.to(DEV)                                  # encoder case: reference points are constants
+    out = MSDeformAttnFusedFunction.apply(v, st, ls, rf, r, p)
+    out.backward(gout.to(DEV))
+    assert rf.grad is None and v.grad is not None and r.grad is not None
+    assert not fused_supported(value.to(DEV).double(), raw.to(DEV).double(), 2, 1, p)          # fp64
+    assert not fused_supported(torch.zeros(1, 4, 2, 8, device=DEV), raw.to(DEV), 2, 1, p)      # D=8
+    assert not fused_supported(value.to(DEV), raw.to(DEV), 2, 5, 4)                            # L*P = 20 > 16
