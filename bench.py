@@ -171,11 +171,12 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profile(kind):
-    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+def traffic_from_profile(kind, dtype="f32"):
+    """dram__bytes_read+write per launch of the kernel from the committed ncu capture
+    (profiles/ncu_summary.json, same workload), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-            return json.load(f).get(kind, {}).get("dram_bytes_per_launch")
+            return json.load(f).get(dtype, {}).get(kind, {}).get("dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -225,6 +226,121 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def _time_events(torch, fn, iters, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def encoder_extras(torch, dev, world, dist, n_frames=8, iters=10):
+    """BASELINE.json "encoder frames/sec": the 6-layer DeformableTransformerEncoder of
+    configs[1] (inference, COCO pyramid, batch 8 per GPU, synthetic features), bf16 weights and
+    activations, replayed from a CUDA graph; plus the same encoder in fp32 (the reference's dtype)."""
+    from dfvod_b200 import transformer_layers as tl
+    lsi, s = level_start(COCO_SHAPES)
+    st = torch.as_tensor(COCO_SHAPES, dtype=torch.long, device=dev)
+    ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
+    torch.manual_seed(1)
+    enc = tl.DeformableTransformerEncoder(tl.DeformableTransformerEncoderLayer(256, 1024, 0.1, "relu", 4, 8, 4), 6)
+    enc = enc.to(dev).eval()
+    src = torch.randn(n_frames, s, 256, device=dev)
+    pos = torch.randn(n_frames, s, 256, device=dev)
+    vr = torch.ones(n_frames, len(COCO_SHAPES), 2, device=dev)
+    out = {"frames_per_gpu": n_frames, "layers": 6, "tokens_per_frame": s}
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        ms32 = reduce_max(_time_events(torch, lambda: enc(src, st, ls, vr, pos, None), 3, 2))
+        out["fp32_eager_ms"] = ms32
+        out["fp32_eager_fps"] = n_frames * world / ms32 * 1e3
+        enc16, src16, pos16 = enc.bfloat16(), src.bfloat16(), pos.bfloat16()
+        run16 = lambda: enc16(src16, st, ls, vr, pos16, None)
+        ms16 = reduce_max(_time_events(torch, run16, iters, 3))
+        out["bf16_eager_ms"] = ms16
+        out["bf16_eager_fps"] = n_frames * world / ms16 * 1e3
+        try:
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run16()
+            torch.cuda.current_stream().wait_stream(side)
+            with torch.cuda.graph(graph):
+                run16()
+            msg = reduce_max(_time_events(torch, graph.replay, iters, 3))
+            out["bf16_graph_ms"] = msg
+            out["bf16_graph_fps"] = n_frames * world / msg * 1e3
+        except Exception as exc:      # report, do not hide
+            out["bf16_graph_error"] = repr(exc)[:160]
+    return out
+
+
+def train_step_extras(torch, dev, world, dist, n_frames=4, iters=5):
+    """BASELINE.json configs[4]: Encoder-Cross-Fusion training step (fwd + bwd + AdamW), frames
+    sharded over GPUs, gradients all-reduced over NCCL by dfvod_b200.data_parallel.  Model:
+    RGBDDeformableTransformerEncoderV2 (6 encoder + 4 fusion layers) + 6 decoder layers, COCO
+    pyramid for RGB and depth, 300 queries, bf16 parameters, synthetic features, loss = mean(hs^2)."""
+    from dfvod_b200 import data_parallel
+    from dfvod_b200 import transformer_layers as tl
+    lsi, s = level_start(COCO_SHAPES)
+    st = torch.as_tensor(COCO_SHAPES, dtype=torch.long, device=dev)
+    ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
+    torch.manual_seed(4)                      # identical initial weights on every rank
+    nl = len(COCO_SHAPES)
+    encoder = tl.RGBDDeformableTransformerEncoderV2(
+        tl.DeformableTransformerEncoderLayer(256, 1024, 0.0, "relu", nl, 8, 4),
+        tl.DeformableTransformerFusionLayerV2(256, 1024, 0.0, "gelu", nl, 8, 4), 6, 4, 4, [0, 1, 2, 3])
+    decoder = tl.DeformableTransformerDecoder(tl.DeformableTransformerDecoderLayer(256, 1024, 0.0, "relu", nl, 8, 4), 6)
+    ref_head = torch.nn.Linear(256, 2)
+    model = torch.nn.ModuleDict(dict(encoder=encoder, decoder=decoder, ref=ref_head)).to(dev).bfloat16()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    reducer = data_parallel.GradientAllReducer(model.parameters())
+    rank = dist.get_rank() if world > 1 else 0
+    g = torch.Generator(device="cpu").manual_seed(40 + rank)
+    bf = torch.bfloat16
+    src = torch.randn(n_frames, s, 256, generator=g).to(dev, bf)
+    depth = torch.randn(n_frames, s, 256, generator=g).to(dev, bf)
+    pos = torch.randn(n_frames, s, 256, generator=g).to(dev, bf)
+    query = torch.randn(300, 512, generator=g).to(dev, bf)
+    vr = torch.ones(n_frames, nl, 2, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        memory = model["encoder"](src, st, ls, vr, pos, None, None, depth, st, ls, None, None, None)
+        qpos, tgt = query[:, :256], query[:, 256:]
+        qpos = qpos.unsqueeze(0).expand(n_frames, -1, -1)
+        tgt = tgt.unsqueeze(0).expand(n_frames, -1, -1)
+        refp = model["ref"](qpos).sigmoid()
+        hs, _ = model["decoder"](tgt, refp, memory, st, ls, vr.to(bf), qpos, None)
+        loss = hs.float().square().mean()
+        loss.backward()
+        reducer.finish()
+        opt.step()
+        return loss
+
+    ms = _time_events(torch, step, iters, 2)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    reducer.remove()
+    return {"frames_per_gpu": n_frames, "ms_per_step": ms, "frames_per_s": n_frames * world / ms * 1e3,
+            "gradient_bytes": reducer.gradient_bytes, "dtype": "bf16",
+            "collective": "bucketed all-reduce (NCCL)" if world > 1 else "none (1 GPU)"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -334,11 +450,22 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": "msda_bwd_fast_kernel (+ its grad_value zero-fill"
                                           + (" and bf16 cast" if e_v == 2 else "") + ")",
                 "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
-                "traffic": traffic_from_profile("backward"), "peak_source": peak_src,
+                "traffic": traffic_from_profile("backward", args.dtype), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": bwd_ms}
     roofline_fwd = {"bound": "hbm", "kernel": "msda_fwd_fast_kernel", "achieved": achieved_fwd, "peak": peak,
-                    "unit": "GB/s", "frac": achieved_fwd / peak, "traffic": traffic_from_profile("forward"),
+                    "unit": "GB/s", "frac": achieved_fwd / peak, "traffic": traffic_from_profile("forward", args.dtype),
                     "algorithmic_bytes_per_launch": fwd_bytes, "ms_per_launch": fwd_ms}
+
+    extras = {}
+    if not args.no_extras:
+        del value, loc, attn, gout, host, pinned_out          # give the memory back first
+        torch.cuda.empty_cache()
+        for name, fn in (("encoder", encoder_extras), ("train_step", train_step_extras)):
+            try:
+                extras[name] = fn(torch, dev, world, dist)
+            except Exception as exc:                          # extras never invalidate the main line
+                extras[name] = {"error": repr(exc)[:200]}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -368,6 +495,7 @@ def run_b200(args):
             "per_step_ms": {"fwd_median": fwd_med, "bwd_median": bwd_med, "fwd_min": fwd_all[0],
                             "bwd_min": bwd_all[0], "fwd_max": fwd_all[-1], "bwd_max": bwd_all[-1]},
             "cpu_baseline": cpu_baseline}
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -384,6 +512,7 @@ def main():
     ap.add_argument("--dist", default="grid", choices=["grid", "random"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the encoder / training-step side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
