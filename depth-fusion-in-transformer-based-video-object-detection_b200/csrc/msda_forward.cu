@@ -26,9 +26,10 @@ template <int PAIRS> struct FwdWarps { static constexpr int value = PAIRS >= 16 
 
 // ptxas only keeps the 16 gather loads of a 4-sample batch in flight together when it is told the
 // occupancy target (otherwise it minimises registers and sinks each load next to its FMAs):
-// measured best on B200 (tools/ab_variants.sh): 5 CTAs x 8 warps, <= 48 registers.
-#ifndef MSDA_FWD_MINBLOCKS
-#define MSDA_FWD_MINBLOCKS 5
+// measured best on B200 (tools/ab_variants.sh): 40 resident warps per SM (5 CTAs x 8 warps for fp32
+// D=32, 10 CTAs x 4 warps for bf16 D=32), i.e. <= 48 registers.
+#ifndef MSDA_FWD_MINWARPS
+#define MSDA_FWD_MINWARPS 40
 #endif
 // CTA -> work mapping.  1: a CTA owns WARPS*PAIRS consecutive queries of ONE head (neighbouring
 // queries of a head sample overlapping pixels -> L1 reuse); 0: consecutive pairs (all heads of a
@@ -42,7 +43,8 @@ template <int PAIRS> struct FwdWarps { static constexpr int value = PAIRS >= 16 
 //                outputs (type RT) and the reference points; softmax over the L*P logits of the
 //                pair (group shuffles) and the offset -> location arithmetic happen in phase 1.
 template <typename VT, int D, bool FUSED, typename RT>
-__global__ void __launch_bounds__(FwdWarps<32 / (D / Traits<VT>::kEpl)>::value * 32, MSDA_FWD_MINBLOCKS)
+__global__ void __launch_bounds__(FwdWarps<32 / (D / Traits<VT>::kEpl)>::value * 32,
+                                  MSDA_FWD_MINWARPS / FwdWarps<32 / (D / Traits<VT>::kEpl)>::value)
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const SampleSrc src, VT* __restrict__ out,
                      int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs)
