@@ -239,102 +239,143 @@ def _time_events(torch, fn, iters, warm):
     return e0.elapsed_time(e1) / iters
 
 
+def _reduce_max(torch, dist, world, dev, ms):
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _graph_time(torch, fn, iters):
+    """Capture fn() in a CUDA graph (after a side-stream warm-up) and time the replay."""
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph):
+        fn()
+    return _time_events(torch, graph.replay, iters, 3)
+
+
+def _pyramid(torch, dev, shapes, n, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    srcs = [torch.randn(n, 256, h, w, generator=g).to(dev, dtype) for h, w in shapes]
+    pos = [torch.randn(n, 256, h, w, generator=g).to(dev, dtype) for h, w in shapes]
+    masks = [torch.zeros(n, h, w, dtype=torch.bool, device=dev) for h, w in shapes]
+    return srcs, masks, pos
+
+
 def encoder_extras(torch, dev, world, dist, n_frames=8, iters=10):
-    """BASELINE.json "encoder frames/sec": the 6-layer DeformableTransformerEncoder of
-    configs[1] (inference, COCO pyramid, batch 8 per GPU, synthetic features), bf16 weights and
-    activations, replayed from a CUDA graph; plus the same encoder in fp32 (the reference's dtype)."""
+    """BASELINE.json "encoder frames/sec" and configs[1]: Deformable DETR single-frame 6+6
+    transformer, inference, synthetic ResNet-50-shaped features of an 800x1333 image (4 levels,
+    22223 tokens), batch 8 per GPU, 300 queries.  bf16 weights/activations, CUDA-graph replay;
+    fp32 (the reference's dtype) for the encoder alone."""
     from dfvod_b200 import transformer_layers as tl
+    from dfvod_b200.deformable_transformer import DeformableTransformer
     lsi, s = level_start(COCO_SHAPES)
     st = torch.as_tensor(COCO_SHAPES, dtype=torch.long, device=dev)
     ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
     torch.manual_seed(1)
-    enc = tl.DeformableTransformerEncoder(tl.DeformableTransformerEncoderLayer(256, 1024, 0.1, "relu", 4, 8, 4), 6)
-    enc = enc.to(dev).eval()
-    src = torch.randn(n_frames, s, 256, device=dev)
-    pos = torch.randn(n_frames, s, 256, device=dev)
-    vr = torch.ones(n_frames, len(COCO_SHAPES), 2, device=dev)
-    out = {"frames_per_gpu": n_frames, "layers": 6, "tokens_per_frame": s}
-
-    def reduce_max(ms):
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    model = DeformableTransformer(num_feature_levels=4, return_intermediate_dec=True).to(dev).eval()
+    out = {"frames_per_gpu": n_frames, "tokens_per_frame": s, "queries": 300,
+           "model": "DeformableTransformer(d_model=256, 6 enc + 6 dec, 4 levels)"}
     with torch.no_grad():
-        ms32 = reduce_max(_time_events(torch, lambda: enc(src, st, ls, vr, pos, None), 3, 2))
-        out["fp32_eager_ms"] = ms32
-        out["fp32_eager_fps"] = n_frames * world / ms32 * 1e3
-        enc16, src16, pos16 = enc.bfloat16(), src.bfloat16(), pos.bfloat16()
-        run16 = lambda: enc16(src16, st, ls, vr, pos16, None)
-        ms16 = reduce_max(_time_events(torch, run16, iters, 3))
-        out["bf16_eager_ms"] = ms16
-        out["bf16_eager_fps"] = n_frames * world / ms16 * 1e3
+        src = torch.randn(n_frames, s, 256, device=dev)
+        pos = torch.randn(n_frames, s, 256, device=dev)
+        vr = torch.ones(n_frames, len(COCO_SHAPES), 2, device=dev)
+        ms = _reduce_max(torch, dist, world, dev,
+                         _time_events(torch, lambda: model.encoder(src, st, ls, vr, pos, None), 3, 2))
+        out["encoder_fp32_ms"] = ms
+        out["encoder_fp32_fps"] = n_frames * world / ms * 1e3
+        del src, pos
+        model = model.bfloat16()
+        bf = torch.bfloat16
+        src16 = torch.randn(n_frames, s, 256, device=dev, dtype=bf)
+        pos16 = torch.randn(n_frames, s, 256, device=dev, dtype=bf)
+        enc = lambda: model.encoder(src16, st, ls, vr, pos16, None)
+        ms = _reduce_max(torch, dist, world, dev, _time_events(torch, enc, iters, 3))
+        out["encoder_bf16_eager_fps"] = n_frames * world / ms * 1e3
         try:
-            graph = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                run16()
-            torch.cuda.current_stream().wait_stream(side)
-            with torch.cuda.graph(graph):
-                run16()
-            msg = reduce_max(_time_events(torch, graph.replay, iters, 3))
-            out["bf16_graph_ms"] = msg
-            out["bf16_graph_fps"] = n_frames * world / msg * 1e3
+            ms = _reduce_max(torch, dist, world, dev, _graph_time(torch, enc, iters))
+            out["encoder_bf16_graph_ms"] = ms
+            out["encoder_bf16_graph_fps"] = n_frames * world / ms * 1e3
         except Exception as exc:      # report, do not hide
-            out["bf16_graph_error"] = repr(exc)[:160]
+            out["encoder_bf16_graph_error"] = repr(exc)[:160]
+        del src16, pos16
+        srcs, masks, poss = _pyramid(torch, dev, COCO_SHAPES, n_frames, bf, 2)
+        query = torch.randn(300, 512, device=dev, dtype=bf)
+        full = lambda: model(srcs, masks, poss, None, None, None, query)
+        ms = _reduce_max(torch, dist, world, dev, _time_events(torch, full, iters, 3))
+        out["enc_dec_bf16_eager_fps"] = n_frames * world / ms * 1e3
+        try:
+            ms = _reduce_max(torch, dist, world, dev, _graph_time(torch, full, iters))
+            out["enc_dec_bf16_graph_ms"] = ms
+            out["enc_dec_bf16_graph_fps"] = n_frames * world / ms * 1e3
+        except Exception as exc:
+            out["enc_dec_bf16_graph_error"] = repr(exc)[:160]
+    return out
+
+
+def clip_extras(torch, dev, world, dist, iters=10):
+    """BASELINE.json configs[3]: TransVOD++ multi-frame encoder with Late Fusion, inference.  A clip =
+    1 current + 3 reference frames = batch 4 (frames of a clip are the batch dimension of every
+    MSDeformAttn call, deformable_transformer_multi_plusplus.py:260-444); one feature level
+    (50,84) as in the shipped configs; 8 clips per GPU per step; transformer = Late-Fusion layer +
+    6 encoder + 6 decoder layers, bf16, CUDA graph.  (The temporal query stage is out of scope.)"""
+    from dfvod_b200.deformable_transformer import DeformableTransformer
+    shapes, clip, clips = [(50, 84)], 4, 8
+    torch.manual_seed(3)
+    model = DeformableTransformer(num_feature_levels=1, return_intermediate_dec=True, use_depth=True,
+                                  depth_type="DepthDeform_latefusion_dformer").to(dev).eval().bfloat16()
+    bf = torch.bfloat16
+    n = clip * clips
+    with torch.no_grad():
+        srcs, masks, poss = _pyramid(torch, dev, shapes, n, bf, 5)
+        dsrcs, dmasks, dposs = _pyramid(torch, dev, shapes, n, bf, 6)
+        query = torch.randn(300, 512, device=dev, dtype=bf)
+        run = lambda: model(srcs, masks, poss, dsrcs, dmasks, dposs, query)
+        ms = _reduce_max(torch, dist, world, dev, _time_events(torch, run, iters, 3))
+        out = {"clip_frames": clip, "clips_per_gpu": clips, "level": shapes[0], "eager_fps": n * world / ms * 1e3}
+        try:
+            ms = _reduce_max(torch, dist, world, dev, _graph_time(torch, run, iters))
+            out["graph_ms"] = ms
+            out["graph_fps"] = n * world / ms * 1e3
+        except Exception as exc:
+            out["graph_error"] = repr(exc)[:160]
     return out
 
 
 def train_step_extras(torch, dev, world, dist, n_frames=4, iters=5):
     """BASELINE.json configs[4]: Encoder-Cross-Fusion training step (fwd + bwd + AdamW), frames
     sharded over GPUs, gradients all-reduced over NCCL by dfvod_b200.data_parallel.  Model:
-    RGBDDeformableTransformerEncoderV2 (6 encoder + 4 fusion layers) + 6 decoder layers, COCO
-    pyramid for RGB and depth, 300 queries, bf16 parameters, synthetic features, loss = mean(hs^2)."""
+    DeformableTransformer(depth_type='DepthDeform_encoder_cf_dformer') = 6 encoder + 4 fusion + 6
+    decoder layers, COCO pyramid for RGB and for depth, 300 queries, bf16 parameters, synthetic
+    features, loss = mean(hs^2)."""
     from dfvod_b200 import data_parallel
-    from dfvod_b200 import transformer_layers as tl
-    lsi, s = level_start(COCO_SHAPES)
-    st = torch.as_tensor(COCO_SHAPES, dtype=torch.long, device=dev)
-    ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
+    from dfvod_b200.deformable_transformer import DeformableTransformer
     torch.manual_seed(4)                      # identical initial weights on every rank
-    nl = len(COCO_SHAPES)
-    encoder = tl.RGBDDeformableTransformerEncoderV2(
-        tl.DeformableTransformerEncoderLayer(256, 1024, 0.0, "relu", nl, 8, 4),
-        tl.DeformableTransformerFusionLayerV2(256, 1024, 0.0, "gelu", nl, 8, 4), 6, 4, 4, [0, 1, 2, 3])
-    decoder = tl.DeformableTransformerDecoder(tl.DeformableTransformerDecoderLayer(256, 1024, 0.0, "relu", nl, 8, 4), 6)
-    ref_head = torch.nn.Linear(256, 2)
-    model = torch.nn.ModuleDict(dict(encoder=encoder, decoder=decoder, ref=ref_head)).to(dev).bfloat16()
+    model = DeformableTransformer(num_feature_levels=4, return_intermediate_dec=True, use_depth=True, dropout=0.0,
+                                  depth_type="DepthDeform_encoder_cf_dformer").to(dev).bfloat16()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
     reducer = data_parallel.GradientAllReducer(model.parameters())
     rank = dist.get_rank() if world > 1 else 0
-    g = torch.Generator(device="cpu").manual_seed(40 + rank)
     bf = torch.bfloat16
-    src = torch.randn(n_frames, s, 256, generator=g).to(dev, bf)
-    depth = torch.randn(n_frames, s, 256, generator=g).to(dev, bf)
-    pos = torch.randn(n_frames, s, 256, generator=g).to(dev, bf)
-    query = torch.randn(300, 512, generator=g).to(dev, bf)
-    vr = torch.ones(n_frames, nl, 2, device=dev)
+    srcs, masks, poss = _pyramid(torch, dev, COCO_SHAPES, n_frames, bf, 40 + rank)
+    dsrcs, dmasks, dposs = _pyramid(torch, dev, COCO_SHAPES, n_frames, bf, 140 + rank)
+    query = torch.randn(300, 512, generator=torch.Generator().manual_seed(7)).to(dev, bf)
 
     def step():
         opt.zero_grad(set_to_none=True)
-        memory = model["encoder"](src, st, ls, vr, pos, None, None, depth, st, ls, None, None, None)
-        qpos, tgt = query[:, :256], query[:, 256:]
-        qpos = qpos.unsqueeze(0).expand(n_frames, -1, -1)
-        tgt = tgt.unsqueeze(0).expand(n_frames, -1, -1)
-        refp = model["ref"](qpos).sigmoid()
-        hs, _ = model["decoder"](tgt, refp, memory, st, ls, vr.to(bf), qpos, None)
+        hs = model(srcs, masks, poss, dsrcs, dmasks, dposs, query)[0]
         loss = hs.float().square().mean()
         loss.backward()
         reducer.finish()
         opt.step()
         return loss
 
-    ms = _time_events(torch, step, iters, 2)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = _reduce_max(torch, dist, world, dev, _time_events(torch, step, iters, 2))
     reducer.remove()
     return {"frames_per_gpu": n_frames, "ms_per_step": ms, "frames_per_s": n_frames * world / ms * 1e3,
             "gradient_bytes": reducer.gradient_bytes, "dtype": "bf16",
@@ -461,7 +502,8 @@ def run_b200(args):
     if not args.no_extras:
         del value, loc, attn, gout, host, pinned_out          # give the memory back first
         torch.cuda.empty_cache()
-        for name, fn in (("encoder", encoder_extras), ("train_step", train_step_extras)):
+        for name, fn in (("detr_inference", encoder_extras), ("transvod_clip_inference", clip_extras),
+                         ("train_step", train_step_extras)):
             try:
                 extras[name] = fn(torch, dev, world, dist)
             except Exception as exc:                          # extras never invalidate the main line

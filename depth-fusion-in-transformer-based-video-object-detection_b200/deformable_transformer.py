@@ -1,0 +1,250 @@
+"""``DeformableTransformer`` -- the single-frame transformer that assembles the MSDeformAttn layers
+(host-side mirror of /root/reference/models/deformable_transformer_single.py:23-337).
+
+Same constructor, same ``forward(srcs, masks, pos_embeds, depth_srcs, depth_masks,
+depth_pos_embeds, query_embed, rgbd_query)``, same parameter names (``level_embed``,
+``reference_points``, ``encoder.layers.*``, ``encoder.fusion_layers.*``, ``decoder.layers.*``,
+``depth_encoder_layer.*``) so reference checkpoints load.  The fusion variant is selected, as in the
+reference, by substrings of ``depth_type``:
+
+    "latefusion"  one DepthDeformableTransformerEncoderLayer before the encoder      (:49-52, :212-244)
+    "encoder_cf"  RGBDDeformableTransformerEncoderV2, fusion after layers 0..3       (:55-66, :269-302)
+    otherwise     plain DeformableTransformerEncoder                                 (:68-73)
+
+TransVOD / TransVOD++ (deformable_transformer_multi*.py) run exactly this stack with the frames
+of a clip as the batch dimension; their temporal query stage (mmcv RoIAlign, RCNNHead) is outside
+the hot path.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn.init import constant_, normal_, xavier_uniform_
+
+from .ops.modules import MSDeformAttn
+from .transformer_layers import (DeformableTransformerDecoder, DeformableTransformerDecoderLayer,
+                                 DeformableTransformerEncoder, DeformableTransformerEncoderLayer,
+                                 DeformableTransformerFusionLayerV2, DepthDeformableTransformerEncoderLayer,
+                                 RGBDDeformableTransformerEncoderV2, encoder_reference_points)
+
+
+def _flatten_levels(maps, masks, pos_embeds, level_embed=None):
+    """[N,C,H,W] per level -> tokens [N, sum HW, C], mask [N, sum HW], pos (+ level embedding),
+    shapes (python list of (H, W))."""
+    tokens, flat_masks, flat_pos, shapes = [], [], [], []
+    for lvl, (feat, mask, pos) in enumerate(zip(maps, masks, pos_embeds)):
+        shapes.append((feat.shape[2], feat.shape[3]))
+        tokens.append(feat.flatten(2).transpose(1, 2))
+        flat_masks.append(mask.flatten(1))
+        pos = pos.flatten(2).transpose(1, 2)
+        if level_embed is not None:
+            pos = pos + level_embed[lvl].view(1, 1, -1)
+        flat_pos.append(pos)
+    return torch.cat(tokens, 1), torch.cat(flat_masks, 1), torch.cat(flat_pos, 1), shapes
+
+
+_SHAPE_TENSORS = {}
+
+
+def _shape_tensors(shapes, device):
+    """(spatial_shapes [L,2], level_start_index [L]) int64 on `device`.  Built once per
+    (shapes, device): the reference re-creates them from a python list every forward
+    (single.py:207-208), an H2D copy that also prevents CUDA-graph capture."""
+    key = (tuple(shapes), str(device))
+    hit = _SHAPE_TENSORS.get(key)
+    if hit is None:
+        if len(_SHAPE_TENSORS) >= 64:
+            _SHAPE_TENSORS.clear()
+        st = torch.as_tensor(shapes, dtype=torch.long, device=device)
+        hit = (st, torch.cat((st.new_zeros((1,)), st.prod(1).cumsum(0)[:-1])))
+        _SHAPE_TENSORS[key] = hit
+    return hit
+
+
+class DeformableTransformer(nn.Module):
+    def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=1024,
+                 dropout=0.1, activation="relu", return_intermediate_dec=False, num_feature_levels=4,
+                 dec_n_points=4, enc_n_points=4, two_stage=False, two_stage_num_proposals=300,
+                 use_depth=False, depth_type="Baseline_rgb", dpth_feature_levels=1, dpth_n_points=4):
+        super().__init__()
+        self.use_depth = use_depth
+        self.depth_type = depth_type
+        self.residual_fusion = "noresidual" not in depth_type
+        self.rgbd_query = "concat" in depth_type
+        self.d_model = d_model
+        self.nhead = nhead
+        self.two_stage = two_stage
+        self.two_stage_num_proposals = two_stage_num_proposals
+        self.depth_self_attn = True
+        self.late_fusion_layers = 1
+        self.adaptation_layers = True
+        self.gate = True
+        self.encoder_cross_fusion = True
+
+        if "latefusion" in depth_type:
+            self.depth_encoder_layer = DepthDeformableTransformerEncoderLayer(
+                d_model, dim_feedforward, dropout, activation, dpth_feature_levels, nhead, dpth_n_points,
+                self.depth_self_attn, self.gate, self.adaptation_layers)
+
+        encoder_layer = DeformableTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation,
+                                                          num_feature_levels, nhead, enc_n_points)
+        if "encoder_cf" in depth_type:
+            self.num_depth_encoder_layers = 4
+            self.num_enc_fusion_layers = 4
+            self.enc_fusion_layers_order = [0, 1, 2, 3]
+            fusion_layer = DeformableTransformerFusionLayerV2(d_model, dim_feedforward, dropout, activation,
+                                                              num_feature_levels, nhead, enc_n_points)
+            self.encoder = RGBDDeformableTransformerEncoderV2(
+                encoder_layer, fusion_layer, num_encoder_layers, self.num_depth_encoder_layers,
+                self.num_enc_fusion_layers, self.enc_fusion_layers_order)
+        else:
+            self.encoder = DeformableTransformerEncoder(encoder_layer, num_encoder_layers)
+
+        decoder_layer = DeformableTransformerDecoderLayer(d_model, dim_feedforward, dropout, activation,
+                                                          num_feature_levels, nhead, dec_n_points)
+        self.decoder = DeformableTransformerDecoder(decoder_layer, num_decoder_layers, return_intermediate_dec)
+
+        self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model))
+        if two_stage:
+            self.enc_output = nn.Linear(d_model, d_model)
+            self.enc_output_norm = nn.LayerNorm(d_model)
+            self.pos_trans = nn.Linear(d_model * 2, d_model * 2)
+            self.pos_trans_norm = nn.LayerNorm(d_model * 2)
+        else:
+            self.reference_points = nn.Linear(d_model, 2)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+            elif isinstance(m, nn.LayerNorm):
+                constant_(m.weight, 1.0)
+                constant_(m.bias, 0.0)
+        if not self.two_stage:
+            xavier_uniform_(self.reference_points.weight.data, gain=1.0)
+            constant_(self.reference_points.bias.data, 0.)
+        normal_(self.level_embed)
+
+    # ------------------------------------------------------------------ two-stage helpers (:112-153)
+    def get_proposal_pos_embed(self, proposals):
+        num_pos_feats, temperature = 128, 10000
+        dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=proposals.device)
+        dim_t = temperature ** (2 * (dim_t // 2) / num_pos_feats)
+        pos = (proposals.sigmoid() * (2 * math.pi))[:, :, :, None] / dim_t              # N, L, 4, 128
+        return torch.stack((pos[:, :, :, 0::2].sin(), pos[:, :, :, 1::2].cos()), dim=4).flatten(2)
+
+    def gen_encoder_output_proposals(self, memory, memory_padding_mask, spatial_shapes):
+        N_ = memory.shape[0]
+        proposals, cursor = [], 0
+        for lvl, (H_, W_) in enumerate(spatial_shapes):
+            H_, W_ = int(H_), int(W_)
+            level_mask = memory_padding_mask[:, cursor:cursor + H_ * W_].view(N_, H_, W_, 1)
+            valid_H = torch.sum(~level_mask[:, :, 0, 0], 1)
+            valid_W = torch.sum(~level_mask[:, 0, :, 0], 1)
+            grid_y, grid_x = torch.meshgrid(
+                torch.linspace(0, H_ - 1, H_, dtype=torch.float32, device=memory.device),
+                torch.linspace(0, W_ - 1, W_, dtype=torch.float32, device=memory.device), indexing="ij")
+            grid = torch.cat([grid_x.unsqueeze(-1), grid_y.unsqueeze(-1)], -1)
+            scale = torch.cat([valid_W.unsqueeze(-1), valid_H.unsqueeze(-1)], 1).view(N_, 1, 1, 2)
+            grid = (grid.unsqueeze(0).expand(N_, -1, -1, -1) + 0.5) / scale
+            wh = torch.ones_like(grid) * 0.05 * (2.0 ** lvl)
+            proposals.append(torch.cat((grid, wh), -1).view(N_, -1, 4))
+            cursor += H_ * W_
+        output_proposals = torch.cat(proposals, 1)
+        valid = ((output_proposals > 0.01) & (output_proposals < 0.99)).all(-1, keepdim=True)
+        output_proposals = torch.log(output_proposals / (1 - output_proposals))
+        output_proposals = output_proposals.masked_fill(memory_padding_mask.unsqueeze(-1), float('inf'))
+        output_proposals = output_proposals.masked_fill(~valid, float('inf'))
+        output_memory = memory.masked_fill(memory_padding_mask.unsqueeze(-1), float(0))
+        output_memory = output_memory.masked_fill(~valid, float(0))
+        output_memory = self.enc_output_norm(self.enc_output(output_memory))
+        return output_memory, output_proposals
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        """(w, h) fraction of each [N,H,W] mask that is not padding (:155-162)."""
+        _, H, W = mask.shape
+        valid_h = torch.sum(~mask[:, :, 0], 1).float() / H
+        valid_w = torch.sum(~mask[:, 0, :], 1).float() / W
+        return torch.stack([valid_w, valid_h], -1)
+
+    get_reference_points = staticmethod(encoder_reference_points)
+
+    # ------------------------------------------------------------------ forward (:179-337)
+    def _flatten_depth(self, depth_srcs, depth_masks, depth_pos_embeds):
+        assert depth_srcs is not None and depth_masks is not None and depth_pos_embeds is not None, \
+            "Depth information is required for Deformable DETR with depth"
+        assert len(depth_srcs) == len(depth_masks) == len(depth_pos_embeds), \
+            "The number of depth sources, masks and pos_embeds should be the same"
+        tokens, mask, pos, shapes = _flatten_levels(depth_srcs, depth_masks, depth_pos_embeds, None)
+        st, ls = _shape_tensors(shapes, tokens.device)
+        ratios = torch.stack([self.get_valid_ratio(m) for m in depth_masks], 1)
+        return tokens, mask, pos, shapes, st, ls, ratios
+
+    def forward(self, srcs, masks, pos_embeds, depth_srcs, depth_masks, depth_pos_embeds, query_embed=None,
+                rgbd_query=[]):
+        assert self.two_stage or query_embed is not None
+        src_flatten, mask_flatten, lvl_pos_embed_flatten, shapes = _flatten_levels(
+            srcs, masks, pos_embeds, self.level_embed)
+        rgbd_flatten = None
+        if len(rgbd_query) > 0:
+            rgbd_flatten = torch.cat([q.flatten(2).transpose(1, 2) for q in rgbd_query], 1)
+        spatial_shapes, level_start_index = _shape_tensors(shapes, src_flatten.device)
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+        rgbd_arg = rgbd_flatten if self.rgbd_query else None
+
+        if "latefusion" in self.depth_type and self.use_depth:
+            d_tok, d_mask, d_pos, d_shapes, d_st, d_ls, d_ratios = self._flatten_depth(
+                depth_srcs, depth_masks, depth_pos_embeds)
+            rgb_ref = self.get_reference_points(shapes, valid_ratios, device=src_flatten.device)
+            depth_ref = self.get_reference_points(d_shapes, d_ratios, device=d_tok.device)
+            fused = self.depth_encoder_layer(src_flatten, lvl_pos_embed_flatten, d_pos, spatial_shapes, rgb_ref,
+                                             depth_ref, d_tok, d_st, d_ls, mask_flatten, d_mask)
+            src_flatten = src_flatten + fused
+
+        if "encoder_cf" in self.depth_type and self.use_depth:
+            d_tok, d_mask, d_pos, d_shapes, d_st, d_ls, d_ratios = self._flatten_depth(
+                depth_srcs, depth_masks, depth_pos_embeds)
+            memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, lvl_pos_embed_flatten,
+                                  mask_flatten, rgbd_arg, d_tok, d_st, d_ls, d_ratios, d_pos, d_mask)
+        else:
+            memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, lvl_pos_embed_flatten,
+                                  mask_flatten, rgbd_arg)
+
+        bs, _, c = memory.shape
+        enc_outputs_class = enc_outputs_coord_unact = None
+        if self.two_stage:
+            output_memory, output_proposals = self.gen_encoder_output_proposals(memory, mask_flatten, shapes)
+            enc_outputs_class = self.decoder.class_embed[self.decoder.num_layers](output_memory)
+            enc_outputs_coord_unact = self.decoder.bbox_embed[self.decoder.num_layers](output_memory) + output_proposals
+            topk_proposals = torch.topk(enc_outputs_class[..., 0], self.two_stage_num_proposals, dim=1)[1]
+            topk_coords_unact = torch.gather(enc_outputs_coord_unact, 1,
+                                             topk_proposals.unsqueeze(-1).repeat(1, 1, 4)).detach()
+            reference_points = topk_coords_unact.sigmoid()
+            pos_trans_out = self.pos_trans_norm(self.pos_trans(self.get_proposal_pos_embed(topk_coords_unact)))
+            query_embed, tgt = torch.split(pos_trans_out, c, dim=2)
+        else:
+            query_embed, tgt = torch.split(query_embed, c, dim=1)
+            query_embed = query_embed.unsqueeze(0).expand(bs, -1, -1)
+            tgt = tgt.unsqueeze(0).expand(bs, -1, -1)
+            reference_points = self.reference_points(query_embed).sigmoid()
+        init_reference_out = reference_points
+
+        hs, inter_references = self.decoder(tgt, reference_points, memory, spatial_shapes, level_start_index,
+                                            valid_ratios, query_embed, mask_flatten)
+        return hs, init_reference_out, inter_references, enc_outputs_class, enc_outputs_coord_unact
+
+
+def build_deforamble_transformer(args):
+    """Same (misspelt) name and argument mapping as the reference builder (single.py:766-785)."""
+    return DeformableTransformer(
+        d_model=args.hidden_dim, nhead=args.nheads, num_encoder_layers=args.enc_layers,
+        num_decoder_layers=args.dec_layers, dim_feedforward=args.dim_feedforward, dropout=args.dropout,
+        activation="relu", return_intermediate_dec=True, num_feature_levels=args.num_feature_levels,
+        dec_n_points=args.dec_n_points, enc_n_points=args.enc_n_points, two_stage=args.two_stage,
+        two_stage_num_proposals=args.num_queries, use_depth=args.use_depth, depth_type=args.depth_type,
+        dpth_n_points=args.dpth_n_points)

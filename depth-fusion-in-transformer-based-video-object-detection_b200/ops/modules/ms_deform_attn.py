@@ -20,6 +20,7 @@ reference's unfused sequence around the drop-in op -- still on the GPU, never on
 """
 import math
 import warnings
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -35,22 +36,31 @@ def _is_power_of_2(n):
     return (n & (n - 1) == 0) and n != 0
 
 
-# host copies of spatial_shapes tensors already validated: (data_ptr, version, numel) -> total pixels
+# host-side facts about spatial_shapes tensors already read back once.  Keyed by the identity of the
+# tensor OBJECT (validated through a weak reference, plus its in-place version counter): a new
+# tensor that merely re-uses a freed device address can never alias an old entry.
 _SHAPE_CACHE = {}
 _SHAPE_CACHE_MAX = 64
 
 
-def _total_pixels(spatial_shapes):
-    """sum_l H_l*W_l, read back from the device at most once per tensor (reference :92 syncs
-    on every call)."""
-    key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.numel(), spatial_shapes.device)
+def host_shape_list(spatial_shapes):
+    """[(H, W), ...] as python ints, device->host at most once per tensor object (the reference
+    syncs on every call: ms_deform_attn.py:92, deformable_transformer_single.py:166-169)."""
+    if not torch.is_tensor(spatial_shapes):
+        return [(int(h), int(w)) for h, w in spatial_shapes]
+    key = id(spatial_shapes)
     hit = _SHAPE_CACHE.get(key)
-    if hit is None:
-        if len(_SHAPE_CACHE) >= _SHAPE_CACHE_MAX:
-            _SHAPE_CACHE.clear()
-        hit = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum())
-        _SHAPE_CACHE[key] = hit
-    return hit
+    if hit is not None and hit[0]() is spatial_shapes and hit[1] == spatial_shapes._version:
+        return hit[2]
+    if len(_SHAPE_CACHE) >= _SHAPE_CACHE_MAX:
+        _SHAPE_CACHE.clear()
+    shapes = [(int(h), int(w)) for h, w in spatial_shapes.tolist()]
+    _SHAPE_CACHE[key] = (weakref.ref(spatial_shapes), spatial_shapes._version, shapes)
+    return shapes
+
+
+def _total_pixels(spatial_shapes):
+    return sum(h * w for h, w in host_shape_list(spatial_shapes))
 
 
 class MSDeformAttn(nn.Module):

@@ -24,6 +24,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .ops.modules import MSDeformAttn
+from .ops.modules.ms_deform_attn import host_shape_list
 
 
 def inverse_sigmoid(x, eps=1e-5):
@@ -48,30 +49,11 @@ def _add_pos(tensor, pos):
     return tensor if pos is None else tensor + pos
 
 
-_HOST_SHAPES = {}
-
-
-def _host_shapes(spatial_shapes):
-    """[(H, W), ...] as python ints.  A device tensor is read back once per (storage, version) --
-    the reference iterates the CUDA tensor and syncs on every encoder call (single.py:166-169),
-    which also makes the encoder impossible to capture in a CUDA graph."""
-    if not torch.is_tensor(spatial_shapes):
-        return [(int(h), int(w)) for h, w in spatial_shapes]
-    key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.numel(), spatial_shapes.device)
-    hit = _HOST_SHAPES.get(key)
-    if hit is None:
-        if len(_HOST_SHAPES) >= 64:
-            _HOST_SHAPES.clear()
-        hit = [(int(h), int(w)) for h, w in spatial_shapes.tolist()]
-        _HOST_SHAPES[key] = hit
-    return hit
-
-
 def encoder_reference_points(spatial_shapes, valid_ratios, device):
     """Pixel-centre reference grid of every level, replicated to every level and scaled by the
     valid ratios: [N, sum_l H_l*W_l, L, 2] (x, y).  single.py:164-177 / :573-585 / :483-495."""
     per_level = []
-    for lvl, (H_, W_) in enumerate(_host_shapes(spatial_shapes)):
+    for lvl, (H_, W_) in enumerate(host_shape_list(spatial_shapes)):
         ys = torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device)
         xs = torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device)
         ref_y, ref_x = torch.meshgrid(ys, xs, indexing="ij")

@@ -130,7 +130,7 @@ def save_module_case(name, module, inputs, call, wrt):
     blob["out"] = out.detach().numpy()
     blob["gout"] = gout.numpy()
     for k, gr in zip(wrt, grads[:len(wrt)]):
-        blob[f"grad_in.{k}"] = gr.numpy()
+        blob[f"grad_in.{k}"] = (gr if gr is not None else torch.zeros(())).numpy()
     for (pname, _), gr in zip(module.named_parameters(), grads[len(wrt):]):
         blob[f"grad_param.{pname}"] = (gr if gr is not None else torch.zeros(())).numpy()
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **blob)
@@ -326,6 +326,42 @@ def main():
         lambda m_, t: m_(t["src"], t["spatial_shapes"], t["level_start_index"], t["valid_ratios"], t["pos"],
                         t["padding_mask"]),
         wrt=["src"])
+
+    # whole single-frame transformer (deformable_transformer_single.py:23-337), three variants
+    def transformer_case(name, depth_type, use_depth, levels, seed):
+        torch.manual_seed(seed)
+        model = single.DeformableTransformer(
+            d_model=c, nhead=heads, num_encoder_layers=5 if "encoder_cf" in depth_type else 2,
+            num_decoder_layers=2, dim_feedforward=64, dropout=0.0, activation="relu",
+            return_intermediate_dec=True, num_feature_levels=len(levels), dec_n_points=pts, enc_n_points=pts,
+            use_depth=use_depth, depth_type=depth_type, dpth_n_points=pts).double()
+        perturb(model, seed + 1)
+        ins = {}
+        for i, (h, w) in enumerate(levels):
+            ins[f"src{i}"] = torch.randn(n, c, h, w)
+            ins[f"pos{i}"] = torch.randn(n, c, h, w)
+            mk = torch.zeros(n, h, w, dtype=torch.bool)
+            # valid width = a power of two: torch's CUDA division by a python scalar multiplies by the
+            # reciprocal, so only then is valid_ratio = valid_W / W bit-identical on CPU and GPU
+            mk[1, :, 1 << ((w - 1).bit_length() - 1):] = True
+            ins[f"mask{i}"] = mk
+        ins["depth_src0"] = torch.randn(n, c, levels[0][0], levels[0][1])
+        ins["depth_pos0"] = torch.randn(n, c, levels[0][0], levels[0][1])
+        ins["depth_mask0"] = ins["mask0"].clone()
+        ins["query_embed"] = torch.randn(5, 2 * c)
+        nl_ = len(levels)
+
+        def call(m_, t):
+            hs, init_ref, inter_ref, _, _ = m_(
+                [t[f"src{i}"] for i in range(nl_)], [t[f"mask{i}"] for i in range(nl_)],
+                [t[f"pos{i}"] for i in range(nl_)], [t["depth_src0"]], [t["depth_mask0"]], [t["depth_pos0"]],
+                t["query_embed"])
+            return torch.cat([hs.flatten(), init_ref.flatten(), inter_ref.flatten()])
+        save_module_case(name, model, ins, call, wrt=["src0", "depth_src0", "query_embed"])
+
+    transformer_case("transformer_baseline", "Baseline_rgb", False, [(6, 5), (3, 3)], 50)
+    transformer_case("transformer_latefusion", "DepthDeform_latefusion_dformer", True, [(4, 6)], 52)
+    transformer_case("transformer_encoder_cf", "DepthDeform_encoder_cf_dformer", True, [(4, 6)], 54)
 
     # Backbone Cross Fusion U-DF: fuse_layers + its layer (dformer_crossfusion_backbone.py:387-428,120-181)
     torch.manual_seed(41)

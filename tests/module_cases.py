@@ -3,6 +3,7 @@ Shared by the CPU host-logic tests (oracle patched in) and the GPU tests (real k
 import torch
 
 from dfvod_b200 import backbone_fusion, transformer_layers as tl
+from dfvod_b200.deformable_transformer import DeformableTransformer
 from dfvod_b200.ops.modules import MSDeformAttn
 
 C, HEADS, PTS = 32, 4, 3
@@ -78,6 +79,34 @@ CASES = {
 }
 
 
+def _transformer(depth_type, use_depth, n_levels):
+    return DeformableTransformer(
+        d_model=C, nhead=HEADS, num_encoder_layers=5 if "encoder_cf" in depth_type else 2, num_decoder_layers=2,
+        dim_feedforward=64, dropout=0.0, activation="relu", return_intermediate_dec=True,
+        num_feature_levels=n_levels, dec_n_points=PTS, enc_n_points=PTS, use_depth=use_depth,
+        depth_type=depth_type, dpth_n_points=PTS)
+
+
+def _transformer_call(n_levels):
+    def call(m, t):
+        hs, init_ref, inter_ref, _, _ = m(
+            [t[f"src{i}"] for i in range(n_levels)], [t[f"mask{i}"] for i in range(n_levels)],
+            [t[f"pos{i}"] for i in range(n_levels)], [t["depth_src0"]], [t["depth_mask0"]], [t["depth_pos0"]],
+            t["query_embed"])
+        return torch.cat([hs.flatten(), init_ref.flatten(), inter_ref.flatten()])
+    return call
+
+
+CASES.update({
+    "transformer_baseline": dict(build=lambda: _transformer("Baseline_rgb", False, 2), call=_transformer_call(2),
+                                 wrt=["src0", "depth_src0", "query_embed"]),
+    "transformer_latefusion": dict(build=lambda: _transformer("DepthDeform_latefusion_dformer", True, 1),
+                                   call=_transformer_call(1), wrt=["src0", "depth_src0", "query_embed"]),
+    "transformer_encoder_cf": dict(build=lambda: _transformer("DepthDeform_encoder_cf_dformer", True, 1),
+                                   call=_transformer_call(1), wrt=["src0", "depth_src0", "query_embed"]),
+})
+
+
 def run_case(name, gold, device, dtype=torch.float64):
     """Instantiate, load the reference state_dict (strict), run forward + backward.
     Returns (out, {input grads}, {param grads}) as CPU float64 numpy."""
@@ -102,7 +131,7 @@ def run_case(name, gold, device, dtype=torch.float64):
     params = dict(module.named_parameters())
     grads = torch.autograd.grad(out, [tensors[k] for k in case["wrt"]] + list(params.values()), gout,
                                 allow_unused=True)
-    gin = {k: g.detach().double().cpu().numpy() for k, g in zip(case["wrt"], grads)}
+    gin = {k: (g.detach().double().cpu().numpy() if g is not None else None) for k, g in zip(case["wrt"], grads)}
     gpar = {k: (g.detach().double().cpu().numpy() if g is not None else None)
             for k, g in zip(params.keys(), grads[len(case["wrt"]):])}
     return out.detach().double().cpu().numpy(), gin, gpar

@@ -18,6 +18,9 @@ def test_fp64_matches_reference_class(name):
     out, gin, gpar = module_cases.run_case(name, gold, "cuda", torch.float64)
     np.testing.assert_allclose(out, gold["out"], rtol=1e-7, atol=1e-9)
     for k, g in gin.items():
+        if gold["grad_in." + k].shape == ():
+            assert g is None or not np.any(g)
+            continue
         np.testing.assert_allclose(g, gold["grad_in." + k], rtol=1e-6, atol=1e-8, err_msg=k)
     for k, g in gpar.items():
         ref = gold["grad_param." + k]
@@ -39,6 +42,8 @@ def test_fp32_matches_reference_class(name):
     emax, el2 = nerr(out, gold["out"])
     assert emax <= 2e-5 and el2 <= 2e-5, f"out: {emax:.2e} {el2:.2e}"
     for k, g in gin.items():
+        if gold["grad_in." + k].shape == () or g is None:
+            continue
         emax, el2 = nerr(g, gold["grad_in." + k])
         assert emax <= 1e-4 and el2 <= 1e-4, f"{k}: {emax:.2e} {el2:.2e}"
     for k, g in gpar.items():
