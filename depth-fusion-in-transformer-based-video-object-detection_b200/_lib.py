@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MSDA_B200_LIB selects another build of the same ABI (A/B kernel experiments); default: in-tree
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_HERE, "libmsda_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 DTYPE_F32, DTYPE_F64, DTYPE_BF16, DTYPE_F16 = 0, 1, 2, 3
 FLAG_FORCE_GENERIC = 1
 
@@ -50,6 +50,18 @@ def load():
     lib.msda_fused_forward.argtypes = [c_int, c_int] + fused_common + [c_vp, c_vp]
     lib.msda_fused_backward.restype = c_int
     lib.msda_fused_backward.argtypes = [c_int, c_int, c_vp] + fused_common + [c_vp, c_vp, c_vp, c_fp, c_vp, c_vp]
+    c_f = ctypes.c_float
+    lib.msda_layer_add_layernorm_supported.restype = c_int
+    lib.msda_layer_add_layernorm_supported.argtypes = [c_int, c_int]
+    lib.msda_layer_add_layernorm_partial_blocks.restype = c_int
+    lib.msda_layer_add_layernorm_partial_blocks.argtypes = [c_i64]
+    lib.msda_layer_add_layernorm_forward.restype = c_int
+    lib.msda_layer_add_layernorm_forward.argtypes = [c_int, c_int] + [c_vp] * 5 + [c_i64, c_int, c_f] + [c_vp] * 5
+    lib.msda_layer_add_layernorm_backward.restype = c_int
+    lib.msda_layer_add_layernorm_backward.argtypes = [c_int, c_int] + [c_vp] * 7 + [c_i64, c_int] + [c_vp] * 5 + \
+                                                     [c_int, c_vp]
+    lib.msda_layer_zero_masked_rows.restype = c_int
+    lib.msda_layer_zero_masked_rows.argtypes = [c_int, c_vp, c_vp, c_i64, c_int, c_vp]
     if lib.msda_abi_version() != ABI_VERSION:
         raise MSDAError(f"libmsda_b200.so ABI {lib.msda_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     _lib = lib

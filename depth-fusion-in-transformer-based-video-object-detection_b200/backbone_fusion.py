@@ -14,6 +14,7 @@ off by one stage) and the convolutional stems are outside
 import torch
 from torch import nn
 
+from .ops.functions import add_layer_norm
 from .ops.modules import MSDeformAttn
 from .transformer_layers import _add_pos, _get_activation_fn, encoder_reference_points
 
@@ -30,6 +31,7 @@ class DepthDeformableTransformerEncoderLayer(nn.Module):
         self.norm1 = nn.LayerNorm(d_model)
         self.linear1 = nn.Linear(d_model, d_model)
         self.activation = _get_activation_fn(activation)
+        self._activation_name = activation
         self.dropout4 = nn.Dropout(dropout)
         self.norm3 = nn.LayerNorm(d_model)
         self.depth_scale_adapt = nn.Linear(d_model, d_model)
@@ -40,14 +42,16 @@ class DepthDeformableTransformerEncoderLayer(nn.Module):
         return _add_pos(tensor, pos)
 
     def forward_ffn(self, tgt):
-        return self.norm3(tgt + self.dropout4(self.activation(self.linear1(tgt))))
+        if (self.dropout4.training and self.dropout4.p > 0) or self._activation_name not in ("relu", "gelu"):
+            return add_layer_norm(self.norm3, self.dropout4(self.activation(self.linear1(tgt))), tgt)
+        return add_layer_norm(self.norm3, self.linear1(tgt), tgt, self._activation_name)
 
     def forward(self, tgt, query_pos, src_pos, tgt_spatial_shapes, reference_points, depth_reference_points,
                 src, src_spatial_shapes, frame_start_index, tgt_padding_mask=None, src_padding_mask=None):
-        src = self.norm_depth_scale(self.depth_scale_adapt(src))
+        src = add_layer_norm(self.norm_depth_scale, self.depth_scale_adapt(src))
         sampled = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,
                                   frame_start_index, src_padding_mask)
-        tgt = self.norm1(tgt + self.dropout1(self.cross_scale_adapt(sampled)))
+        tgt = add_layer_norm(self.norm1, self.dropout1(self.cross_scale_adapt(sampled)), tgt)
         return self.forward_ffn(tgt)
 
 

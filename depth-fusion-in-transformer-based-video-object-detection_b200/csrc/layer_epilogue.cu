@@ -1,0 +1,392 @@
+// Layer epilogues around the deformable attention for sm_100a.
+//
+// Every layer class of the reference that owns an MSDeformAttn wraps it as
+//     x = LayerNorm(residual + dropout(branch))                         (deformable_transformer_single.py:538-541,
+//     x = LayerNorm(x + dropout(act(Linear(x))))   (fusion layers)       :393-400, :452-459, :544-548, :617-642)
+// and the next deformable attention queries with `x + pos` (:530-531, :538).  In the reference these
+// are separate element-wise launches (add, LayerNorm, add) that each re-read and re-write the
+// [rows, C] activation; here ONE kernel per direction does
+//     v      = residual + act(branch)              act in {identity, relu, gelu(erf)}
+//     y      = LayerNorm(v) * gamma + beta
+//     y_pos  = y + pos                              (optional second output: the next layer's query)
+// with fp32 arithmetic, 16-byte accesses and one warp per row (row statistics by shuffles, no
+// shared memory, no block barrier).  The backward kernel produces d branch, d residual and
+// per-CTA partial sums of d gamma / d beta that a second tiny kernel folds.
+// These kernels are HBM-bound: algorithmic bytes = every operand once.
+//
+// Also here: zero_masked_rows - `value.masked_fill(padding_mask[..., None], 0)` of
+// MSDeformAttn.forward (models/ops/modules/ms_deform_attn.py:95-96) done in place on the fresh
+// projection output, touching only the mask bytes and the masked rows.
+#include "msda_common.cuh"
+#include "msda_launch.h"
+
+namespace msda {
+
+enum Act { kActNone = 0, kActRelu = 1, kActGelu = 2 };
+
+template <int ACT> __device__ __forceinline__ float act_fwd(float x)
+{
+    if constexpr (ACT == kActRelu) return fmaxf(x, 0.f);
+    if constexpr (ACT == kActGelu) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    return x;
+}
+template <int ACT> __device__ __forceinline__ float act_bwd(float x)      // d act / d x
+{
+    if constexpr (ACT == kActRelu) return x > 0.f ? 1.f : 0.f;
+    if constexpr (ACT == kActGelu) {
+        const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+        return cdf + x * pdf;
+    }
+    return 1.f;
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+template <typename T> struct Vec16 { static constexpr int n = 16 / (int)sizeof(T); };
+
+template <typename T> __device__ __forceinline__ void load16(const T* p, float* f)
+{
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    unpack<T>(raw, f);
+}
+template <typename T> __device__ __forceinline__ void load16_stream(const T* p, float* f)
+{
+    unpack<T>(ldg_stream_v4(p), f);
+}
+template <typename T> __device__ __forceinline__ void store16(T* p, const float* f)
+{
+    *reinterpret_cast<uint4*>(p) = pack<T>(f);
+}
+// round-trip through the storage type (y_pos is defined on the ROUNDED y, like the unfused chain)
+template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32<T>(from_f32<T>(v)); }
+
+constexpr int kLnWarps = 8;
+
+// K = 16-byte chunks per lane: C = K * 32 * (16 / sizeof(T)).
+template <typename T, int K, int ACT>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_layernorm_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ residual,
+                         const T* __restrict__ gamma, const T* __restrict__ beta, const T* __restrict__ pos,
+                         T* __restrict__ y, T* __restrict__ y_pos, float* __restrict__ mean_out,
+                         float* __restrict__ rstd_out, long long rows, float eps)
+{
+    constexpr int V = Vec16<T>::n;
+    constexpr int C = K * 32 * V;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kLnWarps;
+
+    float g[K][V], b[K][V];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        load16<T>(gamma + (k * 32 + lane) * V, g[k]);
+        load16<T>(beta + (k * 32 + lane) * V, b[k]);
+    }
+    for (long long row = warp0; row < rows; row += nwarps) {
+        const long long base = row * C;
+        float v[K][V];
+#pragma unroll
+        for (int k = 0; k < K; ++k) load16_stream<T>(branch + base + (k * 32 + lane) * V, v[k]);
+        if (residual != nullptr) {
+            float r[K][V];
+#pragma unroll
+            for (int k = 0; k < K; ++k) load16_stream<T>(residual + base + (k * 32 + lane) * V, r[k]);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int e = 0; e < V; ++e) v[k][e] = r[k][e] + act_fwd<ACT>(v[k][e]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int e = 0; e < V; ++e) v[k][e] = act_fwd<ACT>(v[k][e]);
+        }
+        float p[K][V];
+        if (y_pos != nullptr) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) load16_stream<T>(pos + base + (k * 32 + lane) * V, p[k]);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < V; ++e) s += v[k][e];
+        const float mean = warp_sum(s) * (1.f / C);
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < V; ++e) { const float d = v[k][e] - mean; ss = fmaf(d, d, ss); }
+        const float rstd = rsqrtf(warp_sum(ss) * (1.f / C) + eps);
+        if (mean_out != nullptr && lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float o[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) o[e] = fmaf((v[k][e] - mean) * rstd, g[k][e], b[k][e]);
+            store16<T>(y + base + (k * 32 + lane) * V, o);
+            if (y_pos != nullptr) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) o[e] = round_to<T>(o[e]) + p[k][e];
+                store16<T>(y_pos + base + (k * 32 + lane) * V, o);
+            }
+        }
+    }
+}
+
+// d_branch = d v * act'(branch), d_residual = d v, with
+//   d v = rstd * (gy*gamma - mean_c(gy*gamma) - xhat * mean_c(gy*gamma*xhat)),  gy = dy (+ dy_pos)
+// partial[blockIdx][0][c] = sum over this CTA's rows of gy*xhat, partial[blockIdx][1][c] = sum of gy.
+template <typename T, int K, int ACT>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_pos, const T* __restrict__ branch,
+                         const T* __restrict__ residual, const T* __restrict__ gamma,
+                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                         T* __restrict__ d_branch, T* __restrict__ d_residual, float* __restrict__ partial,
+                         long long rows)
+{
+    constexpr int V = Vec16<T>::n;
+    constexpr int C = K * 32 * V;
+    __shared__ float s_red[kLnWarps][C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * kLnWarps + warp;
+    const long long nwarps = (long long)gridDim.x * kLnWarps;
+
+    float g[K][V], dg[K][V], db[K][V];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        load16<T>(gamma + (k * 32 + lane) * V, g[k]);
+#pragma unroll
+        for (int e = 0; e < V; ++e) { dg[k][e] = 0.f; db[k][e] = 0.f; }
+    }
+    for (long long row = warp0; row < rows; row += nwarps) {
+        const long long base = row * C;
+        float gy[K][V], x[K][V], v[K][V];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            load16_stream<T>(dy + base + (k * 32 + lane) * V, gy[k]);
+            load16_stream<T>(branch + base + (k * 32 + lane) * V, x[k]);
+        }
+        if (dy_pos != nullptr) {
+            float t[K][V];
+#pragma unroll
+            for (int k = 0; k < K; ++k) load16_stream<T>(dy_pos + base + (k * 32 + lane) * V, t[k]);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int e = 0; e < V; ++e) gy[k][e] += t[k][e];
+        }
+        if (residual != nullptr) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) load16_stream<T>(residual + base + (k * 32 + lane) * V, v[k]);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int e = 0; e < V; ++e) v[k][e] += act_fwd<ACT>(x[k][e]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int e = 0; e < V; ++e) v[k][e] = act_fwd<ACT>(x[k][e]);
+        }
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float xhat = (v[k][e] - mean) * rstd;
+                const float gg = gy[k][e] * g[k][e];
+                dg[k][e] = fmaf(gy[k][e], xhat, dg[k][e]);
+                db[k][e] += gy[k][e];
+                v[k][e] = xhat;
+                gy[k][e] = gg;
+                c1 += gg;
+                c2 = fmaf(gg, xhat, c2);
+            }
+        c1 = warp_sum(c1) * (1.f / C);
+        c2 = warp_sum(c2) * (1.f / C);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float dv[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) dv[e] = rstd * (gy[k][e] - c1 - v[k][e] * c2);
+            if (d_residual != nullptr) store16<T>(d_residual + base + (k * 32 + lane) * V, dv);
+            if (ACT != kActNone || d_residual == nullptr) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) dv[e] *= act_bwd<ACT>(x[k][e]);
+                store16<T>(d_branch + base + (k * 32 + lane) * V, dv);
+            }
+        }
+    }
+    // fold the warps' partial d gamma / d beta through shared memory, one [2, C] row per CTA
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < V; ++e) s_red[warp][(k * 32 + lane) * V + e] = pass == 0 ? dg[k][e] : db[k][e];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += kLnWarps * 32) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kLnWarps; ++w) t += s_red[w][c];
+            partial[((long long)blockIdx.x * 2 + pass) * C + c] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// d_gamma[c] = sum_b partial[b][0][c], d_beta[c] = sum_b partial[b][1][c]
+template <typename T>
+__global__ void fold_partials_kernel(const float* __restrict__ partial, int nblocks, int C,
+                                     T* __restrict__ d_gamma, T* __restrict__ d_beta)
+{
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);      // 32 columns per CTA, 8 row-slices
+    const int slice = threadIdx.x >> 5;
+    __shared__ float s[8][2][33];
+    float a = 0.f, b = 0.f;
+    if (col < C) {
+        for (int r = slice; r < nblocks; r += 8) {
+            a += partial[((long long)r * 2 + 0) * C + col];
+            b += partial[((long long)r * 2 + 1) * C + col];
+        }
+    }
+    s[slice][0][threadIdx.x & 31] = a;
+    s[slice][1][threadIdx.x & 31] = b;
+    __syncthreads();
+    if (slice == 0 && col < C) {
+        float ta = 0.f, tb = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { ta += s[w][0][threadIdx.x]; tb += s[w][1][threadIdx.x]; }
+        d_gamma[col] = from_f32<T>(ta);
+        d_beta[col] = from_f32<T>(tb);
+    }
+}
+
+// rows whose mask byte is non-zero are overwritten with zeros; 32 rows per warp step
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_masked_rows_kernel(T* __restrict__ data, const unsigned char* __restrict__ mask, long long rows, int C)
+{
+    constexpr int V = Vec16<T>::n;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * 8;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (long long r0 = warp0 * 32; r0 < rows; r0 += nwarps * 32) {
+        const long long r = r0 + lane;
+        unsigned hit = __ballot_sync(0xffffffffu, r < rows && mask[r] != 0);
+        while (hit) {
+            const int bit = __ffs(hit) - 1;
+            hit &= hit - 1;
+            T* row = data + (r0 + bit) * C;
+            for (int c = lane * V; c < C; c += 32 * V) *reinterpret_cast<uint4*>(row + c) = z;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static int ln_grid(long long rows)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (rows + kLnWarps - 1) / kLnWarps;
+    const long long cap = (long long)sms * 8;                  // persistent: 8 CTAs x 8 warps per SM
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+int add_layernorm_chunks(int dtype, int C)
+{
+    const int per = dtype == kF32 ? 128 : 256;                 // elements covered by one 16-byte chunk per lane
+    if (dtype != kF32 && dtype != kBF16 && dtype != kF16) return 0;
+    if (C <= 0 || C % per != 0) return 0;
+    const int k = C / per;
+    return (k == 1 || k == 2 || k == 4) ? k : 0;
+}
+
+template <typename T, int K>
+static cudaError_t launch_ln_fwd(const AddLayerNormArgs& a, cudaStream_t st)
+{
+    const int grid = ln_grid(a.rows);
+#define MSDA_LN_FWD(ACT) \
+    add_layernorm_fwd_kernel<T, K, ACT><<<grid, kLnWarps * 32, 0, st>>>( \
+        (const T*)a.branch, (const T*)a.residual, (const T*)a.gamma, (const T*)a.beta, (const T*)a.pos, \
+        (T*)a.y, (T*)a.y_pos, a.mean, a.rstd, a.rows, a.eps)
+    switch (a.act) {
+        case kActNone: MSDA_LN_FWD(kActNone); break;
+        case kActRelu: MSDA_LN_FWD(kActRelu); break;
+        case kActGelu: MSDA_LN_FWD(kActGelu); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef MSDA_LN_FWD
+    return cudaGetLastError();
+}
+
+template <typename T, int K>
+static cudaError_t launch_ln_bwd(const AddLayerNormArgs& a, cudaStream_t st)
+{
+    const int grid = a.partial_blocks;
+#define MSDA_LN_BWD(ACT) \
+    add_layernorm_bwd_kernel<T, K, ACT><<<grid, kLnWarps * 32, 0, st>>>( \
+        (const T*)a.dy, (const T*)a.dy_pos, (const T*)a.branch, (const T*)a.residual, (const T*)a.gamma, \
+        a.mean, a.rstd, (T*)a.d_branch, (T*)a.d_residual, a.partial, a.rows)
+    switch (a.act) {
+        case kActNone: MSDA_LN_BWD(kActNone); break;
+        case kActRelu: MSDA_LN_BWD(kActRelu); break;
+        case kActGelu: MSDA_LN_BWD(kActGelu); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef MSDA_LN_BWD
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    fold_partials_kernel<T><<<(a.C + 31) / 32, 256, 0, st>>>(a.partial, grid, a.C, (T*)a.d_gamma, (T*)a.d_beta);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t dispatch_ln(const AddLayerNormArgs& a, bool backward, cudaStream_t st)
+{
+    switch (add_layernorm_chunks(a.dtype, a.C)) {
+        case 1: return backward ? launch_ln_bwd<T, 1>(a, st) : launch_ln_fwd<T, 1>(a, st);
+        case 2: return backward ? launch_ln_bwd<T, 2>(a, st) : launch_ln_fwd<T, 2>(a, st);
+        case 4: return backward ? launch_ln_bwd<T, 4>(a, st) : launch_ln_fwd<T, 4>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+int add_layernorm_partial_blocks(long long rows) { return ln_grid(rows); }
+
+cudaError_t add_layernorm(const AddLayerNormArgs& a, bool backward, cudaStream_t st)
+{
+    if (a.rows == 0) return cudaSuccess;
+    switch (a.dtype) {
+        case kF32:  return dispatch_ln<float>(a, backward, st);
+        case kBF16: return dispatch_ln<__nv_bfloat16>(a, backward, st);
+        case kF16:  return dispatch_ln<__half>(a, backward, st);
+        default:    return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t zero_masked_rows(int dtype, void* data, const unsigned char* mask, long long rows, int C, cudaStream_t st)
+{
+    if (rows == 0 || C == 0) return cudaSuccess;
+    const int esz = dtype == kF32 ? 4 : (dtype == kBF16 || dtype == kF16 ? 2 : 0);
+    if (esz == 0 || (C * esz) % 16 != 0) return cudaErrorInvalidValue;
+    const long long want = (rows + 255) / 256;
+    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    if (esz == 4) zero_masked_rows_kernel<float><<<grid, 256, 0, st>>>((float*)data, mask, rows, C);
+    else zero_masked_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)data, mask, rows, C);
+    return cudaGetLastError();
+}
+
+}  // namespace msda

@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 1; }
+extern "C" int msda_abi_version(void) { return 2; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -115,4 +115,63 @@ extern "C" int msda_fused_backward(int dtype, int raw_dtype, const void* grad_ou
     a.grad_value = grad_value; a.grad_offsets = grad_offsets_raw; a.grad_logits = grad_logits_raw;
     a.grad_ref = grad_reference_points; a.grad_value_accum = (float*)grad_value_accum_f32;
     return (int)msda::fused_backward(a, (cudaStream_t)stream);
+}
+
+// ---- layer epilogues --------------------------------------------------------------------------
+extern "C" int msda_layer_add_layernorm_supported(int dtype, int channels)
+{
+    return msda::add_layernorm_chunks(dtype, channels) > 0 ? 1 : 0;
+}
+
+extern "C" int msda_layer_add_layernorm_partial_blocks(int64_t rows)
+{
+    return msda::add_layernorm_partial_blocks((long long)rows);
+}
+
+extern "C" int msda_layer_add_layernorm_forward(int dtype, int act, const void* branch, const void* residual,
+                                                const void* gamma, const void* beta, const void* pos,
+                                                int64_t rows, int channels, float eps, void* y, void* y_pos,
+                                                float* mean, float* rstd, void* stream)
+{
+    if (rows < 0 || msda::add_layernorm_chunks(dtype, channels) == 0 || (y_pos != nullptr) != (pos != nullptr) ||
+        (mean != nullptr) != (rstd != nullptr))
+        return (int)cudaErrorInvalidValue;
+    msda::AddLayerNormArgs a = {};
+    a.dtype = dtype; a.act = act; a.rows = rows; a.C = channels; a.eps = eps;
+    a.branch = branch; a.residual = residual; a.gamma = gamma; a.beta = beta; a.pos = pos;
+    a.y = y; a.y_pos = y_pos; a.mean = mean; a.rstd = rstd;
+    return (int)msda::add_layernorm(a, false, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_add_layernorm_backward(int dtype, int act, const void* grad_y, const void* grad_y_pos,
+                                                 const void* branch, const void* residual, const void* gamma,
+                                                 const float* mean, const float* rstd, int64_t rows, int channels,
+                                                 void* grad_branch, void* grad_residual, void* grad_gamma,
+                                                 void* grad_beta, float* partial_scratch, int partial_blocks,
+                                                 void* stream)
+{
+    if (rows < 0 || msda::add_layernorm_chunks(dtype, channels) == 0 || partial_blocks < 1 ||
+        partial_blocks > msda::add_layernorm_partial_blocks((long long)rows) ||
+        (grad_residual == nullptr) != (residual == nullptr))
+        return (int)cudaErrorInvalidValue;
+    msda::AddLayerNormArgs a = {};
+    a.dtype = dtype; a.act = act; a.rows = rows; a.C = channels;
+    a.branch = branch; a.residual = residual; a.gamma = gamma;
+    a.mean = const_cast<float*>(mean); a.rstd = const_cast<float*>(rstd);
+    a.dy = grad_y; a.dy_pos = grad_y_pos; a.d_branch = grad_branch; a.d_residual = grad_residual;
+    a.d_gamma = grad_gamma; a.d_beta = grad_beta; a.partial = partial_scratch; a.partial_blocks = partial_blocks;
+    if (rows == 0) {     // no rows: parameter gradients are zero
+        const size_t esz = dtype == MSDA_DTYPE_F32 ? 4 : 2;
+        cudaError_t e = cudaMemsetAsync(grad_gamma, 0, channels * esz, (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+        return (int)cudaMemsetAsync(grad_beta, 0, channels * esz, (cudaStream_t)stream);
+    }
+    return (int)msda::add_layernorm(a, true, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t* mask, int64_t rows, int channels,
+                                           void* stream)
+{
+    if (rows < 0 || channels < 0) return (int)cudaErrorInvalidValue;
+    return (int)msda::zero_masked_rows(dtype, data, mask, (long long)rows, channels, (cudaStream_t)stream);
 }

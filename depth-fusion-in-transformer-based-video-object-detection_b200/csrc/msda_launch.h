@@ -69,4 +69,37 @@ cudaError_t fused_backward(const FusedArgs& a, cudaStream_t stream);
 cudaError_t forward(const FwdArgs& a, cudaStream_t stream);
 cudaError_t backward(const BwdArgs& a, cudaStream_t stream);
 
+// Layer epilogues (layer_epilogue.cu):  y = LayerNorm(residual + act(branch)) * gamma + beta,
+// optional y_pos = y + pos; backward of the same.
+struct AddLayerNormArgs {
+    int dtype;                // kF32 / kBF16 / kF16: type of every tensor below except mean/rstd/partial
+    int act;                  // 0 identity, 1 relu, 2 gelu (erf)
+    long long rows;
+    int C;
+    float eps;
+    const void* branch;       // [rows, C]
+    const void* residual;     // [rows, C] or null
+    const void* gamma;        // [C]
+    const void* beta;         // [C]   (forward)
+    const void* pos;          // [rows, C] or null (forward, with y_pos)
+    void* y;                  // forward out
+    void* y_pos;              // forward out or null
+    float* mean;              // [rows] forward out (may be null) / backward in
+    float* rstd;
+    // backward
+    const void* dy;           // [rows, C]
+    const void* dy_pos;       // [rows, C] or null
+    void* d_branch;           // written unless (act == 0 and d_residual != null): then d_branch == d_residual
+    void* d_residual;         // or null
+    void* d_gamma;            // [C]
+    void* d_beta;             // [C]
+    float* partial;           // [partial_blocks, 2, C] fp32 scratch
+    int partial_blocks;       // from add_layernorm_partial_blocks(rows)
+};
+int add_layernorm_chunks(int dtype, int C);            // 0 = unsupported shape
+int add_layernorm_partial_blocks(long long rows);
+cudaError_t add_layernorm(const AddLayerNormArgs& a, bool backward, cudaStream_t stream);
+cudaError_t zero_masked_rows(int dtype, void* data, const unsigned char* mask, long long rows, int C,
+                             cudaStream_t stream);
+
 }  // namespace msda

@@ -1,0 +1,195 @@
+"""Autograd bindings of the layer-epilogue kernels (C ABI ``msda_layer_*``, csrc/layer_epilogue.cu).
+
+``add_layer_norm(norm, branch, residual, act, pos)`` is what the reference layer classes spell as
+    norm(residual + act(branch))            deformable_transformer_single.py:538-541, :393-400, :452-459
+    ... + pos                               :530-531 (query of the next deformable attention)
+as ONE kernel per direction.  ``zero_masked_rows_`` is MSDeformAttn's
+``value.masked_fill(mask[..., None], 0)`` (models/ops/modules/ms_deform_attn.py:95-96) in place.
+``linear_relu`` is ``relu(linear1(x))`` with the activation in the GEMM epilogue (library GEMM).
+CUDA tensors only; callers keep the PyTorch composition for shapes the kernels do not cover.
+"""
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ... import _lib
+
+_DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16}
+ACT_CODES = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+
+
+def add_layer_norm_supported(x, channels):
+    return x.is_cuda and x.dtype in _DTYPES and \
+        bool(_lib.load().msda_layer_add_layernorm_supported(_DTYPES[x.dtype], int(channels)))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _dense(t):
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+class AddLayerNormFunction(Function):
+    """apply(branch, residual|None, gamma, beta, eps, act_code, pos|None) -> y  or  (y, y + pos)"""
+
+    @staticmethod
+    def forward(ctx, branch, residual, gamma, beta, eps, act, pos):
+        shape = branch.shape
+        c = shape[-1]
+        dt = branch.dtype
+        branch = _dense(branch)
+        residual = None if residual is None else _dense(residual.to(dt))
+        pos = None if pos is None else _dense(pos.to(dt).expand(shape))
+        gamma_c, beta_c = _dense(gamma.to(dt)), _dense(beta.to(dt))
+        rows = branch.numel() // c if c else 0
+        needs_grad = any(ctx.needs_input_grad)
+        lib = _lib.load()
+        with torch.cuda.device(branch.device):
+            y = torch.empty_like(branch)
+            y_pos = torch.empty_like(branch) if pos is not None else None
+            mean = torch.empty(rows, dtype=torch.float32, device=branch.device) if needs_grad else None
+            rstd = torch.empty_like(mean) if needs_grad else None
+            code = lib.msda_layer_add_layernorm_forward(
+                _DTYPES[dt], act, branch.data_ptr(), _ptr(residual), gamma_c.data_ptr(), beta_c.data_ptr(),
+                _ptr(pos), rows, c, float(eps), y.data_ptr(), _ptr(y_pos), _ptr(mean), _ptr(rstd),
+                torch.cuda.current_stream().cuda_stream)
+        _lib.check(code, "msda_layer_add_layernorm_forward")
+        if needs_grad:
+            ctx.save_for_backward(branch, residual, gamma_c, mean, rstd)
+            ctx.act = act
+            ctx.param_dtypes = (gamma.dtype, beta.dtype)
+            ctx.has_pos = pos is not None
+        if y_pos is None:
+            return y
+        return y, y_pos
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y, grad_y_pos=None):
+        branch, residual, gamma, mean, rstd = ctx.saved_tensors
+        c = branch.shape[-1]
+        rows = branch.numel() // c
+        dt = branch.dtype
+        if grad_y is None and grad_y_pos is None:
+            return (None,) * 7
+        if grad_y is None:            # only the y + pos output was used downstream
+            grad_y, grad_y_pos_k = grad_y_pos, None
+        else:
+            grad_y_pos_k = grad_y_pos
+        grad_y = _dense(grad_y.to(dt))
+        grad_y_pos_k = None if grad_y_pos_k is None else _dense(grad_y_pos_k.to(dt))
+        lib = _lib.load()
+        with torch.cuda.device(branch.device):
+            d_res = torch.empty_like(branch) if residual is not None else None
+            d_branch = torch.empty_like(branch) if (ctx.act != 0 or residual is None) else d_res
+            d_gamma = torch.empty_like(gamma)
+            d_beta = torch.empty_like(gamma)
+            blocks = lib.msda_layer_add_layernorm_partial_blocks(rows)
+            partial = torch.empty((blocks, 2, c), dtype=torch.float32, device=branch.device)
+            code = lib.msda_layer_add_layernorm_backward(
+                _DTYPES[dt], ctx.act, grad_y.data_ptr(), _ptr(grad_y_pos_k), branch.data_ptr(), _ptr(residual),
+                gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, c, d_branch.data_ptr(), _ptr(d_res),
+                d_gamma.data_ptr(), d_beta.data_ptr(), partial.data_ptr(), blocks,
+                torch.cuda.current_stream().cuda_stream)
+        _lib.check(code, "msda_layer_add_layernorm_backward")
+        d_pos = grad_y_pos if ctx.has_pos else None
+        return (d_branch, d_res, d_gamma.to(ctx.param_dtypes[0]), d_beta.to(ctx.param_dtypes[1]), None, None,
+                d_pos)
+
+
+def add_layer_norm(norm, branch, residual=None, act=None, pos=None):
+    """``norm(residual + act(branch))`` and, when ``pos`` is given, also ``that + pos``.
+
+    ``norm`` is the layer's ``nn.LayerNorm`` (parameters / eps are read from it, so state_dict keys
+    stay the reference's).  Returns ``y`` or ``(y, y_pos)``."""
+    c = branch.shape[-1]
+    fusable = (add_layer_norm_supported(branch, c) and norm.elementwise_affine and norm.bias is not None
+               and tuple(norm.normalized_shape) == (c,) and act in ACT_CODES
+               and (residual is None or residual.shape == branch.shape)
+               and (pos is None or pos.shape == branch.shape))
+    if fusable:
+        return AddLayerNormFunction.apply(branch, residual, norm.weight, norm.bias, norm.eps, ACT_CODES[act], pos)
+    # PyTorch composition (shapes the kernel does not cover)
+    h = branch if act in (None, "none") else getattr(F, act)(branch)
+    y = norm(h if residual is None else residual + h)
+    return y if pos is None else (y, y + pos)
+
+
+class ZeroMaskedRowsFunction(Function):
+    """In place: rows of ``value`` [N, S, C] whose ``mask`` [N, S] entry is True become zero."""
+
+    @staticmethod
+    def forward(ctx, value, mask):
+        if not value.is_contiguous():
+            raise RuntimeError("zero_masked_rows_: value must be contiguous")
+        mask8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else (mask != 0).to(torch.uint8)
+        c = value.shape[-1]
+        rows = value.numel() // c if c else 0
+        if mask8.numel() != rows:
+            raise RuntimeError(f"mask has {mask8.numel()} entries for {rows} rows")
+        code = _lib.load().msda_layer_zero_masked_rows(
+            _DTYPES[value.dtype], value.data_ptr(), mask8.data_ptr(), rows, c,
+            torch.cuda.current_stream().cuda_stream)
+        _lib.check(code, "msda_layer_zero_masked_rows")
+        ctx.mark_dirty(value)
+        ctx.save_for_backward(mask8)
+        return value
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        (mask8,) = ctx.saved_tensors
+        # `value` feeds only the deformable-attention op, whose backward allocates this gradient
+        # fresh: zero its masked rows in place instead of copying the whole tensor
+        if not grad.is_contiguous() or grad.data_ptr() % 16:
+            grad = grad.contiguous().clone()
+        c = grad.shape[-1]
+        code = _lib.load().msda_layer_zero_masked_rows(
+            _DTYPES[grad.dtype], grad.data_ptr(), mask8.data_ptr(), grad.numel() // c, c,
+            torch.cuda.current_stream().cuda_stream)
+        _lib.check(code, "msda_layer_zero_masked_rows")
+        return grad, None
+
+
+def zero_masked_rows_(value, mask):
+    """``value.masked_fill(mask[..., None], 0)`` for a freshly produced ``value`` (modified in place)."""
+    c = value.shape[-1]
+    if value.is_cuda and value.dtype in _DTYPES and value.is_contiguous() and (c * value.element_size()) % 16 == 0 \
+            and value.data_ptr() % 16 == 0:
+        with torch.cuda.device(value.device):
+            return ZeroMaskedRowsFunction.apply(value, mask)
+    return value.masked_fill(mask[..., None], float(0))
+
+
+class LinearReLUFunction(Function):
+    """relu(x @ W^T + b) with bias and ReLU in the GEMM epilogue (cuBLASLt through
+    torch._addmm_activation): the pre-activation never reaches HBM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1])
+        out = torch._addmm_activation(bias, x2, weight.t(), use_gelu=False)
+        ctx.save_for_backward(x2, weight, out)
+        ctx.x_shape = x.shape
+        return out.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        x2, weight, out = ctx.saved_tensors
+        g = torch.ops.aten.threshold_backward(grad.reshape(out.shape), out, 0)
+        dx = g @ weight if ctx.needs_input_grad[0] else None
+        dw = g.t() @ x2 if ctx.needs_input_grad[1] else None
+        db = g.sum(0) if ctx.needs_input_grad[2] else None
+        return (None if dx is None else dx.view(ctx.x_shape)), dw, db
+
+
+def linear_relu(linear, x):
+    """``relu(linear(x))``; epilogue-fused on CUDA for 16-bit / fp32 dense inputs."""
+    if x.is_cuda and linear.bias is not None and x.dtype == linear.weight.dtype and x.dtype in _DTYPES:
+        return LinearReLUFunction.apply(x, linear.weight, linear.bias)
+    return F.relu(linear(x))

@@ -27,7 +27,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported, zero_masked_rows_
 
 
 def _is_power_of_2(n):
@@ -146,7 +146,7 @@ class MSDeformAttn(nn.Module):
 
         value = self.value_proj(input_flatten)
         if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
+            value = zero_masked_rows_(value, input_padding_mask)      # in place on the fresh projection
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(

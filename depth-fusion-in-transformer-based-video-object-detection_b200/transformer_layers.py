@@ -14,8 +14,10 @@ its own and load its checkpoints:
   TemporalDeformableTransformerEncoderLayer (frames as levels)          single.py:650-700
   TemporalDeformableTransformerDecoder     (TransVOD++ TDTD)            multi_plusplus.py:1030-1076
 
-Every deformable attention inside them is the sm_100a op (ops/modules/ms_deform_attn.py); the
-dense parts (Linear, LayerNorm, MultiheadAttention) are library kernels, as in the reference.
+Every deformable attention inside them is the sm_100a op (ops/modules/ms_deform_attn.py).  The
+element-wise chains around it -- residual add + LayerNorm, the "+ pos" that forms the next
+query, bias + activation -- run as the fused layer-epilogue kernels of csrc/layer_epilogue.cu
+(ops/functions/layer_epilogue_func.py); Linear / MultiheadAttention stay library GEMMs.
 """
 import copy
 
@@ -23,6 +25,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .ops.functions import add_layer_norm, linear_relu
 from .ops.modules import MSDeformAttn
 from .ops.modules.ms_deform_attn import host_shape_list
 
@@ -78,6 +81,7 @@ class DeformableTransformerEncoderLayer(nn.Module):
         # feed-forward
         self.linear1 = nn.Linear(d_model, d_ffn)
         self.activation = _get_activation_fn(activation)
+        self._activation_name = activation
         self.dropout2 = nn.Dropout(dropout)
         self.linear2 = nn.Linear(d_ffn, d_model)
         self.dropout3 = nn.Dropout(dropout)
@@ -85,16 +89,27 @@ class DeformableTransformerEncoderLayer(nn.Module):
 
     with_pos_embed = staticmethod(_add_pos)
 
-    def forward_ffn(self, src):
-        hidden = self.dropout2(self.activation(self.linear1(src)))
-        return self.norm2(src + self.dropout3(self.linear2(hidden)))
+    def forward_ffn(self, src, pos=None):
+        """norm2(src + linear2(act(linear1(src)))); with ``pos`` also returns that + pos."""
+        hidden = linear_relu(self.linear1, src) if self._activation_name == "relu" \
+            else self.activation(self.linear1(src))
+        return add_layer_norm(self.norm2, self.dropout3(self.linear2(self.dropout2(hidden))), src, None, pos)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
-                rgbd_src=None):
-        query = rgbd_src if rgbd_src is not None else _add_pos(src, pos)
+                rgbd_src=None, query=None, emit_query=False):
+        """Reference signature plus two private keywords used by the encoder loops: ``query`` is a
+        precomputed ``src + pos`` and ``emit_query=True`` makes the call return
+        ``(out, out + pos)`` so the next layer's query costs no extra pass."""
+        if query is None:
+            query = rgbd_src if rgbd_src is not None else _add_pos(src, pos)
         attended = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask)
-        src = self.norm1(src + self.dropout1(attended))
-        return self.forward_ffn(src)
+        src = add_layer_norm(self.norm1, self.dropout1(attended), src)
+        if not emit_query:
+            return self.forward_ffn(src)
+        if pos is None:
+            out = self.forward_ffn(src)
+            return out, out
+        return self.forward_ffn(src, pos)
 
 
 class DeformableTransformerEncoder(nn.Module):
@@ -109,9 +124,19 @@ class DeformableTransformerEncoder(nn.Module):
                 rgbd_src=None):
         reference_points = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
         output = src
-        for layer in self.layers:
-            output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
-                           rgbd_src=rgbd_src)
+        if rgbd_src is not None:
+            for layer in self.layers:
+                output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
+                               rgbd_src=rgbd_src)
+            return output
+        query = None                  # layer i hands layer i+1 its query (output + pos) from its last kernel
+        for i, layer in enumerate(self.layers):
+            if i + 1 < len(self.layers):
+                output, query = layer(output, pos, reference_points, spatial_shapes, level_start_index,
+                                      padding_mask, query=query, emit_query=True)
+            else:
+                output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
+                               query=query)
         return output
 
 
@@ -142,13 +167,18 @@ class _CrossModalFusion(nn.Module):
 
     def forward_ffn(self, tgt):
         drop, norm = getattr(self, self._ffn_dropout), getattr(self, self._ffn_norm)
-        return norm(tgt + drop(self.activation(self.linear1(tgt))))
+        if drop.training and drop.p > 0:
+            return add_layer_norm(norm, drop(self.activation(self.linear1(tgt))), tgt)
+        return add_layer_norm(norm, self.linear1(tgt), tgt, "gelu")       # GELU inside the norm kernel
 
-    def _fuse(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask):
-        src = self.norm_depth_scale(self.depth_scale_adapt(src))
-        sampled = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,
-                                  level_start_index, src_padding_mask)
-        tgt = self.norm1(tgt + self.dropout1(self.cross_scale_adapt(sampled)))
+    def _fuse(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
+              query=None):
+        src = add_layer_norm(self.norm_depth_scale, self.depth_scale_adapt(src))
+        if query is None:
+            query = _add_pos(tgt, query_pos)
+        sampled = self.cross_attn(query, reference_points, src, src_spatial_shapes, level_start_index,
+                                  src_padding_mask)
+        tgt = add_layer_norm(self.norm1, self.dropout1(self.cross_scale_adapt(sampled)), tgt)
         return self.forward_ffn(tgt)
 
 
@@ -179,9 +209,9 @@ class DeformableTransformerFusionLayerV2(_CrossModalFusion):
         self._build(d_model, dropout, n_levels, n_heads, n_points, "dropout3", "norm2")
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                src_padding_mask=None):
+                src_padding_mask=None, query=None):
         return self._fuse(tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                          src_padding_mask)
+                          src_padding_mask, query=query)
 
 
 class RGBDDeformableTransformerEncoderV2(nn.Module):
@@ -211,13 +241,21 @@ class RGBDDeformableTransformerEncoderV2(nn.Module):
                 depth_valid_ratios=None, depth_pos=None, depth_padding_mask=None):
         reference_points = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
         output, fusion_stream = src, depth_src
+        query = None
         for i, layer in enumerate(self.layers):
-            output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask)
-            if i < self.depth_num_layers and i in self.fusion_layers_order:
+            fuse = i < self.depth_num_layers and i in self.fusion_layers_order
+            if fuse or i + 1 < len(self.layers):
+                output, query = layer(output, pos, reference_points, spatial_shapes, level_start_index,
+                                      padding_mask, query=query, emit_query=True)
+            else:
+                output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
+                               query=query)
+            if fuse:
                 fusion_layer = self.fusion_layers[self.fusion_layers_order.index(i)]
                 fusion_stream = fusion_layer(output, pos, reference_points, fusion_stream, depth_spatial_shapes,
-                                             depth_level_start_index, padding_mask)
+                                             depth_level_start_index, padding_mask, query=query)
                 output = output + fusion_stream
+                query = None          # output changed: the next layer forms its own query
         return output
 
 
@@ -239,6 +277,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
         # feed-forward
         self.linear1 = nn.Linear(d_model, d_ffn)
         self.activation = _get_activation_fn(activation)
+        self._activation_name = activation
         self.dropout3 = nn.Dropout(dropout)
         self.linear2 = nn.Linear(d_ffn, d_model)
         self.dropout4 = nn.Dropout(dropout)
@@ -246,19 +285,32 @@ class DeformableTransformerDecoderLayer(nn.Module):
 
     with_pos_embed = staticmethod(_add_pos)
 
-    def forward_ffn(self, tgt):
-        hidden = self.dropout3(self.activation(self.linear1(tgt)))
-        return self.norm3(tgt + self.dropout4(self.linear2(hidden)))
+    def forward_ffn(self, tgt, pos=None):
+        hidden = linear_relu(self.linear1, tgt) if self._activation_name == "relu" \
+            else self.activation(self.linear1(tgt))
+        return add_layer_norm(self.norm3, self.dropout4(self.linear2(self.dropout3(hidden))), tgt, None, pos)
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                src_padding_mask=None):
-        qk = _add_pos(tgt, query_pos).transpose(0, 1)
+                src_padding_mask=None, qk=None, emit_qk=False):
+        """Reference signature plus two private keywords used by the decoder loop: ``qk`` is a
+        precomputed ``tgt + query_pos``; ``emit_qk=True`` returns ``(out, out + query_pos)``."""
+        if qk is None:
+            qk = _add_pos(tgt, query_pos)
+        qk = qk.transpose(0, 1)
         mixed = self.self_attn(qk, qk, tgt.transpose(0, 1))[0].transpose(0, 1)
-        tgt = self.norm2(tgt + self.dropout2(mixed))
-        sampled = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,
-                                  level_start_index, src_padding_mask)
-        tgt = self.norm1(tgt + self.dropout1(sampled))
-        return self.forward_ffn(tgt)
+        if query_pos is not None:
+            tgt, query = add_layer_norm(self.norm2, self.dropout2(mixed), tgt, None, query_pos)
+        else:
+            tgt = query = add_layer_norm(self.norm2, self.dropout2(mixed), tgt)
+        sampled = self.cross_attn(query, reference_points, src, src_spatial_shapes, level_start_index,
+                                  src_padding_mask)
+        tgt = add_layer_norm(self.norm1, self.dropout1(sampled), tgt)
+        if not emit_qk:
+            return self.forward_ffn(tgt)
+        if query_pos is None:
+            out = self.forward_ffn(tgt)
+            return out, out
+        return self.forward_ffn(tgt, query_pos)
 
 
 class TemporalDeformableTransformerEncoderLayer(DeformableTransformerDecoderLayer):
@@ -291,6 +343,7 @@ class DeformableTransformerDecoder(nn.Module):
     def forward(self, tgt, reference_points, src, src_spatial_shapes, src_level_start_index, src_valid_ratios,
                 query_pos=None, src_padding_mask=None):
         output = tgt
+        qk = None
         intermediate, intermediate_reference_points = [], []
         for lid, layer in enumerate(self.layers):
             if reference_points.shape[-1] == 4:
@@ -299,8 +352,12 @@ class DeformableTransformerDecoder(nn.Module):
                 assert reference_points.shape[-1] == 2
                 scale = src_valid_ratios
             reference_points_input = reference_points[:, :, None] * scale[:, None]
-            output = layer(output, query_pos, reference_points_input, src, src_spatial_shapes,
-                           src_level_start_index, src_padding_mask)
+            if lid + 1 < len(self.layers):
+                output, qk = layer(output, query_pos, reference_points_input, src, src_spatial_shapes,
+                                   src_level_start_index, src_padding_mask, qk=qk, emit_qk=True)
+            else:
+                output = layer(output, query_pos, reference_points_input, src, src_spatial_shapes,
+                               src_level_start_index, src_padding_mask, qk=qk)
 
             if self._refine_boxes and self.bbox_embed is not None:       # single.py:729-739
                 delta = self.bbox_embed[lid](output)

@@ -117,6 +117,49 @@ int msda_fused_backward(int dtype, int raw_dtype,
                         void* grad_value, void* grad_offsets_raw, void* grad_logits_raw,
                         float* grad_reference_points, void* grad_value_accum_f32, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Layer epilogues around the deformable attention (no counterpart symbol in the reference, which
+ * runs them as separate PyTorch element-wise kernels).  They replace, in every layer class that owns
+ * an MSDeformAttn,
+ *     x = norm(residual + dropout(branch))                 /root/reference/models/deformable_transformer_single.py:538-541
+ *     x = norm(x + dropout(act(linear1(x))))   (fusion)    :393-400, :452-459  (and :544-548, :617-642)
+ *     query = x + pos                                      :530-531, :538
+ * with ONE kernel per direction:
+ *     v = residual + act(branch);  y = LayerNorm_C(v) * gamma + beta;  y_pos = y + pos (optional)
+ * `act`: 0 identity, 1 ReLU, 2 GELU (exact erf form).
+ * All tensors are [rows, channels] (gamma / beta [channels]) of `dtype` (F32, BF16 or F16), 16-byte
+ * aligned; arithmetic is fp32.  residual / pos / y_pos / mean / rstd may be NULL (pos and y_pos
+ * together, mean and rstd together).  mean / rstd [rows] fp32 are the row statistics the backward
+ * needs.  Supported channel counts: msda_layer_add_layernorm_supported (a multiple of 128 (F32) or
+ * 256 (16-bit) elements with 1, 2 or 4 sixteen-byte chunks per lane, i.e. 128/256/512 or
+ * 256/512/1024).
+ * Backward: grad_y_pos may be NULL.  grad_residual must be given iff residual was.  With act == 0 and
+ * a residual, d branch == d residual and only grad_residual is written (grad_branch is ignored).
+ * partial_scratch: fp32 [partial_blocks, 2, channels]; partial_blocks =
+ * msda_layer_add_layernorm_partial_blocks(rows).  grad_gamma / grad_beta [channels] are overwritten.
+ */
+int msda_layer_add_layernorm_supported(int dtype, int channels);
+int msda_layer_add_layernorm_partial_blocks(int64_t rows);
+int msda_layer_add_layernorm_forward(int dtype, int act,
+                                     const void* branch, const void* residual,
+                                     const void* gamma, const void* beta, const void* pos,
+                                     int64_t rows, int channels, float eps,
+                                     void* y, void* y_pos, float* mean, float* rstd, void* stream);
+int msda_layer_add_layernorm_backward(int dtype, int act,
+                                      const void* grad_y, const void* grad_y_pos,
+                                      const void* branch, const void* residual, const void* gamma,
+                                      const float* mean, const float* rstd,
+                                      int64_t rows, int channels,
+                                      void* grad_branch, void* grad_residual,
+                                      void* grad_gamma, void* grad_beta,
+                                      float* partial_scratch, int partial_blocks, void* stream);
+
+/* value.masked_fill(padding_mask[..., None], 0) of MSDeformAttn.forward
+ * (/root/reference/models/ops/modules/ms_deform_attn.py:95-96), in place: rows of data[rows, channels]
+ * whose mask byte is non-zero are overwritten with zeros; only the mask and those rows are touched. */
+int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t* mask, int64_t rows, int channels,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,147 @@
+"""GPU: the fused layer-epilogue kernels (C ABI msda_layer_*) against a plain PyTorch fp64
+composition of the reference's element-wise chain
+    norm(residual + act(branch)) [+ pos]      /root/reference/models/deformable_transformer_single.py:538-548, :393-400
+Tolerances (normalised max error, max|x-ref| / max|ref|): fp32 1e-5, bf16 / fp16 2^-7 against the
+fp64 composition evaluated on the same (rounded) inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dfvod_b200.ops.functions import add_layer_norm, linear_relu, zero_masked_rows_
+from dfvod_b200.ops.functions import layer_epilogue_func as lef
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2.0 ** -7, torch.float16: 2.0 ** -9}
+
+
+def nerr(x, ref):
+    return float((x.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-300))
+
+
+def ref_chain(norm64, branch, residual, act, pos):
+    h = branch.double()
+    if act == "relu":
+        h = F.relu(h)
+    elif act == "gelu":
+        h = F.gelu(h)
+    v = h if residual is None else residual.double() + h
+    y = norm64(v)
+    return y, (None if pos is None else y + pos.double())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("c", [256, 512, 1024])
+@pytest.mark.parametrize("act", [None, "relu", "gelu"])
+@pytest.mark.parametrize("with_res,with_pos", [(True, True), (True, False), (False, False)])
+def test_add_layer_norm_forward_backward(dtype, c, act, with_res, with_pos):
+    if dtype == torch.float32 and c == 1024:
+        c = 128
+    torch.manual_seed(c + (0 if act is None else len(act)))
+    rows = (3, 347)                      # not a multiple of the warps per CTA
+    norm = torch.nn.LayerNorm(c).to(DEV)
+    with torch.no_grad():
+        norm.weight.add_(torch.randn(c, device=DEV) * 0.3)
+        norm.bias.add_(torch.randn(c, device=DEV) * 0.3)
+    norm = norm.to(dtype)
+    norm64 = torch.nn.LayerNorm(c).to(DEV).double()
+    norm64.load_state_dict({k: v.double() for k, v in norm.state_dict().items()})
+    mk = lambda: (torch.randn(*rows, c, device=DEV) * 1.5).to(dtype)
+    branch, residual, pos = mk(), (mk() if with_res else None), (mk() if with_pos else None)
+    leaves = [t.clone().requires_grad_(True) for t in (branch, residual, pos) if t is not None]
+    it = iter(leaves)
+    b = next(it)
+    r = next(it) if with_res else None
+    p = next(it) if with_pos else None
+    assert lef.add_layer_norm_supported(b, c)
+    out = add_layer_norm(norm, b, r, act, p)
+    y, y_pos = out if with_pos else (out, None)
+
+    leaves64 = [t.detach().double().requires_grad_(True) for t in leaves]
+    it = iter(leaves64)
+    b64 = next(it)
+    r64 = next(it) if with_res else None
+    p64 = next(it) if with_pos else None
+    y64, y_pos64 = ref_chain(norm64, b64, r64, act, p64)
+    tol = TOL[dtype]
+    assert nerr(y, y64.detach()) <= tol
+    if with_pos:
+        assert nerr(y_pos, y_pos64.detach()) <= tol
+
+    gy = torch.randn_like(y)
+    gyp = torch.randn_like(y) if with_pos else None
+    loss = (y.float() * gy.float()).sum() + ((y_pos.float() * gyp.float()).sum() if with_pos else 0)
+    loss.backward()
+    loss64 = (y64 * gy.double()).sum() + ((y_pos64 * gyp.double()).sum() if with_pos else 0)
+    loss64.backward()
+    gtol = tol * 4 if dtype != torch.float32 else 2e-5
+    for got, want in zip(leaves, leaves64):
+        assert nerr(got.grad, want.grad) <= gtol
+    # parameter gradients are sums over 1041 rows of rounded products
+    assert nerr(norm.weight.grad, norm64.weight.grad) <= (gtol if dtype == torch.float32 else 2.0 ** -6)
+    assert nerr(norm.bias.grad, norm64.bias.grad) <= (gtol if dtype == torch.float32 else 2.0 ** -6)
+
+
+def test_add_layer_norm_matches_torch_composition_bf16_bitwise_pos():
+    """y_pos is defined on the ROUNDED y (like the unfused chain): y_pos == bf16(y) + pos exactly."""
+    torch.manual_seed(0)
+    norm = torch.nn.LayerNorm(256).to(DEV).bfloat16()
+    b, r, p = (torch.randn(2, 100, 256, device=DEV).bfloat16() for _ in range(3))
+    y, y_pos = add_layer_norm(norm, b, r, None, p)
+    assert torch.equal(y_pos, y + p)
+
+
+def test_add_layer_norm_unsupported_width_uses_torch():
+    norm = torch.nn.LayerNorm(96).to(DEV)
+    b, r = torch.randn(4, 96, device=DEV), torch.randn(4, 96, device=DEV)
+    assert not lef.add_layer_norm_supported(b, 96)
+    assert torch.allclose(add_layer_norm(norm, b, r), norm(b + r))
+
+
+def test_add_layer_norm_empty():
+    norm = torch.nn.LayerNorm(256).to(DEV)
+    b = torch.zeros(0, 256, device=DEV, requires_grad=True)
+    y = add_layer_norm(norm, b, None)
+    assert y.shape == (0, 256)
+    y.sum().backward()
+    assert float(norm.weight.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_zero_masked_rows(dtype):
+    torch.manual_seed(1)
+    n, s, c = 3, 1237, 256
+    mask = torch.rand(n, s, device=DEV) < 0.3
+    lin = torch.nn.Linear(c, c).to(DEV).to(dtype)
+    x = torch.randn(n, s, c, device=DEV).to(dtype)
+    ref = lin(x).masked_fill(mask[..., None], 0.0)
+    got = zero_masked_rows_(lin(x), mask)
+    assert torch.equal(got, ref)
+    # gradient: masked rows receive nothing
+    x1 = x.clone().requires_grad_(True)
+    g = torch.randn_like(ref)
+    zero_masked_rows_(lin(x1), mask).backward(g.clone())
+    x2 = x.clone().requires_grad_(True)
+    lin(x2).masked_fill(mask[..., None], 0.0).backward(g.clone())
+    assert torch.equal(x1.grad, x2.grad)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_relu(dtype):
+    torch.manual_seed(2)
+    lin = torch.nn.Linear(256, 1024).to(DEV).to(dtype)
+    x = torch.randn(5, 77, 256, device=DEV).to(dtype).requires_grad_(True)
+    out = linear_relu(lin, x)
+    ref = F.relu(lin.double()(x.detach().double())) if False else None
+    lin64 = torch.nn.Linear(256, 1024).to(DEV).double()
+    lin64.load_state_dict({k: v.double() for k, v in lin.state_dict().items()})
+    x64 = x.detach().double().requires_grad_(True)
+    ref = F.relu(lin64(x64))
+    tol = 1e-5 if dtype == torch.float32 else 2.0 ** -7
+    assert nerr(out, ref.detach()) <= tol
+    g = torch.randn_like(out)
+    out.backward(g)
+    ref.backward(g.double())
+    assert nerr(x.grad, x64.grad) <= tol * 4
+    assert nerr(lin.weight.grad, lin64.weight.grad) <= tol * 4
+    assert nerr(lin.bias.grad, lin64.bias.grad) <= tol * 4
