@@ -13,6 +13,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from ... import _lib
+from ... import MultiScaleDeformableAttention as _msda
 
 _DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
 
@@ -60,8 +61,13 @@ class MSDeformAttnFusedFunction(Function):
         with torch.cuda.device(value.device):
             out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
             esz = raw.element_size()
-            code = lib.msda_fused_forward(
-                _DTYPES[value.dtype], _DTYPES[raw.dtype], value.data_ptr(), spatial_shapes.data_ptr(),
+            fused_forward = lib.msda_fused_forward
+            source = value
+            if value.dtype == torch.bfloat16 and _msda.use_paired_forward(value.dtype, d, s, lq, nl, p):
+                source = _msda.pack_value_pairs(value)          # 2 lines per sample instead of 4
+                fused_forward = lib.msda_fused_forward_paired
+            code = fused_forward(
+                _DTYPES[value.dtype], _DTYPES[raw.dtype], source.data_ptr(), spatial_shapes.data_ptr(),
                 level_start_index.data_ptr(), ref.data_ptr(), ref.size(-1),
                 raw.data_ptr(), 3 * mlp, raw.data_ptr() + 2 * mlp * esz, 3 * mlp,
                 n, s, m, d, nl, lq, p, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
