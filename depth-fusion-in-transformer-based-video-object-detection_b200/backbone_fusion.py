@@ -14,7 +14,7 @@ off by one stage) and the convolutional stems are outside
 import torch
 from torch import nn
 
-from .ops.functions import add_layer_norm
+from .ops.functions import add_layer_norm, linear
 from .ops.modules import MSDeformAttn
 from .transformer_layers import _add_pos, _get_activation_fn, encoder_reference_points
 
@@ -43,15 +43,15 @@ class DepthDeformableTransformerEncoderLayer(nn.Module):
 
     def forward_ffn(self, tgt):
         if (self.dropout4.training and self.dropout4.p > 0) or self._activation_name not in ("relu", "gelu"):
-            return add_layer_norm(self.norm3, self.dropout4(self.activation(self.linear1(tgt))), tgt)
-        return add_layer_norm(self.norm3, self.linear1(tgt), tgt, self._activation_name)
+            return add_layer_norm(self.norm3, self.dropout4(self.activation(linear(self.linear1, tgt))), tgt)
+        return add_layer_norm(self.norm3, linear(self.linear1, tgt), tgt, self._activation_name)
 
     def forward(self, tgt, query_pos, src_pos, tgt_spatial_shapes, reference_points, depth_reference_points,
                 src, src_spatial_shapes, frame_start_index, tgt_padding_mask=None, src_padding_mask=None):
-        src = add_layer_norm(self.norm_depth_scale, self.depth_scale_adapt(src))
+        src = add_layer_norm(self.norm_depth_scale, linear(self.depth_scale_adapt, src))
         sampled = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,
                                   frame_start_index, src_padding_mask)
-        tgt = add_layer_norm(self.norm1, self.dropout1(self.cross_scale_adapt(sampled)), tgt)
+        tgt = add_layer_norm(self.norm1, self.dropout1(linear(self.cross_scale_adapt, sampled)), tgt)
         return self.forward_ffn(tgt)
 
 

@@ -292,9 +292,105 @@ zero_masked_rows_kernel(T* __restrict__ data, const unsigned char* __restrict__ 
     }
 }
 
+// Column sums of a [rows, C] matrix (bias gradient of a Linear: grad_bias = sum over tokens of
+// grad_output).  Thread = one 16-byte column chunk x one row lane; per-CTA partials [gridDim, C] in
+// fp32, folded by colsum_fold_kernel.  nch = chunks per row, rl = row lanes per CTA (rl * nch <= 256).
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const T* __restrict__ x, long long rows, int C, int nch, int rl, float* __restrict__ partial)
+{
+    constexpr int V = Vec16<T>::n;
+    extern __shared__ float s_cs[];                    // [rl][C]
+    const int ch = threadIdx.x % nch, lane_r = threadIdx.x / nch;
+    const bool worker = lane_r < rl;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    if (worker) {
+        const long long step = (long long)gridDim.x * rl;
+        long long r = (long long)blockIdx.x * rl + lane_r;
+        // two rows in flight per thread
+        for (; r + step < rows; r += 2 * step) {
+            float a[V], b[V];
+            load16_stream<T>(x + r * C + ch * V, a);
+            load16_stream<T>(x + (r + step) * C + ch * V, b);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += a[e] + b[e];
+        }
+        if (r < rows) {
+            float a[V];
+            load16_stream<T>(x + r * C + ch * V, a);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += a[e];
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) s_cs[lane_r * C + ch * V + e] = acc[e];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+        for (int w = 0; w < rl; ++w) t += s_cs[w * C + c];
+        partial[(long long)blockIdx.x * C + c] = t;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_fold_kernel(const float* __restrict__ partial, int nblocks, int C, T* __restrict__ out)
+{
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int slice = threadIdx.x >> 5;
+    __shared__ float s[8][33];
+    float a = 0.f;
+    if (col < C)
+        for (int r = slice; r < nblocks; r += 8) a += partial[(long long)r * C + col];
+    s[slice][threadIdx.x & 31] = a;
+    __syncthreads();
+    if (slice == 0 && col < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
+        out[col] = from_f32<T>(t);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+int colsum_blocks(int dtype, long long rows, int C)
+{
+    const int V = dtype == kF32 ? 4 : 8;
+    if ((dtype != kF32 && dtype != kBF16 && dtype != kF16) || C <= 0 || C % V != 0 || C / V > 256) return 0;
+    const int rl = 256 / (C / V);
+    long long want = (rows + 4LL * rl - 1) / (4LL * rl);     // >= 4 rows per row lane
+    if (want < 1) want = 1;
+    return (int)(want < 148 * 4 ? want : 148 * 4);
+}
+
+template <typename T>
+static cudaError_t launch_colsum(const T* x, long long rows, int C, T* out, float* partial, int blocks, cudaStream_t st)
+{
+    constexpr int V = Vec16<T>::n;
+    const int nch = C / V, rl = 256 / nch;
+    colsum_partial_kernel<T><<<blocks, 256, (size_t)rl * C * sizeof(float), st>>>(x, rows, C, nch, rl, partial);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    colsum_fold_kernel<T><<<(C + 31) / 32, 256, 0, st>>>(partial, blocks, C, out);
+    return cudaGetLastError();
+}
+
+cudaError_t colsum(int dtype, const void* x, long long rows, int C, void* out, float* partial, int blocks,
+                   cudaStream_t st)
+{
+    if (blocks < 1 || blocks > colsum_blocks(dtype, rows, C)) return cudaErrorInvalidValue;
+    switch (dtype) {
+        case kF32:  return launch_colsum<float>((const float*)x, rows, C, (float*)out, partial, blocks, st);
+        case kBF16: return launch_colsum<__nv_bfloat16>((const __nv_bfloat16*)x, rows, C, (__nv_bfloat16*)out, partial, blocks, st);
+        case kF16:  return launch_colsum<__half>((const __half*)x, rows, C, (__half*)out, partial, blocks, st);
+        default:    return cudaErrorInvalidValue;
+    }
+}
+
 static int ln_grid(long long rows)
 {
     int dev = 0, sms = 148;

@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 3; }
+extern "C" int msda_abi_version(void) { return 4; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -227,4 +227,17 @@ extern "C" int msda_fused_forward_paired(int dtype, int raw_dtype, const void* v
                                    num_query, num_point);
     a.out = output;
     return (int)msda::fused_forward_paired(a, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_colsum_blocks(int dtype, int64_t rows, int channels)
+{
+    return rows < 0 ? 0 : msda::colsum_blocks(dtype, (long long)rows, channels);
+}
+
+extern "C" int msda_layer_colsum(int dtype, const void* x, int64_t rows, int channels, void* out,
+                                 float* partial_scratch, int partial_blocks, void* stream)
+{
+    if (rows < 0) return (int)cudaErrorInvalidValue;
+    return (int)msda::colsum(dtype, x, (long long)rows, channels, out, partial_scratch, partial_blocks,
+                             (cudaStream_t)stream);
 }

@@ -107,6 +107,9 @@ struct AddLayerNormArgs {
 int add_layernorm_chunks(int dtype, int C);            // 0 = unsupported shape
 int add_layernorm_partial_blocks(long long rows);
 cudaError_t add_layernorm(const AddLayerNormArgs& a, bool backward, cudaStream_t stream);
+int colsum_blocks(int dtype, long long rows, int C);   // 0 = unsupported shape
+cudaError_t colsum(int dtype, const void* x, long long rows, int C, void* out, float* partial, int blocks,
+                   cudaStream_t stream);
 cudaError_t zero_masked_rows(int dtype, void* data, const unsigned char* mask, long long rows, int C,
                              cudaStream_t stream);
 

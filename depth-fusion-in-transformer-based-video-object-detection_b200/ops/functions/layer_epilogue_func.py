@@ -165,6 +165,57 @@ def zero_masked_rows_(value, mask):
     return value.masked_fill(mask[..., None], float(0))
 
 
+def column_sum(g2):
+    """sum over rows of a contiguous [rows, C] CUDA matrix -> [C] (bias gradient), at HBM rate."""
+    rows, c = g2.shape
+    lib = _lib.load()
+    blocks = lib.msda_layer_colsum_blocks(_DTYPES[g2.dtype], rows, c) if g2.dtype in _DTYPES and g2.is_cuda else 0
+    if blocks == 0 or not g2.is_contiguous() or g2.data_ptr() % 16:
+        return g2.sum(0)
+    with torch.cuda.device(g2.device):
+        out = torch.empty(c, dtype=g2.dtype, device=g2.device)
+        partial = torch.empty((blocks, c), dtype=torch.float32, device=g2.device)
+        code = lib.msda_layer_colsum(_DTYPES[g2.dtype], g2.data_ptr(), rows, c, out.data_ptr(), partial.data_ptr(),
+                                     blocks, torch.cuda.current_stream().cuda_stream)
+    _lib.check(code, "msda_layer_colsum")
+    return out
+
+
+class LinearFunction(Function):
+    """x @ W^T + b as the library GEMM, with a backward that takes the bias gradient from the
+    column-sum kernel instead of PyTorch's generic reduction."""
+
+    @staticmethod
+    def forward(ctx, x2, weight, bias):              # x2 [rows, in] -> fresh [rows, out] (never a view)
+        ctx.save_for_backward(x2, weight)
+        return torch.addmm(bias, x2, weight.t())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g2):
+        x2, weight = ctx.saved_tensors
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        dx = g2 @ weight if ctx.needs_input_grad[0] else None
+        dw = g2.t() @ x2 if ctx.needs_input_grad[1] else None
+        db = column_sum(g2) if ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear_wb(x, weight, bias):
+    """``F.linear(x, weight, bias)``: same GEMM; the custom backward only when gradients flow."""
+    if x.is_cuda and bias is not None and x.dtype == weight.dtype and x.dtype in _DTYPES \
+            and torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad):
+        out = LinearFunction.apply(x.reshape(-1, x.shape[-1]), weight, bias)
+        return out if x.dim() == 2 else out.view(*x.shape[:-1], weight.shape[0])
+    return F.linear(x, weight, bias)
+
+
+def linear(module, x):
+    """``module(x)`` for an ``nn.Linear``."""
+    return linear_wb(x, module.weight, module.bias)
+
+
 class LinearReLUFunction(Function):
     """relu(x @ W^T + b) with bias and ReLU in the GEMM epilogue (cuBLASLt through
     torch._addmm_activation): the pre-activation never reaches HBM."""
@@ -184,7 +235,7 @@ class LinearReLUFunction(Function):
         g = torch.ops.aten.threshold_backward(grad.reshape(out.shape), out, 0)
         dx = g @ weight if ctx.needs_input_grad[0] else None
         dw = g.t() @ x2 if ctx.needs_input_grad[1] else None
-        db = g.sum(0) if ctx.needs_input_grad[2] else None
+        db = column_sum(g) if ctx.needs_input_grad[2] else None
         return (None if dx is None else dx.view(ctx.x_shape)), dw, db
 
 

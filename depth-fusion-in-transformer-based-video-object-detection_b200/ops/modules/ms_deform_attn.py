@@ -27,7 +27,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported, zero_masked_rows_
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported, linear, linear_wb, zero_masked_rows_
 
 
 def _is_power_of_2(n):
@@ -144,9 +144,11 @@ class MSDeformAttn(nn.Module):
         N, Len_in, _ = input_flatten.shape
         assert _total_pixels(input_spatial_shapes) == Len_in
 
-        value = self.value_proj(input_flatten)
+        # 2-d in, 2-d out: the projection result is a fresh tensor (not a view), so the padding rows
+        # can be zeroed in place without autograd having to copy slices back
+        value = linear(self.value_proj, input_flatten.reshape(N * Len_in, -1))
         if input_padding_mask is not None:
-            value = zero_masked_rows_(value, input_padding_mask)      # in place on the fresh projection
+            value = zero_masked_rows_(value, input_padding_mask.reshape(-1))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(
@@ -156,13 +158,13 @@ class MSDeformAttn(nn.Module):
             # [ offsets | logits ] from one GEMM; parameters stay separate for checkpoint compatibility
             weight = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
             bias = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
-            raw = F.linear(query, weight, bias)
+            raw = linear_wb(query, weight, bias)
             if raw.dtype != value.dtype and value.dtype == torch.float32:
                 raw = raw.float()
             if fused_supported(value, raw, reference_points.shape[-1], self.n_levels, self.n_points):
                 output = MSDeformAttnFusedFunction.apply(
                     value, input_spatial_shapes, input_level_start_index, reference_points, raw, self.n_points)
-                return self.output_proj(output)
+                return linear(self.output_proj, output)
             split = self.n_heads * self.n_levels * self.n_points * 2
             offsets = raw[..., :split].reshape(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
             attention = raw[..., split:].reshape(N, Len_q, self.n_heads, self.n_levels * self.n_points)
@@ -171,7 +173,7 @@ class MSDeformAttn(nn.Module):
             output = MSDeformAttnFunction.apply(
                 value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
                 attention.contiguous(), self.im2col_step)
-            return self.output_proj(output)
+            return linear(self.output_proj, output)
 
         offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         attention = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
@@ -180,4 +182,4 @@ class MSDeformAttn(nn.Module):
         output = MSDeformAttnFunction.apply(
             value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
             attention.contiguous(), self.im2col_step)
-        return self.output_proj(output)
+        return linear(self.output_proj, output)

@@ -25,7 +25,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .ops.functions import add_layer_norm, linear_relu
+from .ops.functions import add_layer_norm, linear, linear_relu
 from .ops.modules import MSDeformAttn
 from .ops.modules.ms_deform_attn import host_shape_list
 
@@ -92,8 +92,8 @@ class DeformableTransformerEncoderLayer(nn.Module):
     def forward_ffn(self, src, pos=None):
         """norm2(src + linear2(act(linear1(src)))); with ``pos`` also returns that + pos."""
         hidden = linear_relu(self.linear1, src) if self._activation_name == "relu" \
-            else self.activation(self.linear1(src))
-        return add_layer_norm(self.norm2, self.dropout3(self.linear2(self.dropout2(hidden))), src, None, pos)
+            else self.activation(linear(self.linear1, src))
+        return add_layer_norm(self.norm2, self.dropout3(linear(self.linear2, self.dropout2(hidden))), src, None, pos)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
                 rgbd_src=None, query=None, emit_query=False):
@@ -168,17 +168,17 @@ class _CrossModalFusion(nn.Module):
     def forward_ffn(self, tgt):
         drop, norm = getattr(self, self._ffn_dropout), getattr(self, self._ffn_norm)
         if drop.training and drop.p > 0:
-            return add_layer_norm(norm, drop(self.activation(self.linear1(tgt))), tgt)
-        return add_layer_norm(norm, self.linear1(tgt), tgt, "gelu")       # GELU inside the norm kernel
+            return add_layer_norm(norm, drop(self.activation(linear(self.linear1, tgt))), tgt)
+        return add_layer_norm(norm, linear(self.linear1, tgt), tgt, "gelu")       # GELU inside the norm kernel
 
     def _fuse(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
               query=None):
-        src = add_layer_norm(self.norm_depth_scale, self.depth_scale_adapt(src))
+        src = add_layer_norm(self.norm_depth_scale, linear(self.depth_scale_adapt, src))
         if query is None:
             query = _add_pos(tgt, query_pos)
         sampled = self.cross_attn(query, reference_points, src, src_spatial_shapes, level_start_index,
                                   src_padding_mask)
-        tgt = add_layer_norm(self.norm1, self.dropout1(self.cross_scale_adapt(sampled)), tgt)
+        tgt = add_layer_norm(self.norm1, self.dropout1(linear(self.cross_scale_adapt, sampled)), tgt)
         return self.forward_ffn(tgt)
 
 
@@ -287,8 +287,8 @@ class DeformableTransformerDecoderLayer(nn.Module):
 
     def forward_ffn(self, tgt, pos=None):
         hidden = linear_relu(self.linear1, tgt) if self._activation_name == "relu" \
-            else self.activation(self.linear1(tgt))
-        return add_layer_norm(self.norm3, self.dropout4(self.linear2(self.dropout3(hidden))), tgt, None, pos)
+            else self.activation(linear(self.linear1, tgt))
+        return add_layer_norm(self.norm3, self.dropout4(linear(self.linear2, self.dropout3(hidden))), tgt, None, pos)
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
                 src_padding_mask=None, qk=None, emit_qk=False):

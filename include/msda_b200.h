@@ -184,6 +184,15 @@ int msda_layer_add_layernorm_backward(int dtype, int act,
                                       void* grad_gamma, void* grad_beta,
                                       float* partial_scratch, int partial_blocks, void* stream);
 
+/* out[c] = sum over rows of x[row, c]: the bias gradient of the Linear layers around the deformable
+ * attention (PyTorch's autograd computes it with a generic reduction; this is the HBM-rate version).
+ * x [rows, channels] and out [channels] of `dtype` (F32 / BF16 / F16), fp32 accumulation.
+ * partial_scratch: fp32 [partial_blocks, channels], partial_blocks = msda_layer_colsum_blocks(...)
+ * (0 = shape not supported: channels*itemsize must be a multiple of 16 and at most 4096 bytes). */
+int msda_layer_colsum_blocks(int dtype, int64_t rows, int channels);
+int msda_layer_colsum(int dtype, const void* x, int64_t rows, int channels, void* out,
+                      float* partial_scratch, int partial_blocks, void* stream);
+
 /* value.masked_fill(padding_mask[..., None], 0) of MSDeformAttn.forward
  * (/root/reference/models/ops/modules/ms_deform_attn.py:95-96), in place: rows of data[rows, channels]
  * whose mask byte is non-zero are overwritten with zeros; only the mask and those rows are touched. */

@@ -7,7 +7,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from dfvod_b200.ops.functions import add_layer_norm, linear_relu, zero_masked_rows_
+from dfvod_b200.ops.functions import add_layer_norm, column_sum, linear, linear_relu, zero_masked_rows_
 from dfvod_b200.ops.functions import layer_epilogue_func as lef
 
 pytestmark = pytest.mark.gpu
@@ -145,3 +145,43 @@ def test_linear_relu(dtype):
     assert nerr(x.grad, x64.grad) <= tol * 4
     assert nerr(lin.weight.grad, lin64.weight.grad) <= tol * 4
     assert nerr(lin.bias.grad, lin64.bias.grad) <= tol * 4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,c", [(1041, 256), (5, 384), (88892, 1024), (300, 128), (7, 2048), (33, 96)])
+def test_column_sum(dtype, rows, c):
+    torch.manual_seed(rows + c)
+    x = torch.randn(rows, c, device=DEV).to(dtype)
+    got = column_sum(x)
+    ref = x.double().sum(0)
+    # the result is rounded once to the storage type; accumulation is fp32
+    tol = 1e-5 if dtype == torch.float32 else (2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -10)
+    assert got.shape == (c,) and got.dtype == dtype
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) <= tol
+
+
+def test_column_sum_unsupported_width_uses_torch():
+    x = torch.randn(10, 30, device=DEV)
+    assert torch.allclose(column_sum(x), x.sum(0))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_custom_backward(dtype):
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(256, 384).to(DEV).to(dtype)
+    x = torch.randn(4, 513, 256, device=DEV).to(dtype).requires_grad_(True)
+    out = linear(lin, x)
+    g = torch.randn_like(out)
+    out.backward(g)
+    got = (x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    x.grad = None
+    lin.zero_grad()
+    ref_out = lin(x)
+    ref_out.backward(g)
+    assert torch.equal(out, ref_out)
+    assert torch.equal(got[0], x.grad) and torch.equal(got[1], lin.weight.grad)
+    tol = 1e-5 if dtype == torch.float32 else 2.0 ** -7
+    assert nerr(got[2], lin.bias.grad.double()) <= tol
+    # no autograd: plain module call
+    with torch.no_grad():
+        assert torch.equal(linear(lin, x), ref_out)
