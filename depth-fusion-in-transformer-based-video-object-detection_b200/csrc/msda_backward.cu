@@ -35,8 +35,10 @@ namespace msda {
 
 template <int PAIRS> struct BwdWarps { static constexpr int value = PAIRS >= 16 ? 2 : (PAIRS >= 8 ? 4 : 8); };
 
+// resident CTAs per SM the register allocation must allow: 3 x 8 warps (<= 80 registers) measured
+// best on B200 (tools/ab_variants.sh: fp32 1.90 -> 1.74 ms, bf16 1.88 -> 1.76 ms vs 2 x 8 warps at 128)
 #ifndef MSDA_BWD_MINBLOCKS
-#define MSDA_BWD_MINBLOCKS 2
+#define MSDA_BWD_MINBLOCKS 3
 #endif
 #ifndef MSDA_CTA_PER_HEAD      // see msda_forward.cu
 #define MSDA_CTA_PER_HEAD 1
@@ -73,6 +75,19 @@ struct GradDst {
 //   softmax backward   g_logit = a * (g_a - sum_j a_j g_a_j)                      :99-100
 // to the finished per-sample gradients in phase 3, so neither the locations / weights nor their
 // gradients ever exist in HBM.
+// Samples per pass.  8 (instead of the forward's 16) halves the per-lane partial-sum registers
+// (3 per sample) and lets a lane keep its own samples' weights in registers between phases: the
+// kernel is bound by load latency under RED traffic (ncu: long-scoreboard stalls, 15 resident
+// warps at 128 registers), so registers buy resident warps.  3*CH must be divisible by G.
+#ifndef MSDA_BWD_CHUNK
+#define MSDA_BWD_CHUNK 8
+#endif
+// samples gathered together per lane: 2 for 16-bit values (8-byte loads), 1 for fp32 (2 would spill
+// at the 80-register budget)
+#ifndef MSDA_BWD_UNROLL
+#define MSDA_BWD_UNROLL 0
+#endif
+
 template <typename VT, int D, bool FUSED, typename RT>
 __global__ void __launch_bounds__(BwdWarps<32 / (D / 4)>::value * 32, MSDA_BWD_MINBLOCKS)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
@@ -85,12 +100,17 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     constexpr int G = D / EPL;
     constexpr int PAIRS = 32 / G;
     constexpr int WARPS = BwdWarps<PAIRS>::value;
-    constexpr int SPL = kChunk / G;              // finished samples per lane after the reduce-scatter
+    constexpr int CH = MSDA_BWD_CHUNK > G ? MSDA_BWD_CHUNK : G;   // samples per pass
+    constexpr int SPL = CH / G;                  // samples a lane owns per pass: j = sub*SPL + i, in phase 1
+                                                 // (footprints) and again after the reduce-scatter (gradients)
+    constexpr int FCH = (kChunk + CH - 1) / CH;  // passes of the fused op (host guarantees L*P <= kChunk)
+    constexpr int U = MSDA_BWD_UNROLL > 0 ? MSDA_BWD_UNROLL : (sizeof(VT) == 2 ? 2 : 1);
     static_assert(G >= 1 && G <= 16 && (G & (G - 1)) == 0, "fast backward needs 1..16 lanes per head");
+    static_assert(CH % G == 0 && CH % U == 0, "pass size must split evenly over the lanes and the unroll");
 
     __shared__ int s_meta[3 * kMaxLevelsFast];
-    __shared__ __align__(16) int4   s_geo[WARPS][PAIRS][kChunk + 1];   // pix00, rowstep, ok, -
-    __shared__ __align__(16) float4 s_frac[WARPS][PAIRS][kChunk + 1];  // lw, lh, a, -
+    __shared__ __align__(16) int4   s_geo[WARPS][PAIRS][CH + 1];   // pix00, rowstep, ok, -
+    __shared__ __align__(16) float4 s_frac[WARPS][PAIRS][CH + 1];  // lw, lh, a, -
 
     if (threadIdx.x < L) {
         s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
@@ -140,36 +160,48 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         for (int c = 0; c < EPL; ++c) g[c] = 0.f;     // clamped duplicate pair contributes nothing
     }
 
-    for (int s0 = 0; s0 < LP; s0 += kChunk) {
-        const int cnt = min(kChunk, LP - s0);
-        const int cnt2 = (cnt + 1) & ~1;
-        // ---- phase 1: footprints --------------------------------------------------------------
-        constexpr int K = (kChunk + G - 1) / G;
-        float prob[K];
-        float inv_sum = 1.f;
-        if constexpr (FUSED) {                           // L*P <= kChunk: a single chunk
-            float mx = -INFINITY;
+    // fused: softmax over the pair's L*P logits; this lane keeps the numerators of its own samples
+    float prob[FCH * SPL];
+    float inv_sum = 1.f;
+    if constexpr (FUSED) {
+        float mx = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int j = sub + k * G;
-                prob[k] = j < cnt ? load_raw1<RT>(gp + j) : -INFINITY;
-                mx = fmaxf(mx, prob[k]);
-            }
-            mx = group_max<G>(mx);
-            float sum = 0.f;
+        for (int c = 0; c < FCH; ++c)
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                prob[k] = (sub + k * G) < cnt ? expf(prob[k] - mx) : 0.f;
-                sum += prob[k];
+            for (int i = 0; i < SPL; ++i) {
+                const int s = c * CH + sub * SPL + i;
+                prob[c * SPL + i] = s < LP ? load_raw1<RT>(gp + s) : -INFINITY;
+                mx = fmaxf(mx, prob[c * SPL + i]);
             }
-            inv_sum = group_sum<G>(sum);
+        mx = group_max<G>(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < FCH * SPL; ++k) {
+            prob[k] = prob[k] == -INFINITY ? 0.f : expf(prob[k] - mx);
+            sum += prob[k];
         }
+        inv_sum = group_sum<G>(sum);
+    }
+    // fused: finished per-sample gradients of this lane's own samples, kept until the softmax
+    // backward can be applied (it needs sum_j a_j * g_a_j over the whole pair)
+    float fin_x[FCH * SPL], fin_y[FCH * SPL], fin_a[FCH * SPL], own_a[FCH * SPL];
+
+    const int passes = FUSED ? FCH : (LP + CH - 1) / CH;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int j = sub + k * G;
-            if (j >= cnt2) break;
+    for (int c = 0; c < (FUSED ? FCH : 1 << 30); ++c) {
+        if (c >= passes) break;
+        const int s0 = c * CH;
+        if (FUSED && s0 >= LP) break;
+        const int cnt = min(CH, LP - s0);
+        const int cntu = (cnt + U - 1) / U * U;
+        // ---- phase 1: footprints of this lane's own samples ------------------------------------
+        float a_own[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            const int j = sub * SPL + i;
             int4 geo = make_int4(0, 0, 0, 0);
             float4 fr = make_float4(0.f, 0.f, 0.f, 0.f);
+            a_own[i] = 0.f;
             if (j < cnt) {
                 const int s = s0 + j;
                 const int l = div_by_points(s, p_magic);
@@ -178,7 +210,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                 if constexpr (FUSED) {
                     xy = fused_location(load_raw2<RT>(op + 2 * s), src.ref + (nq * L + l) * src.ref_dim, src.ref_dim,
                                         s_meta[3 * l], s_meta[3 * l + 1], P);
-                    a = prob[k] / inv_sum;
+                    a = prob[c * SPL + i] / inv_sum;
                 } else {
                     xy = ldg_stream_f32x2(lp + 2 * s);
                     a = ldg_stream_f32(ap + s);
@@ -186,25 +218,26 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                 const Footprint f = footprint<float>(xy.x, xy.y, s_meta[3 * l], s_meta[3 * l + 1], s_meta[3 * l + 2]);
                 geo = make_int4(f.pix00, f.rowstep, (int)f.ok, 0);
                 fr = make_float4(f.lw, f.lh, a, 0.f);
+                a_own[i] = a;
             }
-            s_geo[warp][grp][j] = geo;
+            s_geo[warp][grp][j] = geo;                 // samples past cnt: ok = 0 -> no loads, no reductions
             s_frac[warp][grp][j] = fr;
         }
         __syncwarp();
 
         // ---- phase 2: per-sample gather, dot products, vector reductions into grad_value -----
-        float part[3 * kChunk];
+        float part[3 * CH];
 #pragma unroll
-        for (int i = 0; i < 3 * kChunk; ++i) part[i] = 0.f;
+        for (int i = 0; i < 3 * CH; ++i) part[i] = 0.f;
 
 #pragma unroll
-        for (int j0 = 0; j0 < kChunk; j0 += 2) {
-            if (j0 < cnt2) {
-                int4 geo[2];
-                float4 fr[2];
-                typename SliceT::raw_t raw[2][4];
+        for (int j0 = 0; j0 < CH; j0 += U) {
+            if (j0 < cntu) {
+                int4 geo[U];
+                float4 fr[U];
+                typename SliceT::raw_t raw[U][4];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < U; ++u) {
                     geo[u] = s_geo[warp][grp][j0 + u];
                     fr[u] = s_frac[warp][grp][j0 + u];
                     const VT* p00 = vbase + (long long)geo[u].x * MD;
@@ -215,7 +248,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     raw[u][3] = (geo[u].z & 8) ? SliceT::load(p00 + row + MD) : SliceT::zero();
                 }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const float lw = fr[u].x, lh = fr[u].y, a = fr[u].z;
                     const float hw = 1.f - lw, hh = 1.f - lh;
                     const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
@@ -226,14 +259,14 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     SliceT::unpack(raw[u][3], v4);
                     float px = 0.f, py = 0.f, pa = 0.f;
 #pragma unroll
-                    for (int c = 0; c < EPL; ++c) {
-                        tg[c] = a * g[c];                                        // cuh:113
-                        const float val = w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c];
-                        const float dx = hh * (v2[c] - v1[c]) + lh * (v4[c] - v3[c]);   // cuh:119-151 (grad_w_weight)
-                        const float dy = hw * (v3[c] - v1[c]) + lw * (v4[c] - v2[c]);   // (grad_h_weight)
-                        pa = fmaf(g[c], val, pa);
-                        px = fmaf(tg[c], dx, px);
-                        py = fmaf(tg[c], dy, py);
+                    for (int ch = 0; ch < EPL; ++ch) {
+                        tg[ch] = a * g[ch];                                        // cuh:113
+                        const float val = w1 * v1[ch] + w2 * v2[ch] + w3 * v3[ch] + w4 * v4[ch];
+                        const float dx = hh * (v2[ch] - v1[ch]) + lh * (v4[ch] - v3[ch]);   // cuh:119-151 (grad_w_weight)
+                        const float dy = hw * (v3[ch] - v1[ch]) + lw * (v4[ch] - v2[ch]);   // (grad_h_weight)
+                        pa = fmaf(g[ch], val, pa);
+                        px = fmaf(tg[ch], dx, px);
+                        py = fmaf(tg[ch], dy, py);
                     }
                     part[3 * (j0 + u) + 0] = px;
                     part[3 * (j0 + u) + 1] = py;
@@ -252,8 +285,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         }
         __syncwarp();
 
-        // ---- phase 3: combine the group's partials; each lane finishes SPL samples -----------
-        reduce_scatter<3 * kChunk, G / 2>(part, sub);
+        // ---- phase 3: combine the group's partials; each lane finishes its own SPL samples ----
+        reduce_scatter<3 * CH, G / 2>(part, sub);
         if constexpr (!FUSED) {
             float* grad_loc = static_cast<float*>(dst.loc);
             float* grad_attn = static_cast<float*>(dst.attn);
@@ -272,61 +305,70 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                 }
             }
         } else {
-            // softmax backward needs sum_j a_j * g_a_j over the pair's samples
-            float dot = 0.f;
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
-                const int j = sub * SPL + i;
-                if (j < cnt) dot = fmaf(s_frac[warp][grp][j].z, part[3 * i + 2], dot);
+                fin_x[c * SPL + i] = part[3 * i + 0];
+                fin_y[c * SPL + i] = part[3 * i + 1];
+                fin_a[c * SPL + i] = part[3 * i + 2];
+                own_a[c * SPL + i] = a_own[i];
             }
-            dot = group_sum<G>(dot);
-            if (active) {
-                RT* gop = static_cast<RT*>(dst.loc) + nq * src.loc_stride + (long long)m * LP * 2;
-                RT* ggp = static_cast<RT*>(dst.attn) + nq * src.attn_stride + (long long)m * LP;
-                int run_l = -1;                       // lane-local run of samples on one level -> one grad_ref update
-                float rx = 0.f, ry = 0.f, rw = 0.f, rh = 0.f;
-                auto flush_ref = [&]() {
-                    if (dst.ref != nullptr && run_l >= 0) {
-                        float* gr = dst.ref + (nq * L + run_l) * src.ref_dim;
-                        atomicAdd(gr, rx);
-                        atomicAdd(gr + 1, ry);
-                        if (src.ref_dim == 4) { atomicAdd(gr + 2, rw); atomicAdd(gr + 3, rh); }
-                    }
-                };
+        }
+    }
+
+    if constexpr (FUSED) {
+        // softmax backward needs sum_j a_j * g_a_j over the pair's samples
+        float dot = 0.f;
 #pragma unroll
-                for (int i = 0; i < SPL; ++i) {
-                    const int j = sub * SPL + i;
-                    if (j < cnt) {
-                        const int s = s0 + j;
-                        const int l = div_by_points(s, p_magic);
-                        const float Hf = (float)s_meta[3 * l], Wf = (float)s_meta[3 * l + 1];
-                        const float glx = Wf * part[3 * i + 0], gly = Hf * part[3 * i + 1];   // d/d loc
-                        const float a = s_frac[warp][grp][j].z;
-                        const float glogit = a * (part[3 * i + 2] - dot);
-                        float gox, goy, gwx = 0.f, gwy = 0.f;
-                        if (src.ref_dim == 2) {
-                            gox = glx / Wf;
-                            goy = gly / Hf;
-                        } else {
-                            const float4 r = *reinterpret_cast<const float4*>(src.ref + (nq * L + l) * 4);
-                            gox = glx * (r.z * 0.5f / (float)P);
-                            goy = gly * (r.w * 0.5f / (float)P);
-                            if (dst.ref != nullptr) {
-                                const float2 off = load_raw2<RT>(op + 2 * s);
-                                gwx = glx * (off.x / (float)P * 0.5f);
-                                gwy = gly * (off.y / (float)P * 0.5f);
-                            }
-                        }
-                        store_raw2<RT>(gop + 2 * s, gox, goy);
-                        ggp[s] = from_f32<RT>(glogit);
+        for (int k = 0; k < FCH * SPL; ++k) {
+            const int s = (k / SPL) * CH + sub * SPL + (k % SPL);
+            if (s < LP) dot = fmaf(own_a[k], fin_a[k], dot);
+        }
+        dot = group_sum<G>(dot);
+        if (active) {
+            RT* gop = static_cast<RT*>(dst.loc) + nq * src.loc_stride + (long long)m * LP * 2;
+            RT* ggp = static_cast<RT*>(dst.attn) + nq * src.attn_stride + (long long)m * LP;
+            int run_l = -1;                       // lane-local run of samples on one level -> one grad_ref update
+            float rx = 0.f, ry = 0.f, rw = 0.f, rh = 0.f;
+            auto flush_ref = [&]() {
+                if (dst.ref != nullptr && run_l >= 0) {
+                    float* gr = dst.ref + (nq * L + run_l) * src.ref_dim;
+                    atomicAdd(gr, rx);
+                    atomicAdd(gr + 1, ry);
+                    if (src.ref_dim == 4) { atomicAdd(gr + 2, rw); atomicAdd(gr + 3, rh); }
+                }
+            };
+#pragma unroll
+            for (int k = 0; k < FCH * SPL; ++k) {
+                const int s = (k / SPL) * CH + sub * SPL + (k % SPL);
+                if (s < LP) {
+                    const int l = div_by_points(s, p_magic);
+                    const float Hf = (float)s_meta[3 * l], Wf = (float)s_meta[3 * l + 1];
+                    const float glx = Wf * fin_x[k], gly = Hf * fin_y[k];                     // d/d loc
+                    const float a = own_a[k];
+                    const float glogit = a * (fin_a[k] - dot);
+                    float gox, goy, gwx = 0.f, gwy = 0.f;
+                    if (src.ref_dim == 2) {
+                        gox = glx / Wf;
+                        goy = gly / Hf;
+                    } else {
+                        const float4 r = *reinterpret_cast<const float4*>(src.ref + (nq * L + l) * 4);
+                        gox = glx * (r.z * 0.5f / (float)P);
+                        goy = gly * (r.w * 0.5f / (float)P);
                         if (dst.ref != nullptr) {
-                            if (l != run_l) { flush_ref(); run_l = l; rx = ry = rw = rh = 0.f; }
-                            rx += glx; ry += gly; rw += gwx; rh += gwy;
+                            const float2 off = load_raw2<RT>(op + 2 * s);
+                            gwx = glx * (off.x / (float)P * 0.5f);
+                            gwy = gly * (off.y / (float)P * 0.5f);
                         }
+                    }
+                    store_raw2<RT>(gop + 2 * s, gox, goy);
+                    ggp[s] = from_f32<RT>(glogit);
+                    if (dst.ref != nullptr) {
+                        if (l != run_l) { flush_ref(); run_l = l; rx = ry = rw = rh = 0.f; }
+                        rx += glx; ry += gly; rw += gwx; rh += gwy;
                     }
                 }
-                flush_ref();
             }
+            flush_ref();
         }
     }
 }
