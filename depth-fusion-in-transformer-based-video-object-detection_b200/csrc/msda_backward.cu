@@ -35,10 +35,11 @@ namespace msda {
 
 template <int PAIRS> struct BwdWarps { static constexpr int value = PAIRS >= 16 ? 2 : (PAIRS >= 8 ? 4 : 8); };
 
-// resident CTAs per SM the register allocation must allow: 3 x 8 warps (<= 80 registers) measured
-// best on B200 (tools/ab_variants.sh: fp32 1.90 -> 1.74 ms, bf16 1.88 -> 1.76 ms vs 2 x 8 warps at 128)
+// resident CTAs per SM the register allocation must allow.  Measured on B200 (tools/ab_variants.sh,
+// fp32 / bf16 backward, batch 8): 2 x 8 warps at 128 registers 1.90 / 1.88 ms; 3 x 8 warps at 80
+// registers 1.74 / 1.76 ms; 4 x 8 warps at 64 registers (immediate reduction, no spills) 1.70 / 1.75 ms.
 #ifndef MSDA_BWD_MINBLOCKS
-#define MSDA_BWD_MINBLOCKS 3
+#define MSDA_BWD_MINBLOCKS 4
 #endif
 #ifndef MSDA_CTA_PER_HEAD      // see msda_forward.cu
 #define MSDA_CTA_PER_HEAD 1
@@ -82,10 +83,16 @@ struct GradDst {
 #ifndef MSDA_BWD_CHUNK
 #define MSDA_BWD_CHUNK 8
 #endif
-// samples gathered together per lane: 2 for 16-bit values (8-byte loads), 1 for fp32 (2 would spill
-// at the 80-register budget)
+// samples gathered together per lane (2 spills at the 64-register budget)
 #ifndef MSDA_BWD_UNROLL
-#define MSDA_BWD_UNROLL 0
+#define MSDA_BWD_UNROLL 1
+#endif
+
+// 1: reduce each sample's three dot products across the group right away (3 butterflies per
+// sample) instead of keeping 3*CH partials per lane for one reduce-scatter per pass: more shuffles,
+// 24 fewer registers.
+#ifndef MSDA_BWD_IMMEDIATE
+#define MSDA_BWD_IMMEDIATE 1
 #endif
 
 template <typename VT, int D, bool FUSED, typename RT>
@@ -104,7 +111,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     constexpr int SPL = CH / G;                  // samples a lane owns per pass: j = sub*SPL + i, in phase 1
                                                  // (footprints) and again after the reduce-scatter (gradients)
     constexpr int FCH = (kChunk + CH - 1) / CH;  // passes of the fused op (host guarantees L*P <= kChunk)
-    constexpr int U = MSDA_BWD_UNROLL > 0 ? MSDA_BWD_UNROLL : (sizeof(VT) == 2 ? 2 : 1);
+    constexpr int U = MSDA_BWD_UNROLL;
     static_assert(G >= 1 && G <= 16 && (G & (G - 1)) == 0, "fast backward needs 1..16 lanes per head");
     static_assert(CH % G == 0 && CH % U == 0, "pass size must split evenly over the lanes and the unroll");
 
@@ -226,9 +233,15 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         __syncwarp();
 
         // ---- phase 2: per-sample gather, dot products, vector reductions into grad_value -----
+#if MSDA_BWD_IMMEDIATE
+        float part[3 * SPL];
+#pragma unroll
+        for (int i = 0; i < 3 * SPL; ++i) part[i] = 0.f;
+#else
         float part[3 * CH];
 #pragma unroll
         for (int i = 0; i < 3 * CH; ++i) part[i] = 0.f;
+#endif
 
 #pragma unroll
         for (int j0 = 0; j0 < CH; j0 += U) {
@@ -268,9 +281,20 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                         px = fmaf(tg[ch], dx, px);
                         py = fmaf(tg[ch], dy, py);
                     }
+#if MSDA_BWD_IMMEDIATE
+                    px = group_sum<G>(px);
+                    py = group_sum<G>(py);
+                    pa = group_sum<G>(pa);
+                    if ((j0 + u) / SPL == sub) {
+                        part[3 * ((j0 + u) % SPL) + 0] = px;
+                        part[3 * ((j0 + u) % SPL) + 1] = py;
+                        part[3 * ((j0 + u) % SPL) + 2] = pa;
+                    }
+#else
                     part[3 * (j0 + u) + 0] = px;
                     part[3 * (j0 + u) + 1] = py;
                     part[3 * (j0 + u) + 2] = pa;
+#endif
                     float* q00 = gbase + (long long)geo[u].x * MD;
                     const long long row = (long long)geo[u].y * MD;
                     const float wk[4] = {w1, w2, w3, w4};
@@ -286,7 +310,9 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         __syncwarp();
 
         // ---- phase 3: combine the group's partials; each lane finishes its own SPL samples ----
+#if !MSDA_BWD_IMMEDIATE
         reduce_scatter<3 * CH, G / 2>(part, sub);
+#endif
         if constexpr (!FUSED) {
             float* grad_loc = static_cast<float*>(dst.loc);
             float* grad_attn = static_cast<float*>(dst.attn);
