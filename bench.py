@@ -358,7 +358,7 @@ def train_step_extras(torch, dev, world, dist, n_frames=4, iters=5):
     torch.manual_seed(4)                      # identical initial weights on every rank
     model = DeformableTransformer(num_feature_levels=4, return_intermediate_dec=True, use_depth=True, dropout=0.0,
                                   depth_type="DepthDeform_encoder_cf_dformer").to(dev).bfloat16()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5, fused=True)
     reducer = data_parallel.GradientAllReducer(model.parameters())
     rank = dist.get_rank() if world > 1 else 0
     bf = torch.bfloat16
@@ -377,9 +377,20 @@ def train_step_extras(torch, dev, world, dist, n_frames=4, iters=5):
 
     ms = _reduce_max(torch, dist, world, dev, _time_events(torch, step, iters, 2))
     reducer.remove()
-    return {"frames_per_gpu": n_frames, "ms_per_step": ms, "frames_per_s": n_frames * world / ms * 1e3,
-            "gradient_bytes": reducer.gradient_bytes, "dtype": "bf16",
-            "collective": "bucketed all-reduce (NCCL)" if world > 1 else "none (1 GPU)"}
+    out = {"frames_per_gpu": n_frames, "eager_ms_per_step": ms, "eager_frames_per_s": n_frames * world / ms * 1e3,
+           "gradient_bytes": reducer.gradient_bytes, "dtype": "bf16",
+           "collective": "bucketed all-reduce (NCCL)" if world > 1 else "none (1 GPU)"}
+    try:       # the same step with forward + backward replayed from a CUDA graph (host-launch bound otherwise)
+        loss_fn = lambda: model(srcs, masks, poss, dsrcs, dmasks, dposs, query)[0].float().square().mean()
+        graphed = data_parallel.GraphedTrainStep(model, opt, loss_fn)
+        ms = _reduce_max(torch, dist, world, dev, _time_events(torch, graphed, iters, 2))
+        out["ms_per_step"] = ms
+        out["frames_per_s"] = n_frames * world / ms * 1e3
+        out["mode"] = "CUDA graph (fwd+bwd) + flat-buffer all-reduce + AdamW"
+    except Exception as exc:      # report, do not hide
+        out["graph_error"] = repr(exc)[:200]
+        out["ms_per_step"], out["frames_per_s"] = out["eager_ms_per_step"], out["eager_frames_per_s"]
+    return out
 
 
 def run_b200(args):
