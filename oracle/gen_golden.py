@@ -63,6 +63,24 @@ def import_reference():
     return func, mod, single, backbone_cf
 
 
+def import_transvod_plusplus():
+    """models/deformable_transformer_multi_plusplus.py does ``from mmcv import ops`` (:25) for the
+    RoIAlign of the temporal query stage (out of scope); mmcv is not installed, so a stub module
+    stands in -- the temporal decoder (:1030-1076) never touches it."""
+    mmcv = types.ModuleType("mmcv")
+    ops = types.ModuleType("mmcv.ops")
+
+    class RoIAlign:
+        def __init__(self, *a, **k):
+            raise RuntimeError("mmcv stub: RoIAlign is outside the golden cases")
+
+    ops.RoIAlign = RoIAlign
+    mmcv.ops = ops
+    sys.modules.setdefault("mmcv", mmcv)
+    sys.modules.setdefault("mmcv.ops", ops)
+    return importlib.import_module("models.deformable_transformer_multi_plusplus")
+
+
 def lsi_of(shapes):
     return torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
 
@@ -116,9 +134,25 @@ def grid_reference_points(single, shapes_t, n, dtype):
     return ref.to(dtype)
 
 
-def save_module_case(name, module, inputs, call, wrt):
+def round_to_f32(module, inputs):
+    """Make every parameter and floating-point input exactly fp32-representable (so that an fp32
+    copy of the case is lossless) while the reference still computes in fp64."""
+    with torch.no_grad():
+        for prm in module.parameters():
+            prm.copy_(prm.float().double())
+    return {k: (v.float().double() if torch.is_tensor(v) and v.dtype == torch.float64 else v)
+            for k, v in inputs.items()}
+
+
+def save_module_case(name, module, inputs, call, wrt, store=None, grad_limit=None):
     """Run ``call(module, **inputs)``, save inputs/state/output and the gradients of
-    sum(output * gout) w.r.t. the tensors named in ``wrt`` and every parameter."""
+    sum(output * gout) w.r.t. the tensors named in ``wrt`` and every parameter.
+    ``store=np.float32`` (wide cases): parameters and inputs are first rounded to fp32-representable
+    values, the reference computes in fp64, and the file keeps fp32 copies (lossless for inputs and
+    state, 1e-7 for outputs / gradients -- these cases serve the fp32 / bf16 tests only).
+    ``grad_limit``: parameter gradients larger than this many elements are not stored."""
+    if store is not None:
+        inputs = round_to_f32(module, inputs)
     tensors = {k: (v.clone().requires_grad_(True) if k in wrt else v) for k, v in inputs.items()}
     out = call(module, tensors)
     g = torch.Generator().manual_seed(1234)
@@ -132,7 +166,11 @@ def save_module_case(name, module, inputs, call, wrt):
     for k, gr in zip(wrt, grads[:len(wrt)]):
         blob[f"grad_in.{k}"] = (gr if gr is not None else torch.zeros(())).numpy()
     for (pname, _), gr in zip(module.named_parameters(), grads[len(wrt):]):
+        if grad_limit is not None and gr is not None and gr.numel() > grad_limit and "value_proj" not in pname:
+            continue
         blob[f"grad_param.{pname}"] = (gr if gr is not None else torch.zeros(())).numpy()
+    if store is not None:
+        blob = {k: (v.astype(store) if v.dtype == np.float64 else v) for k, v in blob.items()}
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **blob)
     print(f"{name}: out {tuple(out.shape)} |out|max {out.abs().max():.3e}")
 
@@ -362,6 +400,133 @@ def main():
     transformer_case("transformer_baseline", "Baseline_rgb", False, [(6, 5), (3, 3)], 50)
     transformer_case("transformer_latefusion", "DepthDeform_latefusion_dformer", True, [(4, 6)], 52)
     transformer_case("transformer_encoder_cf", "DepthDeform_encoder_cf_dformer", True, [(4, 6)], 54)
+
+    # ---------------- head width 16 at d_model 128 / 8 heads / 4 points: the narrowest layers for which
+    # BOTH the fused deformable-attention kernels and the fused layer-epilogue kernels (residual +
+    # LayerNorm [+ activation] [+ next query], fp32: 128 channels) run in the fp32 tests ------------
+    cw, hw_, pw, ffw = 128, 8, 4, 128
+    torch.manual_seed(61)
+    feat_w = torch.randn(n, s, cw)
+    pos_w = torch.randn(n, s, cw)
+    enc_w = single.DeformableTransformerEncoderLayer(cw, ffw, 0.0, "relu", 2, hw_, pw).double()
+    perturb(enc_w, 62)
+    save_module_case(
+        "layer_encoder_c128", enc_w,
+        dict(src=feat_w, pos=pos_w, reference_points=ref2, spatial_shapes=shapes_t, level_start_index=lsi,
+             padding_mask=mask),
+        lambda m_, t: m_(t["src"], t["pos"], t["reference_points"], t["spatial_shapes"],
+                        t["level_start_index"], t["padding_mask"]),
+        wrt=["src", "pos"], store=np.float32, grad_limit=20000)
+    enc_stack_w = single.DeformableTransformerEncoder(
+        single.DeformableTransformerEncoderLayer(cw, ffw, 0.0, "relu", 2, hw_, pw), 2).double()
+    perturb(enc_stack_w, 63)
+    save_module_case(
+        "encoder_plain_c128", enc_stack_w,
+        dict(src=feat_w, spatial_shapes=shapes_t, level_start_index=lsi, valid_ratios=vr2, pos=pos_w,
+             padding_mask=mask),
+        lambda m_, t: m_(t["src"], t["spatial_shapes"], t["level_start_index"], t["valid_ratios"], t["pos"],
+                        t["padding_mask"]),
+        wrt=["src"], store=np.float32, grad_limit=20000)
+    torch.manual_seed(64)
+    depth_w = torch.randn(n, sd, cw)
+    fusion_w = single.DeformableTransformerFusionLayerV2(cw, ffw, 0.0, "gelu", 1, hw_, pw).double()
+    perturb(fusion_w, 65)
+    save_module_case(
+        "layer_fusion_v2_c128", fusion_w,
+        dict(tgt=feat_w, query_pos=pos_w, reference_points=ref_d1, src=depth_w, src_spatial_shapes=dshapes,
+             level_start_index=dlsi, src_padding_mask=dmask),
+        lambda m_, t: m_(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                        t["level_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"], store=np.float32, grad_limit=20000)
+    torch.manual_seed(66)
+    tgt7_w = torch.randn(n, 7, cw)
+    qpos7_w = torch.randn(n, 7, cw)
+    dec_stack_w = single.DeformableTransformerDecoder(
+        single.DeformableTransformerDecoderLayer(cw, ffw, 0.0, "relu", 2, hw_, pw), 2, return_intermediate=True).double()
+    perturb(dec_stack_w, 67)
+    ref_q2 = torch.rand(n, 7, 2) * 0.8 + 0.1
+
+    def dec_call(m_, t):
+        hs, refs = m_(t["tgt"], t["reference_points"], t["src"], t["src_spatial_shapes"], t["level_start_index"],
+                      t["valid_ratios"], t["query_pos"], t["src_padding_mask"])
+        return torch.cat([hs.flatten(), refs.flatten()])
+    save_module_case(
+        "decoder_c128", dec_stack_w,
+        dict(tgt=tgt7_w, reference_points=ref_q2, src=feat_w, src_spatial_shapes=shapes_t, level_start_index=lsi,
+             valid_ratios=vr2, query_pos=qpos7_w, src_padding_mask=mask),
+        dec_call, wrt=["tgt", "src", "query_pos"], store=np.float32, grad_limit=20000)
+    udf_w = backbone_cf.DepthDeformableTransformerEncoderLayer(cw, ffw, 0.0, "relu", 1, hw_, pw).double()
+    perturb(udf_w, 68)
+    torch.manual_seed(69)
+    maps_w = dict(src=torch.randn(n, cw, 3, 4), target=torch.randn(n, cw, 6, 8), pos_src=torch.randn(n, cw, 3, 4),
+                  pos_target=torch.randn(n, cw, 6, 8))
+    m_rgb_w = torch.zeros(n, 3, 4, dtype=torch.bool)
+    m_dep_w = torch.zeros(n, 6, 8, dtype=torch.bool)
+    m_dep_w[1, :, -2:] = True
+    m_rgb_w[1, :, -1:] = True
+    save_module_case(
+        "backbone_udf_fuse_c128", udf_w, dict(maps_w, mask_src=m_rgb_w, mask_target=m_dep_w),
+        lambda m_, t: backbone_cf.FusionBackboneBase.fuse_layers(
+            t["src"], t["target"], t["pos_src"], t["pos_target"], t["mask_src"], t["mask_target"], m_),
+        wrt=["src", "target"], store=np.float32, grad_limit=20000)
+    # production width (d_model 256, 8 heads of 32, 4 points): the bf16 kernels' shape; stored as fp32
+    torch.manual_seed(71)
+    feat_p = torch.randn(n, s, 256)
+    pos_p = torch.randn(n, s, 256)
+    enc_p = single.DeformableTransformerEncoderLayer(256, 256, 0.0, "relu", 2, 8, 4).double()
+    perturb(enc_p, 72, std=0.03)
+    save_module_case(
+        "layer_encoder_c256", enc_p,
+        dict(src=feat_p, pos=pos_p, reference_points=ref2, spatial_shapes=shapes_t, level_start_index=lsi,
+             padding_mask=mask),
+        lambda m_, t: m_(t["src"], t["pos"], t["reference_points"], t["spatial_shapes"],
+                        t["level_start_index"], t["padding_mask"]),
+        wrt=["src", "pos"], store=np.float32, grad_limit=20000)
+
+    # ---------------- temporal layers ----------------------------------------------------------------
+    # frames-as-levels layer (deformable_transformer_single.py:650-700): 3 reference frames of (4,5)
+    fshapes = torch.as_tensor([(4, 5)] * 3, dtype=torch.long)
+    flsi = lsi_of(fshapes)
+    fs = int(fshapes.prod(1).sum())
+    torch.manual_seed(81)
+    temporal = single.TemporalDeformableTransformerEncoderLayer(c, 64, 0.0, "relu", 3, heads, pts).double()
+    perturb(temporal, 82)
+    tq = torch.randn(n, 20, c)
+    tqpos = torch.randn(n, 20, c)
+    tmem = torch.randn(n, fs, c)
+    tref = torch.rand(n, 20, 3, 2) * 0.9 + 0.05
+    tmask = torch.zeros(n, fs, dtype=torch.bool)
+    tmask[0, -5:] = True
+    save_module_case(
+        "layer_temporal_encoder", temporal,
+        dict(tgt=tq, query_pos=tqpos, reference_points=tref, src=tmem, src_spatial_shapes=fshapes,
+             frame_start_index=flsi, src_padding_mask=tmask),
+        lambda m_, t: m_(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                        t["frame_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"])
+    # TransVOD++ temporal decoder TDTD (deformable_transformer_multi_plusplus.py:1030-1076) over the
+    # current frame's one-level memory, called with valid_ratios[:, 0:1]
+    pp = import_transvod_plusplus()
+    pp.MSDeformAttn = mod.MSDeformAttn
+    torch.manual_seed(83)
+    tdtd = pp.TemporalDeformableTransformerDecoder(
+        pp.DeformableTransformerDecoderLayer(c, 64, 0.0, "relu", 1, heads, pts), 2, False).double()
+    perturb(tdtd, 84)
+    mem1 = torch.randn(1, sd, c)
+    tgt_t = torch.randn(1, 9, c)
+    ref_t = torch.rand(1, 9, 2) * 0.8 + 0.1
+    vr_t = torch.ones(1, 1, 2)
+    vr_t[0, 0, 0] = 0.5
+
+    def tdtd_call(m_, t):
+        hs, refs = m_(t["tgt"], t["reference_points"], t["src"], t["src_spatial_shapes"], t["level_start_index"],
+                      t["valid_ratios"], None, None)
+        return torch.cat([hs.flatten(), refs.flatten()])
+    save_module_case(
+        "temporal_decoder_pp", tdtd,
+        dict(tgt=tgt_t, reference_points=ref_t, src=mem1, src_spatial_shapes=dshapes, level_start_index=dlsi,
+             valid_ratios=vr_t),
+        tdtd_call, wrt=["tgt", "src"])
 
     # Backbone Cross Fusion U-DF: fuse_layers + its layer (dformer_crossfusion_backbone.py:387-428,120-181)
     torch.manual_seed(41)

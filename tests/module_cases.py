@@ -79,6 +79,54 @@ CASES = {
 }
 
 
+# wide cases (stored as fp32, see oracle/gen_golden.py): d_model 128 / 8 heads / 4 points is the
+# narrowest shape for which the fused deformable-attention kernels AND the fused layer-epilogue
+# kernels run in fp32; d_model 256 is the production width (bf16 kernels).
+CW, HW, PW, FFW = 128, 8, 4, 128
+WIDE = {"layer_encoder_c128", "encoder_plain_c128", "layer_fusion_v2_c128", "decoder_c128",
+        "backbone_udf_fuse_c128", "layer_encoder_c256"}
+
+
+def _decoder_call(m, t):
+    hs, refs = m(t["tgt"], t["reference_points"], t["src"], t["src_spatial_shapes"], t["level_start_index"],
+                 t["valid_ratios"], t.get("query_pos"), t.get("src_padding_mask"))
+    return torch.cat([hs.flatten(), refs.flatten()])
+
+
+CASES.update({
+    "layer_encoder_c128": dict(
+        build=lambda: tl.DeformableTransformerEncoderLayer(CW, FFW, 0.0, "relu", 2, HW, PW),
+        call=CASES["layer_encoder"]["call"], wrt=["src", "pos"]),
+    "layer_encoder_c256": dict(
+        build=lambda: tl.DeformableTransformerEncoderLayer(256, 256, 0.0, "relu", 2, 8, 4),
+        call=CASES["layer_encoder"]["call"], wrt=["src", "pos"]),
+    "encoder_plain_c128": dict(
+        build=lambda: tl.DeformableTransformerEncoder(
+            tl.DeformableTransformerEncoderLayer(CW, FFW, 0.0, "relu", 2, HW, PW), 2),
+        call=CASES["encoder_plain"]["call"], wrt=["src"]),
+    "layer_fusion_v2_c128": dict(
+        build=lambda: tl.DeformableTransformerFusionLayerV2(CW, FFW, 0.0, "gelu", 1, HW, PW),
+        call=CASES["layer_fusion_v2"]["call"], wrt=["tgt", "query_pos", "src"]),
+    "decoder_c128": dict(
+        build=lambda: tl.DeformableTransformerDecoder(
+            tl.DeformableTransformerDecoderLayer(CW, FFW, 0.0, "relu", 2, HW, PW), 2, return_intermediate=True),
+        call=_decoder_call, wrt=["tgt", "src", "query_pos"]),
+    "backbone_udf_fuse_c128": dict(
+        build=lambda: backbone_fusion.DepthDeformableTransformerEncoderLayer(CW, FFW, 0.0, "relu", 1, HW, PW),
+        call=CASES["backbone_udf_fuse"]["call"], wrt=["src", "target"]),
+    # temporal layers
+    "layer_temporal_encoder": dict(
+        build=lambda: tl.TemporalDeformableTransformerEncoderLayer(C, 64, 0.0, "relu", 3, HEADS, PTS),
+        call=lambda m, t: m(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                            t["frame_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"]),
+    "temporal_decoder_pp": dict(
+        build=lambda: tl.TemporalDeformableTransformerDecoder(
+            tl.DeformableTransformerDecoderLayer(C, 64, 0.0, "relu", 1, HEADS, PTS), 2, False),
+        call=_decoder_call, wrt=["tgt", "src"]),
+})
+
+
 def _transformer(depth_type, use_depth, n_levels):
     return DeformableTransformer(
         d_model=C, nhead=HEADS, num_encoder_layers=5 if "encoder_cf" in depth_type else 2, num_decoder_layers=2,
@@ -121,7 +169,8 @@ def run_case(name, gold, device, dtype=torch.float64):
             continue
         t = torch.from_numpy(v).to(device)
         if t.is_floating_point():
-            t = t.to(dtype) if t.dtype == torch.float64 else t     # fp32 inputs (valid ratios) stay fp32
+            # fp32 inputs of the fp64 cases (valid ratios) stay fp32; wide cases are stored as fp32 throughout
+            t = t.to(dtype) if (t.dtype == torch.float64 or name in WIDE) else t
         name_in = k[len("in."):]
         if name_in in case["wrt"]:
             t = t.requires_grad_(True)

@@ -12,7 +12,7 @@ from tests.util import load_golden, nerr
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", sorted(module_cases.CASES))
+@pytest.mark.parametrize("name", sorted(set(module_cases.CASES) - module_cases.WIDE))
 def test_fp64_matches_reference_class(name):
     gold = load_golden(name)
     out, gin, gpar = module_cases.run_case(name, gold, "cuda", torch.float64)
@@ -23,7 +23,9 @@ def test_fp64_matches_reference_class(name):
             continue
         np.testing.assert_allclose(g, gold["grad_in." + k], rtol=1e-6, atol=1e-8, err_msg=k)
     for k, g in gpar.items():
-        ref = gold["grad_param." + k]
+        ref = gold.get("grad_param." + k)
+        if ref is None:
+            continue
         if ref.shape == ():
             assert g is None or not np.any(g)
             continue
@@ -47,8 +49,36 @@ def test_fp32_matches_reference_class(name):
         emax, el2 = nerr(g, gold["grad_in." + k])
         assert emax <= 1e-4 and el2 <= 1e-4, f"{k}: {emax:.2e} {el2:.2e}"
     for k, g in gpar.items():
-        ref = gold["grad_param." + k]
-        if ref.shape == () or g is None:
+        ref = gold.get("grad_param." + k)
+        if ref is None or ref.shape == () or g is None:
             continue
         emax, el2 = nerr(g, ref)
         assert emax <= 1e-4 and el2 <= 1e-4, f"{k}: {emax:.2e} {el2:.2e}"
+
+
+def test_bf16_production_width_layer_matches_reference_class():
+    """d_model 256 / 8 heads of 32 / 4 points in bf16: the fused bf16 deformable-attention kernels,
+    the fused residual + LayerNorm (+ next query) kernels and the ReLU-epilogue GEMM inside the
+    encoder layer, against the real reference class evaluated in fp64.  Stated bf16 tolerance for a
+    whole layer (4 GEMMs + attention + 2 LayerNorms, every intermediate rounded to bf16):
+    normalised max error 2^-5, relative L2 2^-6 on the output; gradients 2^-3 / 2^-5 (the gradient
+    w.r.t. the sampling locations is discontinuous at pixel boundaries, and bf16 rounding of the query
+    moves samples across them: measured 8e-2 / 2.7e-2 on src).  The gradient w.r.t. ``pos`` flows ONLY
+    through that discontinuous path (query -> offsets / logits): relative L2 2^-3 (measured 8e-2)."""
+    gold = load_golden("layer_encoder_c256")
+    out, gin, gpar = module_cases.run_case("layer_encoder_c256", gold, "cuda", torch.bfloat16)
+    emax, el2 = nerr(out, gold["out"])
+    assert emax <= 2.0 ** -5 and el2 <= 2.0 ** -6, f"out: {emax:.2e} {el2:.2e}"
+    for k, g in gin.items():
+        emax, el2 = nerr(g, gold["grad_in." + k])
+        if k == "pos":
+            assert el2 <= 2.0 ** -3, f"{k}: {emax:.2e} {el2:.2e}"
+        else:
+            assert emax <= 2.0 ** -3 and el2 <= 2.0 ** -5, f"{k}: {emax:.2e} {el2:.2e}"
+    for k, g in gpar.items():
+        ref = gold.get("grad_param." + k)
+        if ref is None or ref.shape == () or g is None:
+            continue
+        emax, el2 = nerr(g, ref)
+        loose = "sampling_offsets" in k or "attention_weights" in k      # same discontinuous path
+        assert el2 <= (2.0 ** -3 if loose else 2.0 ** -4), f"{k}: {emax:.2e} {el2:.2e}"

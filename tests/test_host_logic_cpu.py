@@ -29,18 +29,24 @@ def oracle_op(monkeypatch):
 def test_module_matches_reference_class(name, oracle_op):
     gold = load_golden(name)
     out, gin, gpar = module_cases.run_case(name, gold, "cpu")
-    np.testing.assert_allclose(out, gold["out"], rtol=1e-9, atol=1e-11)
+    # wide cases keep fp32 copies of the reference's fp64 results (oracle/gen_golden.py)
+    wide = name in module_cases.WIDE
+    rt_o, at_o = (2e-6, 2e-6) if wide else (1e-9, 1e-11)
+    rt_g, at_g = (2e-6, 2e-6) if wide else (1e-8, 1e-10)
+    np.testing.assert_allclose(out, gold["out"], rtol=rt_o, atol=at_o)
     for k, g in gin.items():
         if gold["grad_in." + k].shape == ():          # input unused by this variant
             assert g is None or not np.any(g)
             continue
-        np.testing.assert_allclose(g, gold["grad_in." + k], rtol=1e-8, atol=1e-10, err_msg=k)
+        np.testing.assert_allclose(g, gold["grad_in." + k], rtol=rt_g, atol=at_g, err_msg=k)
     for k, g in gpar.items():
-        ref = gold["grad_param." + k]
+        ref = gold.get("grad_param." + k)
+        if ref is None:              # large matrices of the wide cases are not stored
+            continue
         if ref.shape == ():          # unused parameter in the reference
             assert g is None or not np.any(g)
             continue
-        np.testing.assert_allclose(g, ref, rtol=1e-8, atol=1e-10, err_msg=k)
+        np.testing.assert_allclose(g, ref, rtol=rt_g, atol=at_g, err_msg=k)
 
 
 def test_state_dict_keys_and_init_match_reference():
