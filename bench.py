@@ -181,6 +181,22 @@ def traffic_from_profile(kind, dtype="f32"):
         return None
 
 
+def limiter_from_profile(kind, dtype="f32"):
+    """The on-chip unit that bounds the kernel, from the committed ncu capture:
+    the gather kernels are not HBM-bound -- the forward saturates the L1 data pipe (128 B/clk/SM),
+    the backward the L1 -> crossbar request path its vector reductions leave the SM through."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            k = json.load(f).get(dtype, {}).get(kind, {})
+        if kind == "forward":
+            return {"unit": "L1 data pipe (l1tex__data_pipe_lsu_wavefronts, 128 B/clk/SM)",
+                    "busy_pct": k.get("l1_data_pipe_pct"), "source": "profiles/ncu_summary.json"}
+        return {"unit": "L1->crossbar request path (l1tex__m_l1tex2xbar_req_cycles_active; RED packets)",
+                "busy_pct": k.get("l1_to_xbar_req_busy_pct"), "source": "profiles/ncu_summary.json"}
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the reference's ms_deform_attn_core_pytorch (restated), fwd + autograd bwd
 # ----------------------------------------------------------------------------------------------
@@ -504,10 +520,12 @@ def run_b200(args):
                                           + (" and bf16 cast" if e_v == 2 else "") + ")",
                 "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
                 "traffic": traffic_from_profile("backward", args.dtype), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": bwd_ms}
+                "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": bwd_ms,
+                "limiter": limiter_from_profile("backward", args.dtype)}
     roofline_fwd = {"bound": "hbm", "kernel": "msda_fwd_fast_kernel", "achieved": achieved_fwd, "peak": peak,
                     "unit": "GB/s", "frac": achieved_fwd / peak, "traffic": traffic_from_profile("forward", args.dtype),
-                    "algorithmic_bytes_per_launch": fwd_bytes, "ms_per_launch": fwd_ms}
+                    "algorithmic_bytes_per_launch": fwd_bytes, "ms_per_launch": fwd_ms,
+                    "limiter": limiter_from_profile("forward", args.dtype)}
 
     extras = {}
     if not args.no_extras:

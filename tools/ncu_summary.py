@@ -35,6 +35,15 @@ KEYS = {
     "launch__block_size": "block",
     "sm__cycles_elapsed.max": "cycles",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct",
+    # what bounds the gather kernels: the L1 data pipe (128 B/clk/SM, forward) and the L1 -> crossbar
+    # request path the reductions leave the SM through (backward)
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_data_pipe_pct",
+    "l1tex__data_pipe_lsu_wavefronts.sum": "l1_data_pipe_wavefronts",
+    "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed": "l1_to_xbar_req_busy_pct",
+    "l1tex__m_l1tex2xbar_write_bytes.sum.pct_of_peak_sustained_elapsed": "l1_to_xbar_write_pct",
+    "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_red.sum": "l1_red_wavefronts",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard_ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio": "stall_lg_throttle_ratio",
 }
 STALLS = "smsp__pcsamp_warps_issue_stalled_"
 
