@@ -1,0 +1,421 @@
+// Fused feed-forward block of the encoder / decoder layers on the 5th-generation tensor cores (sm_100a):
+//
+//     y     = LayerNorm( x + linear2( relu( linear1(x) ) ) ) * gamma + beta        d_model = 256, bf16
+//     y_pos = y + pos                                                             (optional second output)
+//
+// i.e. forward_ffn + norm2 of DeformableTransformerEncoderLayer (reference
+// models/deformable_transformer_single.py:544-548) and the query of the next layer (:530-531, :538), in ONE
+// kernel: the [rows, d_ffn] hidden activation (364 MB at batch 8) never leaves the SM.
+//
+// One CTA owns a 128-row tile (persistent over tiles).  Per 64-wide chunk c of the hidden dimension:
+//     GEMM1(c):  Hacc[c&1] (TMEM, 128 x 64 fp32)  = X (smem, 128 x 256)  @ W1[c]^T (smem, 64 x 256)
+//     epilogue1: Hacc -> + b1 -> ReLU -> bf16 -> sH[c&1] (smem, K-major SWIZZLE_128B: the A operand of GEMM2)
+//     GEMM2(c):  Yacc (TMEM, 128 x 256 fp32)     += sH[c&1] (128 x 64)  @ W2[:, c]^T (smem, 256 x 64)
+// Warp roles (18 warps):
+//   warp 16 MMA issuer.  Warp-uniform control flow, tcgen05.mma issued by one elected lane (descriptors stay
+//           in uniform registers) in the order GEMM1(c+1), GEMM2(c): the tensor pipe has work queued while
+//           the epilogue of chunk c runs.  tcgen05.commit -> mbarrier signals accumulator / buffer reuse.
+//   warp 17 TMA producer.  X / W1 / W2 boxes (SWIZZLE_128B boxes land directly in the UMMA operand layout,
+//           completion by mbarrier transaction bytes), each buffer refilled as soon as its last reader
+//           (a committed MMA group) has finished.
+//   warps 0-15 epilogues (a quarter of a row each).  Final epilogue: Yacc + b2 + x -> bf16 staged in the (idle) W2
+//           buffers -> the X tile and Yacc are released at once so the next tile's loads and first GEMMs
+//           overlap the rest -> row statistics -> normalise -> coalesced copy-out (+ pos).
+// TMEM: 256 (Y) + 2 x 64 (H) columns.  Shared memory: X 64 KB + W1 2 x 32 KB + W2 2 x 32 KB + H 2 x 16 KB.
+#include <cuda.h>
+
+#include "msda_common.cuh"
+#include "msda_launch.h"
+#include "umma.cuh"
+
+namespace msda {
+
+using namespace umma;
+
+constexpr int kFfnC = 256;            // d_model
+constexpr int kFfnTM = 128;           // rows per tile
+constexpr int kFfnCH = 64;            // hidden columns per chunk (one 128-byte k-block of GEMM2)
+#ifndef MSDA_FFN_SPLIT
+#define MSDA_FFN_SPLIT 4              // epilogue warps per 32-row group: each takes 1/SPLIT of the columns
+#endif
+constexpr int kFfnSplit = MSDA_FFN_SPLIT;
+constexpr int kFfnEpiWarps = 4 * kFfnSplit;
+constexpr int kFfnEpiThreads = 32 * kFfnEpiWarps;
+constexpr int kFfnThreads = kFfnEpiThreads + 64;
+constexpr int kSmemX = 4 * kFfnTM * 128;          // 65536
+constexpr int kSmemW1 = 4 * kFfnCH * 128;         // 32768 per buffer
+constexpr int kSmemW2 = kFfnC * 128;              // 32768 per buffer
+constexpr int kSmemH = kFfnTM * 128;              // 16384 per buffer
+constexpr int kSmemStat = 2 * kFfnSplit * kFfnTM * 4;   // partial row statistics (sum, sum of squares)
+constexpr int kSmemBars = 256;
+constexpr int kFfnSmem = kSmemX + 2 * kSmemW1 + 2 * kSmemW2 + 2 * kSmemH + kSmemBars;
+static_assert(kSmemStat <= kSmemH, "row statistics live in the (then idle) first H buffer");
+static_assert(kFfnSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+
+#ifdef MSDA_FFN_TRACE
+__device__ long long g_ffn_trace[2][40][8];
+#define FFN_TRACE(role, c, k) do { if (blockIdx.x == 0 && it == 1) g_ffn_trace[role][c][k] = clock64(); } while (0)
+#else
+#define FFN_TRACE(role, c, k) do { } while (0)
+#endif
+
+struct FfnBars {
+    unsigned long long x, xy_free, tile_free, w1[2], w2[2], g1[2], g2[2], hfull[2];
+    unsigned tmem_base;
+};
+
+// phase parity of the (c >> 1)-th use, in tile iteration `it`, of a per-buffer barrier that is used once
+// per chunk of parity b = c & 1 (nb = number of such chunks per tile)
+__device__ __forceinline__ unsigned chunk_parity(unsigned it, int c, int NC)
+{
+    const int b = c & 1;
+    const unsigned nb = (unsigned)((NC + 1 - b) >> 1);
+    return (it * nb + (unsigned)(c >> 1)) & 1u;
+}
+
+__global__ void __launch_bounds__(kFfnThreads, 1)
+ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
+                     const __grid_constant__ CUtensorMap tm_w2,
+                     const __nv_bfloat16* __restrict__ b1, const __nv_bfloat16* __restrict__ b2,
+                     const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                     const __nv_bfloat16* __restrict__ pos, __nv_bfloat16* __restrict__ y,
+                     __nv_bfloat16* __restrict__ y_pos, long long rows, int F, float eps)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sX = smem;
+    unsigned char* sW1 = sX + kSmemX;              // [2][kSmemW1]
+    unsigned char* sW2 = sW1 + 2 * kSmemW1;        // [2][kSmemW2]; between tiles: the pre-norm staging tile
+    unsigned char* sH = sW2 + 2 * kSmemW2;         // [2][kSmemH]
+    float* s_stat = reinterpret_cast<float*>(sH);  // final epilogue only: every MMA that reads sH has completed,
+                                                   // and the next tile's epilogue1 (same warps) comes later
+    FfnBars* bars = reinterpret_cast<FfnBars*>(sH + 2 * kSmemH);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NC = F / kFfnCH;
+    const long long tiles = (rows + kFfnTM - 1) / kFfnTM;
+
+    if (warp == 0) tmem_alloc(&bars->tmem_base, 512);
+    if (tid == kFfnEpiThreads) {
+        mbar_init(&bars->x, 1);
+        mbar_init(&bars->xy_free, kFfnEpiThreads);
+        mbar_init(&bars->tile_free, kFfnEpiThreads);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->w1[i], 1); mbar_init(&bars->w2[i], 1);
+            mbar_init(&bars->g1[i], 1); mbar_init(&bars->g2[i], 1);
+            mbar_init(&bars->hfull[i], kFfnEpiThreads);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const unsigned tmem = bars->tmem_base;
+    const unsigned tmem_y = tmem;                  // columns [0, 256)
+    const unsigned tmem_h = tmem + 256;            // columns [256, 384): two 64-column buffers
+
+    if (warp == kFfnEpiWarps) {
+        // ======================================= MMA issuer =======================================
+        const unsigned idesc1 = make_idesc_bf16(kFfnTM, kFfnCH);
+        const unsigned idesc2 = make_idesc_bf16(kFfnTM, kFfnC);
+        const unsigned long long dX = make_desc_sw128(sX);
+        const unsigned long long dW1 = make_desc_sw128(sW1), dW2 = make_desc_sw128(sW2), dH = make_desc_sw128(sH);
+        unsigned it = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            // GEMM1(buf): Hacc[buf] = X @ W1buf[buf]^T
+            auto gemm1 = [&](int buf) {
+                tcgen05_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            mma_bf16(tmem_h + buf * kFfnCH, desc_advance(dX, kb * kFfnTM * 128 + j * 32),
+                                     desc_advance(dW1, buf * kSmemW1 + kb * kFfnCH * 128 + j * 32), idesc1, (kb | j) != 0);
+                    mma_commit(&bars->g1[buf]);
+                }
+                __syncwarp();
+            };
+            mbar_wait(&bars->x, it & 1);                                     // X tile landed (sX / Yacc were released)
+            mbar_wait(&bars->w1[0], chunk_parity(it, 0, NC));
+            gemm1(0);
+            for (int c = 0; c < NC; ++c) {
+                const int b = c & 1;
+                FFN_TRACE(0, c, 0);
+                if (c + 1 < NC) {                // queue GEMM1(c+1): Hacc[b^1] was drained by epilogue1(c-1)
+                    mbar_wait(&bars->w1[b ^ 1], chunk_parity(it, c + 1, NC));
+                    FFN_TRACE(0, c, 1);
+                    gemm1(b ^ 1);
+                }
+                FFN_TRACE(0, c, 2);
+                mbar_wait(&bars->hfull[b], chunk_parity(it, c, NC));         // sH[b] written (and Hacc[b] drained)
+                FFN_TRACE(0, c, 3);
+                mbar_wait(&bars->w2[b], chunk_parity(it, c, NC));
+                FFN_TRACE(0, c, 4);
+                tcgen05_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        mma_bf16(tmem_y, desc_advance(dH, b * kSmemH + j * 32), desc_advance(dW2, b * kSmemW2 + j * 32),
+                                 idesc2, (c | j) != 0);
+                    mma_commit(&bars->g2[b]);
+                }
+                __syncwarp();
+                FFN_TRACE(0, c, 5);
+            }
+        }
+    } else if (warp == kFfnEpiWarps + 1) {
+        // ======================================= TMA producer =======================================
+        unsigned it = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            auto load_w1 = [&](int c, int buf) {
+                if (elect_one()) {
+                    mbar_expect_tx(&bars->w1[buf], kSmemW1);
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb)
+                        tma_load_2d(sW1 + buf * kSmemW1 + kb * kFfnCH * 128, &tm_w1, kb * 64, c * kFfnCH, &bars->w1[buf]);
+                }
+                __syncwarp();
+            };
+            auto load_w2 = [&](int c, int buf) {
+                if (elect_one()) {
+                    mbar_expect_tx(&bars->w2[buf], kSmemW2);
+                    tma_load_2d(sW2 + buf * kSmemW2, &tm_w2, c * kFfnCH, 0, &bars->w2[buf]);
+                }
+                __syncwarp();
+            };
+            // the previous tile's epilogue has consumed the X tile and Yacc (all its MMAs are complete)
+            if (it > 0) mbar_wait(&bars->xy_free, (it - 1) & 1);
+            if (elect_one()) {
+                mbar_expect_tx(&bars->x, kSmemX);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+                    tma_load_2d(sX + kb * kFfnTM * 128, &tm_x, kb * 64, (int)(tile * kFfnTM), &bars->x);
+            }
+            __syncwarp();
+            load_w1(0, 0);
+            if (NC > 1) load_w1(1, 1);
+            // the W2 buffers double as the staging tile of the previous tile's final epilogue
+            if (it > 0) mbar_wait(&bars->tile_free, (it - 1) & 1);
+            load_w2(0, 0);
+            for (int c = 0; c < NC; ++c) {
+                const int b = c & 1;
+                if (c + 2 < NC) {                // W1 buffer b is free once GEMM1(c) has completed
+                    mbar_wait(&bars->g1[b], chunk_parity(it, c, NC));
+                    load_w1(c + 2, b);
+                }
+                if (c + 1 < NC) {                // W2 buffer b^1 is free once GEMM2(c-1) has completed
+                    if (c >= 1) mbar_wait(&bars->g2[b ^ 1], chunk_parity(it, c - 1, NC));
+                    load_w2(c + 1, b ^ 1);
+                }
+            }
+        }
+    } else {
+        // ======================================= epilogue warps =======================================
+        const int r = (warp & 3) * 32 + lane;          // row of the tile = TMEM lane
+        const int hsel = warp >> 2;                    // which 1/SPLIT of the columns this warp handles
+        const unsigned lane_base = (unsigned)((warp & 3) * 32) << 16;
+        unsigned char* sStage = sW2;                   // pre-norm tile, same swizzled addressing as sX
+        const int my_ch = tid & 31;                    // column chunk of this thread in the coalesced pass
+        float my_gamma[8], my_beta[8];
+        unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(gamma + my_ch * 8), my_gamma);
+        unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(beta + my_ch * 8), my_beta);
+        unsigned it = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const long long row0 = tile * kFfnTM;
+            for (int c = 0; c < NC; ++c) {
+                const int b = c & 1;
+                constexpr int kCols1 = kFfnCH / kFfnSplit;         // Hacc columns per thread: 32 or 16
+                uint4 braw[kCols1 / 8];
+                const __nv_bfloat16* bias = b1 + c * kFfnCH + hsel * kCols1;
+#pragma unroll
+                for (int q = 0; q < kCols1 / 8; ++q) braw[q] = *reinterpret_cast<const uint4*>(bias + q * 8);
+                if (tid == 0) FFN_TRACE(1, c, 0);
+                mbar_wait(&bars->g1[b], chunk_parity(it, c, NC));            // Hacc[b] = X @ W1[c]^T done
+                if (tid == 0) FFN_TRACE(1, c, 1);
+                tcgen05_fence_after();
+                float v[kCols1];
+                if constexpr (kCols1 == 32) tmem_ld32(tmem_h + b * kFfnCH + hsel * kCols1 + lane_base, v);
+                else tmem_ld16(tmem_h + b * kFfnCH + hsel * kCols1 + lane_base, v);
+                if (tid == 0) FFN_TRACE(1, c, 2);
+                if (c >= 2) mbar_wait(&bars->g2[b], chunk_parity(it, c - 2, NC));   // GEMM2(c-2) done reading sH[b]
+                if (tid == 0) FFN_TRACE(1, c, 3);
+                unsigned char* hrow = sH + b * kSmemH + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+                for (int q = 0; q < kCols1 / 8; ++q) {
+                    float bb[8], o[8];
+                    unpack<__nv_bfloat16>(braw[q], bb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[q * 8 + e] + bb[e], 0.f);
+                    const int ch = hsel * (kCols1 / 8) + q;
+                    *reinterpret_cast<uint4*>(hrow + ((ch ^ (r & 7)) << 4)) = pack<__nv_bfloat16>(o);
+                }
+                fence_proxy_async();
+                tcgen05_fence_before();
+                mbar_arrive(&bars->hfull[b]);
+                if (tid == 0) FFN_TRACE(1, c, 4);
+            }
+            // ---- all MMAs of the tile done (tcgen05.commit covers every earlier MMA) ----
+            mbar_wait(&bars->g2[(NC - 1) & 1], chunk_parity(it, NC - 1, NC));
+            if (tid == 0) FFN_TRACE(1, 32, 0);
+            tcgen05_fence_after();
+            // pass 1 (thread = half a row): v = Yacc + b2 + x -> bf16 into the staging tile; partial sums of
+            // v and v^2 of the rounded values (one pass: |mean| is of the order of the deviation for these
+            // activations, so E[v^2] - mean^2 loses nothing at bf16 output precision)
+            float sum = 0.f, sumsq = 0.f;
+            constexpr int kColsY = kFfnC / kFfnSplit;             // Yacc columns per thread: 128 or 64
+#pragma unroll 1
+            for (int cb = 0; cb < kColsY / 32; ++cb) {
+                float v[32];
+                tmem_ld32(tmem_y + hsel * kColsY + cb * 32 + lane_base, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ch = hsel * (kColsY / 8) + cb * 4 + q;
+                    const unsigned off = sw128_offset(r, ch, kFfnTM);
+                    float xr[8], bb[8], o[8];
+                    unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(sX + off), xr);
+                    unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(b2 + ch * 8), bb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bb[e] + xr[e];
+                    const uint4 packed = pack<__nv_bfloat16>(o);
+                    *reinterpret_cast<uint4*>(sStage + off) = packed;
+                    unpack<__nv_bfloat16>(packed, o);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { sum += o[e]; sumsq = fmaf(o[e], o[e], sumsq); }
+                }
+            }
+            s_stat[hsel * kFfnTM + r] = sum;
+            s_stat[(kFfnSplit + hsel) * kFfnTM + r] = sumsq;
+            tcgen05_fence_before();
+            mbar_arrive(&bars->xy_free);             // the X tile and Yacc may be overwritten by the next tile
+            if (tid == 0) FFN_TRACE(1, 32, 2);
+            named_bar_sync(1, kFfnEpiThreads);
+            if (tid == 0) FFN_TRACE(1, 33, 0);
+            // pass 2 (coalesced: thread = one 16-byte column chunk of 16 rows): normalise, store y (+ pos).
+            // The chunk index of a thread never changes, so its gamma / beta slice lives in registers.
+            constexpr int kRowsPerSweep = kFfnEpiThreads >> 5;       // rows covered by one sweep of all threads
+            constexpr int kSweeps = kFfnTM / kRowsPerSweep;          // 16 (8 warps) or 8 (16 warps)
+#pragma unroll
+            for (int batch = 0; batch < kSweeps / 8; ++batch) {
+                uint4 val[8], pp[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int rr = (tid >> 5) + (batch * 8 + u) * kRowsPerSweep;
+                    const long long gr = row0 + rr;
+                    val[u] = *reinterpret_cast<const uint4*>(sStage + sw128_offset(rr, my_ch, kFfnTM));
+                    pp[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (y_pos != nullptr && gr < rows) pp[u] = ldg_stream_v4(pos + gr * kFfnC + my_ch * 8);
+                }
+                if (tid == 0) FFN_TRACE(1, 33, 1);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int rr = (tid >> 5) + (batch * 8 + u) * kRowsPerSweep;
+                    const long long gr = row0 + rr;
+                    if (gr < rows) {
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int h = 0; h < kFfnSplit; ++h) {
+                            s1 += s_stat[h * kFfnTM + rr];
+                            s2 += s_stat[(kFfnSplit + h) * kFfnTM + rr];
+                        }
+                        const float mean = s1 * (1.f / kFfnC);
+                        const float var = fmaxf(s2 * (1.f / kFfnC) - mean * mean, 0.f);
+                        const float rstd = rsqrtf(var + eps);
+                        float o[8];
+                        unpack<__nv_bfloat16>(val[u], o);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaf((o[e] - mean) * rstd, my_gamma[e], my_beta[e]);
+                        const uint4 outv = pack<__nv_bfloat16>(o);
+                        stg_stream_v4(y + gr * kFfnC + my_ch * 8, outv);
+                        if (y_pos != nullptr) {
+                            float pf[8];
+                            unpack<__nv_bfloat16>(outv, o);          // y_pos is defined on the rounded y
+                            unpack<__nv_bfloat16>(pp[u], pf);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[e] += pf[e];
+                            stg_stream_v4(y_pos + gr * kFfnC + my_ch * 8, pack<__nv_bfloat16>(o));
+                        }
+                    }
+                }
+            }
+            named_bar_sync(1, kFfnEpiThreads);       // s_stat is rewritten by the next tile's pass 1
+            if (tid == 0) FFN_TRACE(1, 32, 1);
+            mbar_arrive(&bars->tile_free);          // the staging tile (= W2 buffers) may be refilled
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// row-major bf16 matrix [n_rows, n_cols]; box = 64 columns (128 bytes, SWIZZLE_128B) x box_rows rows
+static bool make_map(CUtensorMap* map, const void* base, unsigned long long n_rows, unsigned long long n_cols,
+                     unsigned box_rows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return false;
+    const cuuint64_t dims[2] = {n_cols, n_rows};
+    const cuuint64_t strides[1] = {n_cols * 2};
+    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool ffn_layernorm_supported(int dtype, int d_model, int d_ffn)
+{
+    return dtype == kBF16 && d_model == kFfnC && d_ffn >= kFfnCH && d_ffn % kFfnCH == 0;
+}
+
+cudaError_t ffn_layernorm_forward(const FfnArgs& a, cudaStream_t stream)
+{
+    if (!ffn_layernorm_supported(a.dtype, a.C, a.F) || (a.y_pos != nullptr) != (a.pos != nullptr))
+        return cudaErrorInvalidValue;
+    if (a.rows == 0) return cudaSuccess;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ffn_layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    alignas(64) CUtensorMap tm_x, tm_w1, tm_w2;
+    if (!make_map(&tm_x, a.x, (unsigned long long)a.rows, kFfnC, kFfnTM) ||
+        !make_map(&tm_w1, a.w1, (unsigned long long)a.F, kFfnC, kFfnCH) ||
+        !make_map(&tm_w2, a.w2, kFfnC, (unsigned long long)a.F, kFfnC))
+        return cudaErrorNotSupported;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (a.rows + kFfnTM - 1) / kFfnTM;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    using bf = __nv_bfloat16;
+    ffn_layernorm_kernel<<<grid, kFfnThreads, kFfnSmem, stream>>>(
+        tm_x, tm_w1, tm_w2, (const bf*)a.b1, (const bf*)a.b2, (const bf*)a.gamma, (const bf*)a.beta,
+        (const bf*)a.pos, (bf*)a.y, (bf*)a.y_pos, a.rows, a.F, a.eps);
+    return cudaGetLastError();
+}
+
+}  // namespace msda

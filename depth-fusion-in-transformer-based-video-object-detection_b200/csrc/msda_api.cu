@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 4; }
+extern "C" int msda_abi_version(void) { return 5; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -240,4 +240,23 @@ extern "C" int msda_layer_colsum(int dtype, const void* x, int64_t rows, int cha
     if (rows < 0) return (int)cudaErrorInvalidValue;
     return (int)msda::colsum(dtype, x, (long long)rows, channels, out, partial_scratch, partial_blocks,
                              (cudaStream_t)stream);
+}
+
+// ---- fused feed-forward block (tcgen05) ------------------------------------------------------------
+extern "C" int msda_layer_ffn_layernorm_supported(int dtype, int d_model, int d_ffn)
+{
+    return msda::ffn_layernorm_supported(dtype, d_model, d_ffn) ? 1 : 0;
+}
+
+extern "C" int msda_layer_ffn_layernorm_forward(int dtype, const void* x, const void* w1, const void* b1,
+                                                const void* w2, const void* b2, const void* gamma,
+                                                const void* beta, const void* pos, int64_t rows, int d_model,
+                                                int d_ffn, float eps, void* y, void* y_pos, void* stream)
+{
+    if (rows < 0) return (int)cudaErrorInvalidValue;
+    msda::FfnArgs a = {};
+    a.dtype = dtype; a.rows = rows; a.C = d_model; a.F = d_ffn; a.eps = eps;
+    a.x = x; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.gamma = gamma; a.beta = beta; a.pos = pos;
+    a.y = y; a.y_pos = y_pos;
+    return (int)msda::ffn_layernorm_forward(a, (cudaStream_t)stream);
 }

@@ -107,6 +107,26 @@ struct AddLayerNormArgs {
 int add_layernorm_chunks(int dtype, int C);            // 0 = unsupported shape
 int add_layernorm_partial_blocks(long long rows);
 cudaError_t add_layernorm(const AddLayerNormArgs& a, bool backward, cudaStream_t stream);
+// Fused feed-forward block on tcgen05 (ffn_fused.cu): y = LayerNorm(x + W2 relu(W1 x + b1) + b2), y_pos = y + pos
+struct FfnArgs {
+    int dtype;                // kBF16
+    long long rows;
+    int C, F;                 // d_model (256), d_ffn (multiple of 64)
+    float eps;
+    const void* x;            // [rows, C]
+    const void* w1;           // [F, C]   (nn.Linear weight layout)
+    const void* b1;           // [F]
+    const void* w2;           // [C, F]
+    const void* b2;           // [C]
+    const void* gamma;        // [C]
+    const void* beta;         // [C]
+    const void* pos;          // [rows, C] or null
+    void* y;                  // [rows, C]
+    void* y_pos;              // [rows, C] or null
+};
+bool ffn_layernorm_supported(int dtype, int d_model, int d_ffn);
+cudaError_t ffn_layernorm_forward(const FfnArgs& a, cudaStream_t stream);
+
 int colsum_blocks(int dtype, long long rows, int C);   // 0 = unsupported shape
 cudaError_t colsum(int dtype, const void* x, long long rows, int C, void* out, float* partial, int blocks,
                    cudaStream_t stream);

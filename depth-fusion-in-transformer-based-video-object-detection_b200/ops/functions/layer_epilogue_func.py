@@ -244,3 +244,41 @@ def linear_relu(linear, x):
     if x.is_cuda and linear.bias is not None and x.dtype == linear.weight.dtype and x.dtype in _DTYPES:
         return LinearReLUFunction.apply(x, linear.weight, linear.bias)
     return F.relu(linear(x))
+
+
+def ffn_layer_norm_supported(x, linear1, linear2, norm):
+    """The tcgen05 feed-forward kernel covers bf16 inference at d_model 256 (csrc/ffn_fused.cu)."""
+    if not x.is_cuda or x.dtype != torch.bfloat16 or linear1.bias is None or linear2.bias is None:
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or linear1.weight.requires_grad or linear2.weight.requires_grad
+                                    or norm.weight.requires_grad):
+        return False                  # forward only: training keeps the hidden activation for autograd
+    if any(t.dtype != torch.bfloat16 for t in (linear1.weight, linear2.weight, norm.weight)):
+        return False
+    c, f = x.shape[-1], linear1.out_features
+    if linear1.in_features != c or linear2.in_features != f or linear2.out_features != c or \
+            tuple(norm.normalized_shape) != (c,) or not norm.elementwise_affine or norm.bias is None:
+        return False
+    return bool(_lib.load().msda_layer_ffn_layernorm_supported(_lib.DTYPE_BF16, int(c), int(f)))
+
+
+def ffn_layer_norm(linear1, linear2, norm, x, pos=None):
+    """``norm(x + linear2(relu(linear1(x))))`` (and ``that + pos``) in ONE tensor-core kernel; call only
+    when :func:`ffn_layer_norm_supported`."""
+    shape = x.shape
+    c = shape[-1]
+    x2 = _dense(x.reshape(-1, c))
+    rows = x2.shape[0]
+    pos2 = None if pos is None else _dense(pos.to(x.dtype).expand(shape).reshape(-1, c))
+    w1, b1, w2, b2 = (_dense(t.detach()) for t in (linear1.weight, linear1.bias, linear2.weight, linear2.bias))
+    gamma, beta = _dense(norm.weight.detach()), _dense(norm.bias.detach())
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x2)
+        y_pos = torch.empty_like(x2) if pos2 is not None else None
+        code = _lib.load().msda_layer_ffn_layernorm_forward(
+            _lib.DTYPE_BF16, x2.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+            gamma.data_ptr(), beta.data_ptr(), _ptr(pos2), rows, c, linear1.out_features, float(norm.eps),
+            y.data_ptr(), _ptr(y_pos), torch.cuda.current_stream().cuda_stream)
+    _lib.check(code, "msda_layer_ffn_layernorm_forward")
+    y = y.view(shape)
+    return y if y_pos is None else (y, y_pos.view(shape))

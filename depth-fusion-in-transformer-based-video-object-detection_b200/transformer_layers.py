@@ -25,7 +25,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .ops.functions import add_layer_norm, linear, linear_relu
+from .ops.functions import add_layer_norm, ffn_layer_norm, ffn_layer_norm_supported, linear, linear_relu
 from .ops.modules import MSDeformAttn
 from .ops.modules.ms_deform_attn import host_shape_list
 
@@ -87,10 +87,14 @@ class DeformableTransformerEncoderLayer(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
 
+    use_fused_ffn = True      # bf16 inference at d_model 256: the whole feed-forward block in one kernel
     with_pos_embed = staticmethod(_add_pos)
 
     def forward_ffn(self, src, pos=None):
         """norm2(src + linear2(act(linear1(src)))); with ``pos`` also returns that + pos."""
+        if self._activation_name == "relu" and not (self.training and (self.dropout2.p > 0 or self.dropout3.p > 0)) \
+                and self.use_fused_ffn and ffn_layer_norm_supported(src, self.linear1, self.linear2, self.norm2):
+            return ffn_layer_norm(self.linear1, self.linear2, self.norm2, src, pos)     # one tcgen05 kernel
         hidden = linear_relu(self.linear1, src) if self._activation_name == "relu" \
             else self.activation(linear(self.linear1, src))
         return add_layer_norm(self.norm2, self.dropout3(linear(self.linear2, self.dropout2(hidden))), src, None, pos)

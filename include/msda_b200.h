@@ -184,6 +184,21 @@ int msda_layer_add_layernorm_backward(int dtype, int act,
                                       void* grad_gamma, void* grad_beta,
                                       float* partial_scratch, int partial_blocks, void* stream);
 
+/* Fused feed-forward block of the encoder / decoder layers on the tcgen05 tensor cores (inference):
+ *     y = LayerNorm(x + linear2(relu(linear1(x)))) * gamma + beta;   y_pos = y + pos (optional)
+ * = forward_ffn + norm2 (+ the next layer's query) of DeformableTransformerEncoderLayer,
+ * /root/reference/models/deformable_transformer_single.py:544-548 (:530-531).  The [rows, d_ffn] hidden
+ * activation stays in tensor / shared memory.  All tensors BF16, 16-byte aligned; w1 [d_ffn, d_model] and
+ * w2 [d_model, d_ffn] in nn.Linear layout.  Supported: BF16, d_model 256, d_ffn a multiple of 64
+ * (msda_layer_ffn_layernorm_supported); pos / y_pos may be NULL together. */
+int msda_layer_ffn_layernorm_supported(int dtype, int d_model, int d_ffn);
+int msda_layer_ffn_layernorm_forward(int dtype,
+                                     const void* x, const void* w1, const void* b1,
+                                     const void* w2, const void* b2,
+                                     const void* gamma, const void* beta, const void* pos,
+                                     int64_t rows, int d_model, int d_ffn, float eps,
+                                     void* y, void* y_pos, void* stream);
+
 /* out[c] = sum over rows of x[row, c]: the bias gradient of the Linear layers around the deformable
  * attention (PyTorch's autograd computes it with a generic reduction; this is the HBM-rate version).
  * x [rows, channels] and out [channels] of `dtype` (F32 / BF16 / F16), fp32 accumulation.

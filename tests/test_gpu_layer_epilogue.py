@@ -185,3 +185,40 @@ def test_linear_custom_backward(dtype):
     # no autograd: plain module call
     with torch.no_grad():
         assert torch.equal(linear(lin, x), ref_out)
+
+
+@pytest.mark.parametrize("rows,f,with_pos", [(1000, 1024, True), (128, 64, False), (37, 256, True), (5000, 512, False)])
+def test_ffn_layer_norm_tcgen05(rows, f, with_pos):
+    """The tensor-core feed-forward block (csrc/ffn_fused.cu) against the fp64 composition
+    norm(x + linear2(relu(linear1(x)))) [+ pos] on the same bf16 parameters and inputs.  Stated bf16
+    tolerance: normalised max error 2^-6, relative L2 2^-7 (the hidden activation and the
+    pre-norm sum are rounded to bf16 once each, like the unfused bf16 chain)."""
+    from dfvod_b200.ops.functions import ffn_layer_norm, ffn_layer_norm_supported
+    torch.manual_seed(rows + f)
+    c = 256
+    lin1 = torch.nn.Linear(c, f).to(DEV).bfloat16()
+    lin2 = torch.nn.Linear(f, c).to(DEV).bfloat16()
+    norm = torch.nn.LayerNorm(c).to(DEV)
+    with torch.no_grad():
+        norm.weight.add_(torch.randn(c, device=DEV) * 0.3)
+        norm.bias.add_(torch.randn(c, device=DEV) * 0.3)
+    norm = norm.bfloat16()
+    x = torch.randn(rows, c, device=DEV).bfloat16()
+    pos = torch.randn(rows, c, device=DEV).bfloat16() if with_pos else None
+    with torch.no_grad():
+        assert ffn_layer_norm_supported(x, lin1, lin2, norm)
+        out = ffn_layer_norm(lin1, lin2, norm, x, pos)
+        y, y_pos = out if with_pos else (out, None)
+        d = lambda m: {k: v.double() for k, v in m.state_dict().items()}
+        l1, l2, nm = torch.nn.Linear(c, f).to(DEV).double(), torch.nn.Linear(f, c).to(DEV).double(), \
+            torch.nn.LayerNorm(c).to(DEV).double()
+        l1.load_state_dict(d(lin1)); l2.load_state_dict(d(lin2)); nm.load_state_dict(d(norm))
+        ref = nm(x.double() + l2(F.relu(l1(x.double()))))
+    e = (y.double() - ref).abs().max() / ref.abs().max()
+    l2err = (y.double() - ref).norm() / ref.norm()
+    assert float(e) <= 2.0 ** -6 and float(l2err) <= 2.0 ** -7, (float(e), float(l2err))
+    if with_pos:
+        assert torch.equal(y_pos, y + pos)
+    # training (autograd) never takes this kernel
+    x.requires_grad_(True)
+    assert not ffn_layer_norm_supported(x, lin1, lin2, norm)

@@ -71,5 +71,17 @@ for name, dt in (("bf16", torch.bfloat16), ("f32", torch.float32)):
     with torch.no_grad():
         res[f"{name}_linear_relu_ms"] = timeit(lambda: linear_relu(lin, b))
         res[f"{name}_torch_linear_relu_ms"] = timeit(lambda: F.relu(lin(b)))
+# the whole feed-forward block: tcgen05 kernel vs the three-launch composition it replaces
+from dfvod_b200.ops.functions import ffn_layer_norm, linear
+bf = torch.bfloat16
+lin1, lin2 = torch.nn.Linear(c, 1024).to(dev).to(bf), torch.nn.Linear(1024, c).to(dev).to(bf)
+norm = torch.nn.LayerNorm(c).to(dev).to(bf)
+xb, pb = torch.randn(rows, c, device=dev).to(bf), torch.randn(rows, c, device=dev).to(bf)
+with torch.no_grad():
+    ms = timeit(lambda: ffn_layer_norm(lin1, lin2, norm, xb, pb))
+    res["bf16_ffn_ln_tcgen05_ms"] = ms
+    res["bf16_ffn_ln_tcgen05_tflops"] = 4.0 * rows * c * 1024 / ms / 1e9
+    res["bf16_ffn_ln_composition_ms"] = timeit(
+        lambda: add_layer_norm(norm, linear(lin2, linear_relu(lin1, xb)), xb, None, pb))
 res["hbm_peak_gbps"] = PEAK
 print(json.dumps(res, indent=1))
