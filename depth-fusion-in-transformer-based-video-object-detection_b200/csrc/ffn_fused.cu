@@ -11,17 +11,22 @@
 //     GEMM1(c):  Hacc[c&1] (TMEM, 128 x 64 fp32)  = X (smem, 128 x 256)  @ W1[c]^T (smem, 64 x 256)
 //     epilogue1: Hacc -> + b1 -> ReLU -> bf16 -> sH[c&1] (smem, K-major SWIZZLE_128B: the A operand of GEMM2)
 //     GEMM2(c):  Yacc (TMEM, 128 x 256 fp32)     += sH[c&1] (128 x 64)  @ W2[:, c]^T (smem, 256 x 64)
-// Warp roles (18 warps):
-//   warp 16 MMA issuer.  Warp-uniform control flow, tcgen05.mma issued by one elected lane (descriptors stay
-//           in uniform registers) in the order GEMM1(c+1), GEMM2(c): the tensor pipe has work queued while
-//           the epilogue of chunk c runs.  tcgen05.commit -> mbarrier signals accumulator / buffer reuse.
-//   warp 17 TMA producer.  X / W1 / W2 boxes (SWIZZLE_128B boxes land directly in the UMMA operand layout,
-//           completion by mbarrier transaction bytes), each buffer refilled as soon as its last reader
-//           (a committed MMA group) has finished.
-//   warps 0-15 epilogues (a quarter of a row each).  Final epilogue: Yacc + b2 + x -> bf16 staged in the (idle) W2
-//           buffers -> the X tile and Yacc are released at once so the next tile's loads and first GEMMs
-//           overlap the rest -> row statistics -> normalise -> coalesced copy-out (+ pos).
-// TMEM: 256 (Y) + 2 x 64 (H) columns.  Shared memory: X 64 KB + W1 2 x 32 KB + W2 2 x 32 KB + H 2 x 16 KB.
+// Warp roles (14 warps):
+//   warps 0-7   epilogue warps (thread = half a row).  Per chunk: Hacc -> +b1 -> ReLU -> bf16 -> sH.  Per tile:
+//               pass 1: Yacc + b2 + x -> bf16 into the staging tile + row sums; then straight on to the next tile.
+//   warp 8      MMA issuer.  Warp-uniform control flow, tcgen05 instructions issued by one elected lane.  The X
+//               tile is copied once from shared memory into tensor memory (tcgen05.cp) and GEMM1 takes its A
+//               operand from there: no 64 KB re-read of X per chunk (GEMM1 was shared-memory-bandwidth bound),
+//               and the shared-memory X buffer is free for the whole main loop.  Issue order GEMM1(c+1),
+//               GEMM2(c): the tensor pipe has work queued while the epilogue of chunk c runs.
+//   warp 9      TMA producer: X / W1 / W2 boxes (SWIZZLE_128B boxes land directly in the UMMA operand layout,
+//               completion by mbarrier transaction bytes); every buffer is refilled as soon as its last reader
+//               (a committed MMA group) has finished.  X lands in the (then idle) W2 buffers.
+//   warps 10-13 store warps: normalise the staged tile and write y (+ pos) with coalesced 16-byte stores while
+//               the other warps are already in the next tile's main loop (the SM's store egress, 32 B/clk, makes
+//               this the longest phase of a tile: it must not be on the critical path).
+// TMEM (512 columns): Yacc 256 | Hacc 2 x 64 | X tile 128 (bf16 pairs).
+// Shared memory: staging 64 KB + W1 2 x 32 KB + W2 2 x 32 KB (X landing zone) + H 2 x 16 KB + row statistics.
 #include <cuda.h>
 
 #include "msda_common.cuh"
@@ -35,21 +40,19 @@ using namespace umma;
 constexpr int kFfnC = 256;            // d_model
 constexpr int kFfnTM = 128;           // rows per tile
 constexpr int kFfnCH = 64;            // hidden columns per chunk (one 128-byte k-block of GEMM2)
-#ifndef MSDA_FFN_SPLIT
-#define MSDA_FFN_SPLIT 4              // epilogue warps per 32-row group: each takes 1/SPLIT of the columns
-#endif
-constexpr int kFfnSplit = MSDA_FFN_SPLIT;
+constexpr int kFfnSplit = 2;          // epilogue warps per 32-row group: each takes 1/SPLIT of the columns
 constexpr int kFfnEpiWarps = 4 * kFfnSplit;
 constexpr int kFfnEpiThreads = 32 * kFfnEpiWarps;
-constexpr int kFfnThreads = kFfnEpiThreads + 64;
+constexpr int kFfnStoreWarps = 4;
+constexpr int kFfnStoreThreads = 32 * kFfnStoreWarps;
+constexpr int kFfnThreads = kFfnEpiThreads + 64 + kFfnStoreThreads;
 constexpr int kSmemX = 4 * kFfnTM * 128;          // 65536
 constexpr int kSmemW1 = 4 * kFfnCH * 128;         // 32768 per buffer
 constexpr int kSmemW2 = kFfnC * 128;              // 32768 per buffer
 constexpr int kSmemH = kFfnTM * 128;              // 16384 per buffer
 constexpr int kSmemStat = 2 * kFfnSplit * kFfnTM * 4;   // partial row statistics (sum, sum of squares)
 constexpr int kSmemBars = 256;
-constexpr int kFfnSmem = kSmemX + 2 * kSmemW1 + 2 * kSmemW2 + 2 * kSmemH + kSmemBars;
-static_assert(kSmemStat <= kSmemH, "row statistics live in the (then idle) first H buffer");
+constexpr int kFfnSmem = kSmemX + 2 * kSmemW1 + 2 * kSmemW2 + 2 * kSmemH + kSmemStat + kSmemBars;
 static_assert(kFfnSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 
 #ifdef MSDA_FFN_TRACE
@@ -60,7 +63,7 @@ __device__ long long g_ffn_trace[2][40][8];
 #endif
 
 struct FfnBars {
-    unsigned long long x, xy_free, tile_free, w1[2], w2[2], g1[2], g2[2], hfull[2];
+    unsigned long long x, xcopied, xy_free, stage_full, stage_free, w1[2], w2[2], g1[2], g2[2], hfull[2];
     unsigned tmem_base;
 };
 
@@ -82,13 +85,12 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                      __nv_bfloat16* __restrict__ y_pos, long long rows, int F, float eps)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sX = smem;
-    unsigned char* sW1 = sX + kSmemX;              // [2][kSmemW1]
-    unsigned char* sW2 = sW1 + 2 * kSmemW1;        // [2][kSmemW2]; between tiles: the pre-norm staging tile
+    unsigned char* sStage = smem;                  // pre-norm tile of the previous tile, read by the store warps
+    unsigned char* sW1 = sStage + kSmemX;          // [2][kSmemW1]
+    unsigned char* sW2 = sW1 + 2 * kSmemW1;        // [2][kSmemW2]; at a tile boundary: landing zone of the X tile
     unsigned char* sH = sW2 + 2 * kSmemW2;         // [2][kSmemH]
-    float* s_stat = reinterpret_cast<float*>(sH);  // final epilogue only: every MMA that reads sH has completed,
-                                                   // and the next tile's epilogue1 (same warps) comes later
-    FfnBars* bars = reinterpret_cast<FfnBars*>(sH + 2 * kSmemH);
+    float* s_stat = reinterpret_cast<float*>(sH + 2 * kSmemH);
+    FfnBars* bars = reinterpret_cast<FfnBars*>(sH + 2 * kSmemH + kSmemStat);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NC = F / kFfnCH;
@@ -97,8 +99,10 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     if (warp == 0) tmem_alloc(&bars->tmem_base, 512);
     if (tid == kFfnEpiThreads) {
         mbar_init(&bars->x, 1);
+        mbar_init(&bars->xcopied, 1);
         mbar_init(&bars->xy_free, kFfnEpiThreads);
-        mbar_init(&bars->tile_free, kFfnEpiThreads);
+        mbar_init(&bars->stage_full, kFfnEpiThreads);
+        mbar_init(&bars->stage_free, kFfnStoreThreads);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->w1[i], 1); mbar_init(&bars->w2[i], 1);
             mbar_init(&bars->g1[i], 1); mbar_init(&bars->g2[i], 1);
@@ -113,16 +117,16 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const unsigned tmem = bars->tmem_base;
     const unsigned tmem_y = tmem;                  // columns [0, 256)
     const unsigned tmem_h = tmem + 256;            // columns [256, 384): two 64-column buffers
+    const unsigned tmem_x = tmem + 384;            // columns [384, 512): the X tile, two bf16 per column
 
     if (warp == kFfnEpiWarps) {
         // ======================================= MMA issuer =======================================
         const unsigned idesc1 = make_idesc_bf16(kFfnTM, kFfnCH);
         const unsigned idesc2 = make_idesc_bf16(kFfnTM, kFfnC);
-        const unsigned long long dX = make_desc_sw128(sX);
         const unsigned long long dW1 = make_desc_sw128(sW1), dW2 = make_desc_sw128(sW2), dH = make_desc_sw128(sH);
         unsigned it = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            // GEMM1(buf): Hacc[buf] = X @ W1buf[buf]^T
+            // GEMM1(buf): Hacc[buf] = X (TMEM) @ W1buf[buf]^T
             auto gemm1 = [&](int buf) {
                 tcgen05_fence_after();
                 if (elect_one()) {
@@ -130,13 +134,24 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            mma_bf16(tmem_h + buf * kFfnCH, desc_advance(dX, kb * kFfnTM * 128 + j * 32),
-                                     desc_advance(dW1, buf * kSmemW1 + kb * kFfnCH * 128 + j * 32), idesc1, (kb | j) != 0);
+                            mma_bf16_ts(tmem_h + buf * kFfnCH, tmem_x + (kb * 4 + j) * 8,
+                                        desc_advance(dW1, buf * kSmemW1 + kb * kFfnCH * 128 + j * 32), idesc1, (kb | j) != 0);
                     mma_commit(&bars->g1[buf]);
                 }
                 __syncwarp();
             };
-            mbar_wait(&bars->x, it & 1);                                     // X tile landed (sX / Yacc were released)
+            mbar_wait(&bars->x, it & 1);                                     // X tile landed in the W2 buffers
+            if (it > 0) mbar_wait(&bars->xy_free, (it - 1) & 1);             // previous tile's pass 1 is done with Yacc / X
+            tcgen05_fence_after();
+            if (elect_one()) {               // X: shared memory -> tensor memory, 16 slabs of 128 rows x 16 columns
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        tmem_cp_128x256b(tmem_x + (kb * 4 + j) * 8, desc_advance(dW2, kb * kFfnTM * 128 + j * 32));
+                mma_commit(&bars->xcopied);                                  // the W2 buffers may be refilled
+            }
+            __syncwarp();
             mbar_wait(&bars->w1[0], chunk_parity(it, 0, NC));
             gemm1(0);
             for (int c = 0; c < NC; ++c) {
@@ -184,19 +199,18 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 }
                 __syncwarp();
             };
-            // the previous tile's epilogue has consumed the X tile and Yacc (all its MMAs are complete)
-            if (it > 0) mbar_wait(&bars->xy_free, (it - 1) & 1);
+            // every MMA of the previous tile has completed: W1 / W2 buffers are free
+            if (it > 0) mbar_wait(&bars->g2[(NC - 1) & 1], chunk_parity(it - 1, NC - 1, NC));
             if (elect_one()) {
                 mbar_expect_tx(&bars->x, kSmemX);
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb)
-                    tma_load_2d(sX + kb * kFfnTM * 128, &tm_x, kb * 64, (int)(tile * kFfnTM), &bars->x);
+                    tma_load_2d(sW2 + kb * kFfnTM * 128, &tm_x, kb * 64, (int)(tile * kFfnTM), &bars->x);
             }
             __syncwarp();
             load_w1(0, 0);
             if (NC > 1) load_w1(1, 1);
-            // the W2 buffers double as the staging tile of the previous tile's final epilogue
-            if (it > 0) mbar_wait(&bars->tile_free, (it - 1) & 1);
+            mbar_wait(&bars->xcopied, it & 1);       // X has been copied into tensor memory
             load_w2(0, 0);
             for (int c = 0; c < NC; ++c) {
                 const int b = c & 1;
@@ -210,19 +224,13 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 }
             }
         }
-    } else {
+    } else if (warp < kFfnEpiWarps) {
         // ======================================= epilogue warps =======================================
         const int r = (warp & 3) * 32 + lane;          // row of the tile = TMEM lane
         const int hsel = warp >> 2;                    // which 1/SPLIT of the columns this warp handles
         const unsigned lane_base = (unsigned)((warp & 3) * 32) << 16;
-        unsigned char* sStage = sW2;                   // pre-norm tile, same swizzled addressing as sX
-        const int my_ch = tid & 31;                    // column chunk of this thread in the coalesced pass
-        float my_gamma[8], my_beta[8];
-        unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(gamma + my_ch * 8), my_gamma);
-        unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(beta + my_ch * 8), my_beta);
         unsigned it = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            const long long row0 = tile * kFfnTM;
             for (int c = 0; c < NC; ++c) {
                 const int b = c & 1;
                 constexpr int kCols1 = kFfnCH / kFfnSplit;         // Hacc columns per thread: 32 or 16
@@ -257,28 +265,30 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             }
             // ---- all MMAs of the tile done (tcgen05.commit covers every earlier MMA) ----
             mbar_wait(&bars->g2[(NC - 1) & 1], chunk_parity(it, NC - 1, NC));
+            if (it > 0) mbar_wait(&bars->stage_free, (it - 1) & 1);          // store warps are done with the staging tile
             if (tid == 0) FFN_TRACE(1, 32, 0);
             tcgen05_fence_after();
-            // pass 1 (thread = half a row): v = Yacc + b2 + x -> bf16 into the staging tile; partial sums of
+            // pass 1 (thread = 1/SPLIT of a row): v = Yacc + b2 + x -> bf16 into the staging tile; partial sums of
             // v and v^2 of the rounded values (one pass: |mean| is of the order of the deviation for these
             // activations, so E[v^2] - mean^2 loses nothing at bf16 output precision)
             float sum = 0.f, sumsq = 0.f;
             constexpr int kColsY = kFfnC / kFfnSplit;             // Yacc columns per thread: 128 or 64
 #pragma unroll 1
             for (int cb = 0; cb < kColsY / 32; ++cb) {
-                float v[32];
+                float v[32], xp[16];
                 tmem_ld32(tmem_y + hsel * kColsY + cb * 32 + lane_base, v);
+                tmem_ld16(tmem_x + (hsel * kColsY + cb * 32) / 2 + lane_base, xp);      // 32 bf16 of x as 16 pairs
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int ch = hsel * (kColsY / 8) + cb * 4 + q;
-                    const unsigned off = sw128_offset(r, ch, kFfnTM);
                     float xr[8], bb[8], o[8];
-                    unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(sX + off), xr);
+                    unpack<__nv_bfloat16>(make_uint4(__float_as_uint(xp[q * 4]), __float_as_uint(xp[q * 4 + 1]),
+                                                     __float_as_uint(xp[q * 4 + 2]), __float_as_uint(xp[q * 4 + 3])), xr);
                     unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(b2 + ch * 8), bb);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = v[q * 8 + e] + bb[e] + xr[e];
                     const uint4 packed = pack<__nv_bfloat16>(o);
-                    *reinterpret_cast<uint4*>(sStage + off) = packed;
+                    *reinterpret_cast<uint4*>(sStage + sw128_offset(r, ch, kFfnTM)) = packed;
                     unpack<__nv_bfloat16>(packed, o);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) { sum += o[e]; sumsq = fmaf(o[e], o[e], sumsq); }
@@ -287,29 +297,39 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             s_stat[hsel * kFfnTM + r] = sum;
             s_stat[(kFfnSplit + hsel) * kFfnTM + r] = sumsq;
             tcgen05_fence_before();
-            mbar_arrive(&bars->xy_free);             // the X tile and Yacc may be overwritten by the next tile
+            mbar_arrive(&bars->xy_free);             // Yacc and the X columns may be overwritten by the next tile
+            mbar_arrive(&bars->stage_full);          // hand the staged tile to the store warps
             if (tid == 0) FFN_TRACE(1, 32, 2);
-            named_bar_sync(1, kFfnEpiThreads);
-            if (tid == 0) FFN_TRACE(1, 33, 0);
-            // pass 2 (coalesced: thread = one 16-byte column chunk of 16 rows): normalise, store y (+ pos).
-            // The chunk index of a thread never changes, so its gamma / beta slice lives in registers.
-            constexpr int kRowsPerSweep = kFfnEpiThreads >> 5;       // rows covered by one sweep of all threads
-            constexpr int kSweeps = kFfnTM / kRowsPerSweep;          // 16 (8 warps) or 8 (16 warps)
-#pragma unroll
+        }
+    } else {
+        // ======================================= store warps =======================================
+        // pass 2 (coalesced: thread = one 16-byte column chunk of 32 rows): normalise, store y (+ pos).
+        // The chunk index of a thread never changes, so its gamma / beta slice lives in registers.
+        const int stid = tid - (kFfnEpiThreads + 64);
+        const int my_ch = stid & 31;
+        float my_gamma[8], my_beta[8];
+        unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(gamma + my_ch * 8), my_gamma);
+        unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(beta + my_ch * 8), my_beta);
+        constexpr int kRowsPerSweep = kFfnStoreThreads >> 5;     // rows covered by one sweep of the store warps
+        constexpr int kSweeps = kFfnTM / kRowsPerSweep;
+        unsigned it = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const long long row0 = tile * kFfnTM;
+            mbar_wait(&bars->stage_full, it & 1);
+#pragma unroll 1
             for (int batch = 0; batch < kSweeps / 8; ++batch) {
                 uint4 val[8], pp[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int rr = (tid >> 5) + (batch * 8 + u) * kRowsPerSweep;
+                    const int rr = (stid >> 5) + (batch * 8 + u) * kRowsPerSweep;
                     const long long gr = row0 + rr;
                     val[u] = *reinterpret_cast<const uint4*>(sStage + sw128_offset(rr, my_ch, kFfnTM));
                     pp[u] = make_uint4(0u, 0u, 0u, 0u);
                     if (y_pos != nullptr && gr < rows) pp[u] = ldg_stream_v4(pos + gr * kFfnC + my_ch * 8);
                 }
-                if (tid == 0) FFN_TRACE(1, 33, 1);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int rr = (tid >> 5) + (batch * 8 + u) * kRowsPerSweep;
+                    const int rr = (stid >> 5) + (batch * 8 + u) * kRowsPerSweep;
                     const long long gr = row0 + rr;
                     if (gr < rows) {
                         float s1 = 0.f, s2 = 0.f;
@@ -338,9 +358,7 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     }
                 }
             }
-            named_bar_sync(1, kFfnEpiThreads);       // s_stat is rewritten by the next tile's pass 1
-            if (tid == 0) FFN_TRACE(1, 32, 1);
-            mbar_arrive(&bars->tile_free);          // the staging tile (= W2 buffers) may be refilled
+            mbar_arrive(&bars->stage_free);          // the staging tile and the row statistics may be rewritten
         }
     }
     tcgen05_fence_before();

@@ -61,6 +61,23 @@ __device__ __forceinline__ void mma_bf16(unsigned tmem_d, unsigned long long des
         :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((unsigned)accumulate) : "memory");
 }
 
+// A operand from tensor memory (M lanes x K 16-bit elements packed two per 32-bit column), B from shared memory
+__device__ __forceinline__ void mma_bf16_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long desc_b,
+                                            unsigned idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((unsigned)accumulate) : "memory");
+}
+
+// shared memory -> tensor memory: 128 rows x 256 bits (16 bf16 = 8 columns per lane), source described like
+// the A operand of one K=16 MMA step
+__device__ __forceinline__ void tmem_cp_128x256b(unsigned tmem_dst, unsigned long long desc_src)
+{
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" :: "r"(tmem_dst), "l"(desc_src) : "memory");
+}
+
 // all previously issued tcgen05.mma of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(unsigned long long* bar)
 {

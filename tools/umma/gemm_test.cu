@@ -28,7 +28,7 @@ gemm_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row0 = blockIdx.x * TM;
-    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
     // A: 128 rows x 32 chunks of 16 B; B: 256 rows x 32 chunks
     for (int i = tid; i < TM * 32; i += 256) {
@@ -48,6 +48,21 @@ gemm_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict
     const unsigned tmem = tmem_base_s;
     if (tid == 0) {
         const unsigned idesc = make_idesc_bf16(TM, N);
+#ifdef A_FROM_TMEM
+        // A: smem -> TMEM columns [256, 384) (16 slabs of 128 rows x 16 bf16 = 8 columns each), then A from TMEM
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                tmem_cp_128x256b(tmem + 256 + (kb * 4 + j) * 8, make_desc_sw128(sA + kb * TM * 128 + j * 32));
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned long long db = make_desc_sw128(sB + kb * N * 128 + j * 32);
+                mma_bf16_ts(tmem, tmem + 256 + (kb * 4 + j) * 8, db, idesc, (kb | j) != 0);
+            }
+#else
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
@@ -56,6 +71,7 @@ gemm_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict
                 const unsigned long long db = make_desc_sw128(sB + kb * N * 128 + j * 32);
                 mma_bf16(tmem, da, db, idesc, (kb | j) != 0);
             }
+#endif
         mma_commit(&bar);
     }
     mbar_wait(&bar, 0);
@@ -79,7 +95,7 @@ gemm_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_free(tmem, 256);
+    if (warp == 0) tmem_free(tmem, 512);
 }
 
 int main()
