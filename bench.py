@@ -363,6 +363,37 @@ def clip_extras(torch, dev, world, dist, iters=10):
     return out
 
 
+def fusion_layer_extras(torch, dev, world, dist, n_frames=4, iters=10):
+    """BASELINE.json configs[2]: Encoder Cross Fusion RGB-D -- RGB queries deformably attending to the depth
+    feature pyramid -- one DeformableTransformerFusionLayerV2, forward + backward, bf16, batch 4 frames per GPU
+    (Encoder_CrossFusion.sh:18).  (i) as shipped: one level (50,84); (ii) COCO scale: the 4-level pyramid."""
+    from dfvod_b200 import transformer_layers as tl
+    out = {"frames_per_gpu": n_frames, "dtype": "bf16"}
+    bf = torch.bfloat16
+    for tag, shapes in (("shipped_1_level_50x84", [(50, 84)]), ("coco_4_levels", COCO_SHAPES)):
+        lsi, s = level_start(shapes)
+        st = torch.as_tensor(shapes, dtype=torch.long, device=dev)
+        ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
+        torch.manual_seed(2)
+        layer = tl.DeformableTransformerFusionLayerV2(256, 1024, 0.0, "gelu", len(shapes), 8, 4).to(dev).to(bf)
+        g = torch.Generator().manual_seed(2)
+        tgt = torch.randn(n_frames, s, 256, generator=g).to(dev, bf).requires_grad_(True)
+        qpos = torch.randn(n_frames, s, 256, generator=g).to(dev, bf)
+        src = torch.randn(n_frames, s, 256, generator=g).to(dev, bf).requires_grad_(True)
+        ref = tl.encoder_reference_points(shapes, torch.ones(n_frames, len(shapes), 2, device=dev), dev)
+
+        def step():
+            loss = layer(tgt, qpos, ref, src, st, ls, None).float().square().mean()
+            loss.backward()
+            layer.zero_grad(set_to_none=True)
+            tgt.grad = src.grad = None
+
+        ms = _reduce_max(torch, dist, world, dev, _time_events(torch, step, iters, 3))
+        out[tag] = {"tokens_per_frame": s, "fwd_bwd_ms": ms, "frames_per_s": n_frames * world / ms * 1e3}
+        del layer, tgt, qpos, src, ref
+    return out
+
+
 def train_step_extras(torch, dev, world, dist, n_frames=4, iters=5):
     """BASELINE.json configs[4]: Encoder-Cross-Fusion training step (fwd + bwd + AdamW), frames
     sharded over GPUs, gradients all-reduced over NCCL by dfvod_b200.data_parallel.  Model:
@@ -531,8 +562,8 @@ def run_b200(args):
     if not args.no_extras:
         del value, loc, attn, gout, host, pinned_out          # give the memory back first
         torch.cuda.empty_cache()
-        for name, fn in (("detr_inference", encoder_extras), ("transvod_clip_inference", clip_extras),
-                         ("train_step", train_step_extras)):
+        for name, fn in (("detr_inference", encoder_extras), ("encoder_cross_fusion_layer", fusion_layer_extras),
+                         ("transvod_clip_inference", clip_extras), ("train_step", train_step_extras)):
             try:
                 extras[name] = fn(torch, dev, world, dist)
             except Exception as exc:                          # extras never invalidate the main line

@@ -32,6 +32,13 @@ _FORCE_GENERIC = False
 # becomes instruction-issue bound (83 % issue-active: bf16 unpack + FFMA), and with the re-layout
 # pass the two paths tie (0.48 ms).  So it stays OPT-IN: True = use it where supported.
 PAIRED_FORWARD = False
+# With the paired layout: round the per-corner weights to bf16 and accumulate with the mixed-precision
+# FMA (FHFMA.BF16, fp32 accumulator) -- half the math instructions of the issue-bound paired kernel.
+PAIRED_BF16_WEIGHTS = False
+
+
+def paired_flags(dtype):
+    return _lib.FLAG_BF16_WEIGHTS if (PAIRED_BF16_WEIGHTS and dtype == torch.bfloat16) else 0
 
 
 def use_paired_forward(dtype, d, s, lq, nl, p):
@@ -112,7 +119,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
             code = lib.msda_forward_paired(
                 _DTYPES[value.dtype], pairs.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                 sampling_loc.data_ptr(), attn_weight.data_ptr(), n, s, m, d, nl, lq, p, output.data_ptr(),
-                torch.cuda.current_stream().cuda_stream)
+                paired_flags(value.dtype), torch.cuda.current_stream().cuda_stream)
             _lib.check(code, "ms_deform_attn_forward (paired layout)")
             return output
         code = lib.msda_forward(

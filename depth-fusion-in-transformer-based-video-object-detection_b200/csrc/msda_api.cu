@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 5; }
+extern "C" int msda_abi_version(void) { return 6; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -196,7 +196,7 @@ extern "C" int msda_forward_paired(int dtype, const void* value_pairs, const int
                                    const int64_t* level_start_index, const void* sampling_loc,
                                    const void* attn_weight, int batch, int spatial_size, int num_heads,
                                    int channels, int num_levels, int num_query, int num_point, void* output,
-                                   void* stream)
+                                   int flags, void* stream)
 {
     if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point) || num_levels == 0 ||
         num_point == 0)
@@ -207,7 +207,7 @@ extern "C" int msda_forward_paired(int dtype, const void* value_pairs, const int
     a.loc = sampling_loc; a.attn = attn_weight; a.out = output;
     a.N = batch; a.S = spatial_size; a.M = num_heads; a.D = channels;
     a.L = num_levels; a.Lq = num_query; a.P = num_point;
-    a.force_generic = 0;
+    a.force_generic = flags;                    // forward_paired reads the flag bits from here
     return (int)msda::forward_paired(a, (cudaStream_t)stream);
 }
 
@@ -217,7 +217,7 @@ extern "C" int msda_fused_forward_paired(int dtype, int raw_dtype, const void* v
                                          const void* sampling_offsets_raw, int64_t offsets_query_stride,
                                          const void* attention_logits_raw, int64_t logits_query_stride, int batch,
                                          int spatial_size, int num_heads, int channels, int num_levels,
-                                         int num_query, int num_point, void* output, void* stream)
+                                         int num_query, int num_point, void* output, int flags, void* stream)
 {
     if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
         return (int)cudaErrorInvalidValue;
@@ -226,7 +226,7 @@ extern "C" int msda_fused_forward_paired(int dtype, int raw_dtype, const void* v
                                    logits_query_stride, batch, spatial_size, num_heads, channels, num_levels,
                                    num_query, num_point);
     a.out = output;
-    return (int)msda::fused_forward_paired(a, (cudaStream_t)stream);
+    return (int)msda::fused_forward_paired(a, flags, (cudaStream_t)stream);
 }
 
 extern "C" int msda_layer_colsum_blocks(int dtype, int64_t rows, int channels)

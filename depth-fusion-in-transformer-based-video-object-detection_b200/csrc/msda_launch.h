@@ -74,7 +74,7 @@ bool paired_supported(int dtype, int D);
 cudaError_t pack_value_pairs(int dtype, const void* value, void* pairs, int N, int S, int M, int D,
                              cudaStream_t stream);
 cudaError_t forward_paired(const FwdArgs& a, cudaStream_t stream);
-cudaError_t fused_forward_paired(const FusedArgs& a, cudaStream_t stream);
+cudaError_t fused_forward_paired(const FusedArgs& a, int flags, cudaStream_t stream);
 cudaError_t backward(const BwdArgs& a, cudaStream_t stream);
 
 // Layer epilogues (layer_epilogue.cu):  y = LayerNorm(residual + act(branch)) * gamma + beta,

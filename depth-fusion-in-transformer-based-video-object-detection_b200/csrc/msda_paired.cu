@@ -57,7 +57,25 @@ constexpr int kRecPad = 2;       // records: group stride (2*kChunk + 2) * 16 B 
 #define MSDA_PAIRED_MINWARPS 40
 #endif
 
-template <typename VT, int D, bool FUSED, typename RT>
+// acc += v * w with v, w bf16 and acc fp32 in ONE instruction (FHFMA.BF16; the halves of a packed register are
+// selected by the instruction, no unpack)
+__device__ __forceinline__ float fma_bf16_f32(unsigned short v, unsigned short w, float acc)
+{
+    float d;
+    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(v), "h"(w), "f"(acc));
+    return d;
+}
+__device__ __forceinline__ void split_halves(unsigned x, unsigned short& lo, unsigned short& hi)
+{
+    asm("mov.b32 {%0,%1}, %2;" : "=h"(lo), "=h"(hi) : "r"(x));
+}
+
+// WB = true (bf16 only): the per-corner weights (attention weight x bilinear weight) are rounded to bf16 and
+// the accumulation uses the mixed-precision FMA above -- 16 instead of 32 math instructions per sample per
+// lane, which is what bounds this kernel (ncu: 83 % issue-active).  It is the rounding every bf16 tensor-core
+// attention applies to its probabilities; results stay inside the stated bf16 tolerance
+// (tests/test_gpu_paired.py).  WB = false keeps fp32 weights.
+template <typename VT, int D, bool FUSED, typename RT, bool WB>
 __global__ void __launch_bounds__(PairedWarps<32 / (D / 4)>::value * 32,
                                   MSDA_PAIRED_MINWARPS / PairedWarps<32 / (D / 4)>::value)
 msda_fwd_paired_kernel(const VT* __restrict__ pairs, const int64_t* __restrict__ shapes,
@@ -166,8 +184,14 @@ msda_fwd_paired_kernel(const VT* __restrict__ pairs, const int64_t* __restrict__
                 const float w11 = (f.ok & 8u) ? f.lh * f.lw * a : 0.f;
                 // element offsets (< 2^32, checked by the launcher): one IMAD.WIDE.U32 per load in phase 2
                 const int o0 = (int)((unsigned)ry0 * rec_stride), o1 = (int)((unsigned)ry1 * rec_stride);
-                r0 = make_int4(o0, o1, __float_as_int(w00), __float_as_int(w10));       // x0 half
-                r1 = make_int4(o0, o1, __float_as_int(w01), __float_as_int(w11));       // x1 half
+                if constexpr (WB) {
+                    const __nv_bfloat162 p0 = __floats2bfloat162_rn(w00, w10), p1 = __floats2bfloat162_rn(w01, w11);
+                    r0 = make_int4(o0, o1, (int)*reinterpret_cast<const unsigned*>(&p0), 0);   // x0 half: {w(y0), w(y1)}
+                    r1 = make_int4(o0, o1, (int)*reinterpret_cast<const unsigned*>(&p1), 0);   // x1 half
+                } else {
+                    r0 = make_int4(o0, o1, __float_as_int(w00), __float_as_int(w10));   // x0 half
+                    r1 = make_int4(o0, o1, __float_as_int(w01), __float_as_int(w11));   // x1 half
+                }
             }
             s_rec[warp][grp][2 * j] = r0;
             s_rec[warp][grp][2 * j + 1] = r1;
@@ -176,22 +200,40 @@ msda_fwd_paired_kernel(const VT* __restrict__ pairs, const int64_t* __restrict__
         // ---- phase 2: gather, 4 samples x 2 row-pairs in flight ----------------------------
         for (int j0 = 0; j0 < cnt4; j0 += 4) {
             uint4 raw[4][2];
-            float wy0[4], wy1[4];
+            int wz[4], ww[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int4 rec = s_rec[warp][grp][2 * (j0 + u) + half];
-                wy0[u] = __int_as_float(rec.z);
-                wy1[u] = __int_as_float(rec.w);
+                wz[u] = rec.z;
+                ww[u] = rec.w;
                 raw[u][0] = ldg_v4(vbase + (unsigned)rec.x);
                 raw[u][1] = ldg_v4(vbase + (unsigned)rec.y);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                float v0[EPL], v1[EPL];
-                unpack<VT>(raw[u][0], v0);
-                unpack<VT>(raw[u][1], v1);
+                if constexpr (WB) {
+                    unsigned short w0, w1;
+                    split_halves((unsigned)wz[u], w0, w1);
+                    const unsigned a0[4] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w};
+                    const unsigned a1[4] = {raw[u][1].x, raw[u][1].y, raw[u][1].z, raw[u][1].w};
 #pragma unroll
-                for (int c = 0; c < EPL; ++c) acc[c] = fmaf(wy1[u], v1[c], fmaf(wy0[u], v0[c], acc[c]));
+                    for (int i = 0; i < 4; ++i) {
+                        unsigned short lo, hi;
+                        split_halves(a0[i], lo, hi);
+                        acc[2 * i] = fma_bf16_f32(lo, w0, acc[2 * i]);
+                        acc[2 * i + 1] = fma_bf16_f32(hi, w0, acc[2 * i + 1]);
+                        split_halves(a1[i], lo, hi);
+                        acc[2 * i] = fma_bf16_f32(lo, w1, acc[2 * i]);
+                        acc[2 * i + 1] = fma_bf16_f32(hi, w1, acc[2 * i + 1]);
+                    }
+                } else {
+                    const float wy0 = __int_as_float(wz[u]), wy1 = __int_as_float(ww[u]);
+                    float v0[EPL], v1[EPL];
+                    unpack<VT>(raw[u][0], v0);
+                    unpack<VT>(raw[u][1], v1);
+#pragma unroll
+                    for (int c = 0; c < EPL; ++c) acc[c] = fmaf(wy1, v1[c], fmaf(wy0, v0[c], acc[c]));
+                }
             }
         }
         __syncwarp();
@@ -226,7 +268,7 @@ cudaError_t pack_value_pairs(int dtype, const void* value, void* pairs, int N, i
     return cudaGetLastError();
 }
 
-template <typename VT, int D, bool FUSED, typename RT>
+template <typename VT, int D, bool FUSED, typename RT, bool WB>
 static cudaError_t launch_paired(const VT* pairs, const int64_t* shapes, const int64_t* lsi, const SampleSrc& src,
                                  VT* out, int N, int S, int M, int L, int Lq, int P, cudaStream_t stream)
 {
@@ -238,25 +280,25 @@ static cudaError_t launch_paired(const VT* pairs, const int64_t* shapes, const i
     const long long blocks = ((nq_total + WARPS * PAIRS - 1) / (WARPS * PAIRS)) * M;
     if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
     const int p_magic = (65536 + P - 1) / P;
-    msda_fwd_paired_kernel<VT, D, FUSED, RT><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
+    msda_fwd_paired_kernel<VT, D, FUSED, RT, WB><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
         pairs, shapes, lsi, src, out, S, M, L, Lq, P, p_magic, total_pairs);
     return cudaGetLastError();
 }
 
-template <typename VT, bool FUSED, typename RT>
+template <typename VT, bool FUSED, typename RT, bool WB>
 static cudaError_t dispatch_paired(int D, const void* pairs, const int64_t* shapes, const int64_t* lsi,
                                    const SampleSrc& src, void* out, int N, int S, int M, int L, int Lq, int P,
                                    cudaStream_t stream)
 {
     switch (D) {
-        case 16: return launch_paired<VT, 16, FUSED, RT>((const VT*)pairs, shapes, lsi, src, (VT*)out, N, S, M, L, Lq, P, stream);
-        case 32: return launch_paired<VT, 32, FUSED, RT>((const VT*)pairs, shapes, lsi, src, (VT*)out, N, S, M, L, Lq, P, stream);
-        case 64: return launch_paired<VT, 64, FUSED, RT>((const VT*)pairs, shapes, lsi, src, (VT*)out, N, S, M, L, Lq, P, stream);
+        case 16: return launch_paired<VT, 16, FUSED, RT, WB>((const VT*)pairs, shapes, lsi, src, (VT*)out, N, S, M, L, Lq, P, stream);
+        case 32: return launch_paired<VT, 32, FUSED, RT, WB>((const VT*)pairs, shapes, lsi, src, (VT*)out, N, S, M, L, Lq, P, stream);
+        case 64: return launch_paired<VT, 64, FUSED, RT, WB>((const VT*)pairs, shapes, lsi, src, (VT*)out, N, S, M, L, Lq, P, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
-// a.value is the PAIRED tensor [N, S+1, M, 2, D]
+// a.value is the PAIRED tensor [N, S+1, M, 2, D]; a.force_generic carries the flags (bit 1: bf16 weights)
 cudaError_t forward_paired(const FwdArgs& a, cudaStream_t stream)
 {
     if (!paired_supported(a.dtype, a.D) || a.L > kMaxLevelsFast || a.P > 64 || (long long)a.L * a.P * a.P >= 65536 ||
@@ -265,15 +307,18 @@ cudaError_t forward_paired(const FwdArgs& a, cudaStream_t stream)
     if ((long long)a.N * a.Lq * a.M == 0) return cudaSuccess;
     SampleSrc src;
     src.loc = a.loc; src.attn = a.attn; src.ref = nullptr; src.loc_stride = 0; src.attn_stride = 0; src.ref_dim = 0;
+    if (a.dtype == kBF16 && (a.force_generic & 2))
+        return dispatch_paired<__nv_bfloat16, false, float, true>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N, a.S,
+                                                                  a.M, a.L, a.Lq, a.P, stream);
     if (a.dtype == kBF16)
-        return dispatch_paired<__nv_bfloat16, false, float>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N, a.S, a.M,
-                                                            a.L, a.Lq, a.P, stream);
-    return dispatch_paired<__half, false, float>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N, a.S, a.M, a.L, a.Lq,
-                                                 a.P, stream);
+        return dispatch_paired<__nv_bfloat16, false, float, false>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N, a.S,
+                                                                   a.M, a.L, a.Lq, a.P, stream);
+    return dispatch_paired<__half, false, float, false>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N, a.S, a.M, a.L,
+                                                        a.Lq, a.P, stream);
 }
 
 // a.value is the PAIRED tensor; supported: what fused_supported covers with a 16-bit dtype
-cudaError_t fused_forward_paired(const FusedArgs& a, cudaStream_t stream)
+cudaError_t fused_forward_paired(const FusedArgs& a, int flags, cudaStream_t stream)
 {
     if (!fused_supported(a) || a.dtype != kBF16 || (long long)(a.S + 1) * a.M * a.D * 2 >= (1ll << 32))
         return cudaErrorInvalidValue;
@@ -281,11 +326,16 @@ cudaError_t fused_forward_paired(const FusedArgs& a, cudaStream_t stream)
     SampleSrc src;
     src.loc = a.offsets; src.attn = a.logits; src.ref = a.ref;
     src.loc_stride = a.off_stride; src.attn_stride = a.logit_stride; src.ref_dim = a.ref_dim;
+    const bool wb = (flags & 2) != 0;
     if (a.raw_dtype == kF32)
-        return dispatch_paired<__nv_bfloat16, true, float>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N, a.S, a.M,
-                                                           a.L, a.Lq, a.P, stream);
-    return dispatch_paired<__nv_bfloat16, true, __nv_bfloat16>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N, a.S,
-                                                               a.M, a.L, a.Lq, a.P, stream);
+        return wb ? dispatch_paired<__nv_bfloat16, true, float, true>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N, a.S,
+                                                                      a.M, a.L, a.Lq, a.P, stream)
+                  : dispatch_paired<__nv_bfloat16, true, float, false>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N,
+                                                                       a.S, a.M, a.L, a.Lq, a.P, stream);
+    return wb ? dispatch_paired<__nv_bfloat16, true, __nv_bfloat16, true>(a.D, a.value, a.shapes, a.lsi, src, a.out, a.N,
+                                                                          a.S, a.M, a.L, a.Lq, a.P, stream)
+              : dispatch_paired<__nv_bfloat16, true, __nv_bfloat16, false>(a.D, a.value, a.shapes, a.lsi, src, a.out,
+                                                                           a.N, a.S, a.M, a.L, a.Lq, a.P, stream);
 }
 
 }  // namespace msda

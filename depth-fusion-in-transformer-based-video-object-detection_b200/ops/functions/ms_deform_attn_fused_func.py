@@ -61,16 +61,17 @@ class MSDeformAttnFusedFunction(Function):
         with torch.cuda.device(value.device):
             out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
             esz = raw.element_size()
-            fused_forward = lib.msda_fused_forward
-            source = value
+            common = (spatial_shapes.data_ptr(), level_start_index.data_ptr(), ref.data_ptr(), ref.size(-1),
+                      raw.data_ptr(), 3 * mlp, raw.data_ptr() + 2 * mlp * esz, 3 * mlp, n, s, m, d, nl, lq, p,
+                      out.data_ptr())
+            stream = torch.cuda.current_stream().cuda_stream
             if value.dtype == torch.bfloat16 and _msda.use_paired_forward(value.dtype, d, s, lq, nl, p):
-                source = _msda.pack_value_pairs(value)          # 2 lines per sample instead of 4
-                fused_forward = lib.msda_fused_forward_paired
-            code = fused_forward(
-                _DTYPES[value.dtype], _DTYPES[raw.dtype], source.data_ptr(), spatial_shapes.data_ptr(),
-                level_start_index.data_ptr(), ref.data_ptr(), ref.size(-1),
-                raw.data_ptr(), 3 * mlp, raw.data_ptr() + 2 * mlp * esz, 3 * mlp,
-                n, s, m, d, nl, lq, p, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                pairs = _msda.pack_value_pairs(value)           # 2 lines per sample instead of 4
+                code = lib.msda_fused_forward_paired(_DTYPES[value.dtype], _DTYPES[raw.dtype], pairs.data_ptr(),
+                                                     *common, _msda.paired_flags(value.dtype), stream)
+            else:
+                code = lib.msda_fused_forward(_DTYPES[value.dtype], _DTYPES[raw.dtype], value.data_ptr(),
+                                              *common, stream)
         _lib.check(code, "msda_fused_forward")
         ctx.save_for_backward(value, spatial_shapes, level_start_index, ref, raw)
         ctx.n_points = p

@@ -45,6 +45,9 @@ typedef enum {
 
 /* flags */
 #define MSDA_FLAG_FORCE_GENERIC 1   /* route through the shape-generic kernels (testing) */
+#define MSDA_FLAG_BF16_WEIGHTS 2    /* paired BF16 forward only: round the per-corner weights (attention weight x
+                                       bilinear weight) to bf16 and accumulate with the mixed-precision FMA
+                                       (fp32 accumulator) -- half the math instructions; inference option */
 
 /* ABI version of this header (bumped on any signature change). */
 int msda_abi_version(void);
@@ -137,7 +140,7 @@ int msda_forward_paired(int dtype,
                         const void* sampling_loc, const void* attn_weight,
                         int batch, int spatial_size, int num_heads, int channels,
                         int num_levels, int num_query, int num_point,
-                        void* output, void* stream);
+                        void* output, int flags, void* stream);
 int msda_fused_forward_paired(int dtype, int raw_dtype,
                               const void* value_pairs, const int64_t* spatial_shapes, const int64_t* level_start_index,
                               const float* reference_points, int ref_dim,
@@ -145,7 +148,7 @@ int msda_fused_forward_paired(int dtype, int raw_dtype,
                               const void* attention_logits_raw, int64_t logits_query_stride,
                               int batch, int spatial_size, int num_heads, int channels,
                               int num_levels, int num_query, int num_point,
-                              void* output, void* stream);
+                              void* output, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layer epilogues around the deformable attention (no counterpart symbol in the reference, which

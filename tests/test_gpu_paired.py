@@ -23,8 +23,9 @@ BF16_MAX, BF16_L2 = 2.0 ** -7, 4e-3
 
 @pytest.fixture
 def paired(monkeypatch):
-    def set_mode(mode):
+    def set_mode(mode, bf16_weights=False):
         monkeypatch.setattr(MSDA, "PAIRED_FORWARD", mode)
+        monkeypatch.setattr(MSDA, "PAIRED_BF16_WEIGHTS", bf16_weights)
     return set_mode
 
 
@@ -142,3 +143,34 @@ def test_paired_fused_backward_unchanged(paired):
     assert torch.equal(grads[0][0], grads[1][0]) or nerr(grads[0][0].double().cpu().numpy(),
                                                           grads[1][0].double().cpu().numpy())[0] <= 2.0 ** -7
     assert nerr(grads[0][1].double().cpu().numpy(), grads[1][1].double().cpu().numpy())[0] <= 2.0 ** -7
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"L{len(c[0])}_M{c[2]}_D{c[3]}_Lq{c[4]}_P{c[5]}")
+def test_paired_bf16_weights_op(case, paired):
+    """Paired layout + bf16-rounded per-corner weights + mixed-precision FMA (FHFMA.BF16): still inside the
+    stated bf16 tolerance against the fp64 oracle (normalised max 2^-7, relative L2 4e-3)."""
+    shapes, n, m, d, lq, p, rng = case
+    value, loc, attn, _ = util.make_inputs(shapes, n, m, d, lq, p, seed=300 + d + lq, loc_range=rng)
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v16 = value.bfloat16()
+    paired(True, True)
+    got = MSDA.ms_deform_attn_forward(v16.to(DEV), st, ls, loc.to(DEV), attn.to(DEV), 64)
+    ref = msda_oracle.forward_np(v16.double().numpy(), shapes, util.lsi_of(shapes), loc.double().numpy(), attn.double().numpy())
+    mx, l2 = nerr(got.double().cpu().numpy().reshape(ref.shape), ref)
+    assert mx <= BF16_MAX and l2 <= BF16_L2, (mx, l2)
+
+
+@pytest.mark.parametrize("rdtype", [torch.float32, torch.bfloat16])
+def test_paired_bf16_weights_fused(rdtype, paired):
+    shapes, n, m, d, lq, p, ref_dim = FUSED_CASES[0]
+    nl = len(shapes)
+    value, raw, ref, gout = make_case(shapes, n, m, d, lq, p, ref_dim, seed=77)
+    st, ls = util.shapes_tensors(shapes, DEV)
+    v = value.to(DEV, torch.bfloat16)
+    r = raw.to(DEV, rdtype)
+    with torch.no_grad():
+        paired(True, True)
+        got = MSDeformAttnFusedFunction.apply(v, st, ls, ref.to(DEV), r, p)
+    want = run_oracle64(v.float().cpu(), shapes, ref, r.float().cpu(), gout, m, nl, p)[0]
+    mx, l2 = nerr(got.double().cpu().numpy(), want)
+    assert mx <= BF16_MAX and l2 <= BF16_L2, (mx, l2)

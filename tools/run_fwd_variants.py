@@ -13,8 +13,9 @@ st = torch.as_tensor(bench.COCO_SHAPES, dtype=torch.long, device=dev)
 ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
 v = value.to(dev, torch.bfloat16)
 loc, attn = loc.to(dev), attn.to(dev)
-for mode in (False, True):
+for mode, wb in ((False, False), (True, False), (True, True)):
     MSDA.PAIRED_FORWARD = mode
+    MSDA.PAIRED_BF16_WEIGHTS = wb
     for _ in range(3):
         out = MSDA.ms_deform_attn_forward(v, st, ls, loc, attn, 64)
     torch.cuda.synchronize()
@@ -24,4 +25,4 @@ for mode in (False, True):
         out = MSDA.ms_deform_attn_forward(v, st, ls, loc, attn, 64)
     e1.record()
     torch.cuda.synchronize()
-    print("paired" if mode else "plain", e0.elapsed_time(e1) / 10, "ms")
+    print(("paired+bf16w" if wb else "paired") if mode else "plain", e0.elapsed_time(e1) / 10, "ms")
