@@ -354,6 +354,60 @@ colsum_fold_kernel(const float* __restrict__ partial, int nblocks, int C, T* __r
     }
 }
 
+// One pyramid level, NCHW -> token-major: out[n, start + p, c] = x[n, c, p] (+ add[c]), p = y*W + x.
+// The reference does this with flatten(2).transpose(1,2) per level, a level-embedding add and torch.cat
+// (deformable_transformer_single.py:190-206).  32 x 32 tiles through shared memory: reads coalesced along
+// the pixels, writes coalesced along the channels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+flatten_level_kernel(const T* __restrict__ x, const T* __restrict__ add, T* __restrict__ out,
+                     int C, int HW, long long S, long long start)
+{
+    __shared__ T tile[32][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+    const T* xin = x + (long long)n * C * HW;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, p = p0 + tx;
+        if (c < C && p < HW) tile[ty + 8 * k][tx] = xin[(long long)c * HW + p];
+    }
+    __syncthreads();
+    T* o = out + ((long long)n * S + start) * C;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int p = p0 + ty + 8 * k, c = c0 + tx;
+        if (c < C && p < HW) {
+            float v = to_f32<T>(tile[tx][ty + 8 * k]);
+            if (add != nullptr) v = to_f32<T>(from_f32<T>(v + to_f32<T>(add[c])));
+            o[(long long)p * C + c] = from_f32<T>(v);
+        }
+    }
+}
+
+cudaError_t flatten_level(int dtype, const void* x, const void* add, void* out, int N, int C, int HW, long long S,
+                          long long start, cudaStream_t st)
+{
+    if (N <= 0 || C <= 0 || HW <= 0) return cudaSuccess;
+    if (N > 65535) return cudaErrorInvalidValue;
+    const dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
+    switch (dtype) {
+        case kF32:
+            flatten_level_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)add, (float*)out, C, HW, S, start);
+            break;
+        case kBF16:
+            flatten_level_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)add,
+                                                                     (__nv_bfloat16*)out, C, HW, S, start);
+            break;
+        case kF16:
+            flatten_level_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (const __half*)add, (__half*)out, C, HW, S, start);
+            break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------

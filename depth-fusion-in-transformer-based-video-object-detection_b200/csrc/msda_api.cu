@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 6; }
+extern "C" int msda_abi_version(void) { return 7; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -259,4 +259,15 @@ extern "C" int msda_layer_ffn_layernorm_forward(int dtype, const void* x, const 
     a.x = x; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.gamma = gamma; a.beta = beta; a.pos = pos;
     a.y = y; a.y_pos = y_pos;
     return (int)msda::ffn_layernorm_forward(a, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_flatten_level(int dtype, const void* feature_map, const void* channel_add, int batch,
+                                        int channels, int height_x_width, void* tokens, int64_t tokens_per_item,
+                                        int64_t level_start, void* stream)
+{
+    if (batch < 0 || channels < 0 || height_x_width < 0 || level_start < 0 ||
+        level_start + height_x_width > tokens_per_item)
+        return (int)cudaErrorInvalidValue;
+    return (int)msda::flatten_level(dtype, feature_map, channel_add, tokens, batch, channels, height_x_width,
+                                    (long long)tokens_per_item, (long long)level_start, (cudaStream_t)stream);
 }

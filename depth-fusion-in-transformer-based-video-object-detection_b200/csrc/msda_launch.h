@@ -127,6 +127,8 @@ struct FfnArgs {
 bool ffn_layernorm_supported(int dtype, int d_model, int d_ffn);
 cudaError_t ffn_layernorm_forward(const FfnArgs& a, cudaStream_t stream);
 
+cudaError_t flatten_level(int dtype, const void* x, const void* add, void* out, int N, int C, int HW, long long S,
+                          long long start, cudaStream_t stream);
 int colsum_blocks(int dtype, long long rows, int C);   // 0 = unsupported shape
 cudaError_t colsum(int dtype, const void* x, long long rows, int C, void* out, float* partial, int blocks,
                    cudaStream_t stream);

@@ -21,6 +21,7 @@ import torch
 from torch import nn
 from torch.nn.init import constant_, normal_, xavier_uniform_
 
+from .ops.functions import flatten_levels, flatten_levels_supported
 from .ops.modules import MSDeformAttn
 from .transformer_layers import (DeformableTransformerDecoder, DeformableTransformerDecoderLayer,
                                  DeformableTransformerEncoder, DeformableTransformerEncoderLayer,
@@ -31,6 +32,13 @@ from .transformer_layers import (DeformableTransformerDecoder, DeformableTransfo
 def _flatten_levels(maps, masks, pos_embeds, level_embed=None):
     """[N,C,H,W] per level -> tokens [N, sum HW, C], mask [N, sum HW], pos (+ level embedding),
     shapes (python list of (H, W))."""
+    shapes = [(feat.shape[2], feat.shape[3]) for feat in maps]
+    embed_trains = level_embed is not None and torch.is_grad_enabled() and level_embed.requires_grad
+    if not embed_trains and flatten_levels_supported(list(maps)) and flatten_levels_supported(list(pos_embeds)):
+        # inference: one transposing kernel per level writes straight into the flattened tensors
+        adds = None if level_embed is None else [level_embed[lvl] for lvl in range(len(maps))]
+        return (flatten_levels(list(maps)), torch.cat([m.flatten(1) for m in masks], 1),
+                flatten_levels(list(pos_embeds), adds), shapes)
     tokens, flat_masks, flat_pos, shapes = [], [], [], []
     for lvl, (feat, mask, pos) in enumerate(zip(maps, masks, pos_embeds)):
         shapes.append((feat.shape[2], feat.shape[3]))

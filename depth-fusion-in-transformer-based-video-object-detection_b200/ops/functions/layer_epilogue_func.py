@@ -282,3 +282,32 @@ def ffn_layer_norm(linear1, linear2, norm, x, pos=None):
     _lib.check(code, "msda_layer_ffn_layernorm_forward")
     y = y.view(shape)
     return y if y_pos is None else (y, y_pos.view(shape))
+
+
+def flatten_levels(maps, channel_adds=None):
+    """[N,C,H_l,W_l] per level -> tokens [N, sum_l H_l*W_l, C] (+ channel_adds[l] per level), one transposing
+    kernel per level writing straight into its slice (no per-level transposes, adds and torch.cat).
+    Forward only: callers keep the PyTorch composition when gradients are needed."""
+    n, c = maps[0].shape[:2]
+    dt = maps[0].dtype
+    sizes = [m.shape[2] * m.shape[3] for m in maps]
+    total = sum(sizes)
+    lib = _lib.load()
+    with torch.cuda.device(maps[0].device):
+        out = torch.empty((n, total, c), dtype=dt, device=maps[0].device)
+        start = 0
+        stream = torch.cuda.current_stream().cuda_stream
+        for lvl, (m, hw) in enumerate(zip(maps, sizes)):
+            m = m.contiguous()
+            add = None if channel_adds is None else channel_adds[lvl].detach().to(dt).contiguous()
+            code = lib.msda_layer_flatten_level(_DTYPES[dt], m.data_ptr(), _ptr(add), n, c, hw, out.data_ptr(), total,
+                                                start, stream)
+            _lib.check(code, "msda_layer_flatten_level")
+            start += hw
+    return out
+
+
+def flatten_levels_supported(maps):
+    return all(m.is_cuda and m.dim() == 4 and m.dtype in _DTYPES and m.dtype == maps[0].dtype and
+               m.shape[:2] == maps[0].shape[:2] for m in maps) and not (
+        torch.is_grad_enabled() and any(m.requires_grad for m in maps))

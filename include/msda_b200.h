@@ -202,6 +202,16 @@ int msda_layer_ffn_layernorm_forward(int dtype,
                                      int64_t rows, int d_model, int d_ffn, float eps,
                                      void* y, void* y_pos, void* stream);
 
+/* One pyramid level from NCHW to token-major, written into its slice of the flattened token tensor:
+ *     tokens[n, level_start + y*W + x, c] = feature_map[n, c, y, x] (+ channel_add[c])
+ * = src.flatten(2).transpose(1, 2) (+ level_embed[l]) and its share of the concatenation in
+ * DeformableTransformer.forward, /root/reference/models/deformable_transformer_single.py:190-206.
+ * feature_map [batch, channels, H*W] contiguous, tokens [batch, tokens_per_item, channels], channel_add
+ * [channels] or NULL; dtype F32 / BF16 / F16. */
+int msda_layer_flatten_level(int dtype, const void* feature_map, const void* channel_add, int batch,
+                             int channels, int height_x_width, void* tokens, int64_t tokens_per_item,
+                             int64_t level_start, void* stream);
+
 /* out[c] = sum over rows of x[row, c]: the bias gradient of the Linear layers around the deformable
  * attention (PyTorch's autograd computes it with a generic reduction; this is the HBM-rate version).
  * x [rows, channels] and out [channels] of `dtype` (F32 / BF16 / F16), fp32 accumulation.

@@ -222,3 +222,51 @@ def test_ffn_layer_norm_tcgen05(rows, f, with_pos):
     # training (autograd) never takes this kernel
     x.requires_grad_(True)
     assert not ffn_layer_norm_supported(x, lin1, lin2, norm)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("with_add", [False, True])
+def test_flatten_levels_bitwise(dtype, with_add):
+    """msda_layer_flatten_level == flatten(2).transpose(1, 2) (+ level_embed[l]) + cat of
+    /root/reference/models/deformable_transformer_single.py:190-206, bit for bit (a copy and one rounded add)."""
+    from dfvod_b200.ops.functions import flatten_levels, flatten_levels_supported
+    torch.manual_seed(11)
+    n, c = 3, 96                                   # channel count not a multiple of the 32-wide tile
+    shapes = [(13, 21), (7, 11), (1, 1), (5, 33)]
+    maps = [torch.randn(n, c, h, w, device=DEV).to(dtype) for h, w in shapes]
+    adds = [torch.randn(c, device=DEV).to(dtype) for _ in shapes] if with_add else None
+    assert flatten_levels_supported(maps)
+    got = flatten_levels(maps, adds)
+    want = torch.cat([m.flatten(2).transpose(1, 2) + (adds[i].view(1, 1, -1) if with_add else 0)
+                      for i, m in enumerate(maps)], 1)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert torch.equal(got, want)
+
+
+def test_flatten_levels_refuses_when_gradients_are_needed():
+    from dfvod_b200.ops.functions import flatten_levels_supported
+    m = torch.randn(1, 8, 2, 2, device=DEV, requires_grad=True)
+    assert not flatten_levels_supported([m])
+    with torch.no_grad():
+        assert flatten_levels_supported([m])
+    assert not flatten_levels_supported([m.detach().double()])
+
+
+def test_transformer_inference_path_equals_training_path():
+    """DeformableTransformer.forward under no_grad takes the transposing-kernel flatten; it must give what the
+    autograd-visible PyTorch composition gives."""
+    from dfvod_b200.deformable_transformer import DeformableTransformer
+    torch.manual_seed(5)
+    shapes = [(12, 17), (6, 9)]
+    model = DeformableTransformer(d_model=64, nhead=4, num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=128,
+                                  dropout=0.0, num_feature_levels=2, return_intermediate_dec=True).to(DEV).eval()
+    srcs = [torch.randn(2, 64, h, w, device=DEV) for h, w in shapes]
+    poss = [torch.randn(2, 64, h, w, device=DEV) for h, w in shapes]
+    masks = [torch.zeros(2, h, w, dtype=torch.bool, device=DEV) for h, w in shapes]
+    masks[0][1, :, -3:] = True
+    masks[1][1, :, -2:] = True
+    query = torch.randn(10, 128, device=DEV)
+    hs_train = model(srcs, masks, poss, None, None, None, query)[0]
+    with torch.no_grad():
+        hs_infer = model(srcs, masks, poss, None, None, None, query)[0]
+    assert nerr(hs_infer, hs_train.detach().double()) <= 1e-5
