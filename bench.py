@@ -360,6 +360,58 @@ def clip_extras(torch, dev, world, dist, iters=10):
             out["graph_fps"] = n * world / ms * 1e3
         except Exception as exc:
             out["graph_error"] = repr(exc)[:160]
+        del model
+        try:
+            out["with_temporal_stage"] = _clip_temporal(torch, dev, world, dist, shapes, clip, clips, iters,
+                                                        (srcs, masks, poss, dsrcs, dmasks, dposs, query))
+        except Exception as exc:      # report, do not hide
+            out["with_temporal_stage"] = {"error": repr(exc)[:200]}
+    return out
+
+
+def _clip_temporal(torch, dev, world, dist, shapes, clip, clips, iters, inputs):
+    """The same clips through the WHOLE TransVOD++ transformer (dfvod_b200.temporal_stage.DeformableTransformer):
+    per-frame Late Fusion + encoder + decoder with box refinement, then the temporal query stage -- RoIAlign of all
+    300 boxes of every frame (csrc/roi_align.cu), QRF head, 3 x (temporal query encoder + temporal deformable
+    decoder); 8 clips batched clip-major, detection heads with random weights, 31 classes, bf16."""
+    from torch import nn
+    from dfvod_b200 import temporal_stage
+    bf = torch.bfloat16
+    torch.manual_seed(33)
+    tr = temporal_stage.DeformableTransformer(
+        num_feature_levels=1, return_intermediate_dec=True, use_depth=True, num_ref_frames=clip - 1,
+        depth_type="DepthDeform_latefusion_dformer")
+
+    def mlp():
+        return nn.Sequential(nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 4))
+
+    heads = nn.ModuleDict(dict(cls=nn.Linear(256, 31), box=nn.ModuleList(mlp() for _ in range(6)),
+                               tcls=nn.ModuleList(nn.Linear(256, 31) for _ in range(3)),
+                               tbox=nn.ModuleList(mlp() for _ in range(3))))
+    tr.decoder.bbox_embed = heads["box"]                      # --with_box_refine, as TransVOD++ is trained
+    tr = tr.to(dev).eval().to(bf)
+    heads = heads.to(dev).eval().to(bf)
+    srcs, masks, poss, dsrcs, dmasks, dposs, query = inputs
+    h, w = shapes[0]
+    whwh = torch.tensor([[w * 32, h * 32, w * 32, h * 32]], dtype=torch.long, device=dev)
+    n = clip * clips
+    run = lambda: tr(srcs, masks, poss, dsrcs, dmasks, dposs, whwh, query, heads["cls"], heads["box"][-1],
+                     heads["tcls"], heads["tbox"])
+    ms = _reduce_max(torch, dist, world, dev, _time_events(torch, run, iters, 3))
+    out = {"eager_ms": ms, "eager_fps": n * world / ms * 1e3, "eager_clips_per_s": clips * world / ms * 1e3}
+    try:
+        ms = _reduce_max(torch, dist, world, dev, _graph_time(torch, run, iters))
+        out.update(graph_ms=ms, graph_fps=n * world / ms * 1e3, graph_clips_per_s=clips * world / ms * 1e3)
+    except Exception as exc:
+        out["graph_error"] = repr(exc)[:160]
+    # the RoIAlign kernel alone at this size (8 clips x 4 frames x 300 boxes, 7x7x256 out of a 50x84 map)
+    tokens = torch.randn(n, h * w, 256, device=dev, dtype=bf)
+    g = torch.Generator().manual_seed(5)
+    cxy = torch.rand(n * 300, 2, generator=g) * torch.tensor([w * 32.0, h * 32.0])
+    wh = torch.rand(n * 300, 2, generator=g) * torch.tensor([w * 16.0, h * 16.0]) + 8
+    rois = torch.cat([torch.arange(n).repeat_interleave(300)[:, None].float(), cxy - wh / 2, cxy + wh / 2], -1).to(dev)
+    ms = _time_events(torch, lambda: temporal_stage.roi_align_tokens(tokens, rois, h, w, 7, 1 / 32, 2, True), 20, 3)
+    out["roi_align_kernel"] = {"rois": n * 300, "ms": ms, "output_gbytes_per_s": n * 300 * 49 * 256 * 2 / ms / 1e6}
     return out
 
 

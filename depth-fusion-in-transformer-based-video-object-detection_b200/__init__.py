@@ -9,6 +9,8 @@ Layout (only what the hot path needs):
   ops/functions, ops/modules             mirror of the reference's models/ops (MSDeformAttnFunction, MSDeformAttn)
   transformer_layers.py                  encoder / decoder / Late Fusion / Encoder Cross Fusion layer classes
   backbone_fusion.py                     Backbone Cross Fusion (U-DF) layer + fuse_layers
+  deformable_transformer.py              single-frame DeformableTransformer (baseline / Late Fusion / Encoder Cross Fusion)
+  temporal_stage.py                      TransVOD++ multi-frame transformer: RoIAlign, QRF head, TQE, TDTD
 
 The directory name carries hyphens; import it through the alias module ``dfvod_b200`` at the
 repository root (``import dfvod_b200``), or put ``ops`` in place of the reference's ``models/ops``.

@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 7; }
+extern "C" int msda_abi_version(void) { return 8; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -270,4 +270,36 @@ extern "C" int msda_layer_flatten_level(int dtype, const void* feature_map, cons
         return (int)cudaErrorInvalidValue;
     return (int)msda::flatten_level(dtype, feature_map, channel_add, tokens, batch, channels, height_x_width,
                                     (long long)tokens_per_item, (long long)level_start, (cudaStream_t)stream);
+}
+
+static bool bad_roi_dims(int batch, int height, int width, int channels, int num_rois, int ph, int pw)
+{
+    return batch < 0 || height <= 0 || width <= 0 || channels < 0 || num_rois < 0 || ph <= 0 || pw <= 0;
+}
+
+extern "C" int msda_roi_align_forward(int dtype, const void* feature_tokens, const void* rois, int batch, int height,
+                                      int width, int channels, int num_rois, int pooled_height, int pooled_width,
+                                      double spatial_scale, int sampling_ratio, int aligned, void* pooled, void* stream)
+{
+    if (bad_roi_dims(batch, height, width, channels, num_rois, pooled_height, pooled_width) || sampling_ratio < 0)
+        return (int)cudaErrorInvalidValue;
+    msda::RoiAlignArgs a{};
+    a.dtype = dtype; a.feat = feature_tokens; a.rois = rois; a.out = pooled;
+    a.N = batch; a.H = height; a.W = width; a.C = channels; a.K = num_rois; a.PH = pooled_height; a.PW = pooled_width;
+    a.scale = spatial_scale; a.sampling_ratio = sampling_ratio; a.aligned = aligned;
+    return (int)msda::roi_align_forward(a, (cudaStream_t)stream);
+}
+
+extern "C" int msda_roi_align_backward(int dtype, const void* grad_pooled, const void* rois, int batch, int height,
+                                       int width, int channels, int num_rois, int pooled_height, int pooled_width,
+                                       double spatial_scale, int sampling_ratio, int aligned, void* grad_feature_accum,
+                                       void* stream)
+{
+    if (bad_roi_dims(batch, height, width, channels, num_rois, pooled_height, pooled_width) || sampling_ratio < 0)
+        return (int)cudaErrorInvalidValue;
+    msda::RoiAlignArgs a{};
+    a.dtype = dtype; a.grad_out = grad_pooled; a.rois = rois; a.grad_accum = grad_feature_accum;
+    a.N = batch; a.H = height; a.W = width; a.C = channels; a.K = num_rois; a.PH = pooled_height; a.PW = pooled_width;
+    a.scale = spatial_scale; a.sampling_ratio = sampling_ratio; a.aligned = aligned;
+    return (int)msda::roi_align_backward(a, (cudaStream_t)stream);
 }

@@ -129,6 +129,22 @@ cudaError_t ffn_layernorm_forward(const FfnArgs& a, cudaStream_t stream);
 
 cudaError_t flatten_level(int dtype, const void* x, const void* add, void* out, int N, int C, int HW, long long S,
                           long long start, cudaStream_t stream);
+// RoIAlign on token-major maps (roi_align.cu): feat [N, H*W, C], rois [K,5] (batch index, x1, y1, x2, y2) in fp32
+// (fp64 when dtype == kF64), out / grad_out [K, PH*PW, C], grad_accum [N, H*W, C] fp32 (fp64) zero-initialised.
+struct RoiAlignArgs {
+    int dtype;
+    const void* feat;
+    const void* rois;
+    void* out;
+    const void* grad_out;
+    void* grad_accum;
+    int N, H, W, C, K, PH, PW;
+    double scale;
+    int sampling_ratio, aligned;
+};
+cudaError_t roi_align_forward(const RoiAlignArgs& a, cudaStream_t stream);
+cudaError_t roi_align_backward(const RoiAlignArgs& a, cudaStream_t stream);
+
 int colsum_blocks(int dtype, long long rows, int C);   // 0 = unsupported shape
 cudaError_t colsum(int dtype, const void* x, long long rows, int C, void* out, float* partial, int blocks,
                    cudaStream_t stream);

@@ -113,6 +113,7 @@ class DeformableTransformer(nn.Module):
         self.decoder = DeformableTransformerDecoder(decoder_layer, num_decoder_layers, return_intermediate_dec)
 
         self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model))
+        self._build_extra_modules()
         if two_stage:
             self.enc_output = nn.Linear(d_model, d_model)
             self.enc_output_norm = nn.LayerNorm(d_model)
@@ -121,6 +122,10 @@ class DeformableTransformer(nn.Module):
         else:
             self.reference_points = nn.Linear(d_model, 2)
         self._reset_parameters()
+
+    def _build_extra_modules(self):
+        """Hook for the multi-frame transformer (temporal_stage.py): modules registered here take part in
+        ``_reset_parameters`` exactly as in the reference constructor."""
 
     def _reset_parameters(self):
         for p in self.parameters():
@@ -194,7 +199,7 @@ class DeformableTransformer(nn.Module):
         return tokens, mask, pos, shapes, st, ls, ratios
 
     def forward(self, srcs, masks, pos_embeds, depth_srcs, depth_masks, depth_pos_embeds, query_embed=None,
-                rgbd_query=[]):
+                rgbd_query=[], _return_state=False):
         assert self.two_stage or query_embed is not None
         src_flatten, mask_flatten, lvl_pos_embed_flatten, shapes = _flatten_levels(
             srcs, masks, pos_embeds, self.level_embed)
@@ -244,6 +249,9 @@ class DeformableTransformer(nn.Module):
 
         hs, inter_references = self.decoder(tgt, reference_points, memory, spatial_shapes, level_start_index,
                                             valid_ratios, query_embed, mask_flatten)
+        if _return_state:         # what the TransVOD++ temporal stage continues from (temporal_stage.py)
+            return (hs, init_reference_out, inter_references, enc_outputs_class, enc_outputs_coord_unact,
+                    (memory, lvl_pos_embed_flatten, spatial_shapes, level_start_index, valid_ratios, shapes))
         return hs, init_reference_out, inter_references, enc_outputs_class, enc_outputs_coord_unact
 
 

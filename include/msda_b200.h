@@ -227,6 +227,26 @@ int msda_layer_colsum(int dtype, const void* x, int64_t rows, int channels, void
 int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t* mask, int64_t rows, int channels,
                                 void* stream);
 
+/* RoIAlign of the TransVOD++ temporal query stage: mmcv.ops.RoIAlign(output_size, spatial_scale, sampling_ratio,
+ * pool_mode='avg', aligned) as constructed at /root/reference/models/deformable_transformer_multi_plusplus.py:129-132
+ * and called at :499 and :514 (mmcv-full 1.7.0, not vendored by the reference; algorithm of its
+ * roi_align_cuda_kernel.cuh).  Replaces the mmcv binding roi_align_forward / roi_align_backward for pool_mode 'avg'.
+ * Layouts are token-major, i.e. what the encoder produces and what the query head consumes, so the reference's
+ * permute to NCHW (:498) and back (sparse_roi_head/head.py:66) disappear:
+ *   feature_tokens     [batch, height*width, channels]            dtype
+ *   rois               [num_rois, 5] = (batch index, x1, y1, x2, y2) FP32 (FP64 when dtype is F64), image units
+ *   pooled/grad_pooled [num_rois, pooled_height*pooled_width, channels] dtype
+ *   grad_feature_accum [batch, height*width, channels] FP32 (FP64 when dtype is F64), zero-initialised by the
+ *                      caller, accumulated with reductions (cast to dtype by the caller)
+ * sampling_ratio 0 = adaptive ceil(roi_size / pooled_size) grid, as in mmcv. */
+int msda_roi_align_forward(int dtype, const void* feature_tokens, const void* rois, int batch, int height,
+                           int width, int channels, int num_rois, int pooled_height, int pooled_width,
+                           double spatial_scale, int sampling_ratio, int aligned, void* pooled, void* stream);
+int msda_roi_align_backward(int dtype, const void* grad_pooled, const void* rois, int batch, int height,
+                            int width, int channels, int num_rois, int pooled_height, int pooled_width,
+                            double spatial_scale, int sampling_ratio, int aligned, void* grad_feature_accum,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

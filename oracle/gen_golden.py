@@ -27,6 +27,12 @@ import numpy as np
 import torch
 
 REF = os.environ.get("MSDA_REFERENCE", "/root/reference")
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]      # python oracle/gen_golden.py [case-name-prefix ...]
+
+
+def wanted(name):
+    return not ONLY or any(name.startswith(o) for o in ONLY)
+
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
 
 
@@ -65,14 +71,23 @@ def import_reference():
 
 def import_transvod_plusplus():
     """models/deformable_transformer_multi_plusplus.py does ``from mmcv import ops`` (:25) for the
-    RoIAlign of the temporal query stage (out of scope); mmcv is not installed, so a stub module
-    stands in -- the temporal decoder (:1030-1076) never touches it."""
+    RoIAlign of the temporal query stage; mmcv-full 1.7.0 is not installed, so a stub module stands
+    in whose RoIAlign has mmcv's constructor (output_size, spatial_scale, sampling_ratio,
+    pool_mode='avg', aligned=True) and computes with torchvision.ops.roi_align on CPU -- the same
+    Detectron algorithm (oracle/roi_align_oracle.py restates it and is pinned against it)."""
+    import torchvision
     mmcv = types.ModuleType("mmcv")
     ops = types.ModuleType("mmcv.ops")
 
-    class RoIAlign:
-        def __init__(self, *a, **k):
-            raise RuntimeError("mmcv stub: RoIAlign is outside the golden cases")
+    class RoIAlign(torch.nn.Module):
+        def __init__(self, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode="avg", aligned=True,
+                     use_torchvision=False):
+            super().__init__()
+            assert pool_mode == "avg"
+            self.args = (output_size, spatial_scale, sampling_ratio, aligned)
+
+        def forward(self, input, rois):
+            return torchvision.ops.roi_align(input, rois.to(input.dtype), *self.args)
 
     ops.RoIAlign = RoIAlign
     mmcv.ops = ops
@@ -87,6 +102,8 @@ def lsi_of(shapes):
 
 def op_case(func, name, shapes, n, m, d, lq, p, seed, loc_range=(0.0, 1.0), dtype=torch.float64):
     """The recipe of models/ops/test.py:33-36 (fp32 CPU draws, then cast)."""
+    if not wanted("op_" + name):
+        return None
     torch.manual_seed(seed)
     shapes_t = torch.as_tensor(shapes, dtype=torch.long)
     nl = len(shapes)
@@ -151,6 +168,8 @@ def save_module_case(name, module, inputs, call, wrt, store=None, grad_limit=Non
     values, the reference computes in fp64, and the file keeps fp32 copies (lossless for inputs and
     state, 1e-7 for outputs / gradients -- these cases serve the fp32 / bf16 tests only).
     ``grad_limit``: parameter gradients larger than this many elements are not stored."""
+    if not wanted(name):
+        return
     if store is not None:
         inputs = round_to_f32(module, inputs)
     tensors = {k: (v.clone().requires_grad_(True) if k in wrt else v) for k, v in inputs.items()}
@@ -185,7 +204,8 @@ def main():
     out = op_case(func, "toy_seed3", [(6, 4), (3, 2)], n=1, m=2, d=2, lq=2, p=2, seed=3)
     known = [0.001899378416, 0.004602827533, 0.004671175247, 0.004384399819,
              0.003795097174, 0.002512764199, 0.001844426151, 0.003634679248]
-    assert np.allclose(out.detach().numpy().ravel(), known, rtol=0, atol=1e-11), "RNG stream differs from survey"
+    assert out is None or np.allclose(out.detach().numpy().ravel(), known, rtol=0, atol=1e-11), \
+        "RNG stream differs from survey"
     # (2) locations outside [0,1): exercises the zero padding and the in-range test (cuh:288)
     op_case(func, "oob", [(5, 7), (3, 4), (2, 2)], n=2, m=3, d=8, lq=5, p=3, seed=11, loc_range=(-0.3, 1.3))
     # (3) production head width D=32, M=8, one level (shipped configs use 1 level)
@@ -527,6 +547,82 @@ def main():
         dict(tgt=tgt_t, reference_points=ref_t, src=mem1, src_spatial_shapes=dshapes, level_start_index=dlsi,
              valid_ratios=vr_t),
         tdtd_call, wrt=["tgt", "src"])
+
+    # ---------------- TransVOD++ multi-frame transformer with its temporal query stage -----------------
+    # (deformable_transformer_multi_plusplus.py:70-603): per-frame encoder/decoder with box refinement, RoIAlign of
+    # every decoder box (mmcv stand-in above), QRF head, three TQE + TDTD rounds.  80 queries, because the first
+    # round takes the top 80 * num_ref_frames of the reference-frame queries (:531).
+    # "transvodpp_f1": the UNMODIFIED reference (one reference frame: its [1, F, 2] valid-ratio expansion (:425) is
+    #                  then consistent with the one-level memory).
+    # "transvodpp_f2": two reference frames, for which the reference's temporal decoder call is mis-shaped
+    #                  (the oracle raises, the CUDA op mis-indexes); the temporal decoder is given
+    #                  valid_ratios[:, 0:1] instead -- the one documented deviation of this case.
+    class MLP(torch.nn.Module):                      # deformable_detr_multi_plusplus.py:585-597
+        def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+            super().__init__()
+            self.num_layers = num_layers
+            hdim = [hidden_dim] * (num_layers - 1)
+            self.layers = torch.nn.ModuleList(torch.nn.Linear(a, b) for a, b in zip([input_dim] + hdim, hdim + [output_dim]))
+
+        def forward(self, x):
+            for i, layer in enumerate(self.layers):
+                x = torch.relu(layer(x)) if i < self.num_layers - 1 else layer(x)
+            return x
+
+    class TransVODPP(torch.nn.Module):               # the detector's wiring, deformable_detr_multi_plusplus.py:78-81,183-194,320
+        def __init__(self, transformer, width, n_dec, n_cls=3):
+            super().__init__()
+            self.transformer = transformer
+            self.class_embed = torch.nn.ModuleList(torch.nn.Linear(width, n_cls) for _ in range(n_dec))
+            self.bbox_embed = torch.nn.ModuleList(MLP(width, width, 4, 3) for _ in range(n_dec))
+            self.temp_class_embed_list = torch.nn.ModuleList(torch.nn.Linear(width, n_cls) for _ in range(3))
+            self.temp_bbox_embed_list = torch.nn.ModuleList(MLP(width, width, 4, 3) for _ in range(3))
+            self.transformer.decoder.bbox_embed = self.bbox_embed          # with_box_refine (:194)
+
+        def forward(self, t, n_levels=1):
+            hs, init_ref, inter_ref, _, _, final_hs, final_ref, out = self.transformer(
+                [t["src0"]], [t["mask0"]], [t["pos0"]], [t["depth_src0"]], [t["depth_mask0"]], [t["depth_pos0"]],
+                t["imgs_whwh"], t["query_embed"], self.class_embed[-1], self.bbox_embed[-1],
+                self.temp_class_embed_list, self.temp_bbox_embed_list)
+            parts = [hs, init_ref, inter_ref, final_hs, final_ref]
+            for aux in out["aux_outputs"]:
+                parts += [aux["pred_logits"], aux["pred_boxes"]]
+            return torch.cat([p_.flatten() for p_ in parts])
+
+    def transvodpp_case(name, depth_type, use_depth, ref_frames, seed, fix_valid_ratios):
+        if not wanted(name):
+            return
+        torch.manual_seed(seed)
+        nq, (fh, fw) = 80, (4, 6)
+        c = 16                                       # narrow: three QRF heads are 40 k parameters each even so
+        model = TransVODPP(pp.DeformableTransformer(
+            d_model=c, nhead=heads, num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=64, dropout=0.0,
+            activation="relu", return_intermediate_dec=True, num_feature_levels=1, dec_n_points=pts, enc_n_points=pts,
+            num_query=nq, n_temporal_decoder_layers=1, num_ref_frames=ref_frames, use_depth=use_depth,
+            depth_type=depth_type, dpth_n_points=pts), c, 2).double()
+        perturb(model, seed + 1)
+        frames = ref_frames + 1
+        ins = dict(src0=torch.randn(frames, c, fh, fw), pos0=torch.randn(frames, c, fh, fw),
+                   depth_src0=torch.randn(frames, c, fh, fw), depth_pos0=torch.randn(frames, c, fh, fw),
+                   query_embed=torch.randn(nq, 2 * c))
+        mk = torch.zeros(frames, fh, fw, dtype=torch.bool)
+        mk[-1, :, 4:] = True                         # a padded reference frame (valid width 4: a power of two)
+        ins["mask0"] = mk
+        ins["depth_mask0"] = mk.clone()
+        ins["imgs_whwh"] = torch.tensor([[fw * 32, fh * 32, fw * 32, fh * 32]])
+        original = pp.TemporalDeformableTransformerDecoder.forward
+        if fix_valid_ratios:
+            def fixed(self, tgt, reference_points, src, shapes_, lsi_, valid_ratios, query_pos=None, mask=None):
+                return original(self, tgt, reference_points, src, shapes_, lsi_, valid_ratios[:, 0:1], query_pos, mask)
+            pp.TemporalDeformableTransformerDecoder.forward = fixed
+        try:
+            save_module_case(name, model, ins, lambda m_, t: m_(t), wrt=["src0", "depth_src0", "query_embed"],
+                             grad_limit=6000)
+        finally:
+            pp.TemporalDeformableTransformerDecoder.forward = original
+
+    transvodpp_case("transvodpp_f1", "Baseline_rgb", False, 1, 90, False)
+    transvodpp_case("transvodpp_f2_latefusion", "DepthDeform_latefusion_dformer", True, 2, 92, True)
 
     # Backbone Cross Fusion U-DF: fuse_layers + its layer (dformer_crossfusion_backbone.py:387-428,120-181)
     torch.manual_seed(41)

@@ -184,3 +184,58 @@ def run_case(name, gold, device, dtype=torch.float64):
     gpar = {k: (g.detach().double().cpu().numpy() if g is not None else None)
             for k, g in zip(params.keys(), grads[len(case["wrt"]):])}
     return out.detach().double().cpu().numpy(), gin, gpar
+
+
+# ---------------------------------------------------------------------------------------------------
+# TransVOD++ multi-frame transformer with its temporal query stage (dfvod_b200.temporal_stage), wired to the
+# detector's heads exactly like the golden generator wires the reference
+# (oracle/gen_golden.py: TransVODPP; reference deformable_detr_multi_plusplus.py:78-81, 183-194, 320).
+class _MLP(torch.nn.Module):
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        hdim = [hidden_dim] * (num_layers - 1)
+        self.layers = torch.nn.ModuleList(torch.nn.Linear(a, b) for a, b in zip([input_dim] + hdim, hdim + [output_dim]))
+
+    def forward(self, x):
+        for i, layer in enumerate(self.layers):
+            x = torch.relu(layer(x)) if i < self.num_layers - 1 else layer(x)
+        return x
+
+
+class TransVODPP(torch.nn.Module):
+    def __init__(self, transformer, width, n_dec, n_cls=3):
+        super().__init__()
+        self.transformer = transformer
+        self.class_embed = torch.nn.ModuleList(torch.nn.Linear(width, n_cls) for _ in range(n_dec))
+        self.bbox_embed = torch.nn.ModuleList(_MLP(width, width, 4, 3) for _ in range(n_dec))
+        self.temp_class_embed_list = torch.nn.ModuleList(torch.nn.Linear(width, n_cls) for _ in range(3))
+        self.temp_bbox_embed_list = torch.nn.ModuleList(_MLP(width, width, 4, 3) for _ in range(3))
+        self.transformer.decoder.bbox_embed = self.bbox_embed          # with_box_refine
+
+    def forward(self, t):
+        hs, init_ref, inter_ref, _, _, final_hs, final_ref, out = self.transformer(
+            [t["src0"]], [t["mask0"]], [t["pos0"]], [t["depth_src0"]], [t["depth_mask0"]], [t["depth_pos0"]],
+            t["imgs_whwh"], t["query_embed"], self.class_embed[-1], self.bbox_embed[-1],
+            self.temp_class_embed_list, self.temp_bbox_embed_list)
+        parts = [hs, init_ref, inter_ref, final_hs, final_ref]
+        for aux in out["aux_outputs"]:
+            parts += [aux["pred_logits"], aux["pred_boxes"]]
+        return torch.cat([p.flatten() for p in parts])
+
+
+def _transvodpp(depth_type, use_depth, ref_frames, width=16):
+    from dfvod_b200 import temporal_stage
+    return TransVODPP(temporal_stage.DeformableTransformer(
+        d_model=width, nhead=HEADS, num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=64, dropout=0.0,
+        activation="relu", return_intermediate_dec=True, num_feature_levels=1, dec_n_points=PTS, enc_n_points=PTS,
+        num_query=80, n_temporal_decoder_layers=1, num_ref_frames=ref_frames, use_depth=use_depth,
+        depth_type=depth_type, dpth_n_points=PTS), width, 2)
+
+
+CASES.update({
+    "transvodpp_f1": dict(build=lambda: _transvodpp("Baseline_rgb", False, 1), call=lambda m, t: m(t),
+                          wrt=["src0", "depth_src0", "query_embed"]),
+    "transvodpp_f2_latefusion": dict(build=lambda: _transvodpp("DepthDeform_latefusion_dformer", True, 2),
+                                     call=lambda m, t: m(t), wrt=["src0", "depth_src0", "query_embed"]),
+})

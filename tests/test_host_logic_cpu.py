@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import msda_oracle
+from oracle import msda_oracle, roi_align_oracle
 from tests import module_cases
 from tests.util import load_golden
 
@@ -22,7 +22,11 @@ class _OracleFunction:
 
 @pytest.fixture()
 def oracle_op(monkeypatch):
+    from dfvod_b200 import temporal_stage
     monkeypatch.setattr(msda_module, "MSDeformAttnFunction", _OracleFunction)
+    # the op has no gradient w.r.t. the boxes (mmcv RoIAlignFunction.backward returns None for them)
+    monkeypatch.setattr(temporal_stage, "roi_align_tokens",
+                        lambda tokens, rois, *a, **k: roi_align_oracle.roi_align_tokens(tokens, rois.detach(), *a, **k))
 
 
 @pytest.mark.parametrize("name", sorted(module_cases.CASES))
@@ -90,3 +94,35 @@ def test_constructor_validation():
         msda_module.MSDeformAttn(30, 1, 4, 2)
     with pytest.warns(UserWarning, match="power of 2"):
         msda_module.MSDeformAttn(24, 1, 2, 2)
+
+
+def test_transvodpp_clips_batch_like_single_clips(oracle_op):
+    """Several clips in one batch (clip-major) give, per clip, what the reference-shaped single-clip call gives."""
+    torch.manual_seed(21)
+    model = module_cases._transvodpp("DepthDeform_latefusion_dformer", True, 2).double().eval()
+    frames, c, (fh, fw) = 3, 16, (4, 6)
+    mk = lambda *s: torch.randn(*s, dtype=torch.float64)
+    ins = dict(src0=mk(2 * frames, c, fh, fw), pos0=mk(2 * frames, c, fh, fw), depth_src0=mk(2 * frames, c, fh, fw),
+               depth_pos0=mk(2 * frames, c, fh, fw), query_embed=mk(80, 2 * c))
+    mask = torch.zeros(2 * frames, fh, fw, dtype=torch.bool)
+    mask[4, :, 4:] = True
+    ins["mask0"] = mask
+    ins["depth_mask0"] = mask.clone()
+    sizes = torch.tensor([[fw * 32, fh * 32, fw * 32, fh * 32], [fw * 30, fh * 28, fw * 30, fh * 28]])
+
+    def run(sel, whwh):
+        t = {k: (v[sel] if k != "query_embed" else v) for k, v in ins.items()}
+        t["imgs_whwh"] = whwh
+        hs, init_ref, inter_ref, _, _, final_hs, final_ref, out = model.transformer(
+            [t["src0"]], [t["mask0"]], [t["pos0"]], [t["depth_src0"]], [t["depth_mask0"]], [t["depth_pos0"]],
+            t["imgs_whwh"], t["query_embed"], model.class_embed[-1], model.bbox_embed[-1],
+            model.temp_class_embed_list, model.temp_bbox_embed_list)
+        return hs, init_ref, inter_ref, final_hs, final_ref, out["aux_outputs"][1]["pred_boxes"]
+
+    with torch.no_grad():
+        both = run(slice(0, 2 * frames), sizes)
+        for clip in range(2):
+            one = run(slice(clip * frames, (clip + 1) * frames), sizes[clip:clip + 1])
+            for name, b, o in zip(("hs", "init_ref", "inter_ref", "final_hs", "final_ref", "aux_boxes"), both, one):
+                b = b[:, clip:clip + 1] if name in ("hs", "inter_ref") else b[clip:clip + 1]
+                np.testing.assert_allclose(b.numpy(), o.numpy(), rtol=1e-9, atol=1e-11, err_msg=name)

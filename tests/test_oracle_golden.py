@@ -89,3 +89,28 @@ def test_c_oracle_thread_count_independent():
     c_oracle.set_threads(0)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("aligned", [True, False])
+@pytest.mark.parametrize("sampling_ratio", [2, 0, 3])
+def test_roi_align_oracle_pinned_to_torchvision(aligned, sampling_ratio):
+    """mmcv is absent (and the reference has no vector for its RoIAlign), so the restatement of its published
+    algorithm is pinned against torchvision.ops.roi_align on CPU: same Detectron algorithm, same ``aligned`` switch,
+    forward and gradient, incl. boxes hanging over / outside the map and a zero-area box."""
+    import torchvision
+    from oracle import roi_align_oracle
+    torch.manual_seed(0)
+    feat = torch.randn(2, 5, 9, 13, dtype=torch.float64)
+    rois = torch.tensor([[0, 10., 20., 200., 150.], [1, -50., -30., 100., 400.], [0, 300., 100., 310., 104.],
+                         [1, 0., 0., 416., 288.], [1, 500., 500., 600., 600.], [0, 5., 5., 5., 5.]], dtype=torch.float64)
+    f1 = feat.clone().requires_grad_(True)
+    f2 = feat.clone().requires_grad_(True)
+    a = roi_align_oracle.roi_align(f1, rois, 7, 1 / 32, sampling_ratio, aligned)
+    b = torchvision.ops.roi_align(f2, rois, 7, 1 / 32, sampling_ratio, aligned)
+    assert float((a - b).abs().max()) <= 1e-13
+    g = torch.randn(a.shape, dtype=torch.float64)
+    a.backward(g)
+    b.backward(g)
+    assert float((f1.grad - f2.grad).abs().max()) <= 1e-12
+    tok = roi_align_oracle.roi_align_tokens(feat.flatten(2).transpose(1, 2), rois, 9, 13, 7, 1 / 32, sampling_ratio, aligned)
+    assert torch.equal(tok, a.detach().flatten(2).transpose(1, 2))
