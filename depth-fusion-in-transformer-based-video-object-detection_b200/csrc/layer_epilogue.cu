@@ -527,6 +527,123 @@ cudaError_t add_layernorm(const AddLayerNormArgs& a, bool backward, cudaStream_t
     }
 }
 
+// y = act(LayerNorm(x) * gamma + beta): the normalise-then-activate steps of the TransVOD++ dynamic interaction
+// head (features = relu(norm(bmm(...))), /root/reference/models/sparse_roi_head/head.py:156-170), whose rows are
+// narrow (64 channels after the first per-box product).  LANES lanes own a row (32 / LANES rows per warp), K 16-byte
+// chunks per lane: C = LANES * K * 16 / sizeof(T).  In place is fine (y == x): a lane reads its elements before it
+// writes them.  Forward only -- training keeps the PyTorch composition.
+template <typename T, int LANES, int K, int ACT>
+__global__ void __launch_bounds__(kLnWarps * 32)
+norm_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ y,
+                    long long rows, float eps)
+{
+    constexpr int V = Vec16<T>::n;
+    constexpr int C = LANES * K * V;
+    constexpr int RPW = 32 / LANES;
+    const int lane = threadIdx.x & 31, sub = lane % LANES, rw = lane / LANES;
+    const long long first = ((long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5)) * RPW + rw;
+    const long long stride = (long long)gridDim.x * kLnWarps * RPW;
+    float g[K][V], b[K][V];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        load16<T>(gamma + (k * LANES + sub) * V, g[k]);
+        load16<T>(beta + (k * LANES + sub) * V, b[k]);
+    }
+    // every lane of a warp runs the same number of iterations (the shuffles are warp-wide); rows past the end are
+    // clamped for the loads and skipped for the stores
+    const long long iters = (rows + stride - 1) / stride;
+    for (long long it = 0; it < iters; ++it) {
+        const long long row_raw = first + it * stride;
+        const bool live = row_raw < rows;
+        const long long base = (live ? row_raw : rows - 1) * C;
+        float v[K][V];
+#pragma unroll
+        for (int k = 0; k < K; ++k) load16_stream<T>(x + base + (k * LANES + sub) * V, v[k]);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < V; ++e) s += v[k][e];
+#pragma unroll
+        for (int off = LANES / 2; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        const float mean = s * (1.f / C);
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < V; ++e) { const float d = v[k][e] - mean; ss = fmaf(d, d, ss); }
+#pragma unroll
+        for (int off = LANES / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        const float rstd = rsqrtf(ss * (1.f / C) + eps);
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float o[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    // the unfused chain rounds the LayerNorm output to T before the activation
+                    o[e] = act_fwd<ACT>(round_to<T>(fmaf((v[k][e] - mean) * rstd, g[k][e], b[k][e])));
+                }
+                store16<T>(y + base + (k * LANES + sub) * V, o);
+            }
+        }
+    }
+}
+
+template <typename T, int LANES, int K>
+static cudaError_t launch_norm_act(const void* x, const void* gamma, const void* beta, void* y, long long rows,
+                                   float eps, int act, cudaStream_t st)
+{
+    const long long rows_per_cta = (long long)kLnWarps * (32 / LANES);
+    const long long want = (rows + rows_per_cta - 1) / rows_per_cta;
+    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+#define MSDA_NA(ACT) norm_act_fwd_kernel<T, LANES, K, ACT><<<grid, kLnWarps * 32, 0, st>>>( \
+        (const T*)x, (const T*)gamma, (const T*)beta, (T*)y, rows, eps)
+    switch (act) {
+        case kActNone: MSDA_NA(kActNone); break;
+        case kActRelu: MSDA_NA(kActRelu); break;
+        case kActGelu: MSDA_NA(kActGelu); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef MSDA_NA
+    return cudaGetLastError();
+}
+
+bool norm_act_supported(int dtype, int C)
+{
+    const int esz = dtype == kF32 ? 4 : (dtype == kBF16 || dtype == kF16 ? 2 : 0);
+    if (esz == 0 || C <= 0) return false;
+    const int bytes = C * esz;
+    return bytes == 128 || bytes == 256 || bytes == 512 || bytes == 1024 || bytes == 2048;
+}
+
+template <typename T>
+static cudaError_t dispatch_norm_act(int bytes, const void* x, const void* gamma, const void* beta, void* y,
+                                     long long rows, float eps, int act, cudaStream_t st)
+{
+    switch (bytes) {
+        case 128:  return launch_norm_act<T, 8, 1>(x, gamma, beta, y, rows, eps, act, st);
+        case 256:  return launch_norm_act<T, 16, 1>(x, gamma, beta, y, rows, eps, act, st);
+        case 512:  return launch_norm_act<T, 32, 1>(x, gamma, beta, y, rows, eps, act, st);
+        case 1024: return launch_norm_act<T, 32, 2>(x, gamma, beta, y, rows, eps, act, st);
+        case 2048: return launch_norm_act<T, 32, 4>(x, gamma, beta, y, rows, eps, act, st);
+        default:   return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t norm_act_forward(int dtype, const void* x, const void* gamma, const void* beta, void* y, long long rows,
+                             int C, float eps, int act, cudaStream_t st)
+{
+    if (!norm_act_supported(dtype, C)) return cudaErrorInvalidValue;
+    if (rows == 0) return cudaSuccess;
+    switch (dtype) {
+        case kF32:  return dispatch_norm_act<float>(C * 4, x, gamma, beta, y, rows, eps, act, st);
+        case kBF16: return dispatch_norm_act<__nv_bfloat16>(C * 2, x, gamma, beta, y, rows, eps, act, st);
+        case kF16:  return dispatch_norm_act<__half>(C * 2, x, gamma, beta, y, rows, eps, act, st);
+        default:    return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t zero_masked_rows(int dtype, void* data, const unsigned char* mask, long long rows, int C, cudaStream_t st)
 {
     if (rows == 0 || C == 0) return cudaSuccess;

@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 8; }
+extern "C" int msda_abi_version(void) { return 9; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -302,4 +302,17 @@ extern "C" int msda_roi_align_backward(int dtype, const void* grad_pooled, const
     a.N = batch; a.H = height; a.W = width; a.C = channels; a.K = num_rois; a.PH = pooled_height; a.PW = pooled_width;
     a.scale = spatial_scale; a.sampling_ratio = sampling_ratio; a.aligned = aligned;
     return (int)msda::roi_align_backward(a, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_norm_act_supported(int dtype, int channels)
+{
+    return msda::norm_act_supported(dtype, channels) ? 1 : 0;
+}
+
+extern "C" int msda_layer_norm_act_forward(int dtype, const void* x, const void* gamma, const void* beta, int64_t rows,
+                                           int channels, float eps, int act, void* y, void* stream)
+{
+    if (rows < 0) return (int)cudaErrorInvalidValue;
+    return (int)msda::norm_act_forward(dtype, x, gamma, beta, y, (long long)rows, channels, eps, act,
+                                       (cudaStream_t)stream);
 }

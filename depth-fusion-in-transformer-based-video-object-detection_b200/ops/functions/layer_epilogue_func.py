@@ -119,6 +119,31 @@ def add_layer_norm(norm, branch, residual=None, act=None, pos=None):
     return y if pos is None else (y, y + pos)
 
 
+def norm_act(norm, x, act=None, inplace=False):
+    """``act(norm(x))`` -- normalise, then activate (the order of the TransVOD++ dynamic interaction head,
+    /root/reference/models/sparse_roi_head/head.py:156-170; ``add_layer_norm`` activates BEFORE the norm).
+    One kernel when no gradient is needed and the row width is covered (64 .. 1024 channels of bf16, 32 .. 512 of
+    fp32); ``inplace`` lets it overwrite ``x``.  Otherwise the PyTorch composition."""
+    c = x.shape[-1]
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or norm.weight.requires_grad)
+    if (not needs_grad and x.is_cuda and x.dtype in _DTYPES and act in ACT_CODES and norm.elementwise_affine
+            and norm.bias is not None and tuple(norm.normalized_shape) == (c,)
+            and _lib.load().msda_layer_norm_act_supported(_DTYPES[x.dtype], int(c))):
+        dense = x.contiguous()
+        if dense.data_ptr() % 16 != 0:
+            dense = dense.clone()
+        y = dense if (inplace and dense is x) or dense is not x else torch.empty_like(dense)
+        gamma, beta = _dense(norm.weight.detach().to(x.dtype)), _dense(norm.bias.detach().to(x.dtype))
+        with torch.cuda.device(x.device):
+            code = _lib.load().msda_layer_norm_act_forward(
+                _DTYPES[x.dtype], dense.data_ptr(), gamma.data_ptr(), beta.data_ptr(), dense.numel() // c, int(c),
+                float(norm.eps), ACT_CODES[act], y.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(code, "msda_layer_norm_act_forward")
+        return y
+    y = norm(x)
+    return y if act in (None, "none") else getattr(F, act)(y)
+
+
 class ZeroMaskedRowsFunction(Function):
     """In place: rows of ``value`` [N, S, C] whose ``mask`` [N, S] entry is True become zero."""
 

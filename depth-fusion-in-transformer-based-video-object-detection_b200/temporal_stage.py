@@ -35,6 +35,7 @@ from torch import nn
 
 from . import _lib
 from .deformable_transformer import DeformableTransformer as _SingleFrameTransformer
+from .ops.functions import norm_act
 from .transformer_layers import (DeformableTransformerDecoderLayer, TemporalDeformableTransformerDecoder,
                                  _get_activation_fn, _get_clones, inverse_sigmoid)
 
@@ -170,10 +171,11 @@ class DynamicConv(nn.Module):
         parameters = self.dynamic_layer(pro_features).permute(1, 0, 2)
         param1 = parameters[:, :, :self.num_params].view(-1, self.hidden_dim, self.dim_dynamic)
         param2 = parameters[:, :, self.num_params:].view(-1, self.dim_dynamic, self.hidden_dim)
-        features = self.activation(self.norm1(torch.bmm(pooled, param1)))
-        features = self.activation(self.norm2(torch.bmm(features, param2)))
+        # normalise + ReLU as one in-place kernel each when no gradient is needed (ops/functions: norm_act)
+        features = norm_act(self.norm1, torch.bmm(pooled, param1), "relu", inplace=True)
+        features = norm_act(self.norm2, torch.bmm(features, param2), "relu", inplace=True)
         features = self.out_layer(features.flatten(1))
-        return self.activation(self.norm3(features))
+        return norm_act(self.norm3, features, "relu", inplace=True)
 
 
 _DEFAULT_SCALE_CLAMP = math.log(100000.0 / 16)
@@ -210,7 +212,7 @@ class RCNNHead(nn.Module):
         else:                                                          # [K, 49, C]
             pooled = roi_features
         pro = pro_features.reshape(N, nr_boxes, self.d_model).permute(1, 0, 2)
-        pro = self.norm1(pro + self.dropout1(self.self_attn(pro, pro, value=pro)[0]))
+        pro = self.norm1(pro + self.dropout1(self.self_attn(pro, pro, value=pro, need_weights=False)[0]))
         pro = pro.permute(1, 0, 2).reshape(1, N * nr_boxes, self.d_model)
         obj = self.norm2(pro + self.dropout2(self.inst_interact.forward_tokens(pro, pooled)))
         obj2 = self.linear2(self.dropout(self.activation(self.linear1(obj))))
@@ -268,11 +270,12 @@ class TemporalQueryEncoderLayer(nn.Module):
 
     def forward(self, query, ref_query, query_pos=None, ref_query_pos=None):
         q = k = self.with_pos_embed(query, query_pos)
-        tgt2 = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), query.transpose(0, 1))[0].transpose(0, 1)
+        tgt2 = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), query.transpose(0, 1),
+                              need_weights=False)[0].transpose(0, 1)
         tgt = self.norm2(query + self.dropout2(tgt2))
         tgt2 = self.cross_attn(self.with_pos_embed(tgt, query_pos).transpose(0, 1),
                                self.with_pos_embed(ref_query, ref_query_pos).transpose(0, 1),
-                               ref_query.transpose(0, 1))[0].transpose(0, 1)
+                               ref_query.transpose(0, 1), need_weights=False)[0].transpose(0, 1)
         tgt = self.norm1(tgt + self.dropout1(tgt2))
         return self.forward_ffn(tgt)
 
@@ -390,9 +393,9 @@ class DeformableTransformer(_SingleFrameTransformer):
 
         # RoI features + query / RoI fusion.  Current frame: memory (:498-501); reference frames: memory + position
         # embedding (:418-423, :511-517).  Each frame pools from its own map: roi batch index = frame.
-        if frames > 1:
-            mem_c, pos_c = by_clip(memory), by_clip(lvl_pos)
-            maps = torch.cat([mem_c[:, :1], mem_c[:, 1:] + pos_c[:, 1:]], 1).reshape(batch, tokens, c)
+        if frames > 1:              # one fused multiply-add: position embedding on the reference frames only
+            is_ref = (torch.arange(batch, device=device) % frames != 0).to(memory.dtype).view(batch, 1, 1)
+            maps = torch.addcmul(memory, lvl_pos, is_ref)
         else:
             maps = memory
         frame_index = torch.arange(batch, device=device, dtype=boxes_xyxy.dtype).repeat_interleave(nq)

@@ -301,7 +301,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
         if qk is None:
             qk = _add_pos(tgt, query_pos)
         qk = qk.transpose(0, 1)
-        mixed = self.self_attn(qk, qk, tgt.transpose(0, 1))[0].transpose(0, 1)
+        mixed = self.self_attn(qk, qk, tgt.transpose(0, 1), need_weights=False)[0].transpose(0, 1)
         if query_pos is not None:
             tgt, query = add_layer_norm(self.norm2, self.dropout2(mixed), tgt, None, query_pos)
         else:

@@ -227,6 +227,15 @@ int msda_layer_colsum(int dtype, const void* x, int64_t rows, int channels, void
 int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t* mask, int64_t rows, int channels,
                                 void* stream);
 
+/* y = act(LayerNorm(x) * gamma + beta), act 0 identity / 1 relu / 2 gelu(erf): the normalise-then-activate steps
+ * of the TransVOD++ dynamic interaction head, features = relu(norm(bmm(...))),
+ * /root/reference/models/sparse_roi_head/head.py:156-170.  x, y [rows, channels] (y may be x), gamma / beta
+ * [channels], all `dtype` (F32 / BF16 / F16), 16-byte aligned; channels * itemsize in {128, 256, 512, 1024, 2048}
+ * (msda_layer_norm_act_supported).  Forward only. */
+int msda_layer_norm_act_supported(int dtype, int channels);
+int msda_layer_norm_act_forward(int dtype, const void* x, const void* gamma, const void* beta, int64_t rows,
+                                int channels, float eps, int act, void* y, void* stream);
+
 /* RoIAlign of the TransVOD++ temporal query stage: mmcv.ops.RoIAlign(output_size, spatial_scale, sampling_ratio,
  * pool_mode='avg', aligned) as constructed at /root/reference/models/deformable_transformer_multi_plusplus.py:129-132
  * and called at :499 and :514 (mmcv-full 1.7.0, not vendored by the reference; algorithm of its

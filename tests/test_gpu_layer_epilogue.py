@@ -270,3 +270,43 @@ def test_transformer_inference_path_equals_training_path():
     with torch.no_grad():
         hs_infer = model(srcs, masks, poss, None, None, None, query)[0]
     assert nerr(hs_infer, hs_train.detach().double()) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("row_bytes", [128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize("act", [None, "relu", "gelu"])
+def test_norm_act_forward(dtype, row_bytes, act):
+    """msda_layer_norm_act_forward = act(LayerNorm(x)) of the dynamic interaction head
+    (/root/reference/models/sparse_roi_head/head.py:156-170) vs the fp64 composition; rows not a multiple of the
+    rows a warp / CTA owns; out of place and in place."""
+    from dfvod_b200.ops.functions import norm_act
+    c = row_bytes // torch.empty((), dtype=dtype).element_size()
+    torch.manual_seed(c)
+    norm = torch.nn.LayerNorm(c).to(DEV)
+    with torch.no_grad():
+        norm.weight.add_(torch.randn(c, device=DEV) * 0.3)
+        norm.bias.add_(torch.randn(c, device=DEV) * 0.3)
+    norm = norm.to(dtype)
+    x = (torch.randn(7, 53, c, device=DEV) * 1.5 + 0.3).to(dtype)
+    norm64 = torch.nn.LayerNorm(c).to(DEV).double()
+    norm64.load_state_dict({k: v.double() for k, v in norm.state_dict().items()})
+    ref = norm64(x.double())
+    ref = ref if act is None else getattr(F, act)(ref)
+    with torch.no_grad():
+        before = x.clone()
+        y = norm_act(norm, x, act)
+        assert torch.equal(x, before) and y.data_ptr() != x.data_ptr()
+        assert nerr(y, ref) <= TOL[dtype]
+        z = norm_act(norm, x, act, inplace=True)
+        assert z.data_ptr() == x.data_ptr() and torch.equal(z, y)
+
+
+def test_norm_act_keeps_autograd_and_odd_widths():
+    from dfvod_b200.ops.functions import norm_act
+    norm = torch.nn.LayerNorm(48).to(DEV)
+    x = torch.randn(5, 48, device=DEV, requires_grad=True)
+    y = norm_act(norm, x, "relu")                       # gradient needed -> PyTorch composition
+    y.sum().backward()
+    assert x.grad is not None and norm.weight.grad is not None
+    with torch.no_grad():
+        assert torch.equal(norm_act(norm, x, "relu"), F.relu(norm(x)))      # 192-byte rows: composition as well
