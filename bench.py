@@ -446,6 +446,34 @@ def fusion_layer_extras(torch, dev, world, dist, n_frames=4, iters=10):
     return out
 
 
+def input_projection_extras(torch, dev, world, dist, n_frames=8, iters=10):
+    """the input projections in front of the transformer (Conv2d 1x1 + GroupNorm(32, 256) per
+    backbone level, deformable_detr_single.py:101-150) on ResNet-50-shaped features of an 800x1333 image (C3 512 ch
+    100x167, C4 1024 ch 50x84, C5 2048 ch 25x42), batch 8, bf16: the reference's composition (NCHW conv, GroupNorm,
+    flatten + transpose + cat to tokens) against InputProjection.forward_tokens (token-major GEMM + in-place token
+    GroupNorm kernels)."""
+    from dfvod_b200.input_projection import InputProjection
+    bf = torch.bfloat16
+    levels = [(512, 100, 167), (1024, 50, 84), (2048, 25, 42)]
+    torch.manual_seed(8)
+    projs = [InputProjection(cin, 256).to(dev).to(bf).eval() for cin, _, _ in levels]
+    feats = [torch.randn(n_frames, cin, h, w, device=dev).to(bf) for cin, h, w in levels]
+    with torch.no_grad():
+        composition = lambda: torch.cat([p(x).flatten(2).transpose(1, 2) for p, x in zip(projs, feats)], 1)
+        from dfvod_b200.input_projection import project_levels
+        tokens = lambda: project_levels(projs, feats)[0]
+        ms_ref = _reduce_max(torch, dist, world, dev, _time_events(torch, composition, iters, 3))
+        ms_tok = _reduce_max(torch, dist, world, dev, _time_events(torch, tokens, iters, 3))
+        gn_in = torch.randn(n_frames, 16700, 256, device=dev).to(bf)
+        from dfvod_b200.input_projection import group_norm_tokens
+        norm = projs[0][1]
+        ms_gn = _time_events(torch, lambda: group_norm_tokens(gn_in, 32, norm.weight, norm.bias, 1e-5, inplace=True), 20, 3)
+    gn_bytes = gn_in.numel() * 2 * 3                       # read (statistics), read + write (apply)
+    return {"frames_per_gpu": n_frames, "levels": levels, "dtype": "bf16", "reference_composition_ms": ms_ref,
+            "token_major_ms": ms_tok,
+            "group_norm_tokens_kernels": {"rows": n_frames * 16700, "ms": ms_gn, "gbytes_per_s": gn_bytes / ms_gn / 1e6}}
+
+
 def train_step_extras(torch, dev, world, dist, n_frames=4, iters=5):
     """BASELINE.json configs[4]: Encoder-Cross-Fusion training step (fwd + bwd + AdamW), frames
     sharded over GPUs, gradients all-reduced over NCCL by dfvod_b200.data_parallel.  Model:
@@ -615,7 +643,8 @@ def run_b200(args):
         del value, loc, attn, gout, host, pinned_out          # give the memory back first
         torch.cuda.empty_cache()
         for name, fn in (("detr_inference", encoder_extras), ("encoder_cross_fusion_layer", fusion_layer_extras),
-                         ("transvod_clip_inference", clip_extras), ("train_step", train_step_extras)):
+                         ("transvod_clip_inference", clip_extras), ("input_projections", input_projection_extras),
+                         ("train_step", train_step_extras)):
             try:
                 extras[name] = fn(torch, dev, world, dist)
             except Exception as exc:                          # extras never invalidate the main line

@@ -644,6 +644,156 @@ cudaError_t norm_act_forward(int dtype, const void* x, const void* gamma, const 
     }
 }
 
+// GroupNorm on TOKEN-MAJOR activations: x [N, S, C], groups of C / G consecutive channels, statistics per (n, group)
+// over S * C / G elements.  The reference's input projections are Conv2d(1x1) + GroupNorm(32, 256) on NCHW maps that
+// the transformer then flattens and transposes (/root/reference/models/deformable_detr_single.py:101-150, :262-267;
+// deformable_transformer_single.py:190-206); with the projection computed as a token-major GEMM the norm runs here and
+// the NCHW tensor, its transpose and the concatenation never exist.
+//   pass 1: per-CTA partial (sum, sum of squares) of each group over a slab of rows -> partial[n][slab][G][2]
+//   pass 2: every CTA folds its sample's partials (fp64), then y = (x - mean) * rstd * gamma + beta, in place.
+// A 16-byte vector never straddles two groups (host checks (C / G) % V == 0).
+constexpr int kGnWarps = 8;
+constexpr int kGnMaxGroups = 64;
+constexpr int kGnMaxVecs = 256;         // C * sizeof(T) <= 4096 bytes
+
+template <typename T>
+__global__ void __launch_bounds__(kGnWarps * 32)
+group_norm_tokens_stats_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, float* __restrict__ partial,
+                               long long S, int C, int G, int slabs, long long item_stride)
+{
+    constexpr int V = Vec16<T>::n;
+    __shared__ float s_part[kGnWarps][kGnMaxVecs][2];        // fixed-order fold below: results are deterministic
+    const int n = blockIdx.y, slab = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long rows_per = (S + slabs - 1) / slabs;
+    const long long r0 = (long long)slab * rows_per, r1 = r0 + rows_per < S ? r0 + rows_per : S;
+    const int vecs = C / V, cpg = C / G;
+    const T* base = x + (long long)n * item_stride;
+    for (int v = lane; v < vecs; v += 32) {                  // a lane keeps to its own vector columns
+        float sum = 0.f, sq = 0.f, pb[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) pb[e] = 0.f;
+        if (pre_bias != nullptr) load16<T>(pre_bias + v * V, pb);
+        for (long long r = r0 + warp; r < r1; r += kGnWarps) {
+            float f[V];
+            load16_stream<T>(base + r * C + v * V, f);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float t = pre_bias != nullptr ? round_to<T>(f[e] + pb[e]) : f[e];   // the conv output is a T
+                sum += t;
+                sq = fmaf(t, t, sq);
+            }
+        }
+        s_part[warp][v][0] = sum;
+        s_part[warp][v][1] = sq;
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int vpg = cpg / V;                             // vector columns per group
+        float sum = 0.f, sq = 0.f;
+        for (int w = 0; w < kGnWarps; ++w)
+            for (int v = threadIdx.x * vpg; v < (threadIdx.x + 1) * vpg; ++v) { sum += s_part[w][v][0]; sq += s_part[w][v][1]; }
+        float* out = partial + (((long long)n * slabs + slab) * G + threadIdx.x) * 2;
+        out[0] = sum;
+        out[1] = sq;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGnWarps * 32)
+group_norm_tokens_apply_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias,
+                               const float* __restrict__ partial, const T* __restrict__ gamma,
+                               const T* __restrict__ beta, T* __restrict__ y, long long S, int C, int G, int slabs,
+                               float eps, long long item_stride)
+{
+    constexpr int V = Vec16<T>::n;
+    __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
+    const int n = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < G) {
+        double sum = 0.0, sq = 0.0;
+        for (int sl = 0; sl < slabs; ++sl) {
+            const float* p = partial + (((long long)n * slabs + sl) * G + threadIdx.x) * 2;
+            sum += (double)p[0];
+            sq += (double)p[1];
+        }
+        const double cnt = (double)S * (double)(C / G);
+        const double mean = sum / cnt;
+        double var = sq / cnt - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int vecs = C / V, cpg = C / G;
+    const T* xin = x + (long long)n * item_stride;
+    T* yout = y + (long long)n * item_stride;
+    const long long rows_per = (S + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rows_per, r1 = r0 + rows_per < S ? r0 + rows_per : S;
+    for (int v = lane; v < vecs; v += 32) {
+        float g[V], b[V], pb[V];
+        load16<T>(gamma + v * V, g);
+        load16<T>(beta + v * V, b);
+#pragma unroll
+        for (int e = 0; e < V; ++e) pb[e] = 0.f;
+        if (pre_bias != nullptr) load16<T>(pre_bias + v * V, pb);
+        const int grp = v * V / cpg;
+        const float mean = s_mean[grp], rstd = s_rstd[grp];
+        for (long long r = r0 + warp; r < r1; r += kGnWarps) {
+            float f[V];
+            load16_stream<T>(xin + r * C + v * V, f);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float t = pre_bias != nullptr ? round_to<T>(f[e] + pb[e]) : f[e];
+                f[e] = fmaf((t - mean) * rstd, g[e], b[e]);
+            }
+            store16<T>(yout + r * C + v * V, f);
+        }
+    }
+}
+
+int group_norm_tokens_slabs(int dtype, long long S, int C, int G)
+{
+    const int esz = dtype == kF32 ? 4 : (dtype == kBF16 || dtype == kF16 ? 2 : 0);
+    if (esz == 0 || C <= 0 || G <= 0 || G > kGnMaxGroups || C % G != 0 || S <= 0) return 0;
+    const int v = 16 / esz;
+    if ((C / G) % v != 0 || C / v > kGnMaxVecs) return 0;
+    const long long want = (S + 63) / 64;                    // >= 64 rows per slab
+    return (int)(want < 64 ? want : 64);
+}
+
+template <typename T>
+static cudaError_t launch_group_norm_tokens(const void* x, const void* pre_bias, const void* gamma, const void* beta,
+                                            void* y, float* partial, int N, long long S, int C, int G, int slabs,
+                                            float eps, long long item_stride, cudaStream_t st)
+{
+    group_norm_tokens_stats_kernel<T><<<dim3(slabs, N), kGnWarps * 32, 0, st>>>((const T*)x, (const T*)pre_bias, partial,
+                                                                               S, C, G, slabs, item_stride);
+    const long long want = (S + 31) / 32;
+    const int per_sample = (int)(want < 296 ? want : 296);
+    const int blocks = per_sample > 0 ? per_sample : 1;
+    group_norm_tokens_apply_kernel<T><<<dim3(blocks, N), kGnWarps * 32, 0, st>>>(
+        (const T*)x, (const T*)pre_bias, partial, (const T*)gamma, (const T*)beta, (T*)y, S, C, G, slabs, eps, item_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t group_norm_tokens(int dtype, const void* x, const void* pre_bias, const void* gamma, const void* beta,
+                              void* y, float* partial, int N, long long S, int C, int G, int slabs, float eps,
+                              long long item_stride, cudaStream_t st)
+{
+    if (N == 0) return cudaSuccess;
+    if (slabs <= 0 || slabs != group_norm_tokens_slabs(dtype, S, C, G) || N > 65535) return cudaErrorInvalidValue;
+    if (item_stride == 0) item_stride = S * C;
+    const int v = dtype == kF32 ? 4 : 8;
+    if (item_stride < S * C || item_stride % v != 0) return cudaErrorInvalidValue;
+    switch (dtype) {
+        case kF32:  return launch_group_norm_tokens<float>(x, pre_bias, gamma, beta, y, partial, N, S, C, G, slabs, eps, item_stride, st);
+        case kBF16: return launch_group_norm_tokens<__nv_bfloat16>(x, pre_bias, gamma, beta, y, partial, N, S, C, G, slabs, eps, item_stride, st);
+        case kF16:  return launch_group_norm_tokens<__half>(x, pre_bias, gamma, beta, y, partial, N, S, C, G, slabs, eps, item_stride, st);
+        default:    return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t zero_masked_rows(int dtype, void* data, const unsigned char* mask, long long rows, int C, cudaStream_t st)
 {
     if (rows == 0 || C == 0) return cudaSuccess;

@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 9; }
+extern "C" int msda_abi_version(void) { return 11; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -315,4 +315,21 @@ extern "C" int msda_layer_norm_act_forward(int dtype, const void* x, const void*
     if (rows < 0) return (int)cudaErrorInvalidValue;
     return (int)msda::norm_act_forward(dtype, x, gamma, beta, y, (long long)rows, channels, eps, act,
                                        (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_group_norm_tokens_slabs(int dtype, int64_t tokens_per_item, int channels, int groups)
+{
+    return msda::group_norm_tokens_slabs(dtype, (long long)tokens_per_item, channels, groups);
+}
+
+extern "C" int msda_layer_group_norm_tokens(int dtype, const void* x, const void* channel_bias, const void* gamma,
+                                            const void* beta, int batch, int64_t tokens_per_item, int channels,
+                                            int groups, float eps, int64_t item_stride, float* partial_scratch,
+                                            int slabs, void* y, void* stream)
+{
+    if (batch < 0 || tokens_per_item < 0 || item_stride < 0) return (int)cudaErrorInvalidValue;
+    if (tokens_per_item == 0) return 0;
+    return (int)msda::group_norm_tokens(dtype, x, channel_bias, gamma, beta, y, partial_scratch, batch,
+                                        (long long)tokens_per_item, channels, groups, slabs, eps,
+                                        (long long)item_stride, (cudaStream_t)stream);
 }

@@ -127,6 +127,10 @@ struct FfnArgs {
 bool ffn_layernorm_supported(int dtype, int d_model, int d_ffn);
 cudaError_t ffn_layernorm_forward(const FfnArgs& a, cudaStream_t stream);
 
+int group_norm_tokens_slabs(int dtype, long long S, int C, int G);    // 0 = unsupported shape
+cudaError_t group_norm_tokens(int dtype, const void* x, const void* pre_bias, const void* gamma, const void* beta,
+                              void* y, float* partial, int N, long long S, int C, int G, int slabs, float eps,
+                              long long item_stride, cudaStream_t stream);
 bool norm_act_supported(int dtype, int C);
 cudaError_t norm_act_forward(int dtype, const void* x, const void* gamma, const void* beta, void* y, long long rows,
                              int C, float eps, int act, cudaStream_t stream);

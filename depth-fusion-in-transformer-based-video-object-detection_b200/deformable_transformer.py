@@ -29,26 +29,38 @@ from .transformer_layers import (DeformableTransformerDecoder, DeformableTransfo
                                  RGBDDeformableTransformerEncoderV2, encoder_reference_points)
 
 
+def _as_tokens(level):
+    """A level as tokens [N, H*W, C]: NCHW maps are flattened and transposed (single.py:195-198); levels that already
+    are token-major (input_projection.InputProjection.forward_tokens) pass through."""
+    return level if level.dim() == 3 else level.flatten(2).transpose(1, 2)
+
+
 def _flatten_levels(maps, masks, pos_embeds, level_embed=None):
-    """[N,C,H,W] per level -> tokens [N, sum HW, C], mask [N, sum HW], pos (+ level embedding),
-    shapes (python list of (H, W))."""
-    shapes = [(feat.shape[2], feat.shape[3]) for feat in maps]
+    """[N,C,H,W] (or token-major [N,H*W,C]) per level -> tokens [N, sum HW, C], mask [N, sum HW], pos (+ level
+    embedding), shapes (python list of (H, W), read from the masks)."""
+    shapes = [(mask.shape[1], mask.shape[2]) for mask in masks]
+    for feat, (h, w) in zip(maps, shapes):
+        assert (feat.shape[1] == h * w) if feat.dim() == 3 else (tuple(feat.shape[2:]) == (h, w)), \
+            "feature level and its mask disagree on (H, W)"
+    flat_mask = masks[0].flatten(1) if len(masks) == 1 else torch.cat([m.flatten(1) for m in masks], 1)
     embed_trains = level_embed is not None and torch.is_grad_enabled() and level_embed.requires_grad
-    if not embed_trains and flatten_levels_supported(list(maps)) and flatten_levels_supported(list(pos_embeds)):
-        # inference: one transposing kernel per level writes straight into the flattened tensors
+    nchw = [m for m in maps if m.dim() == 4]
+    if all(m.dim() == 3 for m in maps):
+        tokens = maps[0] if len(maps) == 1 else torch.cat(list(maps), 1)
+    elif len(nchw) == len(maps) and flatten_levels_supported(list(maps)):
+        tokens = flatten_levels(list(maps))          # inference: one transposing kernel per level, no cat
+    else:
+        tokens = torch.cat([_as_tokens(m) for m in maps], 1)
+    if not embed_trains and flatten_levels_supported(list(pos_embeds)):
         adds = None if level_embed is None else [level_embed[lvl] for lvl in range(len(maps))]
-        return (flatten_levels(list(maps)), torch.cat([m.flatten(1) for m in masks], 1),
-                flatten_levels(list(pos_embeds), adds), shapes)
-    tokens, flat_masks, flat_pos, shapes = [], [], [], []
-    for lvl, (feat, mask, pos) in enumerate(zip(maps, masks, pos_embeds)):
-        shapes.append((feat.shape[2], feat.shape[3]))
-        tokens.append(feat.flatten(2).transpose(1, 2))
-        flat_masks.append(mask.flatten(1))
-        pos = pos.flatten(2).transpose(1, 2)
-        if level_embed is not None:
-            pos = pos + level_embed[lvl].view(1, 1, -1)
-        flat_pos.append(pos)
-    return torch.cat(tokens, 1), torch.cat(flat_masks, 1), torch.cat(flat_pos, 1), shapes
+        pos = flatten_levels(list(pos_embeds), adds)
+    else:
+        flat_pos = []
+        for lvl, p in enumerate(pos_embeds):
+            p = _as_tokens(p)
+            flat_pos.append(p if level_embed is None else p + level_embed[lvl].view(1, 1, -1))
+        pos = flat_pos[0] if len(flat_pos) == 1 else torch.cat(flat_pos, 1)
+    return tokens, flat_mask, pos, shapes
 
 
 _SHAPE_TENSORS = {}

@@ -227,6 +227,21 @@ int msda_layer_colsum(int dtype, const void* x, int64_t rows, int channels, void
 int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t* mask, int64_t rows, int channels,
                                 void* stream);
 
+/* GroupNorm on token-major activations x [batch, tokens_per_item, channels] (groups of channels / groups consecutive
+ * channels, statistics per (item, group)): the nn.GroupNorm(32, hidden_dim) of the reference's input projections,
+ * /root/reference/models/deformable_detr_single.py:101-150, applied to the projection computed token-major so that
+ * the flatten / transpose / concatenation of deformable_transformer_single.py:190-206 disappear.  y may be x.
+ * channel_bias [channels] or NULL: added to x first (the convolution's bias, so the projection GEMM needs no
+ * epilogue); item_stride: elements between consecutive items of x and y (0 = dense; a level's slice of the
+ * flattened multi-level token tensor has tokens_of_all_levels * channels).
+ * partial_scratch: fp32 [batch, slabs, groups, 2], slabs = msda_layer_group_norm_tokens_slabs(...) (0 = shape not
+ * supported: groups <= 64, channels / groups a multiple of the 16-byte vector).  dtype F32 / BF16 / F16.  Forward. */
+int msda_layer_group_norm_tokens_slabs(int dtype, int64_t tokens_per_item, int channels, int groups);
+int msda_layer_group_norm_tokens(int dtype, const void* x, const void* channel_bias, const void* gamma,
+                                 const void* beta, int batch, int64_t tokens_per_item, int channels, int groups,
+                                 float eps, int64_t item_stride, float* partial_scratch, int slabs, void* y,
+                                 void* stream);
+
 /* y = act(LayerNorm(x) * gamma + beta), act 0 identity / 1 relu / 2 gelu(erf): the normalise-then-activate steps
  * of the TransVOD++ dynamic interaction head, features = relu(norm(bmm(...))),
  * /root/reference/models/sparse_roi_head/head.py:156-170.  x, y [rows, channels] (y may be x), gamma / beta

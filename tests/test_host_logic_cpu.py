@@ -126,3 +126,46 @@ def test_transvodpp_clips_batch_like_single_clips(oracle_op):
             for name, b, o in zip(("hs", "init_ref", "inter_ref", "final_hs", "final_ref", "aux_boxes"), both, one):
                 b = b[:, clip:clip + 1] if name in ("hs", "inter_ref") else b[clip:clip + 1]
                 np.testing.assert_allclose(b.numpy(), o.numpy(), rtol=1e-9, atol=1e-11, err_msg=name)
+
+
+def test_input_projection_is_the_reference_sequential():
+    """input_projection.InputProjection keeps the reference's nn.Sequential(Conv2d, GroupNorm(32, hidden)) state-dict
+    keys (deformable_detr_single.py:101-123) and NCHW forward; forward_tokens is its flatten(2).transpose(1, 2)."""
+    from dfvod_b200.input_projection import InputProjection
+    torch.manual_seed(0)
+    for kwargs in (dict(kernel_size=1), dict(kernel_size=3, stride=2, padding=1)):
+        proj = InputProjection(24, 64, **kwargs).double()
+        ref = torch.nn.Sequential(torch.nn.Conv2d(24, 64, **kwargs), torch.nn.GroupNorm(32, 64)).double()
+        assert sorted(proj.state_dict()) == sorted(ref.state_dict()) == ["0.bias", "0.weight", "1.bias", "1.weight"]
+        with torch.no_grad():
+            for prm in proj.parameters():
+                prm.add_(torch.randn_like(prm) * 0.2)
+        ref.load_state_dict(proj.state_dict())
+        x = torch.randn(2, 24, 7, 9, dtype=torch.float64)
+        want = ref(x)
+        np.testing.assert_allclose(proj(x).detach().numpy(), want.detach().numpy(), rtol=1e-12, atol=1e-12)
+        tokens, (h, w) = proj.forward_tokens(x)
+        assert (h, w) == tuple(want.shape[2:])
+        np.testing.assert_allclose(tokens.detach().numpy(), want.flatten(2).transpose(1, 2).detach().numpy(),
+                                   rtol=1e-10, atol=1e-12)
+
+
+def test_transformer_accepts_token_major_levels(oracle_op):
+    """Levels handed over as [N, H*W, C] tokens (InputProjection.forward_tokens) give what NCHW maps give."""
+    from dfvod_b200.deformable_transformer import DeformableTransformer
+    torch.manual_seed(6)
+    shapes = [(5, 7), (3, 4)]
+    model = DeformableTransformer(d_model=32, nhead=4, num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=64,
+                                  dropout=0.0, num_feature_levels=2, return_intermediate_dec=True).double().eval()
+    srcs = [torch.randn(2, 32, h, w, dtype=torch.float64) for h, w in shapes]
+    poss = [torch.randn(2, 32, h, w, dtype=torch.float64) for h, w in shapes]
+    masks = [torch.zeros(2, h, w, dtype=torch.bool) for h, w in shapes]
+    masks[0][1, :, -2:] = True
+    query = torch.randn(6, 64, dtype=torch.float64)
+    with torch.no_grad():
+        a = model(srcs, masks, poss, None, None, None, query)[0]
+        b = model([s.flatten(2).transpose(1, 2).contiguous() for s in srcs], masks, poss, None, None, None, query)[0]
+        c = model([srcs[0].flatten(2).transpose(1, 2), srcs[1]], masks, poss, None, None, None, query)[0]
+    assert torch.equal(a, b) and torch.equal(a, c)
+    with pytest.raises(AssertionError, match="disagree"):
+        model([srcs[0][:, :, :-1]] + srcs[1:], masks, poss, None, None, None, query)
