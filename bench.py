@@ -599,7 +599,7 @@ def run_b200(args):
     pinned_out = [torch.empty((n, s, M * D), dtype=tdtype).pin_memory(),
                   torch.empty_like(value_h).pin_memory(), torch.empty_like(loc_h).pin_memory(),
                   torch.empty_like(attn_h).pin_memory()]
-    pipe = HostPipelinedMSDA(dev, st.cpu(), ls.cpu(), M, D, P, s, dtype=tdtype, chunk_frames=1, depth=3)
+    pipe = HostPipelinedMSDA(dev, st.cpu(), ls.cpu(), M, D, P, s, dtype=tdtype, chunk_frames=2, depth=3)
 
     def e2e_step():
         pipe.forward_backward(*host, *pinned_out)

@@ -12,7 +12,9 @@ that flow through a three-stage pipeline on three CUDA streams
     copy-out stream: D2H  out / grad_value / grad_loc / grad_attn of chunk i-1
 
 with a ring of device staging buffers guarded by events.  PCIe is full duplex, so the step costs
-about max(H2D, D2H) instead of H2D + compute + D2H.
+about max(H2D, D2H) instead of H2D + compute + D2H.  Consecutive calls pipeline into each other: the
+inputs are HOST tensors (ready when the call is made), so the copy-in of call k+1 does not wait for the
+copy-out of call k; only the ring slots are re-used under their events.
 """
 import torch
 
@@ -50,6 +52,7 @@ class HostPipelinedMSDA:
         self.s_run = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
         self.launches = 0
+        self._uses = 0                 # chunks pushed through the ring so far (across calls)
 
     def forward_backward(self, value, loc, attn, grad_out, out, grad_value, grad_loc, grad_attn):
         """All arguments are pinned host tensors shaped like the op's device tensors with batch N;
@@ -61,15 +64,15 @@ class HostPipelinedMSDA:
         lib = _lib.load()
         n = value.shape[0]
         cur = torch.cuda.current_stream(self.device)
-        for s in (self.s_in, self.s_out):
-            s.wait_stream(cur)
         n_chunks = (n + self.chunk - 1) // self.chunk
         for i in range(n_chunks):
             a, b = i * self.chunk, min(n, (i + 1) * self.chunk)
             k = b - a
-            slot = self.ring[i % self.depth]
+            use = self._uses
+            self._uses += 1
+            slot = self.ring[use % self.depth]
             with torch.cuda.stream(self.s_in):
-                if i >= self.depth:
+                if use >= self.depth:
                     self.s_in.wait_event(slot["drained"])          # slot's previous results are out
                 slot["value"][:k].copy_(value[a:b], non_blocking=True)
                 slot["loc"][:k].copy_(loc[a:b], non_blocking=True)
