@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 11; }
+extern "C" int msda_abi_version(void) { return 12; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -332,4 +332,22 @@ extern "C" int msda_layer_group_norm_tokens(int dtype, const void* x, const void
     return (int)msda::group_norm_tokens(dtype, x, channel_bias, gamma, beta, y, partial_scratch, batch,
                                         (long long)tokens_per_item, channels, groups, slabs, eps,
                                         (long long)item_stride, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_proj_layernorm_supported(int dtype, int d_in, int d_out)
+{
+    return msda::proj_layernorm_supported(dtype, d_in, d_out) ? 1 : 0;
+}
+
+extern "C" int msda_layer_proj_layernorm_forward(int dtype, const void* x, const void* weight, const void* bias,
+                                                 const void* residual, const void* gamma, const void* beta,
+                                                 const void* pos, int64_t rows, int d_model, float eps, void* y,
+                                                 void* y_pos, void* stream)
+{
+    if (rows < 0) return (int)cudaErrorInvalidValue;
+    msda::ProjArgs a{};
+    a.dtype = dtype; a.rows = (long long)rows; a.C = d_model; a.eps = eps;
+    a.x = x; a.w = weight; a.b = bias; a.residual = residual; a.gamma = gamma; a.beta = beta; a.pos = pos;
+    a.y = y; a.y_pos = y_pos;
+    return (int)msda::proj_layernorm_forward(a, (cudaStream_t)stream);
 }

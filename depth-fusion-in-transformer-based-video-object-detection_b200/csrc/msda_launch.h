@@ -127,6 +127,25 @@ struct FfnArgs {
 bool ffn_layernorm_supported(int dtype, int d_model, int d_ffn);
 cudaError_t ffn_layernorm_forward(const FfnArgs& a, cudaStream_t stream);
 
+// Output projection + residual + LayerNorm on tcgen05 (proj_fused.cu): y = LayerNorm(residual + x @ W^T + b), y_pos = y + pos
+struct ProjArgs {
+    int dtype;                // kBF16
+    long long rows;
+    int C;                    // d_model (256): W is [C, C] in nn.Linear layout
+    float eps;
+    const void* x;            // [rows, C]
+    const void* w;            // [C, C]
+    const void* b;            // [C]
+    const void* residual;     // [rows, C] or null
+    const void* gamma;        // [C]
+    const void* beta;         // [C]
+    const void* pos;          // [rows, C] or null
+    void* y;                  // [rows, C]
+    void* y_pos;              // [rows, C] or null
+};
+bool proj_layernorm_supported(int dtype, int d_in, int d_out);
+cudaError_t proj_layernorm_forward(const ProjArgs& a, cudaStream_t stream);
+
 int group_norm_tokens_slabs(int dtype, long long S, int C, int G);    // 0 = unsupported shape
 cudaError_t group_norm_tokens(int dtype, const void* x, const void* pre_bias, const void* gamma, const void* beta,
                               void* y, float* partial, int N, long long S, int C, int G, int slabs, float eps,

@@ -172,6 +172,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tensor_m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         :: "r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// the same box, only as far as L2 (no shared-memory destination, no barrier): hides HBM latency of a later load
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tensor_map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" :: "l"(tensor_map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tensor_map)
 {
     asm volatile("prefetch.tensormap [%0];" :: "l"(tensor_map) : "memory");

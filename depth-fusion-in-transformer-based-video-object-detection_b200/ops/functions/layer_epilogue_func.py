@@ -309,6 +309,48 @@ def ffn_layer_norm(linear1, linear2, norm, x, pos=None):
     return y if y_pos is None else (y, y_pos.view(shape))
 
 
+def proj_layer_norm_supported(x, linear, norm):
+    """The tcgen05 projection + residual + LayerNorm kernel covers bf16 inference at d_model 256 (csrc/proj_fused.cu)."""
+    if not x.is_cuda or x.dtype != torch.bfloat16 or linear.bias is None:
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or linear.weight.requires_grad or norm.weight.requires_grad):
+        return False
+    if linear.weight.dtype != torch.bfloat16 or norm.weight.dtype != torch.bfloat16:
+        return False
+    c = x.shape[-1]
+    if linear.in_features != c or linear.out_features != c or tuple(norm.normalized_shape) != (c,) or \
+            not norm.elementwise_affine or norm.bias is None:
+        return False
+    return bool(_lib.load().msda_layer_proj_layernorm_supported(_lib.DTYPE_BF16, int(c), int(c)))
+
+
+def proj_layer_norm(linear, norm, x, residual=None, pos=None):
+    """``norm(residual + linear(x))`` (and ``that + pos``): the attention's output projection and the layer's
+    residual + LayerNorm in ONE tensor-core kernel when :func:`proj_layer_norm_supported`; otherwise the
+    GEMM + fused add-LayerNorm composition."""
+    if not proj_layer_norm_supported(x, linear, norm) or (residual is not None and (
+            residual.shape != x.shape or residual.dtype != x.dtype or
+            (torch.is_grad_enabled() and residual.requires_grad))):
+        return add_layer_norm(norm, globals()["linear"](linear, x), residual, None, pos)
+    shape = x.shape
+    c = shape[-1]
+    x2 = _dense(x.reshape(-1, c))
+    rows = x2.shape[0]
+    res2 = None if residual is None else _dense(residual.reshape(-1, c))
+    pos2 = None if pos is None else _dense(pos.to(x.dtype).expand(shape).reshape(-1, c))
+    w, b = _dense(linear.weight.detach()), _dense(linear.bias.detach())
+    gamma, beta = _dense(norm.weight.detach()), _dense(norm.bias.detach())
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x2)
+        y_pos = torch.empty_like(x2) if pos2 is not None else None
+        code = _lib.load().msda_layer_proj_layernorm_forward(
+            _lib.DTYPE_BF16, x2.data_ptr(), w.data_ptr(), b.data_ptr(), _ptr(res2), gamma.data_ptr(), beta.data_ptr(),
+            _ptr(pos2), rows, c, float(norm.eps), y.data_ptr(), _ptr(y_pos), torch.cuda.current_stream().cuda_stream)
+    _lib.check(code, "msda_layer_proj_layernorm_forward")
+    y = y.view(shape)
+    return y if y_pos is None else (y, y_pos.view(shape))
+
+
 def flatten_levels(maps, channel_adds=None):
     """[N,C,H_l,W_l] per level -> tokens [N, sum_l H_l*W_l, C] (+ channel_adds[l] per level), one transposing
     kernel per level writing straight into its slice (no per-level transposes, adds and torch.cat).

@@ -127,7 +127,7 @@ class MSDeformAttn(nn.Module):
             'Last dim of reference_points must be 2 or 4, but get {} instead.'.format(reference_points.shape[-1]))
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None):
+                input_padding_mask=None, project_output=True):
         """
         :param query                    (N, Length_{query}, C)
         :param reference_points         (N, Length_{query}, n_levels, 2), range in [0, 1], top-left (0,0),
@@ -139,6 +139,10 @@ class MSDeformAttn(nn.Module):
         :param input_padding_mask       (N, sum_l H_l*W_l), True for padding elements
 
         :return output                  (N, Length_{query}, C)
+
+        ``project_output=False`` (private to this repo's layer classes) returns the heads' output BEFORE
+        ``output_proj``: the layer then runs projection + residual + LayerNorm as one kernel
+        (ops.functions.proj_layer_norm).
         """
         N, Len_q, _ = query.shape
         N, Len_in, _ = input_flatten.shape
@@ -164,7 +168,7 @@ class MSDeformAttn(nn.Module):
             if fused_supported(value, raw, reference_points.shape[-1], self.n_levels, self.n_points):
                 output = MSDeformAttnFusedFunction.apply(
                     value, input_spatial_shapes, input_level_start_index, reference_points, raw, self.n_points)
-                return linear(self.output_proj, output)
+                return linear(self.output_proj, output) if project_output else output
             split = self.n_heads * self.n_levels * self.n_points * 2
             offsets = raw[..., :split].reshape(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
             attention = raw[..., split:].reshape(N, Len_q, self.n_heads, self.n_levels * self.n_points)
@@ -173,7 +177,7 @@ class MSDeformAttn(nn.Module):
             output = MSDeformAttnFunction.apply(
                 value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
                 attention.contiguous(), self.im2col_step)
-            return linear(self.output_proj, output)
+            return linear(self.output_proj, output) if project_output else output
 
         offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         attention = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
@@ -182,4 +186,4 @@ class MSDeformAttn(nn.Module):
         output = MSDeformAttnFunction.apply(
             value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
             attention.contiguous(), self.im2col_step)
-        return linear(self.output_proj, output)
+        return linear(self.output_proj, output) if project_output else output

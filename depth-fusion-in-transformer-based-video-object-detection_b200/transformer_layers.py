@@ -25,7 +25,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .ops.functions import add_layer_norm, ffn_layer_norm, ffn_layer_norm_supported, linear, linear_relu
+from .ops.functions import (add_layer_norm, ffn_layer_norm, ffn_layer_norm_supported, linear, linear_relu,
+                            proj_layer_norm)
 from .ops.modules import MSDeformAttn
 from .ops.modules.ms_deform_attn import host_shape_list
 
@@ -106,8 +107,13 @@ class DeformableTransformerEncoderLayer(nn.Module):
         ``(out, out + pos)`` so the next layer's query costs no extra pass."""
         if query is None:
             query = rgbd_src if rgbd_src is not None else _add_pos(src, pos)
-        attended = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask)
-        src = add_layer_norm(self.norm1, self.dropout1(attended), src)
+        if self.training and self.dropout1.p > 0:
+            attended = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask)
+            src = add_layer_norm(self.norm1, self.dropout1(attended), src)
+        else:       # output projection + residual + LayerNorm as one kernel (bf16 inference), else GEMM + fused norm
+            heads = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask,
+                                   project_output=False)
+            src = proj_layer_norm(self.self_attn.output_proj, self.norm1, heads, src)
         if not emit_query:
             return self.forward_ffn(src)
         if pos is None:
@@ -177,12 +183,16 @@ class _CrossModalFusion(nn.Module):
 
     def _fuse(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
               query=None):
-        src = add_layer_norm(self.norm_depth_scale, linear(self.depth_scale_adapt, src))
+        # Linear + (residual +) LayerNorm pairs: one tcgen05 kernel each for bf16 inference, else GEMM + fused norm
+        src = proj_layer_norm(self.depth_scale_adapt, self.norm_depth_scale, src)
         if query is None:
             query = _add_pos(tgt, query_pos)
         sampled = self.cross_attn(query, reference_points, src, src_spatial_shapes, level_start_index,
                                   src_padding_mask)
-        tgt = add_layer_norm(self.norm1, self.dropout1(linear(self.cross_scale_adapt, sampled)), tgt)
+        if self.training and self.dropout1.p > 0:
+            tgt = add_layer_norm(self.norm1, self.dropout1(linear(self.cross_scale_adapt, sampled)), tgt)
+        else:
+            tgt = proj_layer_norm(self.cross_scale_adapt, self.norm1, sampled, tgt)
         return self.forward_ffn(tgt)
 
 

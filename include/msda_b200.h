@@ -202,6 +202,18 @@ int msda_layer_ffn_layernorm_forward(int dtype,
                                      int64_t rows, int d_model, int d_ffn, float eps,
                                      void* y, void* y_pos, void* stream);
 
+/* y = LayerNorm(residual + (x @ weight^T + bias)) * gamma + beta and, when pos / y_pos are given, y_pos = y + pos:
+ * `output_proj` of MSDeformAttn (/root/reference/models/ops/modules/ms_deform_attn.py:116) together with the
+ * `norm1(src + dropout1(src2))` of the layer that owns it (models/deformable_transformer_single.py:538-541; the
+ * fusion layers' adapt Linear + norm :385-394), as ONE tcgen05 kernel with the weight stationary in tensor memory.
+ * All tensors BF16, 16-byte aligned, x / residual / pos / y / y_pos [rows, d_model], weight [d_model, d_model] in
+ * nn.Linear layout.  Supported: BF16, d_model 256 (msda_layer_proj_layernorm_supported); residual may be NULL,
+ * pos / y_pos NULL together.  Forward only. */
+int msda_layer_proj_layernorm_supported(int dtype, int d_in, int d_out);
+int msda_layer_proj_layernorm_forward(int dtype, const void* x, const void* weight, const void* bias,
+                                      const void* residual, const void* gamma, const void* beta, const void* pos,
+                                      int64_t rows, int d_model, float eps, void* y, void* y_pos, void* stream);
+
 /* One pyramid level from NCHW to token-major, written into its slice of the flattened token tensor:
  *     tokens[n, level_start + y*W + x, c] = feature_map[n, c, y, x] (+ channel_add[c])
  * = src.flatten(2).transpose(1, 2) (+ level_embed[l]) and its share of the concatenation in

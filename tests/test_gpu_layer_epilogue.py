@@ -310,3 +310,46 @@ def test_norm_act_keeps_autograd_and_odd_widths():
     assert x.grad is not None and norm.weight.grad is not None
     with torch.no_grad():
         assert torch.equal(norm_act(norm, x, "relu"), F.relu(norm(x)))      # 192-byte rows: composition as well
+
+
+@pytest.mark.parametrize("rows", [1, 127, 128, 129, 5 * 128 + 77, 148 * 128 * 2 + 31])
+@pytest.mark.parametrize("with_res,with_pos", [(True, False), (True, True), (False, False)])
+def test_proj_layer_norm_tcgen05(rows, with_res, with_pos):
+    """msda_layer_proj_layernorm_forward (weight-stationary tcgen05 kernel, csrc/proj_fused.cu) =
+    norm(residual + linear(x)) [+ pos] of ms_deform_attn.py:116 + deformable_transformer_single.py:538-541, against
+    the fp64 composition on the same bf16 inputs.  Tolerance 2^-7 normalised max (bf16 output)."""
+    from dfvod_b200.ops.functions import proj_layer_norm, proj_layer_norm_supported
+    torch.manual_seed(rows)
+    c = 256
+    lin = torch.nn.Linear(c, c).to(DEV)
+    norm = torch.nn.LayerNorm(c).to(DEV)
+    with torch.no_grad():
+        lin.weight.mul_(2.0)
+        lin.bias.add_(torch.randn(c, device=DEV) * 0.2)
+        norm.weight.add_(torch.randn(c, device=DEV) * 0.3)
+        norm.bias.add_(torch.randn(c, device=DEV) * 0.3)
+    lin, norm = lin.bfloat16(), norm.bfloat16()
+    x = torch.randn(rows, c, device=DEV).bfloat16()
+    res = torch.randn(rows, c, device=DEV).bfloat16() if with_res else None
+    pos = torch.randn(rows, c, device=DEV).bfloat16() if with_pos else None
+    with torch.no_grad():
+        assert proj_layer_norm_supported(x, lin, norm)
+        out = proj_layer_norm(lin, norm, x, res, pos)
+    y, y_pos = out if with_pos else (out, None)
+    lin64, norm64 = torch.nn.Linear(c, c).to(DEV).double(), torch.nn.LayerNorm(c).to(DEV).double()
+    lin64.load_state_dict({k: v.double() for k, v in lin.state_dict().items()})
+    norm64.load_state_dict({k: v.double() for k, v in norm.state_dict().items()})
+    proj = lin64(x.double()).bfloat16().double()              # the unfused chain rounds the GEMM output to bf16
+    ref = norm64(proj if res is None else res.double() + proj)
+    assert nerr(y, ref) <= 2.0 ** -7
+    if with_pos:
+        assert nerr(y_pos, ref + pos.double()) <= 2.0 ** -7
+
+
+def test_proj_layer_norm_falls_back_with_gradients():
+    from dfvod_b200.ops.functions import proj_layer_norm
+    lin, norm = torch.nn.Linear(256, 256).to(DEV).bfloat16(), torch.nn.LayerNorm(256).to(DEV).bfloat16()
+    x = torch.randn(9, 256, device=DEV).bfloat16().requires_grad_(True)
+    res = torch.randn(9, 256, device=DEV).bfloat16()
+    proj_layer_norm(lin, norm, x, res).float().square().sum().backward()
+    assert x.grad is not None and lin.weight.grad is not None
