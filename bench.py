@@ -536,6 +536,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from dfvod_b200 import MultiScaleDeformableAttention as MSDA
+    from dfvod_b200.host_pipeline import bind_host_thread_near_device
+    bound_cores = bind_host_thread_near_device(local)      # pinned buffers below land on the GPU's NUMA node
 
     tdtype = {"f32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
     e_v = 4 if args.dtype == "f32" else 2
@@ -671,7 +673,7 @@ def run_b200(args):
                        "l2": "inputs (%d MB per step) larger than L2" % ((fwd_bytes + bwd_bytes) // (2 << 20)),
                        "parallelism": f"dp{world} (frames sharded, no data-path collective)"},
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "host_cores_bound_near_gpu": bound_cores,
                     "api": "dfvod_b200.host_pipeline.HostPipelinedMSDA.forward_backward (pinned host tensors)"},
             "gpu_launches": args.steps * (2 if e_v == 4 else 3),
             "clocks": clocks.summary(),

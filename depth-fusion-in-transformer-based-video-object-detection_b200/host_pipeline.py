@@ -22,6 +22,35 @@ from . import _lib
 from .MultiScaleDeformableAttention import _DTYPES
 
 
+def bind_host_thread_near_device(device_index):
+    """Pin the calling process to the CPU cores NVML reports as local to the GPU (its NUMA node), so that pinned
+    host buffers allocated afterwards are first-touched on that node and the H2D / D2H copies do not cross sockets.
+    One process per GPU (torchrun) should call this before allocating its pinned buffers.  Returns the number of
+    cores bound to, or 0 when NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        physical = device_index
+        if vis:
+            try:
+                physical = int(vis.split(",")[device_index])
+            except Exception:
+                physical = device_index
+        handle = pynvml.nvmlDeviceGetHandleByIndex(physical)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        local = {i for i in range(n_cpu) if (words[i // 64] >> (i % 64)) & 1}
+        cpus = sorted(local & os.sched_getaffinity(0))
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 class HostPipelinedMSDA:
     def __init__(self, device, spatial_shapes, level_start_index, n_heads, head_dim, n_points, num_query,
                  dtype=torch.float32, chunk_frames=1, depth=3):
