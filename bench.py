@@ -263,16 +263,10 @@ def _reduce_max(torch, dist, world, dev, ms):
 
 
 def _graph_time(torch, fn, iters):
-    """Capture fn() in a CUDA graph (after a side-stream warm-up) and time the replay."""
-    graph = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        fn()
-    torch.cuda.current_stream().wait_stream(side)
-    with torch.cuda.graph(graph):
-        fn()
-    return _time_events(torch, graph.replay, iters, 3)
+    """Capture fn() in a CUDA graph (dfvod_b200.data_parallel.GraphedInference) and time the replay."""
+    from dfvod_b200.data_parallel import GraphedInference
+    run = GraphedInference(fn)
+    return _time_events(torch, run, iters, 3)
 
 
 def _pyramid(torch, dev, shapes, n, dtype, seed):
@@ -305,6 +299,17 @@ def encoder_extras(torch, dev, world, dist, n_frames=8, iters=10):
                          _time_events(torch, lambda: model.encoder(src, st, ls, vr, pos, None), 3, 2))
         out["encoder_fp32_ms"] = ms
         out["encoder_fp32_fps"] = n_frames * world / ms * 1e3
+        # the same fp32 encoder with the library GEMMs allowed to use TF32 tensor cores (the caller's opt-in,
+        # torch.backends.cuda.matmul.allow_tf32; the gather kernels are unaffected).  Not parity-grade: 1e-3 per GEMM.
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            ms = _reduce_max(torch, dist, world, dev,
+                             _time_events(torch, lambda: model.encoder(src, st, ls, vr, pos, None), 3, 2))
+            out["encoder_fp32_tf32_gemm_ms"] = ms
+            out["encoder_fp32_tf32_gemm_fps"] = n_frames * world / ms * 1e3
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
         del src, pos
         model = model.bfloat16()
         bf = torch.bfloat16

@@ -413,19 +413,19 @@ cudaError_t ffn_layernorm_forward(const FfnArgs& a, cudaStream_t stream)
     if (!ffn_layernorm_supported(a.dtype, a.C, a.F) || (a.y_pos != nullptr) != (a.pos != nullptr))
         return cudaErrorInvalidValue;
     if (a.rows == 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    static bool configured[64] = {};          // the attribute is per device: one process may drive several GPUs
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(ffn_layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     alignas(64) CUtensorMap tm_x, tm_w1, tm_w2;
     if (!make_map(&tm_x, a.x, (unsigned long long)a.rows, kFfnC, kFfnTM) ||
         !make_map(&tm_w1, a.w1, (unsigned long long)a.F, kFfnC, kFfnCH) ||
         !make_map(&tm_w2, a.w2, kFfnC, (unsigned long long)a.F, kFfnC))
         return cudaErrorNotSupported;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (a.rows + kFfnTM - 1) / kFfnTM;
     const int grid = (int)(tiles < sms ? tiles : sms);

@@ -348,19 +348,19 @@ cudaError_t proj_layernorm_forward(const ProjArgs& a, cudaStream_t stream)
     if (!proj_layernorm_supported(a.dtype, a.C, a.C) || (a.y_pos != nullptr) != (a.pos != nullptr))
         return cudaErrorInvalidValue;
     if (a.rows == 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    static bool configured[64] = {};          // the attribute is per device: one process may drive several GPUs
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(proj_layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPjSmem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     alignas(64) CUtensorMap tm_a, tm_w, tm_r;
     const void* res_base = a.residual != nullptr ? a.residual : a.x;     // a valid map either way; unused without residual
     if (!pj_make_map(&tm_a, a.x, (unsigned long long)a.rows) || !pj_make_map(&tm_w, a.w, kPjC) ||
         !pj_make_map(&tm_r, res_base, (unsigned long long)a.rows))
         return cudaErrorNotSupported;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (a.rows + kPjTM - 1) / kPjTM;
     const int grid = (int)(tiles < sms ? tiles : sms);
