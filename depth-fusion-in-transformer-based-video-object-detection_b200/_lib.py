@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MSDA_B200_LIB selects another build of the same ABI (A/B kernel experiments); default: in-tree
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_HERE, "libmsda_b200.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 DTYPE_F32, DTYPE_F64, DTYPE_BF16, DTYPE_F16 = 0, 1, 2, 3
 FLAG_FORCE_GENERIC = 1
 FLAG_BF16_WEIGHTS = 2
@@ -49,6 +49,8 @@ def load():
     fused_common = [c_vp, c_vp, c_vp, c_fp, c_int, c_vp, c_i64, c_vp, c_i64] + [c_int] * 7
     lib.msda_fused_forward.restype = c_int
     lib.msda_fused_forward.argtypes = [c_int, c_int] + fused_common + [c_vp, c_vp]
+    lib.msda_fused_forward_strided.restype = c_int
+    lib.msda_fused_forward_strided.argtypes = [c_int, c_int, c_vp, c_i64] + fused_common[1:] + [c_vp, c_vp]
     lib.msda_fused_backward.restype = c_int
     lib.msda_fused_backward.argtypes = [c_int, c_int, c_vp] + fused_common + [c_vp, c_vp, c_vp, c_fp, c_vp, c_vp]
     lib.msda_paired_supported.restype = c_int

@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 12; }
+extern "C" int msda_abi_version(void) { return 13; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -93,6 +93,25 @@ extern "C" int msda_fused_forward(int dtype, int raw_dtype, const void* value, c
                                    logits_query_stride, batch, spatial_size, num_heads, channels, num_levels,
                                    num_query, num_point);
     a.out = output;
+    return (int)msda::fused_forward(a, (cudaStream_t)stream);
+}
+
+extern "C" int msda_fused_forward_strided(int dtype, int raw_dtype, const void* value, int64_t value_pixel_stride,
+                                          const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                          const float* reference_points, int ref_dim,
+                                          const void* sampling_offsets_raw, int64_t offsets_query_stride,
+                                          const void* attention_logits_raw, int64_t logits_query_stride, int batch,
+                                          int spatial_size, int num_heads, int channels, int num_levels,
+                                          int num_query, int num_point, void* output, void* stream)
+{
+    if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point) || value_pixel_stride < 0)
+        return (int)cudaErrorInvalidValue;
+    msda::FusedArgs a = make_fused(dtype, raw_dtype, value, spatial_shapes, level_start_index, reference_points,
+                                   ref_dim, sampling_offsets_raw, offsets_query_stride, attention_logits_raw,
+                                   logits_query_stride, batch, spatial_size, num_heads, channels, num_levels,
+                                   num_query, num_point);
+    a.out = output;
+    a.value_ld = (long long)value_pixel_stride;
     return (int)msda::fused_forward(a, (cudaStream_t)stream);
 }
 

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(FwdWarps<32 / (D / Traits<VT>::kEpl)>::value *
                                   MSDA_FWD_MINWARPS / FwdWarps<32 / (D / Traits<VT>::kEpl)>::value)
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const SampleSrc src, VT* __restrict__ out,
-                     int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs)
+                     int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs, int value_ld)
 {
     constexpr int EPL = Traits<VT>::kEpl;
     constexpr int G = D / EPL;
@@ -98,8 +98,10 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 #endif
     const long long n = nq / Lq;
     const int LP = L * P;
-    const int MD = M * D;
-    const VT* vbase = value + (n * S * M + m) * (long long)D + sub * EPL;
+    // value_ld: elements between consecutive pixels of `value` (M*D when dense; larger when the caller hands in a
+    // column slice of a wider projection output, e.g. the decoder's six value projections computed as one GEMM)
+    const int MD = value_ld;
+    const VT* vbase = value + n * S * (long long)value_ld + (long long)m * D + sub * EPL;
     const float* lp = nullptr;
     const float* ap = nullptr;
     const RT* op = nullptr;
@@ -291,7 +293,7 @@ static cudaError_t launch_fwd_fast(const FwdArgs& a, cudaStream_t stream)
     SampleSrc src;
     src.loc = a.loc; src.attn = a.attn; src.ref = nullptr; src.loc_stride = 0; src.attn_stride = 0; src.ref_dim = 0;
     msda_fwd_fast_kernel<VT, D, false, float><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
-        (const VT*)a.value, a.shapes, a.lsi, src, (VT*)a.out, a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+        (const VT*)a.value, a.shapes, a.lsi, src, (VT*)a.out, a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs, a.M * D);
     return cudaGetLastError();
 }
 
@@ -314,7 +316,8 @@ static cudaError_t launch_fwd_fused(const FusedArgs& a, cudaStream_t stream)
     src.loc = a.offsets; src.attn = a.logits; src.ref = a.ref;
     src.loc_stride = a.off_stride; src.attn_stride = a.logit_stride; src.ref_dim = a.ref_dim;
     msda_fwd_fast_kernel<VT, D, true, RT><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
-        (const VT*)a.value, a.shapes, a.lsi, src, (VT*)a.out, a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+        (const VT*)a.value, a.shapes, a.lsi, src, (VT*)a.out, a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs,
+        a.value_ld > 0 ? (int)a.value_ld : a.M * D);
     return cudaGetLastError();
 }
 
@@ -376,6 +379,9 @@ static cudaError_t dispatch_fwd_fused(const FusedArgs& a, cudaStream_t stream)
 cudaError_t fused_forward(const FusedArgs& a, cudaStream_t stream)
 {
     if (!fused_supported(a)) return cudaErrorInvalidValue;
+    if (a.value_ld != 0 && (a.value_ld < (long long)a.M * a.D || a.value_ld % (16 / (a.dtype == kF32 ? 4 : 2)) != 0 ||
+                            (long long)a.S * a.value_ld >= (1ll << 31)))
+        return cudaErrorInvalidValue;
     if ((long long)a.N * a.Lq * a.M * a.D == 0) return cudaSuccess;
     if (a.dtype == kF32) return dispatch_fwd_fused<float, float>(a, stream);
     if (a.raw_dtype == kF32) return dispatch_fwd_fused<__nv_bfloat16, float>(a, stream);

@@ -60,6 +60,7 @@ struct FusedArgs {
     void* grad_logits;        // same addressing as logits, fully written
     float* grad_ref;          // [N*Lq, L, ref_dim] fp32, accumulated with atomics (caller zero-fills); may be null
     int N, S, M, D, L, Lq, P;
+    long long value_ld;       // forward only: elements between consecutive pixels of value (0 = dense, M*D)
 };
 
 bool fused_supported(const FusedArgs& a);

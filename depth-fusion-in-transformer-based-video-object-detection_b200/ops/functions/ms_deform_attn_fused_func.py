@@ -29,6 +29,19 @@ def fused_supported(value, raw, ref_dim, n_levels, n_points):
                                                  int(m), int(d), int(n_levels), int(n_points)))
 
 
+def _pixel_strided(value):
+    """Pixel stride (elements) of a [N,S,M,D] value view whose pixels are dense rows of M*D elements spaced evenly
+    -- a column slice of a wider projection output -- or 0 when the view is not of that form."""
+    n, s, m, d = value.shape
+    ld = value.stride(1)
+    if value.stride(3) != 1 or value.stride(2) != d or ld < m * d or (n > 1 and value.stride(0) != s * ld):
+        return 0
+    vec = 16 // value.element_size()
+    if ld % vec != 0 or value.data_ptr() % 16 != 0 or s * ld >= 2 ** 31:
+        return 0
+    return ld
+
+
 def _aligned(t, nbytes=16):
     return t if t.data_ptr() % nbytes == 0 else t.clone()
 
@@ -52,7 +65,12 @@ class MSDeformAttnFusedFunction(Function):
                                f"{tuple(reference_points.shape)}")
         if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
             raise RuntimeError("spatial_shapes and level_start_index must be int64 (torch.long)")
-        value = _aligned(value.contiguous())
+        # a strided column slice is read in place when no gradient will be asked for (backward needs it dense)
+        ld = 0
+        if not value.is_contiguous() and not any(ctx.needs_input_grad):
+            ld = _pixel_strided(value)
+        if ld == 0:
+            value = _aligned(value.contiguous())
         raw = _aligned(raw.contiguous())
         ref = _aligned(reference_points.detach().to(torch.float32).contiguous())
         spatial_shapes = spatial_shapes.contiguous()
@@ -65,7 +83,10 @@ class MSDeformAttnFusedFunction(Function):
                       raw.data_ptr(), 3 * mlp, raw.data_ptr() + 2 * mlp * esz, 3 * mlp, n, s, m, d, nl, lq, p,
                       out.data_ptr())
             stream = torch.cuda.current_stream().cuda_stream
-            if value.dtype == torch.bfloat16 and _msda.use_paired_forward(value.dtype, d, s, lq, nl, p):
+            if ld:
+                code = lib.msda_fused_forward_strided(_DTYPES[value.dtype], _DTYPES[raw.dtype], value.data_ptr(), ld,
+                                                      *common, stream)
+            elif value.dtype == torch.bfloat16 and _msda.use_paired_forward(value.dtype, d, s, lq, nl, p):
                 pairs = _msda.pack_value_pairs(value)           # 2 lines per sample instead of 4
                 code = lib.msda_fused_forward_paired(_DTYPES[value.dtype], _DTYPES[raw.dtype], pairs.data_ptr(),
                                                      *common, _msda.paired_flags(value.dtype), stream)

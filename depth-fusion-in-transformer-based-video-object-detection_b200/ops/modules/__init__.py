@@ -1,3 +1,3 @@
-from .ms_deform_attn import MSDeformAttn
+from .ms_deform_attn import MSDeformAttn, project_values
 
-__all__ = ["MSDeformAttn"]
+__all__ = ["MSDeformAttn", "project_values"]

@@ -127,7 +127,7 @@ class MSDeformAttn(nn.Module):
             'Last dim of reference_points must be 2 or 4, but get {} instead.'.format(reference_points.shape[-1]))
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None, project_output=True):
+                input_padding_mask=None, project_output=True, precomputed_value=None):
         """
         :param query                    (N, Length_{query}, C)
         :param reference_points         (N, Length_{query}, n_levels, 2), range in [0, 1], top-left (0,0),
@@ -140,6 +140,8 @@ class MSDeformAttn(nn.Module):
 
         :return output                  (N, Length_{query}, C)
 
+        ``precomputed_value`` (private): this module's ``value_proj(input_flatten)`` with the padding rows already
+        zeroed, as a ``[N, Len_in, n_heads, head_dim]`` tensor or pixel-strided view -- see :func:`project_values`.
         ``project_output=False`` (private to this repo's layer classes) returns the heads' output BEFORE
         ``output_proj``: the layer then runs projection + residual + LayerNorm as one kernel
         (ops.functions.proj_layer_norm).
@@ -150,10 +152,13 @@ class MSDeformAttn(nn.Module):
 
         # 2-d in, 2-d out: the projection result is a fresh tensor (not a view), so the padding rows
         # can be zeroed in place without autograd having to copy slices back
-        value = linear(self.value_proj, input_flatten.reshape(N * Len_in, -1))
-        if input_padding_mask is not None:
-            value = zero_masked_rows_(value, input_padding_mask.reshape(-1))
-        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        if precomputed_value is not None:
+            value = precomputed_value
+        else:
+            value = linear(self.value_proj, input_flatten.reshape(N * Len_in, -1))
+            if input_padding_mask is not None:
+                value = zero_masked_rows_(value, input_padding_mask.reshape(-1))
+            value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(
                 'Last dim of reference_points must be 2 or 4, but get {} instead.'.format(reference_points.shape[-1]))
@@ -175,7 +180,7 @@ class MSDeformAttn(nn.Module):
             attention = F.softmax(attention, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
             sampling_locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
             output = MSDeformAttnFunction.apply(
-                value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
+                value.contiguous(), input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
                 attention.contiguous(), self.im2col_step)
             return linear(self.output_proj, output) if project_output else output
 
@@ -184,6 +189,32 @@ class MSDeformAttn(nn.Module):
         attention = F.softmax(attention, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
         sampling_locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
         output = MSDeformAttnFunction.apply(
-            value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
+            value.contiguous(), input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
             attention.contiguous(), self.im2col_step)
         return linear(self.output_proj, output) if project_output else output
+
+
+def project_values(modules, input_flatten, input_padding_mask=None):
+    """``value_proj`` of SEVERAL ``MSDeformAttn`` modules that attend to the same ``input_flatten`` (the decoder
+    layers all re-project the encoder memory, reference deformable_transformer_single.py:617-628 ->
+    ms_deform_attn.py:94-96) as ONE GEMM: the memory is read once instead of once per layer, padding rows are zeroed
+    once.  Returns one pixel-strided ``[N, Len_in, n_heads, head_dim]`` view per module for ``precomputed_value``
+    (the fused forward kernel reads the slice in place).  Inference only; returns ``None`` when gradients are
+    needed or the modules differ in shape."""
+    first = modules[0]
+    if len(modules) < 2 or not input_flatten.is_cuda or any(
+            m.d_model != first.d_model or m.n_heads != first.n_heads or
+            m.value_proj.weight.dtype != input_flatten.dtype for m in modules):
+        return None
+    if torch.is_grad_enabled() and (input_flatten.requires_grad or
+                                    any(m.value_proj.weight.requires_grad for m in modules)):
+        return None
+    N, Len_in, _ = input_flatten.shape
+    weight = torch.cat([m.value_proj.weight for m in modules], 0)
+    bias = torch.cat([m.value_proj.bias for m in modules], 0)
+    values = linear_wb(input_flatten.reshape(N * Len_in, -1), weight, bias)          # [N*Len_in, layers*C]
+    if input_padding_mask is not None:
+        values = zero_masked_rows_(values, input_padding_mask.reshape(-1))
+    c, heads = first.d_model, first.n_heads
+    values = values.view(N, Len_in, len(modules), heads, c // heads)
+    return [values[:, :, i] for i in range(len(modules))]

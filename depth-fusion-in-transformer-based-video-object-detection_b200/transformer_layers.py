@@ -27,7 +27,7 @@ from torch import nn
 
 from .ops.functions import (add_layer_norm, ffn_layer_norm, ffn_layer_norm_supported, linear, linear_relu,
                             proj_layer_norm)
-from .ops.modules import MSDeformAttn
+from .ops.modules import MSDeformAttn, project_values
 from .ops.modules.ms_deform_attn import host_shape_list
 
 
@@ -305,9 +305,10 @@ class DeformableTransformerDecoderLayer(nn.Module):
         return add_layer_norm(self.norm3, self.dropout4(linear(self.linear2, self.dropout3(hidden))), tgt, None, pos)
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                src_padding_mask=None, qk=None, emit_qk=False):
-        """Reference signature plus two private keywords used by the decoder loop: ``qk`` is a
-        precomputed ``tgt + query_pos``; ``emit_qk=True`` returns ``(out, out + query_pos)``."""
+                src_padding_mask=None, qk=None, emit_qk=False, value=None):
+        """Reference signature plus private keywords used by the decoder loop: ``qk`` is a precomputed
+        ``tgt + query_pos``; ``emit_qk=True`` returns ``(out, out + query_pos)``; ``value`` is this layer's
+        ``cross_attn.value_proj(src)`` computed together with the other layers' (ops.modules.project_values)."""
         if qk is None:
             qk = _add_pos(tgt, query_pos)
         qk = qk.transpose(0, 1)
@@ -317,7 +318,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
         else:
             tgt = query = add_layer_norm(self.norm2, self.dropout2(mixed), tgt)
         sampled = self.cross_attn(query, reference_points, src, src_spatial_shapes, level_start_index,
-                                  src_padding_mask)
+                                  src_padding_mask, precomputed_value=value)
         tgt = add_layer_norm(self.norm1, self.dropout1(sampled), tgt)
         if not emit_qk:
             return self.forward_ffn(tgt)
@@ -359,6 +360,8 @@ class DeformableTransformerDecoder(nn.Module):
         output = tgt
         qk = None
         intermediate, intermediate_reference_points = [], []
+        # every layer re-projects the same memory with its own value_proj: one GEMM for all of them (inference)
+        values = project_values([layer.cross_attn for layer in self.layers], src, src_padding_mask)
         for lid, layer in enumerate(self.layers):
             if reference_points.shape[-1] == 4:
                 scale = torch.cat([src_valid_ratios, src_valid_ratios], -1)
@@ -368,10 +371,12 @@ class DeformableTransformerDecoder(nn.Module):
             reference_points_input = reference_points[:, :, None] * scale[:, None]
             if lid + 1 < len(self.layers):
                 output, qk = layer(output, query_pos, reference_points_input, src, src_spatial_shapes,
-                                   src_level_start_index, src_padding_mask, qk=qk, emit_qk=True)
+                                   src_level_start_index, src_padding_mask, qk=qk, emit_qk=True,
+                                   value=None if values is None else values[lid])
             else:
                 output = layer(output, query_pos, reference_points_input, src, src_spatial_shapes,
-                               src_level_start_index, src_padding_mask, qk=qk)
+                               src_level_start_index, src_padding_mask, qk=qk,
+                               value=None if values is None else values[lid])
 
             if self._refine_boxes and self.bbox_embed is not None:       # single.py:729-739
                 delta = self.bbox_embed[lid](output)

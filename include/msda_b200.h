@@ -109,6 +109,21 @@ int msda_fused_forward(int dtype, int raw_dtype,
                        int num_levels, int num_query, int num_point,
                        void* output, void* stream);
 
+/* msda_fused_forward reading `value` with a pixel stride: pixel r of item n starts at
+ * value[(n * spatial_size + r) * value_pixel_stride] (elements; >= num_heads * channels, a multiple of the 16-byte
+ * vector; 0 = dense).  Lets one GEMM compute the value projections of several layers that attend to the same
+ * memory (the six decoder layers each re-project the encoder memory, /root/reference/models/
+ * deformable_transformer_single.py:617-628 via ms_deform_attn.py:94) and hand each layer its column slice. */
+int msda_fused_forward_strided(int dtype, int raw_dtype,
+                               const void* value, int64_t value_pixel_stride,
+                               const int64_t* spatial_shapes, const int64_t* level_start_index,
+                               const float* reference_points, int ref_dim,
+                               const void* sampling_offsets_raw, int64_t offsets_query_stride,
+                               const void* attention_logits_raw, int64_t logits_query_stride,
+                               int batch, int spatial_size, int num_heads, int channels,
+                               int num_levels, int num_query, int num_point,
+                               void* output, void* stream);
+
 int msda_fused_backward(int dtype, int raw_dtype,
                         const void* grad_output,
                         const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,

@@ -143,3 +143,61 @@ def test_fused_no_ref_grad_and_unsupported_shapes():
     assert not fused_supported(value.to(DEV).double(), raw.to(DEV).double(), 2, 1, p)          # fp64
     assert not fused_supported(torch.zeros(1, 4, 2, 8, device=DEV), raw.to(DEV), 2, 1, p)      # D=8
     assert not fused_supported(value.to(DEV), raw.to(DEV), 2, 5, 4)                            # L*P = 20 > 16
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_forward_reads_a_pixel_strided_value_slice_in_place(dtype):
+    """msda_fused_forward_strided: the value of one layer as a column slice of a wider projection output (the
+    decoder's six value projections computed as one GEMM, ops.modules.project_values) gives exactly what the dense
+    copy of that slice gives."""
+    from dfvod_b200.ops.functions import MSDeformAttnFusedFunction
+    from dfvod_b200.ops.functions import ms_deform_attn_fused_func as ff
+    torch.manual_seed(17)
+    shapes = [(20, 31), (10, 16)]
+    n, m, d, p, lq, layers = 2, 8, 32, 4, 77, 3
+    s = sum(h * w for h, w in shapes)
+    st = torch.as_tensor(shapes, dtype=torch.long, device="cuda")
+    ls = torch.as_tensor([0, shapes[0][0] * shapes[0][1]], dtype=torch.long, device="cuda")
+    wide = torch.randn(n, s, layers, m, d, device="cuda").to(dtype)
+    ref = torch.rand(n, lq, 2, 2, device="cuda")
+    raw = torch.randn(n, lq, 3 * m * 2 * p, device="cuda").to(dtype)
+    with torch.no_grad():
+        for i in range(layers):
+            view = wide[:, :, i]
+            assert not view.is_contiguous() and ff._pixel_strided(view) == layers * m * d
+            got = MSDeformAttnFusedFunction.apply(view, st, ls, ref, raw, p)
+            want = MSDeformAttnFusedFunction.apply(view.contiguous(), st, ls, ref, raw, p)
+            assert torch.equal(got, want)
+    # with gradients the slice is densified (backward needs the dense layout) -- same numbers
+    view = wide[:, :, 1].detach().requires_grad_(True)
+    out = MSDeformAttnFusedFunction.apply(view, st, ls, ref, raw, p)
+    out.float().sum().backward()
+    assert view.grad is not None and torch.equal(out.detach(), MSDeformAttnFusedFunction.apply(
+        wide[:, :, 1].contiguous(), st, ls, ref, raw, p))
+
+
+def test_decoder_batched_value_projection_matches_per_layer_projection():
+    """DeformableTransformerDecoder under no_grad computes all layers' value_proj(memory) as ONE GEMM
+    (project_values); with gradients enabled every layer projects for itself -- same outputs."""
+    from dfvod_b200 import transformer_layers as tl
+    torch.manual_seed(19)
+    shapes = [(16, 24), (8, 12)]
+    s = sum(h * w for h, w in shapes)
+    st = torch.as_tensor(shapes, dtype=torch.long, device="cuda")
+    ls = torch.as_tensor([0, 16 * 24], dtype=torch.long, device="cuda")
+    dec = tl.DeformableTransformerDecoder(tl.DeformableTransformerDecoderLayer(256, 512, 0.0, "relu", 2, 8, 4), 3,
+                                          return_intermediate=True).to("cuda").eval()
+    with torch.no_grad():
+        for prm in dec.parameters():
+            prm.add_(torch.randn_like(prm) * 0.02)
+    tgt, qpos = torch.randn(2, 30, 256, device="cuda"), torch.randn(2, 30, 256, device="cuda")
+    mem = torch.randn(2, s, 256, device="cuda")
+    mask = torch.zeros(2, s, dtype=torch.bool, device="cuda")
+    mask[1, -40:] = True
+    refs = torch.rand(2, 30, 2, device="cuda")
+    vr = torch.ones(2, 2, 2, device="cuda")
+    hs_grad, _ = dec(tgt, refs, mem, st, ls, vr, qpos, mask)
+    with torch.no_grad():
+        hs_nograd, _ = dec(tgt, refs, mem, st, ls, vr, qpos, mask)
+    err = float((hs_nograd - hs_grad.detach()).abs().max() / hs_grad.detach().abs().max())
+    assert err <= 1e-5, err
