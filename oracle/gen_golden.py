@@ -161,7 +161,7 @@ def round_to_f32(module, inputs):
             for k, v in inputs.items()}
 
 
-def save_module_case(name, module, inputs, call, wrt, store=None, grad_limit=None):
+def save_module_case(name, module, inputs, call, wrt, store=None, grad_limit=None, state_store=None):
     """Run ``call(module, **inputs)``, save inputs/state/output and the gradients of
     sum(output * gout) w.r.t. the tensors named in ``wrt`` and every parameter.
     ``store=np.float32`` (wide cases): parameters and inputs are first rounded to fp32-representable
@@ -172,6 +172,10 @@ def save_module_case(name, module, inputs, call, wrt, store=None, grad_limit=Non
         return
     if store is not None:
         inputs = round_to_f32(module, inputs)
+    if state_store is not None:          # parameters made exactly representable in `state_store` (e.g. fp16): the
+        with torch.no_grad():            # state is then kept in that type without loss
+            for prm in module.parameters():
+                prm.copy_(prm.to(getattr(torch, np.dtype(state_store).name)).double())
     tensors = {k: (v.clone().requires_grad_(True) if k in wrt else v) for k, v in inputs.items()}
     out = call(module, tensors)
     g = torch.Generator().manual_seed(1234)
@@ -188,6 +192,9 @@ def save_module_case(name, module, inputs, call, wrt, store=None, grad_limit=Non
         if grad_limit is not None and gr is not None and gr.numel() > grad_limit and "value_proj" not in pname:
             continue
         blob[f"grad_param.{pname}"] = (gr if gr is not None else torch.zeros(())).numpy()
+    if state_store is not None:
+        blob = {k: (v.astype(state_store) if k.startswith("state.") and v.dtype == np.float64 else v)
+                for k, v in blob.items()}
     if store is not None:
         blob = {k: (v.astype(store) if v.dtype == np.float64 else v) for k, v in blob.items()}
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **blob)
@@ -547,6 +554,39 @@ def main():
         dict(tgt=tgt_t, reference_points=ref_t, src=mem1, src_spatial_shapes=dshapes, level_start_index=dlsi,
              valid_ratios=vr_t),
         tdtd_call, wrt=["tgt", "src"])
+
+    # two-stage variant of the single-frame transformer (single.py:82-86, :112-153, :308-322): encoder proposals,
+    # top-k, proposal position embedding.  get_proposal_pos_embed hard-codes 128 features per coordinate, so the
+    # model must be 256 wide; parameters are made fp16-representable and the state is stored as fp16.
+    def two_stage_case(name, seed):
+        if not wanted(name):
+            return
+        torch.manual_seed(seed)
+        wide, levels, k = 256, [(5, 6), (3, 3)], 6
+        model = single.DeformableTransformer(
+            d_model=wide, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=64, dropout=0.0,
+            activation="relu", return_intermediate_dec=True, num_feature_levels=len(levels), dec_n_points=2,
+            enc_n_points=2, two_stage=True, two_stage_num_proposals=k).double()
+        model.decoder.class_embed = torch.nn.ModuleList(torch.nn.Linear(wide, 3) for _ in range(2)).double()
+        model.decoder.bbox_embed = torch.nn.ModuleList(
+            torch.nn.Sequential(torch.nn.Linear(wide, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4)) for _ in range(2)).double()
+        perturb(model, seed + 1, std=0.03)
+        ins = {}
+        for i, (h, w) in enumerate(levels):
+            ins[f"src{i}"] = torch.randn(n, wide, h, w)
+            ins[f"pos{i}"] = torch.randn(n, wide, h, w)
+            mk = torch.zeros(n, h, w, dtype=torch.bool)
+            mk[1, :, 1 << ((w - 1).bit_length() - 1):] = True
+            ins[f"mask{i}"] = mk
+
+        def call(m_, t):
+            hs, init_ref, inter_ref, enc_cls, enc_coord = m_(
+                [t["src0"], t["src1"]], [t["mask0"], t["mask1"]], [t["pos0"], t["pos1"]], None, None, None, None)
+            enc_coord = torch.where(torch.isinf(enc_coord), torch.zeros_like(enc_coord), enc_coord)
+            return torch.cat([hs.flatten(), init_ref.flatten(), inter_ref.flatten(), enc_cls.flatten(), enc_coord.flatten()])
+        save_module_case(name, model, ins, call, wrt=["src0"], store=np.float32, grad_limit=3000, state_store=np.float16)
+
+    two_stage_case("transformer_two_stage", 96)
 
     # ---------------- TransVOD++ multi-frame transformer with its temporal query stage -----------------
     # (deformable_transformer_multi_plusplus.py:70-603): per-frame encoder/decoder with box refinement, RoIAlign of

@@ -239,3 +239,27 @@ CASES.update({
     "transvodpp_f2_latefusion": dict(build=lambda: _transvodpp("DepthDeform_latefusion_dformer", True, 2),
                                      call=lambda m, t: m(t), wrt=["src0", "depth_src0", "query_embed"]),
 })
+
+
+# two-stage transformer (reference single.py:82-86, :112-153, :308-322); 256 wide because get_proposal_pos_embed
+# hard-codes 128 features per box coordinate.  Stored like the wide cases (fp32 results, fp16-representable state).
+def _two_stage():
+    model = DeformableTransformer(
+        d_model=256, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=64, dropout=0.0,
+        activation="relu", return_intermediate_dec=True, num_feature_levels=2, dec_n_points=2, enc_n_points=2,
+        two_stage=True, two_stage_num_proposals=6)
+    model.decoder.class_embed = torch.nn.ModuleList(torch.nn.Linear(256, 3) for _ in range(2))
+    model.decoder.bbox_embed = torch.nn.ModuleList(
+        torch.nn.Sequential(torch.nn.Linear(256, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4)) for _ in range(2))
+    return model
+
+
+def _two_stage_call(m, t):
+    hs, init_ref, inter_ref, enc_cls, enc_coord = m(
+        [t["src0"], t["src1"]], [t["mask0"], t["mask1"]], [t["pos0"], t["pos1"]], None, None, None, None)
+    enc_coord = torch.where(torch.isinf(enc_coord), torch.zeros_like(enc_coord), enc_coord)
+    return torch.cat([hs.flatten(), init_ref.flatten(), inter_ref.flatten(), enc_cls.flatten(), enc_coord.flatten()])
+
+
+CASES["transformer_two_stage"] = dict(build=_two_stage, call=_two_stage_call, wrt=["src0"])
+WIDE.add("transformer_two_stage")
