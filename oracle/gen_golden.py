@@ -424,6 +424,34 @@ def main():
             return torch.cat([hs.flatten(), init_ref.flatten(), inter_ref.flatten()])
         save_module_case(name, model, ins, call, wrt=["src0", "depth_src0", "query_embed"])
 
+    # RGB-D features as the encoder's query ("concat" depth types: rgbd_query replaces src + pos as the query of every
+    # encoder layer, single.py:185-189, :556-559)
+    def rgbd_query_case(name, seed, levels=((4, 6), (2, 3))):
+        if not wanted(name):
+            return
+        torch.manual_seed(seed)
+        model = single.DeformableTransformer(
+            d_model=c, nhead=heads, num_encoder_layers=2, num_decoder_layers=1, dim_feedforward=64, dropout=0.0,
+            activation="relu", return_intermediate_dec=True, num_feature_levels=len(levels), dec_n_points=pts,
+            enc_n_points=pts, use_depth=False, depth_type="Baseline_concat").double()
+        perturb(model, seed + 1)
+        ins = {"query_embed": torch.randn(5, 2 * c)}
+        for i, (h, w) in enumerate(levels):
+            ins[f"src{i}"] = torch.randn(n, c, h, w)
+            ins[f"pos{i}"] = torch.randn(n, c, h, w)
+            ins[f"rgbd{i}"] = torch.randn(n, c, h, w)
+            ins[f"mask{i}"] = torch.zeros(n, h, w, dtype=torch.bool)
+        nl_ = len(levels)
+
+        def call(m_, t):
+            hs, init_ref, inter_ref, _, _ = m_(
+                [t[f"src{i}"] for i in range(nl_)], [t[f"mask{i}"] for i in range(nl_)],
+                [t[f"pos{i}"] for i in range(nl_)], None, None, None, t["query_embed"],
+                [t[f"rgbd{i}"] for i in range(nl_)])
+            return torch.cat([hs.flatten(), init_ref.flatten(), inter_ref.flatten()])
+        save_module_case(name, model, ins, call, wrt=["src0", "rgbd0", "query_embed"])
+
+    rgbd_query_case("transformer_rgbd_query", 56)
     transformer_case("transformer_baseline", "Baseline_rgb", False, [(6, 5), (3, 3)], 50)
     transformer_case("transformer_latefusion", "DepthDeform_latefusion_dformer", True, [(4, 6)], 52)
     transformer_case("transformer_encoder_cf", "DepthDeform_encoder_cf_dformer", True, [(4, 6)], 54)

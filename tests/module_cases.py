@@ -263,3 +263,18 @@ def _two_stage_call(m, t):
 
 CASES["transformer_two_stage"] = dict(build=_two_stage, call=_two_stage_call, wrt=["src0"])
 WIDE.add("transformer_two_stage")
+
+
+def _rgbd_query_call(m, t):
+    hs, init_ref, inter_ref, _, _ = m(
+        [t["src0"], t["src1"]], [t["mask0"], t["mask1"]], [t["pos0"], t["pos1"]], None, None, None, t["query_embed"],
+        [t["rgbd0"], t["rgbd1"]])
+    return torch.cat([hs.flatten(), init_ref.flatten(), inter_ref.flatten()])
+
+
+CASES["transformer_rgbd_query"] = dict(
+    build=lambda: DeformableTransformer(
+        d_model=C, nhead=HEADS, num_encoder_layers=2, num_decoder_layers=1, dim_feedforward=64, dropout=0.0,
+        activation="relu", return_intermediate_dec=True, num_feature_levels=2, dec_n_points=PTS, enc_n_points=PTS,
+        use_depth=False, depth_type="Baseline_concat"),
+    call=_rgbd_query_call, wrt=["src0", "rgbd0", "query_embed"])
