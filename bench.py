@@ -67,7 +67,10 @@ def make_inputs(torch, n, seed, dist):
         comp = comp / comp.abs().max(-1, keepdim=True)[0]
         steps = torch.arange(1, P + 1, dtype=torch.float32)
         off = comp[:, None, None, :] * steps[None, None, :, None]
-        off = off.expand(M, nl, P, 2) + torch.randn(n, lq, M, nl, P, 2, generator=g)
+        noise = torch.randn(n, lq, M, nl, P, 2, generator=g)
+        if dist == "init":                     # a freshly initialised layer: offsets are the compass pattern exactly
+            noise = noise * 0.0
+        off = off.expand(M, nl, P, 2) + noise
         norm = torch.tensor([[w, h] for h, w in COCO_SHAPES], dtype=torch.float32)
         loc = ref[None, :, None, None, None, :] + off / norm[None, None, None, :, None, :]
     grad_out = torch.randn(n, lq, M * D, generator=g)
@@ -701,7 +704,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
-    ap.add_argument("--dist", default="grid", choices=["grid", "random"])
+    ap.add_argument("--dist", default="grid", choices=["grid", "random", "init"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the encoder / training-step side measurements")

@@ -95,6 +95,18 @@ struct GradDst {
 #define MSDA_BWD_IMMEDIATE 1
 #endif
 
+// 1: before the reductions leave the SM, merge the corner rows that several samples of one (query, head, level)
+// share.  Every sample of a pair scatters coefficient * grad_output[pair] -- the SAME row -- so two samples that
+// touch the same pixel need one reduction of the summed coefficient, not two.  With the encoder's geometry (points
+// a pixel apart along the head's direction) 17 % of the corner rows are such duplicates (25-50 % at initialisation,
+// where the offsets are exact integers and half the bilinear weights are exactly zero -- zero-coefficient rows are
+// dropped as well).  The kernel is bound by the SM -> L2 reduction path (5 cycles per row), so rows saved are time
+// saved; the price is ~30 shuffles and ~100 compares per lane per pass in phase 1.  Only for one sample per lane
+// per pass (head width >= 32).
+#ifndef MSDA_BWD_DEDUP
+#define MSDA_BWD_DEDUP 1
+#endif
+
 template <typename VT, int D, bool FUSED, typename RT>
 __global__ void __launch_bounds__(BwdWarps<32 / (D / 4)>::value * 32, MSDA_BWD_MINBLOCKS)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
@@ -118,6 +130,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     __shared__ int s_meta[3 * kMaxLevelsFast];
     __shared__ __align__(16) int4   s_geo[WARPS][PAIRS][CH + 1];   // pix00, rowstep, ok, -
     __shared__ __align__(16) float4 s_frac[WARPS][PAIRS][CH + 1];  // lw, lh, a, -
+    constexpr bool DEDUP = MSDA_BWD_DEDUP && SPL == 1;
+    __shared__ __align__(16) float4 s_coef[DEDUP ? WARPS : 1][DEDUP ? PAIRS : 1][DEDUP ? CH + 1 : 1];   // merged corner coefficients
 
     if (threadIdx.x < L) {
         s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
@@ -229,6 +243,60 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             }
             s_geo[warp][grp][j] = geo;                 // samples past cnt: ok = 0 -> no loads, no reductions
             s_frac[warp][grp][j] = fr;
+            if constexpr (DEDUP) {
+                // coefficient of each corner row in grad_value: bilinear weight x attention weight (cuh:113-116);
+                // zero for corners outside the map
+                const float hw = 1.f - fr.x, hh = 1.f - fr.y;
+                const float own[4] = {(geo.z & 1) ? hh * hw * fr.z : 0.f, (geo.z & 2) ? hh * fr.x * fr.z : 0.f,
+                                      (geo.z & 4) ? fr.y * hw * fr.z : 0.f, (geo.z & 8) ? fr.y * fr.x * fr.z : 0.f};
+                float merged[4] = {own[0], own[1], own[2], own[3]};
+                int dup = 0;
+                const int my_level = div_by_points(s0 + j, p_magic);
+                const int W = geo.y;
+                // corner mask / coefficient vector of a neighbour, moved by (dx, dy) pixels into MY corner frame:
+                // my corner (cx, cy) is their corner (cx - dx, cy - dy).  Bits / slots: 0 (0,0) 1 (1,0) 2 (0,1) 3 (1,1).
+                auto decode = [&](int delta, int& dx, int& dy) -> bool {       // delta = their corner 00 - mine
+                    dy = delta > 1 ? 1 : (delta < -1 ? -1 : 0);
+                    dx = delta - dy * W;
+                    return W > 2 && dx >= -1 && dx <= 1;
+                };
+                auto shift_mask = [](int m, int dx, int dy) -> int {
+                    m = dx == 0 ? m : (dx > 0 ? (m & 5) << 1 : (m & 10) >> 1);
+                    return dy == 0 ? m : (dy > 0 ? (m & 3) << 2 : (m & 12) >> 2);
+                };
+                // Only NEIGHBOURING samples are compared (points p and p+1 of a level), but runs are followed to
+                // their end: the sample below owns the pixels we share (it issues those rows, I skip them), and what I
+                // hand down includes what I was handed from above -- `rounds` = samples per level - 1 hand-overs move
+                // every coefficient of a run to its lowest sample.
+                const int lo_pix = __shfl_up_sync(0xffffffffu, geo.x, 1, G);
+                const int lo_ok = __shfl_up_sync(0xffffffffu, geo.z, 1, G);
+                const int hi_pix = __shfl_down_sync(0xffffffffu, geo.x, 1, G);
+                int dx, dy;
+                if (sub >= 1 && div_by_points(s0 + j - 1, p_magic) == my_level && decode(lo_pix - geo.x, dx, dy))
+                    dup = shift_mask(lo_ok, dx, dy);
+                const bool take = sub + 1 < G && div_by_points(s0 + j + 1, p_magic) == my_level &&
+                                  decode(hi_pix - geo.x, dx, dy);
+                const int rounds = min(P, G) - 1;
+                for (int r = 0; r < rounds; ++r) {
+                    float hc[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) hc[k] = __shfl_down_sync(0xffffffffu, merged[k], 1, G);
+                    if (take) {
+                        // x move, then y move, of the neighbour's coefficient vector into my corner frame
+                        const float x0 = dx == 0 ? hc[0] : (dx < 0 ? hc[1] : 0.f), x1 = dx == 0 ? hc[1] : (dx > 0 ? hc[0] : 0.f);
+                        const float x2 = dx == 0 ? hc[2] : (dx < 0 ? hc[3] : 0.f), x3 = dx == 0 ? hc[3] : (dx > 0 ? hc[2] : 0.f);
+                        // only into corners that exist: a slot outside the map must not pass anything on
+                        merged[0] = (geo.z & 1) ? own[0] + (dy == 0 ? x0 : (dy < 0 ? x2 : 0.f)) : 0.f;
+                        merged[1] = (geo.z & 2) ? own[1] + (dy == 0 ? x1 : (dy < 0 ? x3 : 0.f)) : 0.f;
+                        merged[2] = (geo.z & 4) ? own[2] + (dy == 0 ? x2 : (dy > 0 ? x0 : 0.f)) : 0.f;
+                        merged[3] = (geo.z & 8) ? own[3] + (dy == 0 ? x3 : (dy > 0 ? x1 : 0.f)) : 0.f;
+                    }
+                }
+                // a row is mine to issue if the corner lies in the map and no lower sample owns its pixel
+                const int mine = geo.z & ~dup;
+                s_coef[warp][grp][j] = make_float4((mine & 1) ? merged[0] : 0.f, (mine & 2) ? merged[1] : 0.f,
+                                                   (mine & 4) ? merged[2] : 0.f, (mine & 8) ? merged[3] : 0.f);
+            }
         }
         __syncwarp();
 
@@ -297,12 +365,21 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 #endif
                     float* q00 = gbase + (long long)geo[u].x * MD;
                     const long long row = (long long)geo[u].y * MD;
-                    const float wk[4] = {w1, w2, w3, w4};
                     float* const qk[4] = {q00, q00 + MD, q00 + row, q00 + row + MD};
+                    if constexpr (DEDUP) {
+                        const float4 cf = s_coef[warp][grp][j0 + u];       // merged coefficient; 0 = row issued elsewhere / no-op
+                        const float ck[4] = {cf.x, cf.y, cf.z, cf.w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (geo[u].z & (1 << k))
-                            red_add_f32x4(qk[k], wk[k] * tg[0], wk[k] * tg[1], wk[k] * tg[2], wk[k] * tg[3]);
+                        for (int k = 0; k < 4; ++k) {
+                            if (ck[k] != 0.f) red_add_f32x4(qk[k], ck[k] * g[0], ck[k] * g[1], ck[k] * g[2], ck[k] * g[3]);
+                        }
+                    } else {
+                        const float wk[4] = {w1, w2, w3, w4};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (geo[u].z & (1 << k))
+                                red_add_f32x4(qk[k], wk[k] * tg[0], wk[k] * tg[1], wk[k] * tg[2], wk[k] * tg[3]);
+                        }
                     }
                 }
             }
