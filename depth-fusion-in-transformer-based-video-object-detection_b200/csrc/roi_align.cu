@@ -105,44 +105,73 @@ roi_align_fwd_kernel(const T* __restrict__ feat, const CT* __restrict__ rois, T*
     }
 }
 
-// vector path (fp32 / bf16 / fp16, C a multiple of the 16-byte vector): the sample geometry is computed once per
-// warp-lane-slot and every corner row is fetched with 16-byte loads.
-template <typename T>
+// vector path (fp32 / bf16 / fp16, C a multiple of the 16-byte vector): one warp per (box, bin ROW) walks the PW bins
+// of that row, so the box geometry and the y terms of the row's samples are computed once per PW bins instead of once
+// per bin; every corner row is fetched with 16-byte loads, the GRID x GRID samples of a bin (16 loads for the
+// reference's sampling_ratio 2) are unrolled so they are all in flight together.  GRID = 0: run-time sampling grid.
+template <typename CT> struct AxisTerm { int low, high; CT l, h; bool valid; };
+
+template <typename CT>
+__device__ __forceinline__ AxisTerm<CT> axis_term(CT v, int size)       // one coordinate of mmcv's bilinear_interpolate
+{
+    AxisTerm<CT> t;
+    t.valid = !(v < (CT)-1 || v > (CT)size);
+    if (v <= (CT)0) v = (CT)0;
+    t.low = (int)v;
+    if (t.low >= size - 1) { t.high = t.low = size - 1; v = (CT)t.low; } else t.high = t.low + 1;
+    t.l = v - (CT)t.low;
+    t.h = (CT)1 - t.l;
+    return t;
+}
+
+template <typename T, int GRID>
 __global__ void __launch_bounds__(256)
 roi_align_fwd_vec_kernel(const T* __restrict__ feat, const float* __restrict__ rois, T* __restrict__ out, int N, int H,
-                         int W, int C, long long bins, int PH, int PW, float scale, int sampling_ratio, int aligned)
+                         int W, int C, long long bin_rows, int PH, int PW, float scale, int sampling_ratio, int aligned)
 {
     constexpr int V = 16 / (int)sizeof(T);
-    const long long bin = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long brow = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (bin >= bins) return;
-    const int pw = (int)(bin % PW), ph = (int)((bin / PW) % PH);
-    const long long k = bin / ((long long)PW * PH);
+    if (brow >= bin_rows) return;
+    const int ph = (int)(brow % PH);
+    const long long k = brow / PH;
     const RoiGeom<float> g = roi_geom<float>(rois + 5 * k, scale, sampling_ratio, aligned, PH, PW);
     const bool batch_ok = g.batch >= 0 && g.batch < N;
     const T* map = feat + (long long)(batch_ok ? g.batch : 0) * H * W * C;
+    const int gh = GRID > 0 ? GRID : g.grid_h, gw = GRID > 0 ? GRID : g.grid_w;
     for (int c = lane * V; c < C; c += 32 * V) {
-        float acc[V];
+        for (int pw = 0; pw < PW; ++pw) {
+            float acc[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = 0.f;
-        for (int iy = 0; iy < g.grid_h; ++iy) {
-            const float y = g.y0 + (float)ph * g.bin_h + ((float)iy + 0.5f) * g.bin_h / (float)g.grid_h;
-            for (int ix = 0; ix < g.grid_w; ++ix) {
-                const float x = g.x0 + (float)pw * g.bin_w + ((float)ix + 0.5f) * g.bin_w / (float)g.grid_w;
-                const BinSample<float> s = bin_sample<float>(y, x, H, W);
-                if (!batch_ok) continue;
-                float v1[V], v2[V], v3[V], v4[V];
-                unpack<T>(ldg_v4(map + (long long)s.p1 * C + c), v1);
-                unpack<T>(ldg_v4(map + (long long)s.p2 * C + c), v2);
-                unpack<T>(ldg_v4(map + (long long)s.p3 * C + c), v3);
-                unpack<T>(ldg_v4(map + (long long)s.p4 * C + c), v4);
+            for (int i = 0; i < V; ++i) acc[i] = 0.f;
+            if (batch_ok) {
 #pragma unroll
-                for (int i = 0; i < V; ++i) acc[i] += s.w1 * v1[i] + s.w2 * v2[i] + s.w3 * v3[i] + s.w4 * v4[i];
+                for (int iy = 0; iy < (GRID > 0 ? GRID : 1 << 30); ++iy) {
+                    if (iy >= gh) break;
+                    const AxisTerm<float> ty =
+                        axis_term<float>(g.y0 + (float)ph * g.bin_h + ((float)iy + 0.5f) * g.bin_h / (float)gh, H);
+#pragma unroll
+                    for (int ix = 0; ix < (GRID > 0 ? GRID : 1 << 30); ++ix) {
+                        if (ix >= gw) break;
+                        const AxisTerm<float> tx =
+                            axis_term<float>(g.x0 + (float)pw * g.bin_w + ((float)ix + 0.5f) * g.bin_w / (float)gw, W);
+                        const float live = (ty.valid && tx.valid) ? 1.f : 0.f;       // outside samples contribute 0
+                        const float w1 = ty.h * tx.h * live, w2 = ty.h * tx.l * live, w3 = ty.l * tx.h * live,
+                                    w4 = ty.l * tx.l * live;
+                        float v1[V], v2[V], v3[V], v4[V];
+                        unpack<T>(ldg_v4(map + (long long)(ty.low * W + tx.low) * C + c), v1);
+                        unpack<T>(ldg_v4(map + (long long)(ty.low * W + tx.high) * C + c), v2);
+                        unpack<T>(ldg_v4(map + (long long)(ty.high * W + tx.low) * C + c), v3);
+                        unpack<T>(ldg_v4(map + (long long)(ty.high * W + tx.high) * C + c), v4);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) acc[i] += w1 * v1[i] + w2 * v2[i] + w3 * v3[i] + w4 * v4[i];
+                    }
+                }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] *= g.inv_count;
-        *reinterpret_cast<uint4*>(out + bin * C + c) = pack<T>(acc);
+            for (int i = 0; i < V; ++i) acc[i] *= g.inv_count;
+            *reinterpret_cast<uint4*>(out + ((k * PH + ph) * PW + pw) * C + c) = pack<T>(acc);
+        }
     }
 }
 
@@ -203,9 +232,13 @@ cudaError_t roi_align_forward(const RoiAlignArgs& a, cudaStream_t st)
     if (bins == 0 || a.C == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((bins + 7) / 8);
     const bool aligned16 = ((uintptr_t)a.feat % 16 == 0) && ((uintptr_t)a.out % 16 == 0);
-#define ROI_VEC(T)                                                                                                  \
-    roi_align_fwd_vec_kernel<T><<<blocks, 256, 0, st>>>((const T*)a.feat, (const float*)a.rois, (T*)a.out, a.N, a.H, \
-                                                        a.W, a.C, bins, a.PH, a.PW, (float)a.scale, a.sampling_ratio, a.aligned)
+    const long long bin_rows = (long long)a.K * a.PH;
+    const unsigned row_blocks = (unsigned)((bin_rows + 7) / 8);
+#define ROI_VEC_G(T, GRID)                                                                                           \
+    roi_align_fwd_vec_kernel<T, GRID><<<row_blocks, 256, 0, st>>>((const T*)a.feat, (const float*)a.rois, (T*)a.out, \
+                                                                 a.N, a.H, a.W, a.C, bin_rows, a.PH, a.PW,           \
+                                                                 (float)a.scale, a.sampling_ratio, a.aligned)
+#define ROI_VEC(T) do { if (a.sampling_ratio == 2) ROI_VEC_G(T, 2); else ROI_VEC_G(T, 0); } while (0)
 #define ROI_SCALAR(T, CT)                                                                                          \
     roi_align_fwd_kernel<T, CT><<<blocks, 256, 0, st>>>((const T*)a.feat, (const CT*)a.rois, (T*)a.out, a.N, a.H,   \
                                                         a.W, a.C, bins, a.PH, a.PW, (CT)a.scale, a.sampling_ratio, a.aligned)
@@ -216,6 +249,7 @@ cudaError_t roi_align_forward(const RoiAlignArgs& a, cudaStream_t st)
         case kF64:  ROI_SCALAR(double, double); break;
         default: return cudaErrorInvalidValue;
     }
+#undef ROI_VEC_G
 #undef ROI_VEC
 #undef ROI_SCALAR
     return cudaGetLastError();
