@@ -43,9 +43,26 @@ constexpr int kPjStoreThreads = 32 * kPjStoreWarps;
 constexpr int kPjThreads = kPjEpiThreads + 64 + kPjStoreThreads;
 constexpr int kPjSmemA = 4 * kPjTM * 128;         // 65536: 4 k-blocks of [128 rows x 128 B]
 constexpr int kPjSmemRes = 4 * kPjTM * 128;       // 65536: the residual tile, same SWIZZLE_128B box layout
-constexpr int kPjSmemPart = kPjStoreWarps * 2 * (kPjTM / kPjStoreWarps) * 33 * 4;   // 33792: per-lane partial row statistics
+// 1: the residual is added BY THE TENSOR CORE (Y^T += I R^T with a 128 x 128 identity in shared memory as A operand and
+// the residual tile as B operand): exact (the products are the residual's bf16 values, accumulated in fp32 with the
+// projection before anything is rounded), the residual buffer is free again as soon as the MMAs are done (so the next
+// tile's residual loads while this one is normalised), and the LayerNorm warps unpack one staged operand, not two.
+// 0 (default): the residual is added by the LayerNorm warps from its shared-memory tile.
+// Measured (8 x 22223 rows): 67.0 us with 0, 68.0 us with 1 (129.6 vs 117.0 us with the `pos` output).  Neither the
+// instruction count of the LayerNorm phase nor its global stores are what a tile waits for (removing the stores
+// leaves the phase at 7 k cycles): the kernel is bound by the SHARED-MEMORY pipe (128 B/clk).  Per tile it carries
+// ~6.4 k wavefronts: TMA writes of the token and residual tiles (1 k), the B operand read once per 128-channel block
+// (1 k), the epilogue's 2-byte staging stores (1 k half-filled wavefronts), two LayerNorm passes over staged value
+// and residual (2 k), the partial-statistics round trip (1.3 k).  The tensor-core residual only swaps LayerNorm reads
+// for operand reads, hence the tie; it also costs 32 KB more shared memory and 60 bytes of spills at the 72-register
+// cap of an 832-thread CTA.  It stays as a build option (parity-tested on the B200 with either setting).
+#ifndef MSDA_PROJ_TC_RESIDUAL
+#define MSDA_PROJ_TC_RESIDUAL 0
+#endif
+constexpr int kPjSmemPart = MSDA_PROJ_TC_RESIDUAL ? 0 : kPjStoreWarps * 2 * (kPjTM / kPjStoreWarps) * 33 * 4;   // per-lane partial row statistics
+constexpr int kPjSmemId = MSDA_PROJ_TC_RESIDUAL ? 2 * kPjTM * 128 : 0;   // 32768: identity, 2 k-blocks of [128 rows x 128 B]
 constexpr int kPjSmemBars = 256;
-constexpr int kPjSmem = 2 * kPjSmemA + kPjSmemRes + kPjSmemPart + kPjSmemBars;
+constexpr int kPjSmem = 2 * kPjSmemA + kPjSmemRes + kPjSmemPart + kPjSmemId + kPjSmemBars;
 static_assert(kPjSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 
 #ifdef MSDA_PROJ_TRACE
@@ -56,7 +73,7 @@ __device__ long long g_proj_trace[4][8][8];      // [role][tile iteration][event
 #endif
 
 struct ProjBars {
-    unsigned long long w_full, w_copied, a_full[2], mma_done[2], yacc_free, stage_full, res_full, store_done;
+    unsigned long long w_full, w_copied, a_full[2], mma_done[2], yacc_free, stage_full, res_full, store_done, store_done2[2];
     unsigned tmem_base;
 };
 
@@ -72,7 +89,8 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     unsigned char* sA = smem;                              // [2][kPjSmemA]: token tile, then (MMAs done) its staged result
     unsigned char* sRes = smem + 2 * kPjSmemA;
     float* s_part = reinterpret_cast<float*>(sRes + kPjSmemRes);
-    ProjBars* bars = reinterpret_cast<ProjBars*>(sRes + kPjSmemRes + kPjSmemPart);
+    unsigned char* sId = sRes + kPjSmemRes + kPjSmemPart;
+    ProjBars* bars = reinterpret_cast<ProjBars*>(sRes + kPjSmemRes + kPjSmemPart + kPjSmemId);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long tiles = (rows + kPjTM - 1) / kPjTM;
@@ -86,9 +104,22 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         mbar_init(&bars->stage_full, kPjEpiThreads);
         mbar_init(&bars->res_full, 1);
         mbar_init(&bars->store_done, kPjStoreThreads);
+        mbar_init(&bars->store_done2[0], kPjStoreThreads);
+        mbar_init(&bars->store_done2[1], kPjStoreThreads);
         fence_mbar_init();
         tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_r);
     }
+#if MSDA_PROJ_TC_RESIDUAL
+    // identity [128 x 128] bf16 in the K-major SWIZZLE_128B operand layout (16-byte chunk c of row r: ones at k = r)
+    for (int idx = tid; idx < kPjTM * 16; idx += kPjThreads) {
+        const int r = idx >> 4, c = idx & 15;
+        const unsigned one = ((r >> 3) == c) ? ((r & 1) ? 0x3f800000u : 0x00003f80u) : 0u;   // bf16 1.0 at column k = r
+        const int word = (r & 7) >> 1;
+        *reinterpret_cast<uint4*>(sId + sw128_offset(r, c, kPjTM)) =
+            make_uint4(word == 0 ? one : 0u, word == 1 ? one : 0u, word == 2 ? one : 0u, word == 3 ? one : 0u);
+    }
+    fence_proxy_async();
+#endif
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -133,9 +164,30 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                         for (int j = 0; j < 4; ++j)
                             mma_bf16_ts(tmem_y + mb * 128, tmem_w + mb * 128 + (kb * 4 + j) * 8,
                                         desc_advance(dA, buf * kPjSmemA + kb * kPjTM * 128 + j * 32), idesc, (kb | j) != 0);
+#if !MSDA_PROJ_TC_RESIDUAL
                 mma_commit(&bars->mma_done[buf]);
+#else
+                if (!has_residual) mma_commit(&bars->mma_done[buf]);
+#endif
             }
             __syncwarp();
+#if MSDA_PROJ_TC_RESIDUAL
+            if (has_residual) {
+                mbar_wait(&bars->res_full, it & 1);                      // residual tile landed
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const unsigned long long dI = make_desc_sw128(sId), dR = make_desc_sw128(sRes);
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                        for (int s8 = 0; s8 < 8; ++s8)                   // Y^T[mb] += I (128 x 128) @ R[:, mb*128 : +128]^T
+                            mma_bf16(tmem_y + mb * 128, desc_advance(dI, (s8 >> 2) * kPjTM * 128 + (s8 & 3) * 32),
+                                     desc_advance(dR, (2 * mb + (s8 >> 2)) * kPjTM * 128 + (s8 & 3) * 32), idesc, true);
+                    mma_commit(&bars->mma_done[buf]);                    // covers the projection MMAs issued above too
+                }
+                __syncwarp();
+            }
+#endif
             PJ_TRACE(0, 3);
         }
     } else if (warp == kPjEpiWarps + 1) {
@@ -153,7 +205,10 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         unsigned it = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            // buffer `buf` was the staging tile of tile it-2: its store phase was awaited in the previous iteration
+#if MSDA_PROJ_TC_RESIDUAL
+            // buffer `buf` was the staging tile of tile it-2
+            if (it >= 2) mbar_wait(&bars->store_done2[buf], ((it - 2) >> 1) & 1);
+#endif
             PJ_TRACE(1, 0);
             if (elect_one()) {
                 mbar_expect_tx(&bars->a_full[buf], kPjSmemA);
@@ -167,7 +222,13 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                 }
             }
             __syncwarp();
+#if MSDA_PROJ_TC_RESIDUAL
+            // the residual buffer is free once the MMAs of the previous tile (its only readers) are done
+            if (it > 0) mbar_wait(&bars->mma_done[buf ^ 1], ((it - 1) >> 1) & 1);
+#else
+            // (buffer `buf` of the NEXT iteration was the staging tile of tile it-1: awaited here)
             if (it > 0) mbar_wait(&bars->store_done, (it - 1) & 1);      // the residual buffer (and buffer buf^1) are free
+#endif
             PJ_TRACE(1, 1);
             if (has_residual) {
                 if (elect_one()) {
@@ -175,8 +236,7 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb)
                         tma_load_2d(sRes + kb * kPjTM * 128, &tm_r, kb * 64, (int)(tile * kPjTM), &bars->res_full);
-                    // the next tile's residual can only land once this tile's LayerNorm is done: pull it into L2 now
-                    if (tile + gridDim.x < tiles) {
+                    if (tile + gridDim.x < tiles) {  // and the next residual tile as far as L2
 #pragma unroll
                         for (int kb = 0; kb < 4; ++kb)
                             tma_prefetch_l2_2d(&tm_r, kb * 64, (int)((tile + gridDim.x) * kPjTM));
@@ -214,6 +274,74 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
     } else {
         // ======================================= LayerNorm + store warps =======================================
+#if MSDA_PROJ_TC_RESIDUAL
+        // The staged tile already holds bf16(projection + bias + residual).  A warp owns kPjTM / kPjStoreWarps token
+        // rows, lane = one 16-byte chunk (8 channels) of the 256-wide row: every shared / global access is a
+        // coalesced 512-byte row.  Pass 1: per-row partial (sum, sum of squares), the rows' 2 x 8 butterflies are
+        // independent of one another (the other three warps of the scheduler fill the shuffle latency); pass 2
+        // re-reads the rows, normalises with 2 FMAs per element and stores.
+        const int swarp = warp - (kPjEpiWarps + 2);
+        float g[8], b[8];
+        unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(gamma + lane * 8), g);
+        unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(beta + lane * 8), b);
+        constexpr int kRowsPerWarp = kPjTM / kPjStoreWarps;      // 8
+        unsigned it = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const long long row0 = tile * kPjTM;
+            const unsigned char* sStage = sA + (it & 1) * kPjSmemA + (swarp * kRowsPerWarp) * (kPjC * 2) + lane * 16;
+            if (swarp == 0) PJ_TRACE(3, 0);
+            mbar_wait(&bars->stage_full, it & 1);
+            if (swarp == 0) PJ_TRACE(3, 2);
+            constexpr int kHalf = kRowsPerWarp / 2;      // 4 rows at a time: 8 statistics registers instead of 16
+#pragma unroll 1
+            for (int h0 = 0; h0 < kRowsPerWarp; h0 += kHalf) {
+                float sum[kHalf], sq[kHalf];
+#pragma unroll
+                for (int r = 0; r < kHalf; ++r) {
+                    float v[8];
+                    unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(sStage + (h0 + r) * (kPjC * 2)), v);
+                    sum[r] = 0.f; sq[r] = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { sum[r] += v[e]; sq[r] = fmaf(v[e], v[e], sq[r]); }
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                    for (int r = 0; r < kHalf; ++r) {
+                        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], off);
+                        sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], off);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kHalf; ++r) {
+                    const long long gr = row0 + swarp * kRowsPerWarp + h0 + r;
+                    const float mean = sum[r] * (1.f / kPjC);
+                    const float rstd = rsqrtf(fmaxf(sq[r] * (1.f / kPjC) - mean * mean, 0.f) + eps);
+                    const float shift = -mean * rstd;
+                    if (gr < rows) {
+                        float v[8], o[8];
+                        unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(sStage + (h0 + r) * (kPjC * 2)), v);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaf(fmaf(v[e], rstd, shift), g[e], b[e]);
+                        const uint4 outv = pack<__nv_bfloat16>(o);
+                        stg_stream_v4(y + gr * kPjC + lane * 8, outv);
+                        if (y_pos != nullptr) {
+                            float pf[8];
+                            unpack<__nv_bfloat16>(outv, o);          // y_pos is defined on the rounded y
+                            unpack<__nv_bfloat16>(ldg_stream_v4(pos + gr * kPjC + lane * 8), pf);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[e] += pf[e];
+                            stg_stream_v4(y_pos + gr * kPjC + lane * 8, pack<__nv_bfloat16>(o));
+                        }
+                    }
+                }
+            }
+            if (swarp == 0) PJ_TRACE(3, 3);
+            fence_proxy_async();                     // generic-proxy reads of a buffer the TMA (async proxy) refills next
+            mbar_arrive(&bars->store_done2[it & 1]); // the staging buffer may be refilled with a token tile
+        }
+    }
+#else
         // A warp owns kPjTM / kPjStoreWarps token rows; lane = one 16-byte chunk (8 channels) of the 256-wide row, so every shared /
         // global access is a coalesced 512-byte row.  Row statistics WITHOUT shuffle chains (a single warp per
         // scheduler cannot hide ten dependent shuffles per row): pass 1 parks each lane's partial (sum, sum of
@@ -297,6 +425,7 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             mbar_arrive(&bars->store_done);          // staging buffer and residual buffer may be refilled
         }
     }
+#endif
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) tmem_free(tmem, 512);
