@@ -342,16 +342,18 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
     }
 #else
-        // A warp owns kPjTM / kPjStoreWarps token rows; lane = one 16-byte chunk (8 channels) of the 256-wide row, so every shared /
-        // global access is a coalesced 512-byte row.  Row statistics WITHOUT shuffle chains (a single warp per
-        // scheduler cannot hide ten dependent shuffles per row): pass 1 parks each lane's partial (sum, sum of
-        // squares) of each row in shared memory, then lane l folds row l's 32 partials; pass 2 re-reads the rows,
-        // normalises and stores.
+        // A warp owns kPjTM / kPjStoreWarps token rows; lane = one 16-byte chunk (8 channels) of the 256-wide row, so
+        // every shared / global access is a coalesced 512-byte row.  The kernel is bound by the shared-memory pipe, so
+        // each row is read ONCE (4 rows at a time stay in registers between the statistics and the normalisation),
+        // and the statistics avoid shuffle chains (a warp cannot hide ten dependent shuffles per row): each lane
+        // parks its partial (sum, sum of squares) of a row in shared memory, 8 lanes fold a row's 32 partials
+        // (4 each, conflict-free, + 3 butterfly steps).
         const int swarp = warp - (kPjEpiWarps + 2);
         float g[8], b[8];
         unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(gamma + lane * 8), g);
         unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(beta + lane * 8), b);
-        constexpr int kRowsPerWarp = kPjTM / kPjStoreWarps;      // 32
+        constexpr int kRowsPerWarp = kPjTM / kPjStoreWarps;      // 8
+        constexpr int kGroup = 4;                                // rows kept in registers at a time
         float* part_sum = s_part + swarp * (2 * kRowsPerWarp * 33);
         float* part_sq = part_sum + kRowsPerWarp * 33;
         unsigned it = 0;
@@ -363,60 +365,59 @@ proj_layernorm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             if (swarp == 0) PJ_TRACE(3, 1);
             if (has_residual) mbar_wait(&bars->res_full, it & 1);
             if (swarp == 0) PJ_TRACE(3, 2);
-            // ---- pass 1: partial statistics of v = bf16(projection) + residual ----
+#pragma unroll 1
+            for (int h0 = 0; h0 < kRowsPerWarp; h0 += kGroup) {
+                float v[kGroup][8];
+                // ---- v = bf16(projection) + residual, partial statistics ----
 #pragma unroll
-            for (int r = 0; r < kRowsPerWarp; ++r) {
-                const int rr = swarp * kRowsPerWarp + r;
-                float v[8], rs[8];
-                unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(sStage + rr * (kPjC * 2) + lane * 16), v);
-                if (has_residual) {
-                    unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(sRes + sw128_offset(rr, lane, kPjTM)), rs);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] += rs[e];
-                }
-                float s = 0.f, q = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { s += v[e]; q = fmaf(v[e], v[e], q); }
-                part_sum[r * 33 + lane] = s;
-                part_sq[r * 33 + lane] = q;
-            }
-            __syncwarp();
-            float s = 0.f, q = 0.f;                  // lane l < rows per warp: totals of row l
-            if (lane < kRowsPerWarp) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { s += part_sum[lane * 33 + i]; q += part_sq[lane * 33 + i]; }
-            }
-            const float my_mean = s * (1.f / kPjC);
-            const float my_rstd = rsqrtf(fmaxf(q * (1.f / kPjC) - my_mean * my_mean, 0.f) + eps);
-            __syncwarp();
-            // ---- pass 2: normalise, store y (+ pos) ----
-#pragma unroll
-            for (int r = 0; r < kRowsPerWarp; ++r) {
-                const int rr = swarp * kRowsPerWarp + r;
-                const long long gr = row0 + rr;
-                const float mean = __shfl_sync(0xffffffffu, my_mean, r), rstd = __shfl_sync(0xffffffffu, my_rstd, r);
-                if (gr < rows) {
-                    float v[8], rs[8];
-                    uint4 pp = make_uint4(0u, 0u, 0u, 0u);
-                    if (y_pos != nullptr) pp = ldg_stream_v4(pos + gr * kPjC + lane * 8);
-                    unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(sStage + rr * (kPjC * 2) + lane * 16), v);
+                for (int r = 0; r < kGroup; ++r) {
+                    const int rr = swarp * kRowsPerWarp + h0 + r;
+                    unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(sStage + rr * (kPjC * 2) + lane * 16), v[r]);
                     if (has_residual) {
+                        float rs[8];
                         unpack<__nv_bfloat16>(*reinterpret_cast<const uint4*>(sRes + sw128_offset(rr, lane, kPjTM)), rs);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] += rs[e];
+                        for (int e = 0; e < 8; ++e) v[r][e] += rs[e];
                     }
-                    float o[8];
+                    float s = 0.f, q = 0.f;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = fmaf((v[e] - mean) * rstd, g[e], b[e]);
-                    const uint4 outv = pack<__nv_bfloat16>(o);
-                    stg_stream_v4(y + gr * kPjC + lane * 8, outv);
-                    if (y_pos != nullptr) {
-                        float pf[8];
-                        unpack<__nv_bfloat16>(outv, o);          // y_pos is defined on the rounded y
-                        unpack<__nv_bfloat16>(pp, pf);
+                    for (int e = 0; e < 8; ++e) { s += v[r][e]; q = fmaf(v[r][e], v[r][e], q); }
+                    part_sum[(h0 + r) * 33 + lane] = s;
+                    part_sq[(h0 + r) * 33 + lane] = q;
+                }
+                __syncwarp();
+                // ---- lanes 8r .. 8r+7 fold row r: 4 partials each, then 3 butterfly steps ----
+                const int fr = h0 + (lane >> 3), seg = (lane & 7) * 4;
+                float s = 0.f, q = 0.f;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] += pf[e];
-                        stg_stream_v4(y_pos + gr * kPjC + lane * 8, pack<__nv_bfloat16>(o));
+                for (int i = 0; i < 4; ++i) { s += part_sum[fr * 33 + seg + i]; q += part_sq[fr * 33 + seg + i]; }
+#pragma unroll
+                for (int off = 1; off <= 4; off <<= 1) {
+                    s += __shfl_xor_sync(0xffffffffu, s, off);
+                    q += __shfl_xor_sync(0xffffffffu, q, off);
+                }
+                const float my_mean = s * (1.f / kPjC);
+                const float my_rstd = rsqrtf(fmaxf(q * (1.f / kPjC) - my_mean * my_mean, 0.f) + eps);
+                __syncwarp();
+                // ---- normalise from registers, store y (+ pos) ----
+#pragma unroll
+                for (int r = 0; r < kGroup; ++r) {
+                    const long long gr = row0 + swarp * kRowsPerWarp + h0 + r;
+                    const float mean = __shfl_sync(0xffffffffu, my_mean, r * 8), rstd = __shfl_sync(0xffffffffu, my_rstd, r * 8);
+                    if (gr < rows) {
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaf((v[r][e] - mean) * rstd, g[e], b[e]);
+                        const uint4 outv = pack<__nv_bfloat16>(o);
+                        stg_stream_v4(y + gr * kPjC + lane * 8, outv);
+                        if (y_pos != nullptr) {
+                            float pf[8];
+                            unpack<__nv_bfloat16>(outv, o);          // y_pos is defined on the rounded y
+                            unpack<__nv_bfloat16>(ldg_stream_v4(pos + gr * kPjC + lane * 8), pf);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[e] += pf[e];
+                            stg_stream_v4(y_pos + gr * kPjC + lane * 8, pack<__nv_bfloat16>(o));
+                        }
                     }
                 }
             }
