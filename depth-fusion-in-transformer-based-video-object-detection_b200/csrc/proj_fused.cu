@@ -48,14 +48,12 @@ constexpr int kPjSmemRes = 4 * kPjTM * 128;       // 65536: the residual tile, s
 // projection before anything is rounded), the residual buffer is free again as soon as the MMAs are done (so the next
 // tile's residual loads while this one is normalised), and the LayerNorm warps unpack one staged operand, not two.
 // 0 (default): the residual is added by the LayerNorm warps from its shared-memory tile.
-// Measured (8 x 22223 rows): 67.0 us with 0, 68.0 us with 1 (129.6 vs 117.0 us with the `pos` output).  Neither the
-// instruction count of the LayerNorm phase nor its global stores are what a tile waits for (removing the stores
-// leaves the phase at 7 k cycles): the kernel is bound by the SHARED-MEMORY pipe (128 B/clk).  Per tile it carries
-// ~6.4 k wavefronts: TMA writes of the token and residual tiles (1 k), the B operand read once per 128-channel block
-// (1 k), the epilogue's 2-byte staging stores (1 k half-filled wavefronts), two LayerNorm passes over staged value
-// and residual (2 k), the partial-statistics round trip (1.3 k).  The tensor-core residual only swaps LayerNorm reads
-// for operand reads, hence the tie; it also costs 32 KB more shared memory and 60 bytes of spills at the 72-register
-// cap of an 832-thread CTA.  It stays as a build option (parity-tested on the B200 with either setting).
+// Measured (8 x 22223 rows, two-pass LayerNorm at the time): 67.0 us with 0, 68.0 us with 1 (129.6 vs 117.0 us with the
+// `pos` output).  Neither the instruction count of the LayerNorm phase nor its global stores were what a tile waited
+// for (removing the stores left the phase at 7 k cycles); its shared-memory passes were -- the tensor-core residual
+// only swaps LayerNorm reads for operand reads, hence the tie.  It also costs 32 KB more shared memory and 60 bytes of
+// spills at the 72-register cap of an 832-thread CTA.  It stays as a build option (parity-tested on the B200 with
+// either setting); the default path was then cut to ONE pass over the staged rows (61 us).
 #ifndef MSDA_PROJ_TC_RESIDUAL
 #define MSDA_PROJ_TC_RESIDUAL 0
 #endif
