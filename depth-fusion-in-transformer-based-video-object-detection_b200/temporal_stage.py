@@ -434,6 +434,103 @@ class DeformableTransformer(_SingleFrameTransformer):
                 final_references_out, out)
 
 
+class TransVODDeformableTransformer(_SingleFrameTransformer):
+    """TransVOD multi-frame transformer (the reference's ``DeformableTransformer`` of
+    /root/reference/models/deformable_transformer_multi.py:24-379; TransVOD++ above adds RoIAlign + QRF to it).
+    Frames of a clip -- current first -- are the batch of the per-frame encoder / decoder; then three temporal query
+    encoder rounds over the top 80 / 50 / 30 (x num_ref_frames) reference-frame queries ranked by their best
+    non-background class score (:352-368), and ONE temporal deformable decoder over the current frame's memory (:371).
+    Same constructor, forward signature and parameter names (``temporal_encoder_layer`` -- the frames-as-levels
+    layer, built but unused because the reference hard-codes ``self.TDAM = False`` (:46) --,
+    ``temporal_query_layer{1,2,3}``, ``temporal_decoder``).  Clips batch clip-major like the TransVOD++ class, and
+    the temporal decoder gets ``valid_ratios[:, 0:1]``.
+
+    forward(...) -> (hs[:, 0:1], init_reference[0:1], inter_references[:, 0:1], None, None, final_hs,
+                     final_references)                                                                 (:374)
+    """
+
+    TOPK_PER_REF_FRAME = (80, 50, 30)
+
+    def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=1024,
+                 dropout=0.1, activation="relu", return_intermediate_dec=False, num_feature_levels=4,
+                 dec_n_points=4, enc_n_points=4, two_stage=False, two_stage_num_proposals=300,
+                 n_temporal_decoder_layers=1, num_ref_frames=3, fixed_pretrained_model=False, args=None,
+                 use_depth=False, depth_type='', dpth_feature_levels=1, dpth_n_points=4):
+        self._temporal_cfg = dict(d_model=d_model, nhead=nhead, dim_feedforward=dim_feedforward, dropout=dropout,
+                                  activation=activation, num_feature_levels=num_feature_levels,
+                                  dec_n_points=dec_n_points, enc_n_points=enc_n_points,
+                                  n_temporal_decoder_layers=n_temporal_decoder_layers)
+        self.num_ref_frames = num_ref_frames
+        self.fixed_pretrained_model = fixed_pretrained_model
+        self.n_temporal_query_layers = 3
+        self.TDAM = False                                                                                # :46
+        super().__init__(d_model, nhead, num_encoder_layers, num_decoder_layers, dim_feedforward, dropout, activation,
+                         return_intermediate_dec, num_feature_levels, dec_n_points, enc_n_points, two_stage,
+                         two_stage_num_proposals, use_depth, depth_type, dpth_feature_levels, dpth_n_points)
+
+    def _build_extra_modules(self):
+        from .transformer_layers import TemporalDeformableTransformerEncoderLayer
+        t = self._temporal_cfg
+        d_model, nhead, dff, dropout, activation = t["d_model"], t["nhead"], t["dim_feedforward"], t["dropout"], t["activation"]
+        self.temporal_encoder_layer = TemporalDeformableTransformerEncoderLayer(
+            d_model, dff, dropout, activation, self.num_ref_frames, nhead, t["enc_n_points"])            # :84-86
+        for i in (1, 2, 3):
+            setattr(self, f"temporal_query_layer{i}", TemporalQueryEncoderLayer(d_model, dff, dropout, activation, nhead))
+        decoder_layer = DeformableTransformerDecoderLayer(d_model, dff, dropout, activation, t["num_feature_levels"],
+                                                          nhead, t["dec_n_points"])
+        self.temporal_decoder = TemporalDeformableTransformerDecoder(decoder_layer, t["n_temporal_decoder_layers"], False)
+
+    def forward(self, srcs, masks, pos_embeds, depth_srcs, depth_masks, depth_pos_embeds, query_embed=None,
+                class_embed=None, rgbd_query=[]):
+        hs, init_reference_out, inter_references, enc_cls, enc_coord, state = super().forward(
+            srcs, masks, pos_embeds, depth_srcs, depth_masks, depth_pos_embeds, query_embed, rgbd_query,
+            _return_state=True)
+        if self.two_stage:                                                                              # :318-319
+            return hs, init_reference_out, inter_references, enc_cls, enc_coord
+        memory, lvl_pos, spatial_shapes, level_start_index, valid_ratios, shapes = state
+        if self.fixed_pretrained_model:                                                                 # :321-325
+            memory, hs, inter_references = memory.detach(), hs.detach(), inter_references.detach()
+
+        frames = self.num_ref_frames + 1
+        batch, tokens, c = memory.shape
+        if batch % frames != 0:
+            raise RuntimeError(f"batch of {batch} frames is not a whole number of {frames}-frame clips")
+        clips = batch // frames
+        by_clip = lambda t: t.view(clips, frames, *t.shape[1:])
+        cur_memory = by_clip(memory)[:, 0]
+        if self.TDAM:                                       # frames-as-levels attention of the current frame (:328-343)
+            if len(shapes) != 1:
+                raise RuntimeError("the temporal encoder layer treats the reference FRAMES as levels: one feature level")
+            ref_memory = (by_clip(memory)[:, 1:] + by_clip(lvl_pos)[:, 1:]).reshape(clips, self.num_ref_frames * tokens, c)
+            ref_shapes = spatial_shapes.expand(self.num_ref_frames, 2).contiguous()
+            frame_start = torch.cat((ref_shapes.new_zeros((1,)), ref_shapes.prod(1).cumsum(0)[:-1])).contiguous()
+            # the current frame's pixel grid, once per reference frame (the reference gets there by expanding the
+            # valid ratios to num_ref_frames pseudo-levels, :336-338)
+            ref_points = self.get_reference_points([shapes[0]], by_clip(valid_ratios)[:, 0, 0:1], device=memory.device)
+            ref_points = ref_points.expand(-1, -1, self.num_ref_frames, -1).contiguous()
+            cur_memory = self.temporal_encoder_layer(cur_memory, by_clip(lvl_pos)[:, 0], ref_points, ref_memory,
+                                                     ref_shapes, frame_start)
+
+        last_hs, last_ref = by_clip(hs[-1]), by_clip(inter_references[-1])
+        nq = last_hs.shape[2]
+        cur_hs, cur_reference_out = last_hs[:, 0], last_ref[:, 0]
+        ref_hs = last_hs[:, 1:].reshape(clips, self.num_ref_frames * nq, c)
+        prob = class_embed(ref_hs).sigmoid()
+        n_cls = prob.shape[2] - 1                                                   # the last class is left out (:353)
+        scores = prob[:, :, :-1].reshape(clips, -1)
+        for stage, per_frame in enumerate(self.TOPK_PER_REF_FRAME):
+            topk_indexes = torch.topk(scores, per_frame * self.num_ref_frames, dim=1)[1] // n_cls
+            ref_in = torch.gather(ref_hs, 1, topk_indexes.unsqueeze(-1).expand(-1, -1, c))
+            cur_hs = getattr(self, f"temporal_query_layer{stage + 1}")(cur_hs, ref_in)
+        vr = by_clip(valid_ratios)[:, 0, 0:1]
+        final_hs, final_references_out = self.temporal_decoder(
+            cur_hs, cur_reference_out, cur_memory, spatial_shapes[0:1] if len(shapes) > 1 else spatial_shapes,
+            level_start_index[0:1] if len(shapes) > 1 else level_start_index, vr, None, None)
+        cur = slice(0, batch, frames)
+        return (hs[:, cur], init_reference_out[cur], inter_references[:, cur], None, None, final_hs,
+                final_references_out)
+
+
 def build_deforamble_transformer(args):
     """Same (misspelt) name and argument mapping as the reference builder (:1145-1170)."""
     return DeformableTransformer(

@@ -692,6 +692,58 @@ def main():
     transvodpp_case("transvodpp_f1", "Baseline_rgb", False, 1, 90, False)
     transvodpp_case("transvodpp_f2_latefusion", "DepthDeform_latefusion_dformer", True, 2, 92, True)
 
+    # ---------------- TransVOD multi-frame transformer (deformable_transformer_multi.py:24-379) -------------------------
+    # "transvod_f1": the UNMODIFIED reference class, one reference frame.  "transvod_f2_tdam": two reference frames,
+    # with the frames-as-levels temporal encoder layer switched on (``TDAM = True`` set on the instance; the reference
+    # hard-codes False, :46) and the temporal decoder given valid_ratios[:, 0:1] (as for TransVOD++).
+    tv = importlib.import_module("models.deformable_transformer_multi")
+    tv.MSDeformAttn = mod.MSDeformAttn
+
+    class TransVOD(torch.nn.Module):
+        def __init__(self, transformer, width, n_cls=4):
+            super().__init__()
+            self.transformer = transformer
+            self.class_embed = torch.nn.Linear(width, n_cls)
+
+        def forward(self, t):
+            hs, init_ref, inter_ref, _, _, final_hs, final_ref = self.transformer(
+                [t["src0"]], [t["mask0"]], [t["pos0"]], [t["depth_src0"]], [t["depth_mask0"]], [t["depth_pos0"]],
+                t["query_embed"], self.class_embed)
+            return torch.cat([x.flatten() for x in (hs, init_ref, inter_ref, final_hs, final_ref)])
+
+    def transvod_case(name, depth_type, use_depth, ref_frames, seed, tdam):
+        if not wanted(name):
+            return
+        torch.manual_seed(seed)
+        nq, (fh, fw), cw_ = 80, (4, 6), 16
+        model = TransVOD(tv.DeformableTransformer(
+            d_model=cw_, nhead=heads, num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=64, dropout=0.0,
+            activation="relu", return_intermediate_dec=True, num_feature_levels=1, dec_n_points=pts, enc_n_points=pts,
+            n_temporal_decoder_layers=1, num_ref_frames=ref_frames, use_depth=use_depth, depth_type=depth_type,
+            dpth_n_points=pts), cw_).double()
+        model.transformer.TDAM = tdam
+        perturb(model, seed + 1)
+        frames = ref_frames + 1
+        ins = dict(src0=torch.randn(frames, cw_, fh, fw), pos0=torch.randn(frames, cw_, fh, fw),
+                   depth_src0=torch.randn(frames, cw_, fh, fw), depth_pos0=torch.randn(frames, cw_, fh, fw),
+                   query_embed=torch.randn(nq, 2 * cw_))
+        mk = torch.zeros(frames, fh, fw, dtype=torch.bool)
+        mk[-1, :, 4:] = True
+        ins["mask0"] = mk
+        ins["depth_mask0"] = mk.clone()
+        original = tv.TemporalDeformableTransformerDecoder.forward
+        if ref_frames > 1:
+            def fixed(self, tgt, reference_points, src, shapes_, lsi_, valid_ratios, query_pos=None, mask=None):
+                return original(self, tgt, reference_points, src, shapes_, lsi_, valid_ratios[:, 0:1], query_pos, mask)
+            tv.TemporalDeformableTransformerDecoder.forward = fixed
+        try:
+            save_module_case(name, model, ins, lambda m_, t: m_(t), wrt=["src0", "depth_src0", "query_embed"])
+        finally:
+            tv.TemporalDeformableTransformerDecoder.forward = original
+
+    transvod_case("transvod_f1", "Baseline_rgb", False, 1, 100, False)
+    transvod_case("transvod_f2_tdam", "DepthDeform_latefusion_dformer", True, 2, 102, True)
+
     # Backbone Cross Fusion U-DF: fuse_layers + its layer (dformer_crossfusion_backbone.py:387-428,120-181)
     torch.manual_seed(41)
     udf = backbone_cf.DepthDeformableTransformerEncoderLayer(c, 64, 0.0, "relu", 1, heads, pts).double()

@@ -278,3 +278,36 @@ CASES["transformer_rgbd_query"] = dict(
         activation="relu", return_intermediate_dec=True, num_feature_levels=2, dec_n_points=PTS, enc_n_points=PTS,
         use_depth=False, depth_type="Baseline_concat"),
     call=_rgbd_query_call, wrt=["src0", "rgbd0", "query_embed"])
+
+
+# TransVOD multi-frame transformer (reference deformable_transformer_multi.py), wired like oracle/gen_golden.py: TransVOD
+class TransVOD(torch.nn.Module):
+    def __init__(self, transformer, width, n_cls=4):
+        super().__init__()
+        self.transformer = transformer
+        self.class_embed = torch.nn.Linear(width, n_cls)
+
+    def forward(self, t):
+        hs, init_ref, inter_ref, _, _, final_hs, final_ref = self.transformer(
+            [t["src0"]], [t["mask0"]], [t["pos0"]], [t["depth_src0"]], [t["depth_mask0"]], [t["depth_pos0"]],
+            t["query_embed"], self.class_embed)
+        return torch.cat([x.flatten() for x in (hs, init_ref, inter_ref, final_hs, final_ref)])
+
+
+def _transvod(depth_type, use_depth, ref_frames, tdam, width=16):
+    from dfvod_b200 import temporal_stage
+    model = TransVOD(temporal_stage.TransVODDeformableTransformer(
+        d_model=width, nhead=HEADS, num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=64, dropout=0.0,
+        activation="relu", return_intermediate_dec=True, num_feature_levels=1, dec_n_points=PTS, enc_n_points=PTS,
+        n_temporal_decoder_layers=1, num_ref_frames=ref_frames, use_depth=use_depth, depth_type=depth_type,
+        dpth_n_points=PTS), width)
+    model.transformer.TDAM = tdam
+    return model
+
+
+CASES.update({
+    "transvod_f1": dict(build=lambda: _transvod("Baseline_rgb", False, 1, False), call=lambda m, t: m(t),
+                        wrt=["src0", "depth_src0", "query_embed"]),
+    "transvod_f2_tdam": dict(build=lambda: _transvod("DepthDeform_latefusion_dformer", True, 2, True),
+                             call=lambda m, t: m(t), wrt=["src0", "depth_src0", "query_embed"]),
+})
