@@ -37,7 +37,7 @@ from . import _lib
 from .deformable_transformer import DeformableTransformer as _SingleFrameTransformer
 from .ops.functions import norm_act
 from .transformer_layers import (DeformableTransformerDecoderLayer, TemporalDeformableTransformerDecoder,
-                                 _get_activation_fn, _get_clones, inverse_sigmoid)
+                                 _get_activation_fn, _get_clones, inverse_sigmoid, mha_batch_first)
 
 _DTYPES = {torch.float32: _lib.DTYPE_F32, torch.float64: _lib.DTYPE_F64, torch.bfloat16: _lib.DTYPE_BF16,
            torch.float16: _lib.DTYPE_F16}
@@ -211,9 +211,9 @@ class RCNNHead(nn.Module):
             pooled = roi_features.flatten(2).transpose(1, 2)
         else:                                                          # [K, 49, C]
             pooled = roi_features
-        pro = pro_features.reshape(N, nr_boxes, self.d_model).permute(1, 0, 2)
-        pro = self.norm1(pro + self.dropout1(self.self_attn(pro, pro, value=pro, need_weights=False)[0]))
-        pro = pro.permute(1, 0, 2).reshape(1, N * nr_boxes, self.d_model)
+        pro = pro_features.reshape(N, nr_boxes, self.d_model)                 # batch-first: no [boxes, N, C] round trip
+        pro = self.norm1(pro + self.dropout1(mha_batch_first(self.self_attn, pro, pro, pro)))
+        pro = pro.reshape(1, N * nr_boxes, self.d_model)
         obj = self.norm2(pro + self.dropout2(self.inst_interact.forward_tokens(pro, pooled)))
         obj2 = self.linear2(self.dropout(self.activation(self.linear1(obj))))
         return self.norm3(obj + self.dropout3(obj2))
@@ -269,13 +269,11 @@ class TemporalQueryEncoderLayer(nn.Module):
         return self.norm3(tgt + self.dropout4(tgt2))
 
     def forward(self, query, ref_query, query_pos=None, ref_query_pos=None):
-        q = k = self.with_pos_embed(query, query_pos)
-        tgt2 = self.self_attn(q.transpose(0, 1), k.transpose(0, 1), query.transpose(0, 1),
-                              need_weights=False)[0].transpose(0, 1)
+        q = self.with_pos_embed(query, query_pos)
+        tgt2 = mha_batch_first(self.self_attn, q, q, query)
         tgt = self.norm2(query + self.dropout2(tgt2))
-        tgt2 = self.cross_attn(self.with_pos_embed(tgt, query_pos).transpose(0, 1),
-                               self.with_pos_embed(ref_query, ref_query_pos).transpose(0, 1),
-                               ref_query.transpose(0, 1), need_weights=False)[0].transpose(0, 1)
+        tgt2 = mha_batch_first(self.cross_attn, self.with_pos_embed(tgt, query_pos),
+                               self.with_pos_embed(ref_query, ref_query_pos), ref_query)
         tgt = self.norm1(tgt + self.dropout1(tgt2))
         return self.forward_ffn(tgt)
 

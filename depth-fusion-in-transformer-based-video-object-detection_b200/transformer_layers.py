@@ -49,6 +49,30 @@ def _get_activation_fn(activation):
     return table[activation]
 
 
+def mha_batch_first(mha, query, key, value):
+    """``nn.MultiheadAttention`` (no masks, attention weights not needed) on BATCH-FIRST ``[N, L, E]`` tensors, computed
+    from the module's own parameters: the reference hands ``[L, N, E]`` transposes to the module
+    (deformable_transformer_single.py:621-623), which then copies them into head-major layouts and back -- here the
+    heads are strided views of the projection outputs, q and k share one GEMM when they are the same tensor, and the
+    fused scaled-dot-product kernel reads the views in place.  Same arithmetic, same parameters / state-dict keys."""
+    e, heads = mha.embed_dim, mha.num_heads
+    w, b = mha.in_proj_weight, mha.in_proj_bias
+    bias = (lambda lo, hi: None) if b is None else (lambda lo, hi: b[lo:hi])
+    if query is key:
+        qk = F.linear(query, w[:2 * e], bias(0, 2 * e))
+        q, k = qk[..., :e], qk[..., e:]
+    else:
+        q = F.linear(query, w[:e], bias(0, e))
+        k = F.linear(key, w[e:2 * e], bias(e, 2 * e))
+    v = F.linear(value, w[2 * e:], bias(2 * e, 3 * e))
+    n, lq, lk = q.shape[0], q.shape[1], k.shape[1]
+    split = lambda t, length: t.view(n, length, heads, e // heads).transpose(1, 2)         # [N, heads, L, head_dim] view
+    out = F.scaled_dot_product_attention(split(q, lq), split(k, lk), split(v, lk),
+                                         dropout_p=mha.dropout if mha.training else 0.0)
+    out = out.transpose(1, 2).reshape(n, lq, e)
+    return F.linear(out, mha.out_proj.weight, mha.out_proj.bias)
+
+
 def _add_pos(tensor, pos):
     return tensor if pos is None else tensor + pos
 
@@ -311,8 +335,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
         ``cross_attn.value_proj(src)`` computed together with the other layers' (ops.modules.project_values)."""
         if qk is None:
             qk = _add_pos(tgt, query_pos)
-        qk = qk.transpose(0, 1)
-        mixed = self.self_attn(qk, qk, tgt.transpose(0, 1), need_weights=False)[0].transpose(0, 1)
+        mixed = mha_batch_first(self.self_attn, qk, qk, tgt)
         if query_pos is not None:
             tgt, query = add_layer_norm(self.norm2, self.dropout2(mixed), tgt, None, query_pos)
         else:
