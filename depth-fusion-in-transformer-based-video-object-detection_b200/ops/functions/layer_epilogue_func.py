@@ -328,7 +328,10 @@ def proj_layer_norm(linear, norm, x, residual=None, pos=None):
     """``norm(residual + linear(x))`` (and ``that + pos``): the attention's output projection and the layer's
     residual + LayerNorm in ONE tensor-core kernel when :func:`proj_layer_norm_supported`; otherwise the
     GEMM + fused add-LayerNorm composition."""
-    if not proj_layer_norm_supported(x, linear, norm) or (residual is not None and (
+    # with a `pos` output the one-kernel path (117 us at 8 x 22223 rows) loses to GEMM + fused norm (111 us): the
+    # LayerNorm warps have no registers left to prefetch the pos rows.  The C ABI keeps the option; the layers use
+    # the composition there.
+    if pos is not None or not proj_layer_norm_supported(x, linear, norm) or (residual is not None and (
             residual.shape != x.shape or residual.dtype != x.dtype or
             (torch.is_grad_enabled() and residual.requires_grad))):
         return add_layer_norm(norm, globals()["linear"](linear, x), residual, None, pos)

@@ -334,7 +334,20 @@ def test_proj_layer_norm_tcgen05(rows, with_res, with_pos):
     pos = torch.randn(rows, c, device=DEV).bfloat16() if with_pos else None
     with torch.no_grad():
         assert proj_layer_norm_supported(x, lin, norm)
-        out = proj_layer_norm(lin, norm, x, res, pos)
+        if with_pos:          # the Python helper prefers GEMM + fused norm when `pos` is asked for: call the kernel directly
+            from dfvod_b200 import _lib
+            y, y_pos = torch.empty_like(x), torch.empty_like(x)
+            code = _lib.load().msda_layer_proj_layernorm_forward(
+                _lib.DTYPE_BF16, x.data_ptr(), lin.weight.data_ptr(), lin.bias.data_ptr(), res.data_ptr(),
+                norm.weight.data_ptr(), norm.bias.data_ptr(), pos.data_ptr(), rows, c, float(norm.eps), y.data_ptr(),
+                y_pos.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            _lib.check(code, "msda_layer_proj_layernorm_forward")
+            out = (y, y_pos)
+            # and the helper's own route gives the same
+            y2, y2_pos = proj_layer_norm(lin, norm, x, res, pos)
+            assert nerr(y2, y.double()) <= 2.0 ** -6 and nerr(y2_pos, y_pos.double()) <= 2.0 ** -6
+        else:
+            out = proj_layer_norm(lin, norm, x, res, pos)
     y, y_pos = out if with_pos else (out, None)
     lin64, norm64 = torch.nn.Linear(c, c).to(DEV).double(), torch.nn.LayerNorm(c).to(DEV).double()
     lin64.load_state_dict({k: v.double() for k, v in lin.state_dict().items()})
