@@ -669,7 +669,7 @@ def run_b200(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cb = time_cpu_reference(torch, 3, 1, args.dist)
+        cb = time_cpu_reference(torch, 30, 1, args.dist)          # ~10 s of host work
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": METRIC, "value": value_qps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
