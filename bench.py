@@ -476,9 +476,22 @@ def input_projection_extras(torch, dev, world, dist, n_frames=8, iters=10):
         from dfvod_b200.input_projection import group_norm_tokens
         norm = projs[0][1]
         ms_gn = _time_events(torch, lambda: group_norm_tokens(gn_in, 32, norm.weight, norm.bias, 1e-5, inplace=True), 20, 3)
+        # sine position embedding of the 4-level pyramid + level embedding -> lvl_pos_embed_flatten
+        # (position_encoding.py:35-56, backbone_scratch.py:185, deformable_transformer_single.py:196-206)
+        from dfvod_b200.position_encoding import PositionEmbeddingSine
+        sine = PositionEmbeddingSine(128, normalize=True)
+        masks = [torch.zeros(n_frames, h, w, dtype=torch.bool, device=dev) for h, w in COCO_SHAPES]
+        lvl_embed = torch.randn(len(COCO_SHAPES), 256, device=dev).to(bf)
+        pos_ref = lambda: torch.cat([sine._host_composition(m).permute(0, 3, 1, 2).to(bf).flatten(2).transpose(1, 2)
+                                     + lvl_embed[i].view(1, 1, -1) for i, m in enumerate(masks)], 1)
+        pos_tok = lambda: sine.forward_tokens(masks, lvl_embed, dtype=bf)
+        ms_pos_ref = _time_events(torch, pos_ref, iters, 3)
+        ms_pos_tok = _time_events(torch, pos_tok, iters, 3)
     gn_bytes = gn_in.numel() * 2 * 3                       # read (statistics), read + write (apply)
     return {"frames_per_gpu": n_frames, "levels": levels, "dtype": "bf16", "reference_composition_ms": ms_ref,
             "token_major_ms": ms_tok,
+            "sine_position_tokens": {"tokens_per_frame": sum(h * w for h, w in COCO_SHAPES),
+                                     "reference_composition_ms": ms_pos_ref, "kernel_ms": ms_pos_tok},
             "group_norm_tokens_kernels": {"rows": n_frames * 16700, "ms": ms_gn, "gbytes_per_s": gn_bytes / ms_gn / 1e6}}
 
 

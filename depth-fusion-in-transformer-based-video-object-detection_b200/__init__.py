@@ -10,6 +10,7 @@ Layout (only what the hot path needs):
   transformer_layers.py                  encoder / decoder / Late Fusion / Encoder Cross Fusion layer classes
   backbone_fusion.py                     Backbone Cross Fusion (U-DF) layer + fuse_layers
   deformable_transformer.py              single-frame DeformableTransformer (baseline / Late Fusion / Encoder Cross Fusion)
+  position_encoding.py                   PositionEmbeddingSine written token-major (lvl_pos_embed_flatten in one pass)
   temporal_stage.py                      TransVOD++ multi-frame transformer: RoIAlign, QRF head, TQE, TDTD
 
 The directory name carries hyphens; import it through the alias module ``dfvod_b200`` at the

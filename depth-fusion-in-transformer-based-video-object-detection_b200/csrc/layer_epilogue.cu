@@ -794,6 +794,58 @@ cudaError_t group_norm_tokens(int dtype, const void* x, const void* pre_bias, co
     }
 }
 
+// Sine position embedding written TOKEN-MAJOR: the reference's PositionEmbeddingSine
+// (/root/reference/models/position_encoding.py:20-56) builds [N, 2F, H, W] in fp32 (divide the cumulative row / column
+// coordinate by temperature^(2*(k/2)/F), sin on even k, cos on odd k, y block then x block), the backbone joiner casts it
+// to the feature dtype, and DeformableTransformer.forward flattens, transposes and adds level_embed[l]
+// (deformable_transformer_single.py:196-199).  Here the (tiny) coordinate maps come from the same torch ops and one
+// kernel writes pos[n, start + p, c] = T(T(sin|cos(coord[n, p] / dim_t[c % F])) + add[c]) -- one pass, no NCHW tensor.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sine_position_tokens_kernel(const float* __restrict__ y_embed, const float* __restrict__ x_embed,
+                            const float* __restrict__ dim_t, const T* __restrict__ add, T* __restrict__ out, int F,
+                            long long HW, long long S, long long start, long long pixels)
+{
+    const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);      // one warp per pixel of one item
+    if (pix >= pixels) return;
+    const int lane = threadIdx.x & 31;
+    const long long n = pix / HW, p = pix - n * HW;
+    const float ye = y_embed[pix], xe = x_embed[pix];
+    T* o = out + (n * S + start + p) * (2 * F);
+    for (int c = lane; c < 2 * F; c += 32) {
+        const int k = c < F ? c : c - F;
+        const float arg = __fdiv_rn(c < F ? ye : xe, dim_t[k]);
+        float v = to_f32<T>(from_f32<T>((k & 1) ? cosf(arg) : sinf(arg)));
+        if (add != nullptr) v = v + to_f32<T>(add[c]);
+        o[c] = from_f32<T>(v);
+    }
+}
+
+cudaError_t sine_position_tokens(int dtype, const float* y_embed, const float* x_embed, const float* dim_t,
+                                 const void* add, void* out, int N, long long HW, int F, long long S, long long start,
+                                 cudaStream_t st)
+{
+    const long long pixels = (long long)N * HW;
+    if (pixels == 0 || F == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((pixels + 7) / 8);
+    switch (dtype) {
+        case kF32:
+            sine_position_tokens_kernel<float><<<blocks, 256, 0, st>>>(y_embed, x_embed, dim_t, (const float*)add,
+                                                                      (float*)out, F, HW, S, start, pixels);
+            break;
+        case kBF16:
+            sine_position_tokens_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+                y_embed, x_embed, dim_t, (const __nv_bfloat16*)add, (__nv_bfloat16*)out, F, HW, S, start, pixels);
+            break;
+        case kF16:
+            sine_position_tokens_kernel<__half><<<blocks, 256, 0, st>>>(y_embed, x_embed, dim_t, (const __half*)add,
+                                                                       (__half*)out, F, HW, S, start, pixels);
+            break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t zero_masked_rows(int dtype, void* data, const unsigned char* mask, long long rows, int C, cudaStream_t st)
 {
     if (rows == 0 || C == 0) return cudaSuccess;

@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 13; }
+extern "C" int msda_abi_version(void) { return 14; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -369,4 +369,17 @@ extern "C" int msda_layer_proj_layernorm_forward(int dtype, const void* x, const
     a.x = x; a.w = weight; a.b = bias; a.residual = residual; a.gamma = gamma; a.beta = beta; a.pos = pos;
     a.y = y; a.y_pos = y_pos;
     return (int)msda::proj_layernorm_forward(a, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_sine_position_tokens(int dtype, const float* y_embed, const float* x_embed, const float* dim_t,
+                                               int num_pos_feats, const void* channel_add, int batch,
+                                               int64_t height_x_width, void* tokens, int64_t tokens_per_item,
+                                               int64_t level_start, void* stream)
+{
+    if (batch < 0 || num_pos_feats < 0 || height_x_width < 0 || level_start < 0 ||
+        level_start + height_x_width > tokens_per_item)
+        return (int)cudaErrorInvalidValue;
+    return (int)msda::sine_position_tokens(dtype, y_embed, x_embed, dim_t, channel_add, tokens, batch,
+                                           (long long)height_x_width, num_pos_feats, (long long)tokens_per_item,
+                                           (long long)level_start, (cudaStream_t)stream);
 }

@@ -154,6 +154,9 @@ cudaError_t group_norm_tokens(int dtype, const void* x, const void* pre_bias, co
 bool norm_act_supported(int dtype, int C);
 cudaError_t norm_act_forward(int dtype, const void* x, const void* gamma, const void* beta, void* y, long long rows,
                              int C, float eps, int act, cudaStream_t stream);
+cudaError_t sine_position_tokens(int dtype, const float* y_embed, const float* x_embed, const float* dim_t,
+                                 const void* add, void* out, int N, long long HW, int F, long long S, long long start,
+                                 cudaStream_t stream);
 cudaError_t flatten_level(int dtype, const void* x, const void* add, void* out, int N, int C, int HW, long long S,
                           long long start, cudaStream_t stream);
 // RoIAlign on token-major maps (roi_align.cu): feat [N, H*W, C], rois [K,5] (batch index, x1, y1, x2, y2) in fp32

@@ -51,7 +51,13 @@ def _flatten_levels(maps, masks, pos_embeds, level_embed=None):
         tokens = flatten_levels(list(maps))          # inference: one transposing kernel per level, no cat
     else:
         tokens = torch.cat([_as_tokens(m) for m in maps], 1)
-    if not embed_trains and flatten_levels_supported(list(pos_embeds)):
+    if isinstance(pos_embeds, torch.Tensor):
+        # already lvl_pos_embed_flatten [N, sum HW, C], level embedding included
+        # (position_encoding.PositionEmbeddingSine.forward_tokens)
+        assert pos_embeds.dim() == 3 and pos_embeds.shape[1] == flat_mask.shape[1], \
+            "flattened position embedding and masks disagree on the token count"
+        pos = pos_embeds
+    elif not embed_trains and flatten_levels_supported(list(pos_embeds)):
         adds = None if level_embed is None else [level_embed[lvl] for lvl in range(len(maps))]
         pos = flatten_levels(list(pos_embeds), adds)
     else:

@@ -254,6 +254,19 @@ int msda_layer_colsum(int dtype, const void* x, int64_t rows, int channels, void
 int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t* mask, int64_t rows, int channels,
                                 void* stream);
 
+/* Sine position embedding of one pyramid level, written into its slice of the flattened token tensor:
+ *     tokens[n, level_start + p, c] = T( T( f(coord[n, p] / dim_t[c mod F]) ) + channel_add[c] ),  F = num_pos_feats,
+ *     coord = y_embed for c < F, x_embed for c >= F;  f = sin for even c mod F, cos for odd
+ * = PositionEmbeddingSine.forward (/root/reference/models/position_encoding.py:35-56), the joiner's cast to the
+ * feature dtype, and flatten(2).transpose(1, 2) + level_embed[l] of DeformableTransformer.forward
+ * (deformable_transformer_single.py:196-199) in one pass.  y_embed / x_embed [batch, H*W] FP32 are the (normalised)
+ * cumulative coordinates the reference computes from the padding mask (:41-46), dim_t [F] FP32 its
+ * temperature ** (2 * (k / 2) / F) (:48-49); tokens [batch, tokens_per_item, 2 * F] of `dtype` (F32 / BF16 / F16),
+ * channel_add [2 * F] of `dtype` or NULL. */
+int msda_layer_sine_position_tokens(int dtype, const float* y_embed, const float* x_embed, const float* dim_t,
+                                    int num_pos_feats, const void* channel_add, int batch, int64_t height_x_width,
+                                    void* tokens, int64_t tokens_per_item, int64_t level_start, void* stream);
+
 /* GroupNorm on token-major activations x [batch, tokens_per_item, channels] (groups of channels / groups consecutive
  * channels, statistics per (item, group)): the nn.GroupNorm(32, hidden_dim) of the reference's input projections,
  * /root/reference/models/deformable_detr_single.py:101-150, applied to the projection computed token-major so that

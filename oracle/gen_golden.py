@@ -763,6 +763,30 @@ def main():
             t["src"], t["target"], t["pos_src"], t["pos_target"], t["mask_src"], t["mask_target"], m_),
         wrt=["src", "target"])
 
+    # Sine position embedding (position_encoding.py:20-56) on padded masks, the shipped configuration
+    # (N_steps = hidden_dim // 2, normalize=True: position_encoding.py:88-91) and the un-normalised default
+    if wanted("position_sine"):
+        pe = importlib.import_module("models.position_encoding")
+        misc = sys.modules["util.misc"]
+        pmasks = []
+        for (h, w), (ph, pw) in zip([(7, 9), (4, 5), (2, 3)], [(2, 3), (1, 2), (1, 1)]):
+            pm = torch.zeros(2, h, w, dtype=torch.bool)
+            pm[1, h - ph:, :] = True
+            pm[1, :, w - pw:] = True
+            pmasks.append(pm)
+        store = {}
+        for tag, module in (("norm", pe.PositionEmbeddingSine(16, normalize=True)),
+                            ("raw", pe.PositionEmbeddingSine(16, temperature=20, normalize=False))):
+            for lvl, pm in enumerate(pmasks):
+                feat = torch.zeros(2, 1, *pm.shape[1:], dtype=torch.float32)
+                store[f"{tag}_pos{lvl}"] = module(misc.NestedTensor(feat, pm)).numpy()
+        for lvl, pm in enumerate(pmasks):
+            store[f"mask{lvl}"] = pm.numpy()
+        torch.manual_seed(43)
+        store["level_embed"] = torch.randn(3, 32, dtype=torch.float32).numpy()
+        np.savez_compressed(os.path.join(OUT, "position_sine.npz"), **store)
+        print("wrote position_sine")
+
 
 if __name__ == "__main__":
     main()
