@@ -821,6 +821,66 @@ sine_position_tokens_kernel(const float* __restrict__ y_embed, const float* __re
     }
 }
 
+// The cumulative coordinates of PositionEmbeddingSine (position_encoding.py:39-46): y_embed = cumsum over rows of
+// ~mask, x_embed = cumsum over columns, optionally (c - 0.5) / (last + 1e-6) * scale -- the ~10 tiny launches per level
+// that otherwise dominate the embedding's time.  Counts are exact integers in fp32 and the normalisation uses the
+// reference's operation order with IEEE roundings (no contraction), so the maps equal the torch ops bit for bit.
+// One warp per row (ballot prefix counts) for x, one lane per column (serial over rows, coalesced) for y.
+__global__ void __launch_bounds__(256)
+sine_coordinates_kernel(const unsigned char* __restrict__ mask, float* __restrict__ y_embed,
+                        float* __restrict__ x_embed, int N, int H, int W, int normalize, float scale)
+{
+    const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const long long row_warps = (long long)N * H;
+    const int col_groups = (W + 31) / 32;
+    if (warp < row_warps) {
+        const unsigned char* m = mask + warp * W;
+        float* x = x_embed + warp * W;
+        int carry = 0;
+        for (int j0 = 0; j0 < W; j0 += 32) {
+            const int j = j0 + lane;
+            const bool valid = j < W && m[j] == 0;
+            const unsigned bits = __ballot_sync(0xffffffffu, valid);
+            if (j < W) x[j] = (float)(carry + __popc(bits & (0xffffffffu >> (31 - lane))));
+            carry += __popc(bits);
+        }
+        if (normalize) {
+            const float denom = __fadd_rn((float)carry, 1e-6f);
+            for (int j = lane; j < W; j += 32)          // each lane re-reads what it wrote
+                x[j] = __fmul_rn(__fdiv_rn(__fsub_rn(x[j], 0.5f), denom), scale);
+        }
+        return;
+    }
+    const long long group = warp - row_warps;
+    if (group >= (long long)N * col_groups) return;
+    const long long n = group / col_groups;
+    const int j = (int)(group - n * col_groups) * 32 + lane;
+    if (j >= W) return;
+    const unsigned char* m = mask + n * H * W + j;
+    float* y = y_embed + n * H * W + j;
+    int count = 0;
+    for (int i = 0; i < H; ++i) {
+        count += m[(long long)i * W] == 0;
+        y[(long long)i * W] = (float)count;
+    }
+    if (normalize) {
+        const float denom = __fadd_rn((float)count, 1e-6f);
+        for (int i = 0; i < H; ++i)
+            y[(long long)i * W] = __fmul_rn(__fdiv_rn(__fsub_rn(y[(long long)i * W], 0.5f), denom), scale);
+    }
+}
+
+cudaError_t sine_coordinates(const unsigned char* mask, float* y_embed, float* x_embed, int N, int H, int W,
+                             int normalize, float scale, cudaStream_t st)
+{
+    if (N == 0 || H == 0 || W == 0) return cudaSuccess;
+    const long long warps = (long long)N * H + (long long)N * ((W + 31) / 32);
+    sine_coordinates_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(mask, y_embed, x_embed, N, H, W, normalize,
+                                                                        scale);
+    return cudaGetLastError();
+}
+
 cudaError_t sine_position_tokens(int dtype, const float* y_embed, const float* x_embed, const float* dim_t,
                                  const void* add, void* out, int N, long long HW, int F, long long S, long long start,
                                  cudaStream_t st)

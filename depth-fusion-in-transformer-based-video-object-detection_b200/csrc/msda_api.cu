@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 14; }
+extern "C" int msda_abi_version(void) { return 15; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -382,4 +382,12 @@ extern "C" int msda_layer_sine_position_tokens(int dtype, const float* y_embed, 
     return (int)msda::sine_position_tokens(dtype, y_embed, x_embed, dim_t, channel_add, tokens, batch,
                                            (long long)height_x_width, num_pos_feats, (long long)tokens_per_item,
                                            (long long)level_start, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_sine_coordinates(const uint8_t* padding_mask, int batch, int height, int width, int normalize,
+                                           float scale, float* y_embed, float* x_embed, void* stream)
+{
+    if (batch < 0 || height < 0 || width < 0) return (int)cudaErrorInvalidValue;
+    return (int)msda::sine_coordinates(padding_mask, y_embed, x_embed, batch, height, width, normalize, scale,
+                                       (cudaStream_t)stream);
 }

@@ -8,10 +8,10 @@ transposes, adds ``level_embed[l]`` and concatenates the levels (deformable_tran
 
 ``PositionEmbeddingSine`` here has the reference's constructor and ``forward(tensor_list)`` (same ``[N, 2F, H, W]``
 values; on a CUDA mask it is a permuted view of the token-major kernel output), plus ``forward_tokens``: all levels
-written by one kernel per level straight into ``lvl_pos_embed_flatten [N, sum_l H_l*W_l, 2F]`` (C ABI
+written by two kernels per level (coordinates, embedding) straight into ``lvl_pos_embed_flatten [N, sum_l H_l*W_l, 2F]`` (C ABI
 ``msda_layer_sine_position_tokens``, csrc/layer_epilogue.cu).  ``DeformableTransformer.forward`` accepts that tensor in
-place of the per-level ``pos_embeds`` list.  The cumulative coordinates (``[N, H, W]`` fp32, 1/2F of the output) stay
-the reference's own torch ops, so padding masks behave identically.
+place of the per-level ``pos_embeds`` list.  The cumulative coordinates (``[N, H, W]`` fp32, 1/2F of the output) come
+from ``msda_layer_sine_coordinates``, which reproduces the reference's cumsum / normalise ops bit for bit.
 """
 import math
 
@@ -60,10 +60,27 @@ class PositionEmbeddingSine(nn.Module):
             x_embed = (x_embed - 0.5) / (x_embed[:, :, -1:] + eps) * self.scale
         return y_embed, x_embed
 
+    def _device_coordinates(self, mask, stream):
+        """`_coordinates` as one kernel (C ABI ``msda_layer_sine_coordinates``; bit-identical maps)."""
+        n, h, w = mask.shape
+        mask = mask.contiguous()
+        y_embed = torch.empty((n, h, w), dtype=torch.float32, device=mask.device)
+        x_embed = torch.empty_like(y_embed)
+        code = _lib.load().msda_layer_sine_coordinates(mask.data_ptr(), n, h, w, int(bool(self.normalize)),
+                                                       float(self.scale), y_embed.data_ptr(), x_embed.data_ptr(), stream)
+        _lib.check(code, "msda_layer_sine_coordinates")
+        return y_embed, x_embed
+
     def _dim_t(self, device):
-        """position_encoding.py:48-49."""
+        """position_encoding.py:48-49 (a constant of the module: computed once per device)."""
+        key = (str(device), self.num_pos_feats, self.temperature)
+        cached = getattr(self, "_dim_t_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
         dim_t = torch.arange(self.num_pos_feats, dtype=torch.float32, device=device)
-        return self.temperature ** (2 * (dim_t // 2) / self.num_pos_feats)
+        dim_t = self.temperature ** (2 * (dim_t // 2) / self.num_pos_feats)
+        self._dim_t_cache = (key, dim_t)
+        return dim_t
 
     def _host_composition(self, mask):
         """The reference's composition (position_encoding.py:51-56) for masks that live on the host."""
@@ -100,7 +117,10 @@ class PositionEmbeddingSine(nn.Module):
             stream = torch.cuda.current_stream().cuda_stream
             start = 0
             for lvl, (mask, hw) in enumerate(zip(masks, sizes)):
-                y_embed, x_embed = (t.contiguous() for t in self._coordinates(mask))
+                if mask.dtype == torch.bool:
+                    y_embed, x_embed = self._device_coordinates(mask, stream)
+                else:
+                    y_embed, x_embed = (t.contiguous() for t in self._coordinates(mask))
                 add = None if level_embed is None else level_embed[lvl].detach().to(dtype).contiguous()
                 code = lib.msda_layer_sine_position_tokens(
                     _DTYPES[dtype], y_embed.data_ptr(), x_embed.data_ptr(), dim_t.data_ptr(), f,

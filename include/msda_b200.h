@@ -254,6 +254,14 @@ int msda_layer_colsum(int dtype, const void* x, int64_t rows, int channels, void
 int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t* mask, int64_t rows, int channels,
                                 void* stream);
 
+/* Cumulative coordinates of the sine position embedding (PositionEmbeddingSine.forward,
+ * /root/reference/models/position_encoding.py:39-46): padding_mask [batch, height, width] bytes (non-zero = padding),
+ * y_embed / x_embed [batch, height, width] FP32 = cumsum of the valid pixels down the rows / along the columns and,
+ * when normalize != 0, (c - 0.5) / (last + 1e-6) * scale with the reference's operation order (bit-identical to the
+ * reference's tensor ops). */
+int msda_layer_sine_coordinates(const uint8_t* padding_mask, int batch, int height, int width, int normalize,
+                                float scale, float* y_embed, float* x_embed, void* stream);
+
 /* Sine position embedding of one pyramid level, written into its slice of the flattened token tensor:
  *     tokens[n, level_start + p, c] = T( T( f(coord[n, p] / dim_t[c mod F]) ) + channel_add[c] ),  F = num_pos_feats,
  *     coord = y_embed for c < F, x_embed for c >= F;  f = sin for even c mod F, cos for odd

@@ -89,3 +89,23 @@ def test_bad_arguments_are_errors():
                                                8, buf.data_ptr(), 8, 0, None)      # fp64 not offered
     assert code != 0
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("n,h,w", [(3, 100, 167), (2, 13, 21), (1, 1, 1), (2, 5, 64), (2, 33, 32)])
+def test_coordinates_kernel_is_bitwise_the_reference_ops(normalize, n, h, w):
+    """msda_layer_sine_coordinates == cumsum / (c - 0.5) / (last + eps) * scale of position_encoding.py:39-46 evaluated
+    by PyTorch on the device, bit for bit -- ragged padding, a fully padded row and column included."""
+    torch.manual_seed(h * w)
+    module = PositionEmbeddingSine(8, normalize=normalize, scale=3.0 if normalize else None)
+    mask = torch.zeros(n, h, w, dtype=torch.bool, device=DEV)
+    mask[0] = torch.rand(h, w, device=DEV) < 0.3                 # holes anywhere (the op only sees a byte map)
+    if n > 1:
+        mask[1, h - h // 3:, :] = True
+        mask[1, :, w - w // 4:] = True
+    if n > 2:
+        mask[2, 0, :] = True                                     # a row / column with no valid pixel at all
+        mask[2, :, 0] = True
+    want_y, want_x = module._coordinates(mask)
+    got_y, got_x = module._device_coordinates(mask, torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(got_y, want_y) and torch.equal(got_x, want_x)
