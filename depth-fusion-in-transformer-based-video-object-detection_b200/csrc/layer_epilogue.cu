@@ -386,23 +386,79 @@ flatten_level_kernel(const T* __restrict__ x, const T* __restrict__ add, T* __re
     }
 }
 
+// The same transpose for channel counts that are whole 16-byte vectors (every model of the reference: 256 channels):
+// 64 pixels x 128 bytes of channels per CTA, 16 independent loads per thread in flight before the tile is written,
+// and one 16-byte store per thread per pixel -- 8 consecutive lanes write one pixel's whole 128-byte line.  The 32 x 32
+// kernel above issues ~43 instructions per element (ncu: 84 % issue-active at 2.4 TB/s); this one ~6.
+template <typename T>
+__global__ void __launch_bounds__(256)
+flatten_level_vec_kernel(const T* __restrict__ x, const T* __restrict__ add, T* __restrict__ out,
+                         int C, int HW, long long S, long long start)
+{
+    constexpr int VEC = 16 / sizeof(T), CT = 8 * VEC, PT = 64, PITCH = PT + 4 / sizeof(T);
+    __shared__ T tile[CT][PITCH];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * PT, c0 = blockIdx.y * CT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T* row = x + ((long long)n * C + c0 + warp) * HW + p0 + lane;
+    const long long step = 8LL * HW;
+    T r[CT / 8][2];
+    const bool in0 = p0 + lane < HW, in1 = p0 + lane + 32 < HW;
+#pragma unroll
+    for (int k = 0; k < CT / 8; ++k, row += step) {
+        const bool ok = c0 + warp + 8 * k < C;
+        r[k][0] = ok && in0 ? row[0] : T();
+        r[k][1] = ok && in1 ? row[32] : T();
+    }
+#pragma unroll
+    for (int k = 0; k < CT / 8; ++k) {
+        tile[warp + 8 * k][lane] = r[k][0];
+        tile[warp + 8 * k][lane + 32] = r[k][1];
+    }
+    __syncthreads();
+    const int chunk = threadIdx.x & 7;
+    const int c = c0 + chunk * VEC;
+    if (c >= C) return;                                         // C is a multiple of VEC: chunks are whole or absent
+    float addv[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) addv[v] = add != nullptr ? to_f32<T>(add[c + v]) : 0.f;
+    T* o = out + ((long long)n * S + start + p0) * C + c;
+#pragma unroll
+    for (int pp = threadIdx.x >> 3; pp < PT; pp += 32) {
+        if (p0 + pp >= HW) break;
+        alignas(16) T v16[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const T t = tile[chunk * VEC + v][pp];
+            v16[v] = add != nullptr ? from_f32<T>(to_f32<T>(t) + addv[v]) : t;
+        }
+        *reinterpret_cast<uint4*>(o + (long long)pp * C) = *reinterpret_cast<const uint4*>(v16);
+    }
+}
+
+template <typename T>
+static void launch_flatten(const void* x, const void* add, void* out, int N, int C, int HW, long long S,
+                           long long start, cudaStream_t st)
+{
+    constexpr int VEC = 16 / sizeof(T);
+    if (C % VEC == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+        const dim3 grid((HW + 63) / 64, (C + 8 * VEC - 1) / (8 * VEC), N);
+        flatten_level_vec_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)add, (T*)out, C, HW, S, start);
+    } else {
+        const dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
+        flatten_level_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)add, (T*)out, C, HW, S, start);
+    }
+}
+
 cudaError_t flatten_level(int dtype, const void* x, const void* add, void* out, int N, int C, int HW, long long S,
                           long long start, cudaStream_t st)
 {
     if (N <= 0 || C <= 0 || HW <= 0) return cudaSuccess;
     if (N > 65535) return cudaErrorInvalidValue;
-    const dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
     switch (dtype) {
-        case kF32:
-            flatten_level_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)add, (float*)out, C, HW, S, start);
-            break;
-        case kBF16:
-            flatten_level_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)add,
-                                                                     (__nv_bfloat16*)out, C, HW, S, start);
-            break;
-        case kF16:
-            flatten_level_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (const __half*)add, (__half*)out, C, HW, S, start);
-            break;
+        case kF32: launch_flatten<float>(x, add, out, N, C, HW, S, start, st); break;
+        case kBF16: launch_flatten<__nv_bfloat16>(x, add, out, N, C, HW, S, start, st); break;
+        case kF16: launch_flatten<__half>(x, add, out, N, C, HW, S, start, st); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -812,12 +868,23 @@ sine_position_tokens_kernel(const float* __restrict__ y_embed, const float* __re
     const long long n = pix / HW, p = pix - n * HW;
     const float ye = y_embed[pix], xe = x_embed[pix];
     T* o = out + (n * S + start + p) * (2 * F);
-    for (int c = lane; c < 2 * F; c += 32) {
+    // channels 2j and 2j + 1 share dim_t (temperature ** (2 * (k / 2) / F)) and therefore the argument: one division
+    // and one sincosf per pair, no divergence between the sin and the cos lanes, a paired store
+    for (int c = 2 * lane; c < 2 * F; c += 64) {
         const int k = c < F ? c : c - F;
         const float arg = __fdiv_rn(c < F ? ye : xe, dim_t[k]);
-        float v = to_f32<T>(from_f32<T>((k & 1) ? cosf(arg) : sinf(arg)));
-        if (add != nullptr) v = v + to_f32<T>(add[c]);
-        o[c] = from_f32<T>(v);
+        float sn, cs;
+        sincosf(arg, &sn, &cs);
+        float v0 = to_f32<T>(from_f32<T>(sn)), v1 = to_f32<T>(from_f32<T>(cs));
+        if (add != nullptr) {
+            v0 = v0 + to_f32<T>(add[c]);
+            v1 = v1 + to_f32<T>(add[c + 1]);
+        }
+        struct alignas(2 * sizeof(T)) Pair { T a, b; };             // channel pairs are pair-aligned: 2F and c are even
+        Pair pr;
+        pr.a = from_f32<T>(v0);
+        pr.b = from_f32<T>(v1);
+        *reinterpret_cast<Pair*>(o + c) = pr;
     }
 }
 
@@ -887,6 +954,7 @@ cudaError_t sine_position_tokens(int dtype, const float* y_embed, const float* x
 {
     const long long pixels = (long long)N * HW;
     if (pixels == 0 || F == 0) return cudaSuccess;
+    if (F & 1) return cudaErrorInvalidValue;      // the reference's 0::2 / 1::2 interleave needs an even F as well
     const unsigned blocks = (unsigned)((pixels + 7) / 8);
     switch (dtype) {
         case kF32:

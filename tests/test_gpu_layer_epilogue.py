@@ -226,12 +226,13 @@ def test_ffn_layer_norm_tcgen05(rows, f, with_pos):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("with_add", [False, True])
-def test_flatten_levels_bitwise(dtype, with_add):
+@pytest.mark.parametrize("c", [96, 256, 6])
+def test_flatten_levels_bitwise(dtype, with_add, c):
     """msda_layer_flatten_level == flatten(2).transpose(1, 2) (+ level_embed[l]) + cat of
     /root/reference/models/deformable_transformer_single.py:190-206, bit for bit (a copy and one rounded add)."""
     from dfvod_b200.ops.functions import flatten_levels, flatten_levels_supported
     torch.manual_seed(11)
-    n, c = 3, 96                                   # channel count not a multiple of the 32-wide tile
+    n = 3            # 96: partial channel tile of the 16-byte-vector kernel; 6: no whole vector -> the 32 x 32 tile kernel
     shapes = [(13, 21), (7, 11), (1, 1), (5, 33)]
     maps = [torch.randn(n, c, h, w, device=DEV).to(dtype) for h, w in shapes]
     adds = [torch.randn(c, device=DEV).to(dtype) for _ in shapes] if with_add else None
