@@ -892,49 +892,67 @@ sine_position_tokens_kernel(const float* __restrict__ y_embed, const float* __re
 // ~mask, x_embed = cumsum over columns, optionally (c - 0.5) / (last + 1e-6) * scale -- the ~10 tiny launches per level
 // that otherwise dominate the embedding's time.  Counts are exact integers in fp32 and the normalisation uses the
 // reference's operation order with IEEE roundings (no contraction), so the maps equal the torch ops bit for bit.
-// One warp per row (ballot prefix counts) for x, one lane per column (serial over rows, coalesced) for y.
+// x: one warp per row (ballot prefix counts).  y: one CTA per 32 columns of an item, a band of rows per warp, the band
+// counts exchanged through shared memory.  Both count first and write the final value once (no read-back).
+__device__ __forceinline__ float sine_coordinate(int count, int total, int normalize, float scale)
+{
+    const float c = (float)count;
+    return normalize ? __fmul_rn(__fdiv_rn(__fsub_rn(c, 0.5f), __fadd_rn((float)total, 1e-6f)), scale) : c;
+}
+
 __global__ void __launch_bounds__(256)
 sine_coordinates_kernel(const unsigned char* __restrict__ mask, float* __restrict__ y_embed,
-                        float* __restrict__ x_embed, int N, int H, int W, int normalize, float scale)
+                        float* __restrict__ x_embed, int N, int H, int W, int normalize, float scale, int row_blocks)
 {
-    const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    const long long row_warps = (long long)N * H;
-    const int col_groups = (W + 31) / 32;
-    if (warp < row_warps) {
-        const unsigned char* m = mask + warp * W;
-        float* x = x_embed + warp * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x < row_blocks) {
+        // x: one warp per row; the row is counted, then re-read (L1) for the running prefix
+        const long long row = (long long)blockIdx.x * 8 + warp;
+        if (row >= (long long)N * H) return;
+        const unsigned char* m = mask + row * W;
+        float* x = x_embed + row * W;
+        int total = 0;
+        for (int j0 = 0; j0 < W; j0 += 32)
+            total += __popc(__ballot_sync(0xffffffffu, j0 + lane < W && m[j0 + lane] == 0));
         int carry = 0;
         for (int j0 = 0; j0 < W; j0 += 32) {
             const int j = j0 + lane;
-            const bool valid = j < W && m[j] == 0;
-            const unsigned bits = __ballot_sync(0xffffffffu, valid);
-            if (j < W) x[j] = (float)(carry + __popc(bits & (0xffffffffu >> (31 - lane))));
+            const unsigned bits = __ballot_sync(0xffffffffu, j < W && m[j] == 0);
+            if (j < W)
+                x[j] = sine_coordinate(carry + __popc(bits & (0xffffffffu >> (31 - lane))), total, normalize, scale);
             carry += __popc(bits);
-        }
-        if (normalize) {
-            const float denom = __fadd_rn((float)carry, 1e-6f);
-            for (int j = lane; j < W; j += 32)          // each lane re-reads what it wrote
-                x[j] = __fmul_rn(__fdiv_rn(__fsub_rn(x[j], 0.5f), denom), scale);
         }
         return;
     }
-    const long long group = warp - row_warps;
-    if (group >= (long long)N * col_groups) return;
-    const long long n = group / col_groups;
-    const int j = (int)(group - n * col_groups) * 32 + lane;
-    if (j >= W) return;
-    const unsigned char* m = mask + n * H * W + j;
-    float* y = y_embed + n * H * W + j;
+    // y: one CTA per (item, 32 columns); warp w owns a band of rows, band counts meet in shared memory
+    __shared__ int band[8][32];
+    const int col_groups = (W + 31) / 32;
+    const int group = blockIdx.x - row_blocks;
+    const int n = group / col_groups;
+    const int j = (group - n * col_groups) * 32 + lane;
+    const int rows = (H + 7) / 8;
+    const int i0 = warp * rows, i1 = min(H, i0 + rows);
+    const unsigned char* m = mask + (long long)n * H * W + j;
     int count = 0;
-    for (int i = 0; i < H; ++i) {
-        count += m[(long long)i * W] == 0;
-        y[(long long)i * W] = (float)count;
+    if (j < W) {
+#pragma unroll 4
+        for (int i = i0; i < i1; ++i) count += m[(long long)i * W] == 0;
     }
-    if (normalize) {
-        const float denom = __fadd_rn((float)count, 1e-6f);
-        for (int i = 0; i < H; ++i)
-            y[(long long)i * W] = __fmul_rn(__fdiv_rn(__fsub_rn(y[(long long)i * W], 0.5f), denom), scale);
+    band[warp][lane] = count;
+    __syncthreads();
+    if (j >= W) return;
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int b = band[w][lane];
+        before += w < warp ? b : 0;
+        total += b;
+    }
+    float* y = y_embed + (long long)n * H * W + j;
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) {
+        before += m[(long long)i * W] == 0;
+        y[(long long)i * W] = sine_coordinate(before, total, normalize, scale);
     }
 }
 
@@ -942,9 +960,11 @@ cudaError_t sine_coordinates(const unsigned char* mask, float* y_embed, float* x
                              int normalize, float scale, cudaStream_t st)
 {
     if (N == 0 || H == 0 || W == 0) return cudaSuccess;
-    const long long warps = (long long)N * H + (long long)N * ((W + 31) / 32);
-    sine_coordinates_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(mask, y_embed, x_embed, N, H, W, normalize,
-                                                                        scale);
+    const long long row_blocks = ((long long)N * H + 7) / 8;
+    const long long blocks = row_blocks + (long long)N * ((W + 31) / 32);
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    sine_coordinates_kernel<<<(unsigned)blocks, 256, 0, st>>>(mask, y_embed, x_embed, N, H, W, normalize, scale,
+                                                             (int)row_blocks);
     return cudaGetLastError();
 }
 
