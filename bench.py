@@ -313,6 +313,17 @@ def encoder_extras(torch, dev, world, dist, n_frames=8, iters=10):
             out["encoder_fp32_tf32_gemm_fps"] = n_frames * world / ms * 1e3
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        # fp32-grade GEMMs on the tensor cores: the error-compensated three-GEMM TF32 split
+        # (dfvod_b200.ops.functions.set_fp32_gemm_mode("tf32x3"); <= 2e-6 normalised against fp64 per GEMM)
+        from dfvod_b200.ops.functions import set_fp32_gemm_mode
+        set_fp32_gemm_mode("tf32x3")
+        try:
+            ms = _reduce_max(torch, dist, world, dev,
+                             _time_events(torch, lambda: model.encoder(src, st, ls, vr, pos, None), 3, 2))
+            out["encoder_fp32_tf32x3_gemm_ms"] = ms
+            out["encoder_fp32_tf32x3_gemm_fps"] = n_frames * world / ms * 1e3
+        finally:
+            set_fp32_gemm_mode("library")
         del src, pos
         model = model.bfloat16()
         bf = torch.bfloat16

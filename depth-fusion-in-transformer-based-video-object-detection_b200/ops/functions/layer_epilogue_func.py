@@ -227,8 +227,56 @@ class LinearFunction(Function):
         return dx, dw, db
 
 
+# How the fp32 projections of an inference pass are evaluated (the gather kernels are not affected):
+#   "library"  whatever torch.backends.cuda.matmul says (IEEE SGEMM unless the caller allowed TF32) -- the default;
+#   "tf32x3"   error-compensated split on the tensor cores: x = x_hi + x_lo, W = W_hi + W_lo with the *_hi parts exactly
+#              TF32-representable, y = x_lo W_hi^T + x_hi W_lo^T + x_hi W_hi^T (three TF32 library GEMMs accumulating in
+#              fp32; the dropped x_lo W_lo^T term and the rounding of the *_lo operands are O(2^-22)).  fp32-grade
+#              results (tests/test_gpu_layer_epilogue.py: <= 2e-6 normalised against fp64, where one TF32 GEMM is at
+#              ~5e-4) at a third of the TF32 rate instead of the SGEMM rate.
+FP32_GEMM_MODE = "library"
+TF32X3_MIN_ROWS = 1024              # below this the three launches + two splits cost more than the SGEMM
+
+
+def set_fp32_gemm_mode(mode):
+    global FP32_GEMM_MODE
+    if mode not in ("library", "tf32x3"):
+        raise ValueError(f"unknown fp32 GEMM mode {mode!r}")
+    previous, FP32_GEMM_MODE = FP32_GEMM_MODE, mode
+    return previous
+
+
+def _tf32_split(t):
+    """t (fp32) -> (hi, lo): hi = t rounded to TF32's 10 mantissa bits (nearest, ties away), lo = t - hi (exact)."""
+    hi = ((t.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+    return hi, t - hi
+
+
+def _tf32x3_wanted(x, weight):
+    return (FP32_GEMM_MODE == "tf32x3" and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and x.numel() // max(x.shape[-1], 1) >= TF32X3_MIN_ROWS
+            and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)))
+
+
+def linear_tf32x3(x, weight, bias):
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    xh, xl = _tf32_split(x2)
+    wh, wl = _tf32_split(weight.detach().contiguous())
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        y = torch.mm(xl, wh.t()) if bias is None else torch.addmm(bias.detach(), xl, wh.t())   # small terms first
+        y.addmm_(xh, wl.t())
+        y.addmm_(xh, wh.t())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return y.view(*x.shape[:-1], weight.shape[0])
+
+
 def linear_wb(x, weight, bias):
     """``F.linear(x, weight, bias)``: same GEMM; the custom backward only when gradients flow."""
+    if _tf32x3_wanted(x, weight):
+        return linear_tf32x3(x, weight, bias)
     if x.is_cuda and bias is not None and x.dtype == weight.dtype and x.dtype in _DTYPES \
             and torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad):
         out = LinearFunction.apply(x.reshape(-1, x.shape[-1]), weight, bias)
@@ -266,6 +314,8 @@ class LinearReLUFunction(Function):
 
 def linear_relu(linear, x):
     """``relu(linear(x))``; epilogue-fused on CUDA for 16-bit / fp32 dense inputs."""
+    if _tf32x3_wanted(x, linear.weight):
+        return torch.relu_(linear_tf32x3(x, linear.weight, linear.bias))
     if x.is_cuda and linear.bias is not None and x.dtype == linear.weight.dtype and x.dtype in _DTYPES:
         return LinearReLUFunction.apply(x, linear.weight, linear.bias)
     return F.relu(linear(x))

@@ -367,3 +367,68 @@ def test_proj_layer_norm_falls_back_with_gradients():
     res = torch.randn(9, 256, device=DEV).bfloat16()
     proj_layer_norm(lin, norm, x, res).float().square().sum().backward()
     assert x.grad is not None and lin.weight.grad is not None
+
+
+def test_tf32x3_linear_is_fp32_grade():
+    """The error-compensated three-GEMM split (ops/functions/layer_epilogue_func.py: linear_tf32x3) against fp64:
+    fp32-grade (<= 2e-6 normalised, the IEEE SGEMM's own order of magnitude), where one TF32 GEMM is >= 20x worse."""
+    from dfvod_b200.ops.functions import layer_epilogue_func as L
+    torch.manual_seed(0)
+    x = torch.randn(20000, 256, device=DEV) * 3
+    w = torch.randn(1024, 256, device=DEV) / 16
+    b = torch.randn(1024, device=DEV)
+    ref = F.linear(x.double(), w.double(), b.double())
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        e_ieee = nerr(F.linear(x, w, b), ref)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        e_tf32 = nerr(F.linear(x, w, b), ref)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    e_split = nerr(L.linear_tf32x3(x, w, b), ref)
+    print(f"normalised error vs fp64: ieee {e_ieee:.2e}  tf32 {e_tf32:.2e}  tf32x3 {e_split:.2e}")
+    assert e_split <= 2e-6 and e_split <= 10 * e_ieee
+    assert e_tf32 >= 20 * e_split
+    assert torch.backends.cuda.matmul.allow_tf32 == prev          # the switch is restored
+
+
+def test_tf32x3_mode_routes_the_layer_gemms():
+    """set_fp32_gemm_mode('tf32x3'): the fp32 transformer gives the library-SGEMM result within the fp32 parity
+    tolerance (1e-5 normalised); gradients-needed calls and 16-bit inputs keep the library path."""
+    from dfvod_b200.deformable_transformer import DeformableTransformer
+    from dfvod_b200.ops.functions import layer_epilogue_func as L
+    torch.manual_seed(7)
+    shapes = [(24, 31), (12, 16)]
+    model = DeformableTransformer(d_model=64, nhead=4, num_encoder_layers=2, num_decoder_layers=2, dim_feedforward=128,
+                                  dropout=0.0, num_feature_levels=2, return_intermediate_dec=True).to(DEV).eval()
+    srcs = [torch.randn(2, 64, h, w, device=DEV) for h, w in shapes]
+    poss = [torch.randn(2, 64, h, w, device=DEV) for h, w in shapes]
+    masks = [torch.zeros(2, h, w, dtype=torch.bool, device=DEV) for h, w in shapes]
+    query = torch.randn(10, 128, device=DEV)
+    prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    prev_rows = L.TF32X3_MIN_ROWS
+    try:
+        with torch.no_grad():
+            want = model(srcs, masks, poss, None, None, None, query)[0]
+            assert L.set_fp32_gemm_mode("tf32x3") == "library"
+            L.TF32X3_MIN_ROWS = 1
+            calls = []
+            original = L.linear_tf32x3
+            L.linear_tf32x3 = lambda *a: (calls.append(1), original(*a))[1]
+            try:
+                got = model(srcs, masks, poss, None, None, None, query)[0]
+            finally:
+                L.linear_tf32x3 = original
+        assert len(calls) >= 10                                   # the projections did take the split path
+        assert nerr(got, want.double()) <= 1e-5
+        xg = torch.randn(2048, 64, device=DEV, requires_grad=True)
+        lin = torch.nn.Linear(64, 64).to(DEV)
+        assert not L._tf32x3_wanted(xg, lin.weight) and not L._tf32x3_wanted(xg.detach().bfloat16(), lin.weight)
+        with pytest.raises(ValueError):
+            L.set_fp32_gemm_mode("fp8")
+    finally:
+        L.set_fp32_gemm_mode("library")
+        L.TF32X3_MIN_ROWS = prev_rows
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
