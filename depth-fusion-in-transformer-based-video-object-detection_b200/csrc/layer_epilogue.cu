@@ -994,6 +994,45 @@ cudaError_t sine_position_tokens(int dtype, const float* y_embed, const float* x
     return cudaGetLastError();
 }
 
+// x [rows, cols] (fp32) -> out [rows, 3 * cols] = [ lo | hi | hi ] per row, hi = x rounded to TF32's 10 mantissa bits
+// (nearest, ties away from zero: add half an ulp to the bit pattern, clear the 13 low bits), lo = x - hi (exact in fp32).
+// One pass builds the left operand of the error-compensated TF32 product
+//     x W^T ~= [ lo_x | hi_x | hi_x ] [ hi_W | lo_W | hi_W ]^T          (ops/functions/layer_epilogue_func.py: linear_tf32x3)
+// so that ONE tensor-core GEMM with a 3x longer reduction replaces the SGEMM.  cols % 4 == 0, 16-byte aligned buffers.
+__global__ void __launch_bounds__(256)
+tf32_split_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int cols)
+{
+    const int vpr = cols / 4;                                  // float4 per row
+    const long long vecs = rows * vpr;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vecs; i += stride) {
+        const long long r = i / vpr;
+        const int k = (int)(i - r * vpr);
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+        float4 h, l;
+        h.x = __int_as_float((__float_as_int(v.x) + 0x1000) & 0xffffe000);
+        h.y = __int_as_float((__float_as_int(v.y) + 0x1000) & 0xffffe000);
+        h.z = __int_as_float((__float_as_int(v.z) + 0x1000) & 0xffffe000);
+        h.w = __int_as_float((__float_as_int(v.w) + 0x1000) & 0xffffe000);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        float4* o = reinterpret_cast<float4*>(out) + r * 3 * vpr + k;
+        o[0] = l;
+        o[vpr] = h;
+        o[2 * vpr] = h;
+    }
+}
+
+cudaError_t tf32_split(const float* x, float* out, long long rows, int cols, cudaStream_t st)
+{
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    if (cols % 4 != 0 || (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) % 16 != 0)
+        return cudaErrorInvalidValue;
+    long long blocks = (rows * (cols / 4) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tf32_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, out, rows, cols);
+    return cudaGetLastError();
+}
+
 cudaError_t zero_masked_rows(int dtype, void* data, const unsigned char* mask, long long rows, int C, cudaStream_t st)
 {
     if (rows == 0 || C == 0) return cudaSuccess;

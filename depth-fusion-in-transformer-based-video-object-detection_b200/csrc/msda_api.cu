@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 15; }
+extern "C" int msda_abi_version(void) { return 16; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -390,4 +390,10 @@ extern "C" int msda_layer_sine_coordinates(const uint8_t* padding_mask, int batc
     if (batch < 0 || height < 0 || width < 0) return (int)cudaErrorInvalidValue;
     return (int)msda::sine_coordinates(padding_mask, y_embed, x_embed, batch, height, width, normalize, scale,
                                        (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_tf32_split(const float* x, int64_t rows, int cols, float* out, void* stream)
+{
+    if (rows < 0 || cols < 0) return (int)cudaErrorInvalidValue;
+    return (int)msda::tf32_split(x, out, (long long)rows, cols, (cudaStream_t)stream);
 }

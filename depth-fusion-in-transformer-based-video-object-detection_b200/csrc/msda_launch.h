@@ -154,6 +154,7 @@ cudaError_t group_norm_tokens(int dtype, const void* x, const void* pre_bias, co
 bool norm_act_supported(int dtype, int C);
 cudaError_t norm_act_forward(int dtype, const void* x, const void* gamma, const void* beta, void* y, long long rows,
                              int C, float eps, int act, cudaStream_t stream);
+cudaError_t tf32_split(const float* x, float* out, long long rows, int cols, cudaStream_t stream);
 cudaError_t sine_coordinates(const unsigned char* mask, float* y_embed, float* x_embed, int N, int H, int W,
                              int normalize, float scale, cudaStream_t stream);
 cudaError_t sine_position_tokens(int dtype, const float* y_embed, const float* x_embed, const float* dim_t,

@@ -230,12 +230,13 @@ class LinearFunction(Function):
 # How the fp32 projections of an inference pass are evaluated (the gather kernels are not affected):
 #   "library"  whatever torch.backends.cuda.matmul says (IEEE SGEMM unless the caller allowed TF32) -- the default;
 #   "tf32x3"   error-compensated split on the tensor cores: x = x_hi + x_lo, W = W_hi + W_lo with the *_hi parts exactly
-#              TF32-representable, y = x_lo W_hi^T + x_hi W_lo^T + x_hi W_hi^T (three TF32 library GEMMs accumulating in
-#              fp32; the dropped x_lo W_lo^T term and the rounding of the *_lo operands are O(2^-22)).  fp32-grade
-#              results (tests/test_gpu_layer_epilogue.py: <= 2e-6 normalised against fp64, where one TF32 GEMM is at
-#              ~5e-4) at a third of the TF32 rate instead of the SGEMM rate.
+#              TF32-representable, y = x_lo W_hi^T + x_hi W_lo^T + x_hi W_hi^T as ONE TF32 library GEMM over the
+#              concatenated reduction [lo | hi | hi] x [hi | lo | hi] (fp32 accumulation; the dropped x_lo W_lo^T term and
+#              the rounding of the *_lo operands are O(2^-22)).  fp32-grade results (tests/test_gpu_layer_epilogue.py:
+#              8e-7 normalised against fp64, IEEE SGEMM 7e-7, one TF32 GEMM 3e-4) at a third of the TF32 rate instead of
+#              the SGEMM rate; the left operand is written by one kernel (msda_layer_tf32_split).
 FP32_GEMM_MODE = "library"
-TF32X3_MIN_ROWS = 1024              # below this the three launches + two splits cost more than the SGEMM
+TF32X3_MIN_ROWS = 1024              # below this the split pass + the longer reduction cost more than the SGEMM
 
 
 def set_fp32_gemm_mode(mode):
@@ -247,9 +248,18 @@ def set_fp32_gemm_mode(mode):
 
 
 def _tf32_split(t):
-    """t (fp32) -> (hi, lo): hi = t rounded to TF32's 10 mantissa bits (nearest, ties away), lo = t - hi (exact)."""
-    hi = ((t.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
-    return hi, t - hi
+    """t [rows, cols] (fp32) -> [rows, 3 * cols] = [lo | hi | hi]: hi = t rounded to TF32's 10 mantissa bits (nearest, ties
+    away), lo = t - hi (exact).  One kernel (C ABI ``msda_layer_tf32_split``) on CUDA; the torch composition otherwise."""
+    rows, cols = t.shape
+    if t.is_cuda and t.is_contiguous() and cols % 4 == 0 and t.data_ptr() % 16 == 0 and rows > 0:
+        out = torch.empty((rows, 3 * cols), dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            code = _lib.load().msda_layer_tf32_split(t.data_ptr(), rows, cols, out.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream)
+        _lib.check(code, "msda_layer_tf32_split")
+        return out
+    hi = ((t.contiguous().view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+    return torch.cat([t - hi, hi, hi], 1)
 
 
 def _tf32x3_wanted(x, weight):
@@ -259,15 +269,14 @@ def _tf32x3_wanted(x, weight):
 
 
 def linear_tf32x3(x, weight, bias):
-    x2 = x.reshape(-1, x.shape[-1]).contiguous()
-    xh, xl = _tf32_split(x2)
-    wh, wl = _tf32_split(weight.detach().contiguous())
+    k = x.shape[-1]
+    a = _tf32_split(x.reshape(-1, k).contiguous())                       # [rows, 3k] = [lo | hi | hi]
+    w = _tf32_split(weight.detach().contiguous())
+    w = torch.cat([w[:, k:2 * k], w[:, :k], w[:, 2 * k:]], 1)            # [n, 3k]    = [hi | lo | hi]
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        y = torch.mm(xl, wh.t()) if bias is None else torch.addmm(bias.detach(), xl, wh.t())   # small terms first
-        y.addmm_(xh, wl.t())
-        y.addmm_(xh, wh.t())
+        y = torch.mm(a, w.t()) if bias is None else torch.addmm(bias.detach(), a, w.t())
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     return y.view(*x.shape[:-1], weight.shape[0])

@@ -254,6 +254,14 @@ int msda_layer_colsum(int dtype, const void* x, int64_t rows, int channels, void
 int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t* mask, int64_t rows, int channels,
                                 void* stream);
 
+/* Left operand of an error-compensated TF32 product: x [rows, cols] FP32 -> out [rows, 3 * cols] = [ lo | hi | hi ] per
+ * row, hi = x rounded to TF32 (10 mantissa bits, nearest), lo = x - hi (exact).  With W [n, cols] arranged as
+ * [ hi_W | lo_W | hi_W ], out W'^T = lo_x hi_W^T + hi_x lo_W^T + hi_x hi_W^T in ONE TF32 tensor-core GEMM is FP32-grade: it
+ * stands in for the IEEE SGEMMs of the reference's FP32 nn.Linear layers
+ * (/root/reference/models/ops/modules/ms_deform_attn.py:94-116, deformable_transformer_single.py:544-548) when the caller
+ * selects it.  cols % 4 == 0; x and out 16-byte aligned. */
+int msda_layer_tf32_split(const float* x, int64_t rows, int cols, float* out, void* stream);
+
 /* Cumulative coordinates of the sine position embedding (PositionEmbeddingSine.forward,
  * /root/reference/models/position_encoding.py:39-46): padding_mask [batch, height, width] bytes (non-zero = padding),
  * y_embed / x_embed [batch, height, width] FP32 = cumsum of the valid pixels down the rows / along the columns and,

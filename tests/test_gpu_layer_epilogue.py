@@ -432,3 +432,21 @@ def test_tf32x3_mode_routes_the_layer_gemms():
         L.set_fp32_gemm_mode("library")
         L.TF32X3_MIN_ROWS = prev_rows
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+
+
+@pytest.mark.parametrize("rows,cols", [(177, 256), (5, 1024), (1, 4), (3000, 64)])
+def test_tf32_split_kernel_bitwise(rows, cols):
+    """msda_layer_tf32_split == the integer-arithmetic definition (round the bit pattern to 10 mantissa bits, subtract),
+    bit for bit; hi is TF32-representable and lo + hi == x exactly."""
+    from dfvod_b200.ops.functions import layer_epilogue_func as L
+    torch.manual_seed(rows)
+    x = torch.randn(rows, cols, device=DEV) * torch.exp(torch.randn(rows, cols, device=DEV) * 4)
+    got = L._tf32_split(x)
+    hi = ((x.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+    want = torch.cat([x - hi, hi, hi], 1)
+    assert got.shape == (rows, 3 * cols) and torch.equal(got, want)
+    assert int((got[:, cols:2 * cols].contiguous().view(torch.int32) & 0x1fff).abs().max()) == 0
+    assert torch.equal(got[:, :cols] + got[:, cols:2 * cols], x)
+    odd = torch.randn(7, 6, device=DEV)                       # cols % 4 != 0 -> torch composition, same definition
+    hi6 = ((odd.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+    assert torch.equal(L._tf32_split(odd), torch.cat([odd - hi6, hi6, hi6], 1))
