@@ -83,14 +83,16 @@ class PositionEmbeddingSine(nn.Module):
         return dim_t
 
     def _host_composition(self, mask):
-        """The reference's composition (position_encoding.py:51-56) for masks that live on the host."""
-        y_embed, x_embed = self._coordinates(mask)
+        """What position_encoding.py:51-56 evaluates, for masks that live on the host: channel k of the y block is
+        sin(y_embed / dim_t[k]) for even k and cos for odd k (the reference interleaves the 0::2 sines with the 1::2
+        cosines), then the x block.  Returns [N, H, W, 2F]."""
+        odd = (torch.arange(self.num_pos_feats, device=mask.device) % 2).bool()
         dim_t = self._dim_t(mask.device)
-        pos_x = x_embed[:, :, :, None] / dim_t
-        pos_y = y_embed[:, :, :, None] / dim_t
-        pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
-        pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
-        return torch.cat((pos_y, pos_x), dim=3)                     # [N, H, W, 2F]
+        blocks = []
+        for coord in self._coordinates(mask):                       # y first, then x
+            arg = coord.unsqueeze(-1) / dim_t
+            blocks.append(torch.where(odd, arg.cos(), arg.sin()))
+        return torch.cat(blocks, dim=-1)
 
     def forward_tokens(self, masks, level_embed=None, dtype=torch.float32):
         """masks: one bool ``[N, H_l, W_l]`` per level (True = padding).  Returns ``[N, sum_l H_l*W_l, 2F]`` of `dtype`:
