@@ -107,6 +107,28 @@ struct GradDst {
 #define MSDA_BWD_DEDUP 1
 #endif
 
+// 1: the fused kernel's passes run as a real loop instead of FCH unrolled copies.  Unrolled, the D = 32 bf16 kernel is
+// 4832 instructions (77 KB of SASS) that every warp walks end to end, and ncu shows 14 % of its stall samples waiting for
+// instructions (`no_instructions`, profiles/ncu_r1k.json); the per-pass register arrays are then indexed through
+// reg_pick / reg_put (selects over a static index) so that they stay in registers.
+#ifndef MSDA_BWD_FUSED_ROLLED
+#define MSDA_BWD_FUSED_ROLLED 1
+#endif
+template <int K>
+__device__ __forceinline__ float reg_pick(const float (&a)[K], int idx)
+{
+    float r = a[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) r = idx == k ? a[k] : r;
+    return r;
+}
+template <int K>
+__device__ __forceinline__ void reg_put(float (&a)[K], int idx, float v)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) a[k] = idx == k ? v : a[k];
+}
+
 template <typename VT, int D, bool FUSED, typename RT>
 __global__ void __launch_bounds__(BwdWarps<32 / (D / 4)>::value * 32, MSDA_BWD_MINBLOCKS)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
@@ -208,7 +230,11 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     float fin_x[FCH * SPL], fin_y[FCH * SPL], fin_a[FCH * SPL], own_a[FCH * SPL];
 
     const int passes = FUSED ? FCH : (LP + CH - 1) / CH;
+#if MSDA_BWD_FUSED_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int c = 0; c < (FUSED ? FCH : 1 << 30); ++c) {
         if (c >= passes) break;
         const int s0 = c * CH;
@@ -231,7 +257,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                 if constexpr (FUSED) {
                     xy = fused_location(load_raw2<RT>(op + 2 * s), src.ref + (nq * L + l) * src.ref_dim, src.ref_dim,
                                         s_meta[3 * l], s_meta[3 * l + 1], P);
-                    a = prob[c * SPL + i] / inv_sum;
+                    a = reg_pick(prob, c * SPL + i) / inv_sum;
                 } else {
                     xy = ldg_stream_f32x2(lp + 2 * s);
                     a = ldg_stream_f32(ap + s);
@@ -410,10 +436,10 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         } else {
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
-                fin_x[c * SPL + i] = part[3 * i + 0];
-                fin_y[c * SPL + i] = part[3 * i + 1];
-                fin_a[c * SPL + i] = part[3 * i + 2];
-                own_a[c * SPL + i] = a_own[i];
+                reg_put(fin_x, c * SPL + i, part[3 * i + 0]);
+                reg_put(fin_y, c * SPL + i, part[3 * i + 1]);
+                reg_put(fin_a, c * SPL + i, part[3 * i + 2]);
+                reg_put(own_a, c * SPL + i, a_own[i]);
             }
         }
     }
