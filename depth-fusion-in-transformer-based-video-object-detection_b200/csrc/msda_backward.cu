@@ -114,6 +114,36 @@ struct GradDst {
 #ifndef MSDA_BWD_FUSED_ROLLED
 #define MSDA_BWD_FUSED_ROLLED 1
 #endif
+// 1: the per-channel arithmetic of phase 2 runs on channel PAIRS with Blackwell's packed fp32 instructions
+// (fma / mul / add / sub .f32x2 -> FFMA2 / FMUL2 / FADD2; nvcc emits them only from inline PTX).  Each half is an
+// ordinary IEEE operation, so only the order of the per-sample channel sums changes (two partial sums instead of one
+// chain).  The fused backward is issue-bound after the pass loop was rolled (77 % issue-active, ncu r1l).
+#ifndef MSDA_BWD_F32X2
+#define MSDA_BWD_F32X2 1
+#endif
+struct alignas(8) F2 { float x, y; };
+__device__ __forceinline__ unsigned long long f2_bits(F2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+__device__ __forceinline__ F2 f2_from(unsigned long long a) { return *reinterpret_cast<F2*>(&a); }
+__device__ __forceinline__ F2 f2_dup(float a) { F2 r; r.x = a; r.y = a; return r; }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return f2_from(d);
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+__device__ __forceinline__ F2 sub2(F2 a, F2 b)
+{
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+
 template <int K>
 __device__ __forceinline__ float reg_pick(const float (&a)[K], int idx)
 {
@@ -365,6 +395,34 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     SliceT::unpack(raw[u][2], v3);
                     SliceT::unpack(raw[u][3], v4);
                     float px = 0.f, py = 0.f, pa = 0.f;
+#if MSDA_BWD_F32X2
+                    {
+                        const F2 W1 = f2_dup(w1), W2 = f2_dup(w2), W3 = f2_dup(w3), W4 = f2_dup(w4);
+                        const F2 HH = f2_dup(hh), LH = f2_dup(lh), HW = f2_dup(hw), LW = f2_dup(lw), A2 = f2_dup(a);
+                        F2 pa2 = f2_dup(0.f), px2 = f2_dup(0.f), py2 = f2_dup(0.f);
+#pragma unroll
+                        for (int ch = 0; ch < EPL; ch += 2) {
+                            F2 V1, V2, V3, V4, G;
+                            V1.x = v1[ch]; V1.y = v1[ch + 1];
+                            V2.x = v2[ch]; V2.y = v2[ch + 1];
+                            V3.x = v3[ch]; V3.y = v3[ch + 1];
+                            V4.x = v4[ch]; V4.y = v4[ch + 1];
+                            G.x = g[ch]; G.y = g[ch + 1];
+                            const F2 TG = mul2(A2, G);                                          // cuh:113
+                            tg[ch] = TG.x;
+                            tg[ch + 1] = TG.y;
+                            const F2 val = fma2(W4, V4, fma2(W3, V3, fma2(W2, V2, mul2(W1, V1))));
+                            const F2 dx = fma2(LH, sub2(V4, V3), mul2(HH, sub2(V2, V1)));       // cuh:119-151 (grad_w_weight)
+                            const F2 dy = fma2(LW, sub2(V4, V2), mul2(HW, sub2(V3, V1)));       // (grad_h_weight)
+                            pa2 = fma2(G, val, pa2);
+                            px2 = fma2(TG, dx, px2);
+                            py2 = fma2(TG, dy, py2);
+                        }
+                        pa = pa2.x + pa2.y;
+                        px = px2.x + px2.y;
+                        py = py2.x + py2.y;
+                    }
+#else
 #pragma unroll
                     for (int ch = 0; ch < EPL; ++ch) {
                         tg[ch] = a * g[ch];                                        // cuh:113
@@ -375,6 +433,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                         px = fmaf(tg[ch], dx, px);
                         py = fmaf(tg[ch], dy, py);
                     }
+#endif
 #if MSDA_BWD_IMMEDIATE
                     px = group_sum<G>(px);
                     py = group_sum<G>(py);
