@@ -456,7 +456,17 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                         const float ck[4] = {cf.x, cf.y, cf.z, cf.w};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
+#if MSDA_BWD_F32X2
+                            if (ck[k] != 0.f) {
+                                F2 g01, g23;
+                                g01.x = g[0]; g01.y = g[1]; g23.x = g[2]; g23.y = g[3];
+                                const F2 c2 = f2_dup(ck[k]);
+                                const F2 lo = mul2(c2, g01), hi = mul2(c2, g23);     // the same IEEE products, two per instruction
+                                red_add_f32x4(qk[k], lo.x, lo.y, hi.x, hi.y);
+                            }
+#else
                             if (ck[k] != 0.f) red_add_f32x4(qk[k], ck[k] * g[0], ck[k] * g[1], ck[k] * g[2], ck[k] * g[3]);
+#endif
                         }
                     } else {
                         const float wk[4] = {w1, w2, w3, w4};
