@@ -121,29 +121,6 @@ struct GradDst {
 #ifndef MSDA_BWD_F32X2
 #define MSDA_BWD_F32X2 1
 #endif
-struct alignas(8) F2 { float x, y; };
-__device__ __forceinline__ unsigned long long f2_bits(F2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
-__device__ __forceinline__ F2 f2_from(unsigned long long a) { return *reinterpret_cast<F2*>(&a); }
-__device__ __forceinline__ F2 f2_dup(float a) { F2 r; r.x = a; r.y = a; return r; }
-__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c)
-{
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
-    return f2_from(d);
-}
-__device__ __forceinline__ F2 mul2(F2 a, F2 b)
-{
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return f2_from(d);
-}
-__device__ __forceinline__ F2 sub2(F2 a, F2 b)
-{
-    unsigned long long d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return f2_from(d);
-}
-
 template <int K>
 __device__ __forceinline__ float reg_pick(const float (&a)[K], int idx)
 {

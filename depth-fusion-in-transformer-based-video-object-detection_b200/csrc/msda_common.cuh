@@ -274,4 +274,29 @@ __device__ __forceinline__ float2 fused_location(float2 off, const float* __rest
 // exact s / P for 0 <= s < 65536 / P  (magic = ceil(65536 / P), computed on the host)
 __device__ __forceinline__ int div_by_points(int s, int magic) { return (s * magic) >> 16; }
 
+// Packed fp32 arithmetic (Blackwell: fma / mul / sub .f32x2 -> FFMA2 / FMUL2 / FADD2).  nvcc emits these only from inline
+// PTX; each half is an ordinary IEEE operation.
+struct alignas(8) F2 { float x, y; };
+__device__ __forceinline__ unsigned long long f2_bits(F2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+__device__ __forceinline__ F2 f2_from(unsigned long long a) { return *reinterpret_cast<F2*>(&a); }
+__device__ __forceinline__ F2 f2_dup(float a) { F2 r; r.x = a; r.y = a; return r; }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return f2_from(d);
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+__device__ __forceinline__ F2 sub2(F2 a, F2 b)
+{
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+
 }  // namespace msda

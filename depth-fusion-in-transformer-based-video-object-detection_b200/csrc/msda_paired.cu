@@ -53,6 +53,14 @@ pack_value_pairs_kernel(const VT* __restrict__ value, VT* __restrict__ pairs, in
 template <int PAIRS> struct PairedWarps { static constexpr int value = PAIRS >= 16 ? 2 : (PAIRS >= 8 ? 4 : 8); };
 constexpr int kRecPad = 2;       // records: group stride (2*kChunk + 2) * 16 B -> the groups of a warp hit distinct banks
 
+// 1: accumulate channel pairs with packed fp32 FMAs (msda_common.cuh) -- 8 FFMA2 instead of 16 FFMA per sample per lane in
+// the kernel that ncu showed issue-bound (83 % issue-active).  Bit-identical arithmetic.  Compile-checked (no spills, 64
+// FFMA2 in the D = 32 bf16 kernel) but NOT yet run on a GPU: off by default, first A/B of the next round
+// (make EXTRA=-DMSDA_PAIRED_F32X2=1; tests/test_gpu_paired.py; MultiScaleDeformableAttention.PAIRED_FORWARD = True).
+#ifndef MSDA_PAIRED_F32X2
+#define MSDA_PAIRED_F32X2 0
+#endif
+
 #ifndef MSDA_PAIRED_MINWARPS
 #define MSDA_PAIRED_MINWARPS 40
 #endif
@@ -231,8 +239,22 @@ msda_fwd_paired_kernel(const VT* __restrict__ pairs, const int64_t* __restrict__
                     float v0[EPL], v1[EPL];
                     unpack<VT>(raw[u][0], v0);
                     unpack<VT>(raw[u][1], v1);
+#if MSDA_PAIRED_F32X2
+                    const F2 W0 = f2_dup(wy0), W1 = f2_dup(wy1);
+#pragma unroll
+                    for (int c = 0; c < EPL; c += 2) {                     // the same two fmas per channel, two channels at once
+                        F2 a, x0, x1;
+                        a.x = acc[c]; a.y = acc[c + 1];
+                        x0.x = v0[c]; x0.y = v0[c + 1];
+                        x1.x = v1[c]; x1.y = v1[c + 1];
+                        a = fma2(W1, x1, fma2(W0, x0, a));
+                        acc[c] = a.x;
+                        acc[c + 1] = a.y;
+                    }
+#else
 #pragma unroll
                     for (int c = 0; c < EPL; ++c) acc[c] = fmaf(wy1, v1[c], fmaf(wy0, v0[c], acc[c]));
+#endif
                 }
             }
         }
