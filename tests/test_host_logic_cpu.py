@@ -169,3 +169,25 @@ def test_transformer_accepts_token_major_levels(oracle_op):
     assert torch.equal(a, b) and torch.equal(a, c)
     with pytest.raises(AssertionError, match="disagree"):
         model([srcs[0][:, :, :-1]] + srcs[1:], masks, poss, None, None, None, query)
+
+
+def test_tf32_split_definition_and_three_term_product():
+    """Host restatement of the split behind set_fp32_gemm_mode('tf32x3'): hi keeps 10 mantissa bits, lo + hi == x
+    exactly, |lo| <= 2^-11 |x|, and [lo | hi | hi] x [hi | lo | hi]^T equals x W^T minus the (dropped) lo_x lo_W^T term."""
+    import torch
+    from dfvod_b200.ops.functions import layer_epilogue_func as L
+    torch.manual_seed(0)
+    x = torch.randn(64, 24) * torch.exp(torch.randn(64, 24) * 3)
+    w = torch.randn(10, 24)
+    parts = L._tf32_split(x)
+    lo, hi, hi2 = parts[:, :24], parts[:, 24:48], parts[:, 48:]
+    assert torch.equal(hi, hi2) and torch.equal(lo + hi, x)
+    assert int((hi.contiguous().view(torch.int32) & 0x1fff).abs().max()) == 0
+    assert bool((lo.abs() <= x.abs() * 2.0 ** -11).all())
+    wp = L._tf32_split(w)
+    wlo, whi = wp[:, :24], wp[:, 24:48]
+    got = L.linear_tf32x3(x, w, None).double()
+    want = x.double() @ w.double().t() - lo.double() @ wlo.double().t()
+    scale = (x.double().abs() @ w.double().abs().t()).max()
+    assert float((got - want).abs().max() / scale) <= 1e-6        # fp32 accumulation of exact terms (on the host)
+    assert L.FP32_GEMM_MODE == "library" and not L._tf32x3_wanted(x, w)   # host tensors never take the split path
