@@ -785,7 +785,7 @@ static cudaError_t run_bwd_fused(const FusedArgs& a, cudaStream_t stream)
 
 cudaError_t fused_backward(const FusedArgs& a, cudaStream_t stream)
 {
-    if (!fused_supported(a)) return cudaErrorInvalidValue;
+    if (!fused_supported(a) || !fused_raw_layout_ok(a)) return cudaErrorInvalidValue;
     if (a.dtype == kF32) return run_bwd_fused<float, float>(a, stream);
     if (a.raw_dtype == kF32) return run_bwd_fused<__nv_bfloat16, float>(a, stream);
     return run_bwd_fused<__nv_bfloat16, __nv_bfloat16>(a, stream);
@@ -793,6 +793,13 @@ cudaError_t fused_backward(const FusedArgs& a, cudaStream_t stream)
 
 cudaError_t backward(const BwdArgs& a, cudaStream_t stream)
 {
+    if (a.L == 0 || a.P == 0) {
+        // empty sum (the forward writes zeros, msda_forward): grad_value is all zeros, grad_loc / grad_attn have no
+        // elements.  Also keeps P = 0 away from the launchers' 65536 / P.
+        if (a.dtype < kF32 || a.dtype > kF16) return cudaErrorInvalidValue;
+        const size_t esz = a.dtype == kF64 ? 8 : (a.dtype == kF32 ? 4 : 2);
+        return cudaMemsetAsync(a.grad_value, 0, (size_t)a.N * a.S * a.M * a.D * esz, stream);
+    }
     switch (a.dtype) {
         case kF32:  return run_bwd_16or32<float>(a, stream);
         case kBF16: return run_bwd_16or32<__nv_bfloat16>(a, stream);

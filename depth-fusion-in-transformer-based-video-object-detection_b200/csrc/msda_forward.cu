@@ -362,7 +362,19 @@ bool fused_supported(const FusedArgs& a)
                           (a.dtype == kBF16 && (a.raw_dtype == kF32 || a.raw_dtype == kBF16));
     return dtype_ok && (a.D == 16 || a.D == 32 || a.D == 64) && a.L >= 1 && a.P >= 1 && a.L * a.P <= kChunk &&
            a.L <= kMaxLevelsFast && (a.ref_dim == 2 || a.ref_dim == 4) &&
-           (long long)a.S * a.M * a.D < (1ll << 31) && (a.P % 2 == 0 || a.raw_dtype == kF32);
+           (long long)a.S * a.M * a.D < (1ll << 31) && (a.P % 2 == 0 || a.raw_dtype == kF32) &&
+           // offset pairs are moved with one 8-byte (fp32) / 4-byte (16-bit) access: every query row of the raw
+           // projection output must start on such a boundary.  The module's row is [offsets (2 MLP) | logits (MLP)],
+           // 3*M*L*P elements, so an odd M*L*P would leave every odd row misaligned.
+           ((long long)a.M * a.L * a.P) % 2 == 0;
+}
+
+// run-time layout of the raw projection outputs handed to the fused kernels (see fused_supported)
+bool fused_raw_layout_ok(const FusedArgs& a)
+{
+    const size_t pair_bytes = a.raw_dtype == kF32 ? 8 : 4;
+    const auto aligned = [&](const void* p) { return p == nullptr || ((size_t)p % pair_bytes) == 0; };
+    return a.off_stride % 2 == 0 && aligned(a.offsets) && aligned(a.grad_offsets);
 }
 
 template <typename VT, typename RT>
@@ -378,7 +390,7 @@ static cudaError_t dispatch_fwd_fused(const FusedArgs& a, cudaStream_t stream)
 
 cudaError_t fused_forward(const FusedArgs& a, cudaStream_t stream)
 {
-    if (!fused_supported(a)) return cudaErrorInvalidValue;
+    if (!fused_supported(a) || !fused_raw_layout_ok(a)) return cudaErrorInvalidValue;
     if (a.value_ld != 0 && (a.value_ld < (long long)a.M * a.D || a.value_ld % (16 / (a.dtype == kF32 ? 4 : 2)) != 0 ||
                             (long long)a.S * a.value_ld >= (1ll << 31)))
         return cudaErrorInvalidValue;
@@ -391,6 +403,7 @@ cudaError_t fused_forward(const FusedArgs& a, cudaStream_t stream)
 cudaError_t forward(const FwdArgs& a, cudaStream_t stream)
 {
     if ((long long)a.N * a.Lq * a.M * a.D == 0) return cudaSuccess;
+    if (!a.no_tc && tc_forward_supported(a)) return tc_forward(a, stream);
     switch (a.dtype) {
         case kF32:  return dispatch_fwd_16or32<float>(a, stream);
         case kBF16: return dispatch_fwd_16or32<__nv_bfloat16>(a, stream);

@@ -17,6 +17,7 @@ struct FwdArgs {
     void* out;                // [N,Lq,M,D] dtype
     int N, S, M, D, L, Lq, P;
     int force_generic;        // tests: route through the generic kernel
+    int no_tc;                // A/B and tests: keep the lane-group gather where the tensor-core kernel would run
 };
 
 struct BwdArgs {
@@ -33,6 +34,7 @@ struct BwdArgs {
     float* grad_value_accum;  // 16-bit dtypes only: fp32 [N,S,M,D] scratch the atomics land in
     int N, S, M, D, L, Lq, P;
     int force_generic;
+    int no_tc;
 };
 
 // Fused layer op: sampling locations and attention weights are NOT materialised.  The kernels
@@ -64,10 +66,16 @@ struct FusedArgs {
 };
 
 bool fused_supported(const FusedArgs& a);
+bool fused_raw_layout_ok(const FusedArgs& a);   // strides / alignment of offsets, grad_offsets
 cudaError_t fused_forward(const FusedArgs& a, cudaStream_t stream);
 cudaError_t fused_backward(const FusedArgs& a, cudaStream_t stream);
 
 cudaError_t forward(const FwdArgs& a, cudaStream_t stream);
+
+// Tensor-core formulation (msda_tc_forward.cu / msda_tc_backward.cu): bf16 values, 32 channels per head, <= 4 levels,
+// <= 4 points.  forward() / backward() route to it when it applies.
+bool tc_forward_supported(const FwdArgs& a);
+cudaError_t tc_forward(const FwdArgs& a, cudaStream_t stream);
 
 // Paired value layout (msda_paired.cu): pairs[n, r, m, 0|1, :] = value[n, r-1 | r, m, :], r = 0..S.
 // In forward_paired / fused_forward_paired the `value` member points at that tensor.

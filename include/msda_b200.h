@@ -49,6 +49,9 @@ typedef enum {
                                        bilinear weight) to bf16 and accumulate with the mixed-precision FMA
                                        (fp32 accumulator) -- half the math instructions; inference option */
 
+#define MSDA_FLAG_NO_TC 4           /* msda_forward / msda_backward: keep the lane-group gather kernels where the
+                                       tensor-core (tcgen05) formulation would run -- A/B measurements, tests */
+
 /* ABI version of this header (bumped on any signature change). */
 int msda_abi_version(void);
 
