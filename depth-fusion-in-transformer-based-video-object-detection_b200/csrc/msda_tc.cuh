@@ -69,6 +69,28 @@ __device__ __forceinline__ int seg_row_shift(int bw)
     return bw <= 8 ? 4 : (bw <= 16 ? 3 : (bw <= 32 ? 2 : 1));
 }
 
+// streaming loads that stay where they are written (asm volatile): the kernels issue a level's loads one level ahead,
+// and a plain asm load is free to sink down to its first use
+__device__ __forceinline__ uint4 ldg_prefetch_v4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ldg_prefetch_f32x2(const float* p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_prefetch_f32(const float* p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ void sts_u16(unsigned addr, unsigned short v)
 {
     asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"(v) : "memory");

@@ -7,20 +7,23 @@
 // per (query, corner) and is bound by that pipe (profiles/ncu_summary.json: 96 % for bf16); here a value window enters
 // the SM once per tile by TMA and the products run on tcgen05.mma.
 //
-// One persistent CTA per SM, 18 warps:
-//   warps 0-15  512 "build" threads: thread t owns query slot t / 4 and point t % 4.  Per tile: load the sample
-//               (location, attention weight), bilinear footprint, bounding boxes of the tile's corner pixels per level
-//               (warp redux + shared atomics) -> windows and segments.  Per segment: clear the entries this thread
-//               wrote into the C block two segments ago, write the new ones, fence, arrive.  The 4 lanes of a query
-//               split the CORNERS BY PIXEL PARITY (x & 1, y & 1): every sample has exactly one corner of each parity,
-//               so two lanes never write the same C element and no atomics are needed; the entries of one lane that
-//               fall on the same pixel are merged in registers.  Warps 0-3 also read the finished accumulator rows
-//               back (tcgen05.ld) and store the output.
-//   warp 16     TMA producer: one box {32 channels of the head, BW pixels} per window row into the V block.
-//   warp 17     MMA issuer: per segment rows * BW / 16 tcgen05.mma (M 128, N 32, K 16) into the tile's accumulator in
-//               tensor memory; tcgen05.commit frees the C block and the V block.
-// Tiles whose windows do not fit are gathered by the build threads with plain loads (4 lanes x 16 bytes per corner row,
-// the mapping of msda_forward.cu).
+// Small persistent CTAs, four per SM (their phases interleave on the SM: while one builds, another's MMAs run):
+//   warps 0-3   128 "build" threads, thread t = query slot t = row t of C = lane t of the accumulator in tensor memory.
+//               Level by level: the query's samples (location, attention weight) -> bilinear footprints -> bounding
+//               box of the tile's corner pixels (warp redux + shared atomics) -> the level's window and its segments,
+//               published to the control warps.  Per segment: add this query's coefficients into its row of the C
+//               block (the row is private to the thread, so duplicates -- samples sharing a pixel -- are summed with
+//               plain shared-memory read-modify-writes), fence, arrive; when the segment's MMAs have completed the same
+//               entries are zeroed again.  After the last level: accumulator row -> output.
+//   warp 4      TMA producer: one box {32 channels of the head, BW pixels} per window row into a V block.
+//   warp 5      MMA issuer: per segment rows * BW / 16 tcgen05.mma (M 128, N 32, K 16) into the tile's accumulator;
+//               tcgen05.commit frees the C block and the V block.
+// The control warps follow a stream of level plans (shared-memory ring), so they never decode tiles themselves.
+// A tile with a level whose window does not fit (scattered sampling locations) is appended to a list and gathered by
+// msda_tc_fwd_fallback_kernel with plain loads (4 lanes x 16 bytes per corner row, the mapping of msda_forward.cu), so
+// the result is exact for any input.
+#include <cstdio>
+#include <cstdlib>
 #include "msda_launch.h"
 #include "msda_tc.cuh"
 
@@ -29,35 +32,65 @@ namespace tc {
 
 using namespace umma;
 
-constexpr int kFwdVStages = 4;
-constexpr int kFwdThreads = kBuildThreads + 64;
-constexpr int kFwdSmem = 2 * kCBytes + kFwdVStages * kVBytes + 1024;
+constexpr int kFwdBuild = kTileQ;
+constexpr int kFwdThreads = kFwdBuild + 64;
+constexpr int kFwdVStages = 2;
+constexpr int kFwdSmem = kCBytes + kFwdVStages * kVBytes + 1024;
+constexpr int kLpRing = 4;
+enum { kLpTileStart = 1, kLpTileEnd = 2, kLpEnd = 4 };
 
-struct FwdPlan {
-    int bad, nseg_total;
-    int bw[kMaxL], rows[kMaxL], rshift[kMaxL], nseg[kMaxL];
-    int pix0[kMaxL];     // TMA pixel coordinate of the window's first pixel: n*S + start + y0*W + x0
-    int W[kMaxL];
+struct LevelPlan {
+    int flags, bw, rows, rshift, nseg;
+    int pix0;        // TMA pixel coordinate of the window's first pixel: n*S + start + y0*W + x0
+    int W, head;
 };
 
 struct FwdBars {
-    unsigned long long c_full[2], mma_done[2], v_full[kFwdVStages], v_free[kFwdVStages];
-    unsigned long long plan_ready[2], plan_free[2], out_ready[2], out_free[2];
+    unsigned long long c_full, mma_done, out_ready;
+    unsigned long long v_full[kFwdVStages], v_free[kFwdVStages];
+    unsigned long long lp_ready[kLpRing], lp_free[kLpRing];
 };
 
-__global__ void __launch_bounds__(kFwdThreads, 1)
-msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __restrict__ value,
-                   const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
+// the samples of one (pair, level): P <= 4 locations and attention weights
+struct LevelSamples { float x[kMaxP], y[kMaxP], a[kMaxP]; };
+
+__device__ __forceinline__ void load_level(LevelSamples& ls, const float* __restrict__ loc, const float* __restrict__ attn,
+                                           int pair, int LP, int l, int P, bool have)
+{
+#pragma unroll
+    for (int s = 0; s < kMaxP; ++s) { ls.x[s] = -4.f; ls.y[s] = -4.f; ls.a[s] = 0.f; }     // far outside: contributes nothing
+    if (!have) return;
+    const float* lp = loc + ((long long)pair * LP + l * P) * 2;
+    const float* ap = attn + (long long)pair * LP + l * P;
+    if (P == kMaxP) {
+        const uint4 u0 = ldg_prefetch_v4(lp), u1 = ldg_prefetch_v4(lp + 4), ua = ldg_prefetch_v4(ap);
+        ls.x[0] = __uint_as_float(u0.x); ls.y[0] = __uint_as_float(u0.y); ls.x[1] = __uint_as_float(u0.z); ls.y[1] = __uint_as_float(u0.w);
+        ls.x[2] = __uint_as_float(u1.x); ls.y[2] = __uint_as_float(u1.y); ls.x[3] = __uint_as_float(u1.z); ls.y[3] = __uint_as_float(u1.w);
+        ls.a[0] = __uint_as_float(ua.x); ls.a[1] = __uint_as_float(ua.y); ls.a[2] = __uint_as_float(ua.z); ls.a[3] = __uint_as_float(ua.w);
+    } else {
+#pragma unroll
+        for (int s = 0; s < kMaxP; ++s)
+            if (s < P) {
+                const float2 xy = ldg_prefetch_f32x2(lp + 2 * s);
+                ls.x[s] = xy.x; ls.y[s] = xy.y;
+                ls.a[s] = ldg_prefetch_f32(ap + s);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 4)
+msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                    const float* __restrict__ loc, const float* __restrict__ attn, __nv_bfloat16* __restrict__ out,
-                   int N, int S, int M, int L, int Lq, int P, int value_ld, int want_pyramid)
+                   int N, int S, int M, int L, int Lq, int P, int want_pyramid, int* __restrict__ bad_list, int bad_cap,
+                   unsigned long long* __restrict__ trace)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* sC = smem;                        // 2 x 32 KB
-    unsigned char* sV = smem + 2 * kCBytes;          // kFwdVStages x 8 KB
+    unsigned char* sC = smem;                    // 32 KB
+    unsigned char* sV = smem + kCBytes;          // kFwdVStages x 8 KB
     __shared__ LevelMeta lm;
-    __shared__ FwdPlan s_plan[2];
-    __shared__ int s_bb[2][kMaxL][4];
+    __shared__ LevelPlan s_lp[kLpRing];
+    __shared__ int s_bb[3][4];
     __shared__ __align__(8) FwdBars bars;
     __shared__ unsigned tmem_base_s;
 
@@ -65,324 +98,350 @@ msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const __nv_bfloat16* __res
 
     if (tid == 0) {
         level_meta_init(&lm, shapes, lsi, L, Lq, want_pyramid);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars.c_full[i], kBuildWarps);
-            mbar_init(&bars.mma_done[i], 1);
-            mbar_init(&bars.plan_ready[i], 1);
-            mbar_init(&bars.plan_free[i], 2);
-            mbar_init(&bars.out_ready[i], 1);
-            mbar_init(&bars.out_free[i], 4);
-        }
+        mbar_init(&bars.c_full, kFwdBuild / 32);
+        mbar_init(&bars.mma_done, 1);
+        mbar_init(&bars.out_ready, 1);
         for (int i = 0; i < kFwdVStages; ++i) { mbar_init(&bars.v_full[i], 1); mbar_init(&bars.v_free[i], 1); }
+        for (int i = 0; i < kLpRing; ++i) { mbar_init(&bars.lp_ready[i], 1); mbar_init(&bars.lp_free[i], 2); }
         fence_mbar_init();
-        for (int i = 0; i < 2 * kMaxL; ++i) {
-            s_bb[0][0][4 * i + 0] = 0x7fffffff; s_bb[0][0][4 * i + 1] = 0x7fffffff;
-            s_bb[0][0][4 * i + 2] = -1;         s_bb[0][0][4 * i + 3] = -1;
-        }
+        for (int i = 0; i < 3; ++i) { s_bb[i][0] = 0x7fffffff; s_bb[i][1] = 0x7fffffff; s_bb[i][2] = -1; s_bb[i][3] = -1; }
     }
-    if (warp == 0) tmem_alloc(&tmem_base_s, 64);
-    for (int i = tid; i < 2 * kCBytes / 16; i += kFwdThreads) reinterpret_cast<uint4*>(sC)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (warp == kBuildWarps && lane < kMaxBW / 8) tma_prefetch_desc(&maps.m[lane]);
+    if (warp == 0) tmem_alloc(&tmem_base_s, 32);
+    // zero the C block (its invariant between segments) and the V blocks (rows no TMA box has written yet must be finite)
+    for (int i = tid; i < (kCBytes + kFwdVStages * kVBytes) / 16; i += kFwdThreads)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 4 && lane < kMaxBW / 8) tma_prefetch_desc(&maps.m[lane]);
     fence_proxy_async();
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const unsigned tmem = tmem_base_s;
-    const int tiles = lm.tiles;
-    const long long total_items = (long long)N * tiles * M;
+    // optional cycle accounting (MSDA_TC_TRACE=1): one representative thread per role accumulates where its time goes
+    unsigned long long tr[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tr_t = 0;
+    const bool tracing = trace != nullptr && lane == 0 && (warp == 0 || warp >= 4);
+#define TR_START() do { if (tracing) tr_t = clock64(); } while (0)
+#define TR_ADD(i) do { if (tracing) { const long long t_ = clock64(); tr[i] += (unsigned long long)(t_ - tr_t); tr_t = t_; } } while (0)
 
-    if (warp == kBuildWarps + 1) {
+    if (warp == 5) {
         // ================================ MMA issuer ================================
         const unsigned idesc = make_idesc(128, kD, 0, 1);
-        unsigned long long descA[2], descB[kFwdVStages];
-        for (int i = 0; i < 2; ++i) descA[i] = make_desc_sw128(sC + i * kCBytes);
+        const unsigned long long descA = make_desc_sw128(sC);
+        unsigned long long descB[kFwdVStages];
+#pragma unroll
         for (int i = 0; i < kFwdVStages; ++i) descB[i] = make_desc(sV + i * kVBytes, 0, 512, 4);
-        unsigned g = 0, good = 0, it = 0;
-        for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-            mbar_wait(&bars.plan_ready[it & 1], (it >> 1) & 1);
-            const FwdPlan& pl = s_plan[it & 1];
-            if (pl.bad || pl.nseg_total == 0) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.plan_free[it & 1]);
-                continue;
-            }
-            const unsigned tb = good & 1;
-            if (good >= 2) mbar_wait(&bars.out_free[tb], ((good >> 1) - 1) & 1);
-            tcgen05_fence_after();
-            bool first = true;
-            for (int l = 0; l < L; ++l) {
-                const int nseg = pl.nseg[l], bw = pl.bw[l], rows = pl.rows[l], rshift = pl.rshift[l];
-                for (int sidx = 0; sidx < nseg; ++sidx, ++g) {
-                    const unsigned b = g & 1, vs = g % kFwdVStages;
-                    int r = min(1 << rshift, rows - (sidx << rshift));
-                    if ((bw & 15) && (r & 1)) ++r;
-                    const int ksteps = (r * bw) >> 4;
-                    mbar_wait(&bars.c_full[b], (g >> 1) & 1);
-                    mbar_wait(&bars.v_full[vs], (g / kFwdVStages) & 1);
-                    tcgen05_fence_after();
-                    if (elect_one()) {
-                        for (int ks = 0; ks < ksteps; ++ks)
-                            mma_bf16(tmem + tb * kD, desc_advance(descA[b], (unsigned)((ks >> 2) * 16384 + (ks & 3) * 32)),
-                                     desc_advance(descB[vs], (unsigned)(ks * 1024)), idesc, !(first && ks == 0));
-                        mma_commit(&bars.mma_done[b]);
-                        mma_commit(&bars.v_free[vs]);
-                    }
-                    __syncwarp();
-                    first = false;
+        unsigned gseg = 0;
+        bool first = true;
+        TR_START();
+        for (unsigned u = 0;; ++u) {
+            mbar_wait(&bars.lp_ready[u % kLpRing], (u / kLpRing) & 1);
+            TR_ADD(0);
+            const LevelPlan pl = s_lp[u % kLpRing];
+            if (pl.flags & kLpEnd) break;
+            if (pl.flags & kLpTileStart) first = true;
+            for (int sidx = 0; sidx < pl.nseg; ++sidx, ++gseg) {
+                const unsigned vs = gseg % kFwdVStages;
+                int r = min(1 << pl.rshift, pl.rows - (sidx << pl.rshift));
+                if ((pl.bw & 15) && (r & 1)) ++r;
+                const int ksteps = (r * pl.bw) >> 4;
+                mbar_wait(&bars.c_full, gseg & 1);
+                TR_ADD(1);
+                mbar_wait(&bars.v_full[vs], (gseg / kFwdVStages) & 1);
+                TR_ADD(2);
+                tcgen05_fence_after();
+                TR_ADD(8);
+                if (elect_one()) {
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        mma_bf16(tmem, desc_advance(descA, (unsigned)((ks >> 2) * 16384 + (ks & 3) * 32)),
+                                 desc_advance(descB[vs], (unsigned)(ks * 1024)), idesc, !(first && ks == 0));
+                    if (tracing) { const long long t_ = clock64(); tr[9] += (unsigned long long)(t_ - tr_t); tr_t = t_; }
+                    mma_commit(&bars.mma_done);
+                    mma_commit(&bars.v_free[vs]);
                 }
+                __syncwarp();
+                first = false;
+                TR_ADD(3);
+                if (tracing) { tr[4] += ksteps; tr[5] += 1; }
             }
-            if (elect_one()) mma_commit(&bars.out_ready[tb]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.plan_free[it & 1]);
-            ++good;
+            if (pl.flags & kLpTileEnd) {
+                if (elect_one()) mma_commit(&bars.out_ready);
+                __syncwarp();
+            }
+            if (lane == 0) mbar_arrive(&bars.lp_free[u % kLpRing]);
         }
-    } else if (warp == kBuildWarps) {
+    } else if (warp == 4) {
         // ================================ TMA producer ================================
-        unsigned g = 0, it = 0;
-        for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-            mbar_wait(&bars.plan_ready[it & 1], (it >> 1) & 1);
-            const FwdPlan& pl = s_plan[it & 1];
-            if (pl.bad || pl.nseg_total == 0) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.plan_free[it & 1]);
-                continue;
-            }
-            const int h = (int)(item % M);
-            for (int l = 0; l < L; ++l) {
-                const int nseg = pl.nseg[l], bw = pl.bw[l], rows = pl.rows[l], rshift = pl.rshift[l];
-                const int W = pl.W[l], pix0 = pl.pix0[l];
-                const CUtensorMap* map = &maps.m[(bw >> 3) - 1];
-                for (int sidx = 0; sidx < nseg; ++sidx, ++g) {
-                    const unsigned vs = g % kFwdVStages;
-                    int r = min(1 << rshift, rows - (sidx << rshift));
-                    if ((bw & 15) && (r & 1)) ++r;
-                    if (g >= kFwdVStages) mbar_wait(&bars.v_free[vs], ((g / kFwdVStages) - 1) & 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(&bars.v_full[vs], (unsigned)(r * bw * 64));
-                        for (int rr = 0; rr < r; ++rr)
-                            tma_load_2d(sV + vs * kVBytes + rr * bw * 64, map, h * kD,
-                                        pix0 + ((sidx << rshift) + rr) * W, &bars.v_full[vs]);
-                    }
-                    __syncwarp();
+        unsigned gseg = 0;
+        TR_START();
+        for (unsigned u = 0;; ++u) {
+            mbar_wait(&bars.lp_ready[u % kLpRing], (u / kLpRing) & 1);
+            TR_ADD(0);
+            const LevelPlan pl = s_lp[u % kLpRing];
+            if (pl.flags & kLpEnd) break;
+            const CUtensorMap* map = &maps.m[(pl.bw >> 3) - 1];
+            for (int sidx = 0; sidx < pl.nseg; ++sidx, ++gseg) {
+                const unsigned vs = gseg % kFwdVStages;
+                int r = min(1 << pl.rshift, pl.rows - (sidx << pl.rshift));
+                if ((pl.bw & 15) && (r & 1)) ++r;
+                if (gseg >= kFwdVStages) mbar_wait(&bars.v_free[vs], ((gseg / kFwdVStages) - 1) & 1);
+                TR_ADD(1);
+                if (elect_one()) {
+                    mbar_expect_tx(&bars.v_full[vs], (unsigned)(r * pl.bw * 64));
+                    for (int rr = 0; rr < r; ++rr)
+                        tma_load_2d(sV + vs * kVBytes + rr * pl.bw * 64, map, pl.head * kD,
+                                    pl.pix0 + ((sidx << pl.rshift) + rr) * pl.W, &bars.v_full[vs]);
                 }
+                __syncwarp();
+                TR_ADD(2);
             }
-            if (lane == 0) mbar_arrive(&bars.plan_free[it & 1]);
+            if (lane == 0) mbar_arrive(&bars.lp_free[u % kLpRing]);
         }
     } else {
         // ================================ build threads ================================
-        const int q = tid >> 2, j = tid & 3;          // query slot, point (= corner parity class)
-        const int px = j & 1, py = j >> 1;
+        const int q = tid;
         const unsigned row_base = c_row_base(q);
         const int q7 = q & 7;
-        const unsigned sC_u32 = smem_u32(sC);
-        unsigned pend_cur0 = 0xffffffffu, pend_cur1 = 0xffffffffu;     // offsets written into the C block of parity g & 1 ...
-        unsigned pend_oth0 = 0xffffffffu, pend_oth1 = 0xffffffffu;     // ... and of the other parity
-        unsigned g = 0, good = 0, it = 0;
+        const unsigned cb = smem_u32(sC);
+        const int tiles = lm.tiles;
+        const int total_items = N * tiles * M;
         const int LP = L * P;
-        for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-            const int h = (int)(item % M);
-            const long long rest = item / M;
-            const int t = (int)(rest % tiles);
-            const int n = (int)(rest / tiles);
-            const Tile tl = tile_decode(lm, t, L, Lq);
-            const int qi = tile_query(tl, q);
-            const bool have = qi >= 0 && j < P;
-            const long long pair = ((long long)n * Lq + (qi >= 0 ? qi : 0)) * M + h;
-            // ---- this thread's sample on every level ----
-            int fx[kMaxL], fy[kMaxL];
-            float flw[kMaxL], flh[kMaxL], fa[kMaxL];
-            unsigned inside = 0;
-            const int pb = it & 1;
-#pragma unroll
-            for (int l = 0; l < kMaxL; ++l) {
-                fx[l] = 0; fy[l] = 0; flw[l] = 0.f; flh[l] = 0.f; fa[l] = 0.f;
-                if (l < L && have) {
-                    const float2 xy = ldg_stream_f32x2(loc + (pair * LP + l * P + j) * 2);
-                    fa[l] = ldg_stream_f32(attn + pair * LP + l * P + j);
-                    const int H = lm.H[l], W = lm.W[l];
-                    const float w_im = xy.x * (float)W - 0.5f, h_im = xy.y * (float)H - 0.5f;      // cuh:285-286
-                    const bool in = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
-                    const float hf = floorf(h_im), wf = floorf(w_im);
-                    fx[l] = (int)wf; fy[l] = (int)hf;
-                    flw[l] = w_im - wf; flh[l] = h_im - hf;
-                    if (in) inside |= 1u << l;
-                }
+        unsigned u = 0;              // level plans published
+        unsigned waited = 0;         // segments whose MMAs this thread has waited for
+        unsigned items_done = 0;
+
+        auto publish = [&](int flags, const Window& w, int pix0, int Wl, int head) {
+            if (tid == 0) {
+                if (u >= kLpRing) mbar_wait(&bars.lp_free[u % kLpRing], ((u / kLpRing) - 1) & 1);
+                LevelPlan& pl = s_lp[u % kLpRing];
+                pl.flags = flags; pl.bw = w.bw; pl.rows = w.rows; pl.rshift = w.rshift; pl.nseg = w.nseg;
+                pl.pix0 = pix0; pl.W = Wl; pl.head = head;
+                mbar_arrive(&bars.lp_ready[u % kLpRing]);
             }
-            // bounding box of the corner pixels per level: warp reduction, then one shared atomic per warp
-#pragma unroll
-            for (int l = 0; l < kMaxL; ++l) {
-                if (l < L) {
-                    const bool in = (inside >> l) & 1u;
-                    const int W = lm.W[l], H = lm.H[l];
-                    const int xa = in ? max(fx[l], 0) : 0x7fffffff, ya = in ? max(fy[l], 0) : 0x7fffffff;
-                    const int xb = in ? min(fx[l] + 1, W - 1) : -1, yb = in ? min(fy[l] + 1, H - 1) : -1;
-                    const int mnx = __reduce_min_sync(0xffffffffu, xa), mny = __reduce_min_sync(0xffffffffu, ya);
-                    const int mxx = __reduce_max_sync(0xffffffffu, xb), mxy = __reduce_max_sync(0xffffffffu, yb);
-                    if (lane == 0 && mxx >= 0) {
-                        atomicMin(&s_bb[pb][l][0], mnx); atomicMin(&s_bb[pb][l][1], mny);
-                        atomicMax(&s_bb[pb][l][2], mxx); atomicMax(&s_bb[pb][l][3], mxy);
-                    }
-                }
-            }
-            named_bar_sync(1, kBuildThreads);
-            Window win[kMaxL];
+        };
+        auto decode = [&](int it, int& h_, int& n_, int& qi_, int& pair_) {
+            h_ = it % M;
+            const int rest = it / M;
+            const Tile tl = tile_decode(lm, rest % tiles, L, Lq);
+            n_ = rest / tiles;
+            qi_ = tile_query(tl, q);
+            pair_ = (n_ * Lq + (qi_ >= 0 ? qi_ : 0)) * M + h_;
+        };
+
+        int item = blockIdx.x;
+        int h = 0, n = 0, qi = -1;
+        int pair = 0;
+        LevelSamples pf;             // prefetched samples of the next (item, level)
+        if (item < total_items) {
+            decode(item, h, n, qi, pair);
+            load_level(pf, loc, attn, pair, LP, 0, P, qi >= 0);
+        }
+        TR_START();
+        while (item < total_items) {
             bool bad = false;
             int nseg_total = 0;
+            // next item (its level-0 samples are prefetched during this item's last level)
+            const int item_next = item + gridDim.x;
+            int h2 = 0, n2 = 0, qi2 = -1;
+            int pair2 = 0;
+            if (item_next < total_items) decode(item_next, h2, n2, qi2, pair2);
+
+            for (int l = 0; l < L; ++l, ++u) {
+                const LevelSamples ls = pf;
+                if (l + 1 < L) load_level(pf, loc, attn, pair, LP, l + 1, P, qi >= 0);
+                else if (item_next < total_items) load_level(pf, loc, attn, pair2, LP, 0, P, qi2 >= 0);
+                const int H = lm.H[l], W = lm.W[l];
+                // ---- footprints (cuh:285-288, :33-84) and the bounding box of this query's corner pixels ----
+                int bx[kMaxP], by[kMaxP];
+                float lw[kMaxP], lh[kMaxP];
+                unsigned inside = 0;
+                int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -1, mxy = -1;
 #pragma unroll
-            for (int l = 0; l < kMaxL; ++l) {
-                win[l].nseg = 0;
-                if (l < L) {
-                    bad |= !window_from_bbox(s_bb[pb][l][0], s_bb[pb][l][1], s_bb[pb][l][2], s_bb[pb][l][3], &win[l]);
-                    nseg_total += win[l].nseg;
-                }
-            }
-            if (tid == 0) {
-                // both control warps are done with the plan of the tile before the previous one
-                if (it >= 2) mbar_wait(&bars.plan_free[pb], ((it >> 1) - 1) & 1);
-                FwdPlan& pl = s_plan[pb];
-                pl.bad = bad; pl.nseg_total = nseg_total;
-#pragma unroll
-                for (int l = 0; l < kMaxL; ++l) {
-                    if (l < L) {
-                        pl.bw[l] = win[l].bw; pl.rows[l] = win[l].rows; pl.rshift[l] = win[l].rshift; pl.nseg[l] = win[l].nseg;
-                        pl.W[l] = lm.W[l];
-                        pl.pix0[l] = n * S + lm.start[l] + win[l].y0 * lm.W[l] + win[l].x0;
+                for (int s = 0; s < kMaxP; ++s) {
+                    const float w_im = ls.x[s] * (float)W - 0.5f, h_im = ls.y[s] * (float)H - 0.5f;
+                    const bool in = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
+                    const float hf = floorf(h_im), wf = floorf(w_im);
+                    bx[s] = (int)wf; by[s] = (int)hf;
+                    lw[s] = w_im - wf; lh[s] = h_im - hf;
+                    if (in) {
+                        inside |= 1u << s;
+                        mnx = min(mnx, max(bx[s], 0)); mxx = max(mxx, min(bx[s] + 1, W - 1));
+                        mny = min(mny, max(by[s], 0)); mxy = max(mxy, min(by[s] + 1, H - 1));
                     }
                 }
-                mbar_arrive(&bars.plan_ready[pb]);
-            }
-            // every thread has read the boxes: reset them for the tile after the next one
-            named_bar_sync(2, kBuildThreads);
-            if (tid < 4 * kMaxL) s_bb[pb][0][tid] = (tid & 2) ? -1 : 0x7fffffff;
-
-            if (bad) {
-                // ---- gather with plain loads: 4 lanes x 16 bytes per corner row ----
-                float acc[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-                const __nv_bfloat16* vbase = value + (long long)n * S * value_ld + h * kD + j * 8;
-#pragma unroll
-                for (int l = 0; l < kMaxL; ++l) {
-                    if (l < L) {
-                        const int W = lm.W[l], H = lm.H[l], start = lm.start[l];
-                        for (int s = 0; s < P; ++s) {
-                            const int bx = __shfl_sync(0xffffffffu, fx[l], s, 4), by = __shfl_sync(0xffffffffu, fy[l], s, 4);
-                            const float lw = __shfl_sync(0xffffffffu, flw[l], s, 4), lh = __shfl_sync(0xffffffffu, flh[l], s, 4);
-                            const float a = __shfl_sync(0xffffffffu, fa[l], s, 4);
-                            const unsigned in = __shfl_sync(0xffffffffu, inside, s, 4) & (1u << l);
-                            if (!in) continue;
-                            const float hw = 1.f - lw, hh = 1.f - lh;
-                            const float wk[4] = {hh * hw * a, hh * lw * a, lh * hw * a, lh * lw * a};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const int x = bx + (k & 1), y = by + (k >> 1);
-                                if (x >= 0 && x < W && y >= 0 && y < H) {
-                                    float v[8];
-                                    unpack<__nv_bfloat16>(ldg_v4(vbase + (long long)(start + y * W + x) * value_ld), v);
-#pragma unroll
-                                    for (int c = 0; c < 8; ++c) acc[c] = fmaf(wk[k], v[c], acc[c]);
-                                }
-                            }
-                        }
-                    }
+                mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+                mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+                int* bb = s_bb[u % 3];
+                if (lane == 0 && mxx >= 0) {
+                    atomicMin(&bb[0], mnx); atomicMin(&bb[1], mny); atomicMax(&bb[2], mxx); atomicMax(&bb[3], mxy);
                 }
-                if (qi >= 0) stg_stream_v4(out + pair * kD + j * 8, pack<__nv_bfloat16>(acc));
-                continue;
-            }
-
-            // ---- segments ----
-            unsigned gl = g;                  // global index of the level's first segment
+                TR_ADD(0);
+                named_bar_sync(1, kFwdBuild);
+                TR_ADD(1);
+                Window w;
+                const bool fits = window_from_bbox(bb[0], bb[1], bb[2], bb[3], &w);
+                if (tid == 0) {          // the box of the previous level: everybody has read it before this barrier
+                    int* pb = s_bb[(u + 2) % 3];
+                    pb[0] = 0x7fffffff; pb[1] = 0x7fffffff; pb[2] = -1; pb[3] = -1;
+                }
+                if (!fits) {
+                    w.nseg = 0;
+                    publish((l == 0 ? kLpTileStart : 0) | kLpTileEnd, w, 0, W, h);
+                    bad = true;
+                    ++u;
+                    // the prefetch holds the next level of THIS item: replace it by the next item's first level
+                    if (l + 1 < L && item_next < total_items) load_level(pf, loc, attn, pair2, LP, 0, P, qi2 >= 0);
+                    break;
+                }
+                publish((l == 0 ? kLpTileStart : 0) | (l == L - 1 ? kLpTileEnd : 0), w,
+                        n * S + lm.start[l] + w.y0 * W + w.x0, W, h);
+                if (w.nseg == 0) continue;
+                nseg_total += w.nseg;
+                // ---- this query's entries of the level: (C offset | segment << 16), coefficient ----
+                unsigned e_pk[4 * kMaxP];
+                unsigned e_cf[2 * kMaxP];        // coefficients, rounded to bf16, two per register
 #pragma unroll
-            for (int l = 0; l < kMaxL; ++l) {
-                if (l < L && win[l].nseg > 0) {
-                    const Window w = win[l];
-                    const int W = lm.W[l], H = lm.H[l];
-                    // my corner (the one of pixel parity (px, py)) of each of the query's samples on this level
-                    unsigned e_off[kMaxP], e_seg[kMaxP];
-                    float e_c[kMaxP];
-                    bool e_ok[kMaxP];
+                for (int s = 0; s < kMaxP; ++s) {
+                    const float hw = 1.f - lw[s], hh = 1.f - lh[s];
+                    const float wk[4] = {hh * hw * ls.a[s], hh * lw[s] * ls.a[s], lh[s] * hw * ls.a[s], lh[s] * lw[s] * ls.a[s]};
 #pragma unroll
-                    for (int s = 0; s < kMaxP; ++s) {
-                        const int bx = __shfl_sync(0xffffffffu, fx[l], s, 4), by = __shfl_sync(0xffffffffu, fy[l], s, 4);
-                        const float lw = __shfl_sync(0xffffffffu, flw[l], s, 4), lh = __shfl_sync(0xffffffffu, flh[l], s, 4);
-                        const float a = __shfl_sync(0xffffffffu, fa[l], s, 4);
-                        const unsigned in = __shfl_sync(0xffffffffu, inside, s, 4) & (1u << l);
-                        const int x = bx + ((bx ^ px) & 1), y = by + ((by ^ py) & 1);
-                        const float wx = x == bx ? 1.f - lw : lw, wy = y == by ? 1.f - lh : lh;
-                        e_ok[s] = in && x >= 0 && x < W && y >= 0 && y < H;
-                        e_c[s] = wy * wx * a;
+                    for (int c = 0; c < 4; ++c) {
+                        const int x = bx[s] + (c & 1), y = by[s] + (c >> 1);
+                        const bool ok = ((inside >> s) & 1u) && x >= 0 && x < W && y >= 0 && y < H;
                         const int yrel = y - w.y0;
                         const int k = (yrel & ((1 << w.rshift) - 1)) * w.bw + (x - w.x0);
-                        e_seg[s] = gl + (unsigned)(yrel >> w.rshift);
-                        e_off[s] = c_offset(row_base, q7, k);
+                        e_pk[4 * s + c] = ok ? (c_offset(row_base, q7, k) | ((unsigned)(yrel >> w.rshift) << 16)) : 0xffff0000u;
                     }
-                    // samples of this lane that share a pixel: one entry with the summed coefficient
+                    e_cf[2 * s + 0] = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(wk[0])) |
+                                      ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(wk[1])) << 16);
+                    e_cf[2 * s + 1] = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(wk[2])) |
+                                      ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(wk[3])) << 16);
+                }
+                TR_ADD(2);
+                for (int sidx = 0; sidx <= w.nseg; ++sidx) {
+                    if (sidx > 0) {
+                        // the MMAs of segment sidx - 1 have read the block: zero what this thread put there
+                        mbar_wait(&bars.mma_done, waited & 1);
+                        TR_ADD(3);
+                        ++waited;
 #pragma unroll
-                    for (int a2 = 0; a2 < kMaxP; ++a2)
+                        for (int e = 0; e < 4 * kMaxP; ++e)
+                            if ((e_pk[e] >> 16) == (unsigned)(sidx - 1)) sts_u16(cb + (e_pk[e] & 0xffffu), 0);
+                        TR_ADD(8);
+                        if (sidx == w.nseg) break;
+                    }
 #pragma unroll
-                        for (int b2 = a2 + 1; b2 < kMaxP; ++b2)
-                            if (e_ok[a2] && e_ok[b2] && e_off[a2] == e_off[b2] && e_seg[a2] == e_seg[b2]) {
-                                e_c[a2] += e_c[b2];
-                                e_ok[b2] = false;
-                            }
-                    for (int sidx = 0; sidx < w.nseg; ++sidx, ++g) {
-                        const unsigned b = g & 1;
-                        if (g >= 2) mbar_wait(&bars.mma_done[b], ((g >> 1) - 1) & 1);
-                        const unsigned cb = sC_u32 + b * kCBytes;
-                        // clear what this thread wrote into this block two segments ago
-                        if ((pend_cur0 & 0xffffu) != 0xffffu) sts_u16(cb + (pend_cur0 & 0xffffu), 0);
-                        if ((pend_cur0 >> 16) != 0xffffu) sts_u16(cb + (pend_cur0 >> 16), 0);
-                        if ((pend_cur1 & 0xffffu) != 0xffffu) sts_u16(cb + (pend_cur1 & 0xffffu), 0);
-                        if ((pend_cur1 >> 16) != 0xffffu) sts_u16(cb + (pend_cur1 >> 16), 0);
-                        unsigned po[kMaxP];
-#pragma unroll
-                        for (int s = 0; s < kMaxP; ++s) {
-                            const bool wr = e_ok[s] && e_seg[s] == g;
-                            if (wr) sts_u16(cb + e_off[s], __bfloat16_as_ushort(__float2bfloat16_rn(e_c[s])));
-                            po[s] = wr ? e_off[s] : 0xffffu;
+                    for (int e = 0; e < 4 * kMaxP; ++e)
+                        if ((e_pk[e] >> 16) == (unsigned)sidx) {
+                            const unsigned addr = cb + (e_pk[e] & 0xffffu);
+                            unsigned short old;
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(old) : "r"(addr) : "memory");
+                            const float cf = __uint_as_float((e & 1) ? (e_cf[e >> 1] & 0xffff0000u) : (e_cf[e >> 1] << 16));
+                            const float sum = __uint_as_float((unsigned)old << 16) + cf;
+                            sts_u16(addr, __bfloat16_as_ushort(__float2bfloat16_rn(sum)));
                         }
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars.c_full[b]);
-                        // the other block is the current one of the next segment
-                        pend_cur0 = pend_oth0; pend_cur1 = pend_oth1;
-                        pend_oth0 = po[0] | (po[1] << 16); pend_oth1 = po[2] | (po[3] << 16);
-                    }
-                    gl = g;
+                    TR_ADD(9);
+                    fence_proxy_async();
+                    TR_ADD(10);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.c_full);
+                    TR_ADD(4);
                 }
             }
-            // ---- epilogue: accumulator rows -> output ----
-            if (nseg_total > 0) {
-                const unsigned tb = good & 1;
-                if (warp < 4) {
-                    mbar_wait(&bars.out_ready[tb], (good >> 1) & 1);
-                    tcgen05_fence_after();
+            // ---- accumulator row -> output ----
+            TR_ADD(5);
+            mbar_wait(&bars.out_ready, items_done & 1);
+            TR_ADD(6);
+            ++items_done;
+            tcgen05_fence_after();
+            if (!bad) {
+                if (nseg_total > 0) {
                     float v[32];
-                    tmem_ld32(tmem + ((unsigned)(warp * 32) << 16) + tb * kD, v);
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars.out_free[tb]);
-                    const int qe = tile_query(tl, tid);
-                    if (qe >= 0) {
-                        __nv_bfloat16* o = out + (((long long)n * Lq + qe) * M + h) * kD;
+                    tmem_ld32(tmem + ((unsigned)(warp * 32) << 16), v);
+                    if (qi >= 0) {
+                        __nv_bfloat16* o = out + (long long)pair * kD;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) stg_stream_v4(o + c * 8, pack<__nv_bfloat16>(v + c * 8));
                     }
-                }
-                ++good;
-            } else if (warp < 4) {
-                const int qe = tile_query(tl, tid);
-                if (qe >= 0) {
-                    __nv_bfloat16* o = out + (((long long)n * Lq + qe) * M + h) * kD;
+                } else if (qi >= 0) {
+                    __nv_bfloat16* o = out + (long long)pair * kD;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) stg_stream_v4(o + c * 8, make_uint4(0u, 0u, 0u, 0u));
                 }
+            } else if (tid == 0) {
+                const int slot = atomicAdd(bad_list, 1);
+                if (slot < bad_cap) bad_list[1 + slot] = item;
             }
+            tcgen05_fence_before();
+            item = item_next; h = h2; n = n2; qi = qi2; pair = pair2;
+            TR_ADD(7);
         }
+        Window wend;
+        wend.bw = 8; wend.rows = 0; wend.rshift = 4; wend.nseg = 0; wend.x0 = 0; wend.y0 = 0;
+        publish(kLpEnd, wend, 0, 0, 0);
     }
+    if (tracing && blockIdx.x < 64) {
+        const int role = warp == 0 ? 0 : warp - 3;          // 0 build, 1 producer, 2 issuer
+#pragma unroll
+        for (int i = 0; i < 12; ++i) trace[(blockIdx.x * 3 + role) * 12 + i] = tr[i];
+    }
+#undef TR_START
+#undef TR_ADD
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_free(tmem, 64);
+    if (warp == 0) tmem_free(tmem, 32);
+}
+
+// Tiles the tensor-core kernel could not take: 4 lanes per query (16 bytes of the head's 64-byte row each), 8 queries
+// per warp, every lane walks all samples of its query.
+__global__ void __launch_bounds__(128)
+msda_tc_fwd_fallback_kernel(const __nv_bfloat16* __restrict__ value, const int64_t* __restrict__ shapes,
+                            const int64_t* __restrict__ lsi, const float* __restrict__ loc, const float* __restrict__ attn,
+                            __nv_bfloat16* __restrict__ out, int N, int S, int M, int L, int Lq, int P, int value_ld,
+                            int want_pyramid, const int* __restrict__ bad_list, int bad_cap)
+{
+    __shared__ LevelMeta lm;
+    const int count = min(bad_list[0], bad_cap);
+    if (count == 0) return;
+    if (threadIdx.x == 0) level_meta_init(&lm, shapes, lsi, L, Lq, want_pyramid);
+    __syncthreads();
+    const int tiles = lm.tiles;
+    const int LP = L * P;
+    const int slot_in_cta = threadIdx.x >> 2, j = threadIdx.x & 3;
+    for (long long unit = blockIdx.x; unit < (long long)count * 4; unit += gridDim.x) {
+        const long long item = bad_list[1 + unit / 4];
+        const int h = (int)(item % M);
+        const long long rest = item / M;
+        const Tile tl = tile_decode(lm, (int)(rest % tiles), L, Lq);
+        const int n = (int)(rest / tiles);
+        const int qi = tile_query(tl, (int)(unit % 4) * 32 + slot_in_cta);
+        if (qi < 0) continue;
+        const long long pair = ((long long)n * Lq + qi) * M + h;
+        const __nv_bfloat16* vbase = value + (long long)n * S * value_ld + h * kD + j * 8;
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+        for (int l = 0; l < L; ++l) {
+            const int H = lm.H[l], W = lm.W[l], start = lm.start[l];
+            for (int s = 0; s < P; ++s) {
+                const float2 xy = *reinterpret_cast<const float2*>(loc + (pair * LP + l * P + s) * 2);
+                const float a = attn[pair * LP + l * P + s];
+                const Footprint f = footprint<float>(xy.x, xy.y, H, W, start);
+                if (!f.ok) continue;
+                const float hw = 1.f - f.lw, hh = 1.f - f.lh;
+                const float wk[4] = {hh * hw * a, hh * f.lw * a, f.lh * hw * a, f.lh * f.lw * a};
+                const int pix[4] = {f.pix00, f.pix00 + 1, f.pix00 + W, f.pix00 + W + 1};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (f.ok & (1u << k)) {
+                        float v[8];
+                        unpack<__nv_bfloat16>(ldg_v4(vbase + (long long)pix[k] * value_ld), v);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[c] = fmaf(wk[k], v[c], acc[c]);
+                    }
+            }
+        }
+        stg_stream_v4(out + pair * kD + j * 8, pack<__nv_bfloat16>(acc));
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -421,13 +480,17 @@ bool make_value_maps(Maps* maps, const void* value, long long pixels, long long 
     return true;
 }
 
+// upper bound of the tiles of one frame for either tiling (host side: the level shapes live on the device)
+long long tile_bound(int L, int Lq) { return (long long)Lq / 5 + L + 2; }
+
 }  // namespace tc
 
 bool tc_forward_supported(const FwdArgs& a)
 {
     return a.dtype == kBF16 && a.D == tc::kD && a.L >= 1 && a.L <= tc::kMaxL && a.P >= 1 && a.P <= tc::kMaxP &&
            !a.force_generic && (long long)a.N * a.S < (1ll << 31) && ((size_t)a.value % 16) == 0 &&
-           (long long)a.N * a.Lq >= 2048;
+           (long long)a.N * a.Lq >= 2048 && (long long)a.N * a.M * tc::tile_bound(a.L, a.Lq) < (1ll << 30) &&
+           (long long)a.N * a.Lq * a.M < (1ll << 30);
 }
 
 cudaError_t tc_forward(const FwdArgs& a, cudaStream_t stream)
@@ -444,10 +507,51 @@ cudaError_t tc_forward(const FwdArgs& a, cudaStream_t stream)
     alignas(64) tc::Maps maps;
     if (!tc::make_value_maps(&maps, a.value, (long long)a.N * a.S, (long long)a.M * a.D)) return cudaErrorNotSupported;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    tc::msda_tc_fwd_kernel<<<sms, tc::kFwdThreads, tc::kFwdSmem, stream>>>(
-        maps, (const __nv_bfloat16*)a.value, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn,
-        (__nv_bfloat16*)a.out, a.N, a.S, a.M, a.L, a.Lq, a.P, a.M * a.D, 1);
-    return cudaGetLastError();
+    // tiles the kernel hands to the plain-load gather: [0] = count, [1 ...] = items
+    const int bad_cap = (int)((long long)a.N * a.M * tc::tile_bound(a.L, a.Lq));
+    int* bad_list = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&bad_list, ((size_t)bad_cap + 1) * sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(bad_list, 0, sizeof(int), stream);
+    static const bool want_trace = getenv("MSDA_TC_TRACE") != nullptr;       // development aid: per-role cycle accounting
+    unsigned long long* trace = nullptr;
+    if (want_trace) { cudaMalloc((void**)&trace, 64 * 3 * 12 * 8); cudaMemset(trace, 0, 64 * 3 * 12 * 8); }
+    if (e == cudaSuccess) {
+        tc::msda_tc_fwd_kernel<<<4 * sms, tc::kFwdThreads, tc::kFwdSmem, stream>>>(
+            maps, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn, (__nv_bfloat16*)a.out,
+            a.N, a.S, a.M, a.L, a.Lq, a.P, 1, bad_list, bad_cap, trace);
+        e = cudaGetLastError();
+    }
+    if (want_trace) {
+        cudaStreamSynchronize(stream);
+        unsigned long long h[64 * 3 * 12];
+        cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(trace);
+        static const char* names[3][12] = {
+            {"load+footprint", "bbox barrier", "window+entries", "wait mma_done", "syncwarp+arrive", "to epilogue",
+             "wait out_ready", "epilogue", "clear", "write", "fence.proxy", "-"},
+            {"wait plan", "wait v_free", "issue TMA", "-", "-", "-", "-", "-", "-", "-", "-", "-"},
+            {"wait plan", "wait c_full", "wait v_full", "commit+syncwarp", "(k-steps)", "(segments)", "-", "-", "fence_after",
+             "issue loop", "-", "-"}};
+        static const char* roles[3] = {"build", "producer", "issuer"};
+        for (int role = 0; role < 3; ++role) {
+            fprintf(stderr, "[tc fwd trace] %-8s:", roles[role]);
+            for (int i = 0; i < 12; ++i) {
+                double sum = 0;
+                for (int b = 0; b < 64; ++b) sum += (double)h[(b * 3 + role) * 12 + i];
+                if (names[role][i][0] != '-') fprintf(stderr, "  %s %.0f", names[role][i], sum / 64);
+            }
+            fprintf(stderr, "\n");
+        }
+    }
+    if (e == cudaSuccess) {
+        tc::msda_tc_fwd_fallback_kernel<<<8 * sms, 128, 0, stream>>>(
+            (const __nv_bfloat16*)a.value, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn,
+            (__nv_bfloat16*)a.out, a.N, a.S, a.M, a.L, a.Lq, a.P, a.M * a.D, 1, bad_list, bad_cap);
+        e = cudaGetLastError();
+    }
+    const cudaError_t e2 = cudaFreeAsync(bad_list, stream);
+    return e != cudaSuccess ? e : e2;
 }
 
 }  // namespace msda

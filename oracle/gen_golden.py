@@ -538,6 +538,40 @@ def main():
                         t["level_start_index"], t["padding_mask"]),
         wrt=["src", "pos"], store=np.float32, grad_limit=20000)
 
+    # BASELINE.json configs[2] / [3] at the production width: Encoder Cross Fusion V2 (:406-461) with a one-level and a
+    # two-level depth pyramid, and the Late Fusion layer (:341-402); d_model 256, 8 heads of 32, 4 points, d_ffn 256
+    torch.manual_seed(73)
+    depth_p = torch.randn(n, sd, 256)
+    fusion_p = single.DeformableTransformerFusionLayerV2(256, 256, 0.0, "gelu", 1, 8, 4).double()
+    perturb(fusion_p, 74, std=0.03)
+    save_module_case(
+        "layer_fusion_v2_c256", fusion_p,
+        dict(tgt=feat_p, query_pos=pos_p, reference_points=ref_d1, src=depth_p, src_spatial_shapes=dshapes,
+             level_start_index=dlsi, src_padding_mask=dmask),
+        lambda m_, t: m_(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                        t["level_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"], store=np.float32, grad_limit=20000)
+    torch.manual_seed(75)
+    depth_p2 = torch.randn(n, s, 256)              # a depth pyramid with the RGB shapes
+    fusion_p2 = single.DeformableTransformerFusionLayerV2(256, 256, 0.0, "gelu", 2, 8, 4).double()
+    perturb(fusion_p2, 76, std=0.03)
+    save_module_case(
+        "layer_fusion_v2_c256_l2", fusion_p2,
+        dict(tgt=feat_p, query_pos=pos_p, reference_points=ref2, src=depth_p2, src_spatial_shapes=shapes_t,
+             level_start_index=lsi, src_padding_mask=mask),
+        lambda m_, t: m_(t["tgt"], t["query_pos"], t["reference_points"], t["src"], t["src_spatial_shapes"],
+                        t["level_start_index"], t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"], store=np.float32, grad_limit=20000)
+    late_p = single.DepthDeformableTransformerEncoderLayer(256, 256, 0.0, "relu", 1, 8, 4, True, True, True).double()
+    perturb(late_p, 77, std=0.03)
+    save_module_case(
+        "layer_late_fusion_c256", late_p,
+        dict(tgt=feat_p, query_pos=pos_p, reference_points=ref_d1, src=depth_p, src_spatial_shapes=dshapes,
+             frame_start_index=dlsi, src_padding_mask=dmask),
+        lambda m_, t: m_(t["tgt"], t["query_pos"], None, None, t["reference_points"], None, t["src"],
+                        t["src_spatial_shapes"], t["frame_start_index"], None, t["src_padding_mask"]),
+        wrt=["tgt", "query_pos", "src"], store=np.float32, grad_limit=20000)
+
     # ---------------- temporal layers ----------------------------------------------------------------
     # frames-as-levels layer (deformable_transformer_single.py:650-700): 3 reference frames of (4,5)
     fshapes = torch.as_tensor([(4, 5)] * 3, dtype=torch.long)

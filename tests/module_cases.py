@@ -84,7 +84,8 @@ CASES = {
 # kernels run in fp32; d_model 256 is the production width (bf16 kernels).
 CW, HW, PW, FFW = 128, 8, 4, 128
 WIDE = {"layer_encoder_c128", "encoder_plain_c128", "layer_fusion_v2_c128", "decoder_c128",
-        "backbone_udf_fuse_c128", "layer_encoder_c256"}
+        "backbone_udf_fuse_c128", "layer_encoder_c256", "layer_fusion_v2_c256", "layer_fusion_v2_c256_l2",
+        "layer_late_fusion_c256"}
 
 
 def _decoder_call(m, t):
@@ -100,6 +101,16 @@ CASES.update({
     "layer_encoder_c256": dict(
         build=lambda: tl.DeformableTransformerEncoderLayer(256, 256, 0.0, "relu", 2, 8, 4),
         call=CASES["layer_encoder"]["call"], wrt=["src", "pos"]),
+    # BASELINE.json configs[2] / [3] at the production width (bf16 kernels incl. the tcgen05 projection + LayerNorm path)
+    "layer_fusion_v2_c256": dict(
+        build=lambda: tl.DeformableTransformerFusionLayerV2(256, 256, 0.0, "gelu", 1, 8, 4),
+        call=CASES["layer_fusion_v2"]["call"], wrt=["tgt", "query_pos", "src"]),
+    "layer_fusion_v2_c256_l2": dict(
+        build=lambda: tl.DeformableTransformerFusionLayerV2(256, 256, 0.0, "gelu", 2, 8, 4),
+        call=CASES["layer_fusion_v2"]["call"], wrt=["tgt", "query_pos", "src"]),
+    "layer_late_fusion_c256": dict(
+        build=lambda: tl.DepthDeformableTransformerEncoderLayer(256, 256, 0.0, "relu", 1, 8, 4, True, True, True),
+        call=CASES["layer_late_fusion"]["call"], wrt=["tgt", "query_pos", "src"]),
     "encoder_plain_c128": dict(
         build=lambda: tl.DeformableTransformerEncoder(
             tl.DeformableTransformerEncoderLayer(CW, FFW, 0.0, "relu", 2, HW, PW), 2),
