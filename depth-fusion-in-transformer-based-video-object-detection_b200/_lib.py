@@ -14,7 +14,7 @@ ABI_VERSION = 16
 DTYPE_F32, DTYPE_F64, DTYPE_BF16, DTYPE_F16 = 0, 1, 2, 3
 FLAG_FORCE_GENERIC = 1
 FLAG_BF16_WEIGHTS = 2
-FLAG_NO_TC = 4
+FLAG_TC = 4
 
 _lib = None
 

@@ -29,7 +29,7 @@ extern "C" int msda_forward(int dtype, const void* value, const int64_t* spatial
     a.N = batch; a.S = spatial_size; a.M = num_heads; a.D = channels;
     a.L = num_levels; a.Lq = num_query; a.P = num_point;
     a.force_generic = (flags & MSDA_FLAG_FORCE_GENERIC) ? 1 : 0;
-    a.no_tc = (flags & MSDA_FLAG_NO_TC) ? 1 : 0;
+    a.no_tc = (flags & MSDA_FLAG_TC) ? 0 : 1;
     if (num_levels == 0 || num_point == 0) {   // empty sum: output is all zeros
         const size_t esz = dtype == MSDA_DTYPE_F64 ? 8 : (dtype == MSDA_DTYPE_F32 ? 4 : 2);
         return (int)cudaMemsetAsync(output, 0, (size_t)batch * num_query * num_heads * channels * esz,
@@ -56,7 +56,7 @@ extern "C" int msda_backward(int dtype, const void* grad_output, const void* val
     a.N = batch; a.S = spatial_size; a.M = num_heads; a.D = channels;
     a.L = num_levels; a.Lq = num_query; a.P = num_point;
     a.force_generic = (flags & MSDA_FLAG_FORCE_GENERIC) ? 1 : 0;
-    a.no_tc = (flags & MSDA_FLAG_NO_TC) ? 1 : 0;
+    a.no_tc = (flags & MSDA_FLAG_TC) ? 0 : 1;
     return (int)msda::backward(a, (cudaStream_t)stream);
 }
 

@@ -17,7 +17,7 @@ struct FwdArgs {
     void* out;                // [N,Lq,M,D] dtype
     int N, S, M, D, L, Lq, P;
     int force_generic;        // tests: route through the generic kernel
-    int no_tc;                // A/B and tests: keep the lane-group gather where the tensor-core kernel would run
+    int no_tc;                // 0: take the tensor-core formulation (msda_tc_forward.cu) where it applies (opt-in)
 };
 
 struct BwdArgs {

@@ -182,5 +182,135 @@ __device__ __forceinline__ int seg_rows(const Window& w, int sidx)
     return r;
 }
 
+// ---- one level of one query: samples -> footprints -> C entries ----------------------------------------------
+// the samples of one (pair, level): P <= 4 locations and attention weights
+struct LevelSamples { float x[kMaxP], y[kMaxP], a[kMaxP]; };
+
+__device__ __forceinline__ void load_level(LevelSamples& ls, const float* __restrict__ loc, const float* __restrict__ attn,
+                                           int pair, int LP, int l, int P, bool have)
+{
+#pragma unroll
+    for (int s = 0; s < kMaxP; ++s) { ls.x[s] = -4.f; ls.y[s] = -4.f; ls.a[s] = 0.f; }     // far outside: contributes nothing
+    if (!have) return;
+    const float* lp = loc + ((long long)pair * LP + l * P) * 2;
+    const float* ap = attn + (long long)pair * LP + l * P;
+    if (P == kMaxP) {
+        const uint4 u0 = ldg_prefetch_v4(lp), u1 = ldg_prefetch_v4(lp + 4), ua = ldg_prefetch_v4(ap);
+        ls.x[0] = __uint_as_float(u0.x); ls.y[0] = __uint_as_float(u0.y); ls.x[1] = __uint_as_float(u0.z); ls.y[1] = __uint_as_float(u0.w);
+        ls.x[2] = __uint_as_float(u1.x); ls.y[2] = __uint_as_float(u1.y); ls.x[3] = __uint_as_float(u1.z); ls.y[3] = __uint_as_float(u1.w);
+        ls.a[0] = __uint_as_float(ua.x); ls.a[1] = __uint_as_float(ua.y); ls.a[2] = __uint_as_float(ua.z); ls.a[3] = __uint_as_float(ua.w);
+    } else {
+#pragma unroll
+        for (int s = 0; s < kMaxP; ++s)
+            if (s < P) {
+                const float2 xy = ldg_prefetch_f32x2(lp + 2 * s);
+                ls.x[s] = xy.x; ls.y[s] = xy.y;
+                ls.a[s] = ldg_prefetch_f32(ap + s);
+            }
+    }
+}
+
+// bilinear footprints of the level's samples (reference cuh:285-288, :33-84)
+struct Footprints {
+    int bx[kMaxP], by[kMaxP];        // floor of the pixel coordinates
+    float lw[kMaxP], lh[kMaxP];      // fractional parts
+    unsigned inside;                 // bit s: sample s passes the reference's range test (cuh:288)
+};
+__device__ __forceinline__ void footprints_of(const LevelSamples& ls, int H, int W, Footprints& f)
+{
+    f.inside = 0;
+#pragma unroll
+    for (int s = 0; s < kMaxP; ++s) {
+        const float w_im = ls.x[s] * (float)W - 0.5f, h_im = ls.y[s] * (float)H - 0.5f;
+        const bool in = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        f.bx[s] = (int)wf; f.by[s] = (int)hf;
+        f.lw[s] = w_im - wf; f.lh[s] = h_im - hf;
+        if (in) f.inside |= 1u << s;
+    }
+}
+// bounding box of the corner pixels of this thread's samples, reduced over the warp and merged into bb[4]
+// (min x, min y, max x, max y) in shared memory
+__device__ __forceinline__ void bbox_merge(const Footprints& f, int H, int W, int lane, int* bb)
+{
+    int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -2, mxy = -2;
+#pragma unroll
+    for (int s = 0; s < kMaxP; ++s)
+        if ((f.inside >> s) & 1u) {
+            mnx = min(mnx, f.bx[s]); mxx = max(mxx, f.bx[s]);
+            mny = min(mny, f.by[s]); mxy = max(mxy, f.by[s]);
+        }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if (lane == 0 && mxx >= -1) {        // inside samples have bx in [-1, W-1]: clamp the corner range to the map
+        atomicMin(&bb[0], max(mnx, 0)); atomicMin(&bb[1], max(mny, 0));
+        atomicMax(&bb[2], min(mxx + 1, W - 1)); atomicMax(&bb[3], min(mxy + 1, H - 1));
+    }
+}
+
+// C entries of one sample: its 4 corners as (byte offset in the C block, 0xffff = corner outside the map), the
+// segments of its two pixel rows (0xff = row outside the map) and the 4 coefficients rounded to bf16
+struct SampleEntries {
+    unsigned off01, off23;       // corners (y0,x0) | (y0,x1) << 16 ;  (y1,x0) | (y1,x1) << 16
+    unsigned cf01, cf23;         // bf16 coefficients, same packing
+    unsigned segs;               // segment of row y0 | segment of row y1 << 8
+};
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi)
+{
+    return (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+}
+__device__ __forceinline__ void sample_entries(const Footprints& f, int s, float a, const Window& w, int H, int W,
+                                               unsigned row_base, int q7, SampleEntries& e)
+{
+    const bool in = (f.inside >> s) & 1u;
+    const int bx = f.bx[s], by = f.by[s];
+    const bool x0ok = in && bx >= 0, x1ok = in && bx + 1 < W, y0ok = by >= 0, y1ok = by + 1 < H;
+    const int kx = bx - w.x0, y0r = by - w.y0, rmask = (1 << w.rshift) - 1;
+    const int k0 = (y0r & rmask) * w.bw + kx, k1 = ((y0r + 1) & rmask) * w.bw + kx;
+    const unsigned o00 = (x0ok && y0ok) ? c_offset(row_base, q7, k0) : 0xffffu;
+    const unsigned o01 = (x1ok && y0ok) ? c_offset(row_base, q7, k0 + 1) : 0xffffu;
+    const unsigned o10 = (x0ok && y1ok) ? c_offset(row_base, q7, k1) : 0xffffu;
+    const unsigned o11 = (x1ok && y1ok) ? c_offset(row_base, q7, k1 + 1) : 0xffffu;
+    e.off01 = o00 | (o01 << 16);
+    e.off23 = o10 | (o11 << 16);
+    e.segs = ((in && y0ok) ? (unsigned)(y0r >> w.rshift) : 0xffu) | (((in && y1ok) ? (unsigned)((y0r + 1) >> w.rshift) : 0xffu) << 8);
+    const float hw = 1.f - f.lw[s], hh = 1.f - f.lh[s];
+    e.cf01 = pack_bf16x2(hh * hw * a, hh * f.lw[s] * a);            // (bilinear weight) x attention weight, cuh:113-116
+    e.cf23 = pack_bf16x2(f.lh[s] * hw * a, f.lh[s] * f.lw[s] * a);
+}
+// add one pixel row of a sample (two corners) into the thread's row of the C block / zero it again
+__device__ __forceinline__ void c_row_add(unsigned cb, unsigned offs, unsigned cfs)
+{
+    const unsigned o0 = offs & 0xffffu, o1 = offs >> 16;
+    unsigned short v0 = 0, v1 = 0;
+    if (o0 != 0xffffu) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v0) : "r"(cb + o0));
+    if (o1 != 0xffffu) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v1) : "r"(cb + o1));
+    const float s0 = __uint_as_float((unsigned)v0 << 16) + __uint_as_float(cfs << 16);
+    const float s1 = __uint_as_float((unsigned)v1 << 16) + __uint_as_float(cfs & 0xffff0000u);
+    if (o0 != 0xffffu) asm volatile("st.shared.u16 [%0], %1;" :: "r"(cb + o0), "h"(__bfloat16_as_ushort(__float2bfloat16_rn(s0))));
+    if (o1 != 0xffffu) asm volatile("st.shared.u16 [%0], %1;" :: "r"(cb + o1), "h"(__bfloat16_as_ushort(__float2bfloat16_rn(s1))));
+}
+__device__ __forceinline__ void c_row_clear(unsigned cb, unsigned offs)
+{
+    const unsigned o0 = offs & 0xffffu, o1 = offs >> 16;
+    const unsigned short z = 0;
+    if (o0 != 0xffffu) asm volatile("st.shared.u16 [%0], %1;" :: "r"(cb + o0), "h"(z));
+    if (o1 != 0xffffu) asm volatile("st.shared.u16 [%0], %1;" :: "r"(cb + o1), "h"(z));
+}
+
+// mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of re-polling every few cycles:
+// the polling loops of idle roles were a quarter of all executed instructions (profiles/: ncu source page, round 2)
+__device__ __forceinline__ void mbar_wait_parked(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITP_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONEP_%=;\n\t"
+        "bra WAITP_%=;\n\t"
+        "DONEP_%=:\n\t}\n"
+        :: "r"(umma::smem_u32(bar)), "r"(parity), "r"(4096u) : "memory");
+}
+
 }  // namespace tc
 }  // namespace msda

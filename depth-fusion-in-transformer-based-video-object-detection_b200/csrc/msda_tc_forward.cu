@@ -37,6 +37,9 @@ constexpr int kFwdThreads = kFwdBuild + 64;
 constexpr int kFwdVStages = 2;
 constexpr int kFwdSmem = kCBytes + kFwdVStages * kVBytes + 1024;
 constexpr int kLpRing = 4;
+#ifndef MSDA_TC_FWD_CTAS
+#define MSDA_TC_FWD_CTAS 3       // resident CTAs per SM the register budget must allow
+#endif
 enum { kLpTileStart = 1, kLpTileEnd = 2, kLpEnd = 4 };
 
 struct LevelPlan {
@@ -51,34 +54,7 @@ struct FwdBars {
     unsigned long long lp_ready[kLpRing], lp_free[kLpRing];
 };
 
-// the samples of one (pair, level): P <= 4 locations and attention weights
-struct LevelSamples { float x[kMaxP], y[kMaxP], a[kMaxP]; };
-
-__device__ __forceinline__ void load_level(LevelSamples& ls, const float* __restrict__ loc, const float* __restrict__ attn,
-                                           int pair, int LP, int l, int P, bool have)
-{
-#pragma unroll
-    for (int s = 0; s < kMaxP; ++s) { ls.x[s] = -4.f; ls.y[s] = -4.f; ls.a[s] = 0.f; }     // far outside: contributes nothing
-    if (!have) return;
-    const float* lp = loc + ((long long)pair * LP + l * P) * 2;
-    const float* ap = attn + (long long)pair * LP + l * P;
-    if (P == kMaxP) {
-        const uint4 u0 = ldg_prefetch_v4(lp), u1 = ldg_prefetch_v4(lp + 4), ua = ldg_prefetch_v4(ap);
-        ls.x[0] = __uint_as_float(u0.x); ls.y[0] = __uint_as_float(u0.y); ls.x[1] = __uint_as_float(u0.z); ls.y[1] = __uint_as_float(u0.w);
-        ls.x[2] = __uint_as_float(u1.x); ls.y[2] = __uint_as_float(u1.y); ls.x[3] = __uint_as_float(u1.z); ls.y[3] = __uint_as_float(u1.w);
-        ls.a[0] = __uint_as_float(ua.x); ls.a[1] = __uint_as_float(ua.y); ls.a[2] = __uint_as_float(ua.z); ls.a[3] = __uint_as_float(ua.w);
-    } else {
-#pragma unroll
-        for (int s = 0; s < kMaxP; ++s)
-            if (s < P) {
-                const float2 xy = ldg_prefetch_f32x2(lp + 2 * s);
-                ls.x[s] = xy.x; ls.y[s] = xy.y;
-                ls.a[s] = ldg_prefetch_f32(ap + s);
-            }
-    }
-}
-
-__global__ void __launch_bounds__(kFwdThreads, 4)
+__global__ void __launch_bounds__(kFwdThreads, MSDA_TC_FWD_CTAS)
 msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                    const float* __restrict__ loc, const float* __restrict__ attn, __nv_bfloat16* __restrict__ out,
                    int N, int S, int M, int L, int Lq, int P, int want_pyramid, int* __restrict__ bad_list, int bad_cap,
@@ -116,12 +92,20 @@ msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const int64_t* __restrict_
     __syncthreads();
     tcgen05_fence_after();
     const unsigned tmem = tmem_base_s;
-    // optional cycle accounting (MSDA_TC_TRACE=1): one representative thread per role accumulates where its time goes
+    // optional cycle accounting (compile with -DMSDA_TC_TRACE, run with MSDA_TC_TRACE=1): one representative thread
+    // per role accumulates where its time goes
+#ifdef MSDA_TC_TRACE
     unsigned long long tr[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tr_t = 0;
     const bool tracing = trace != nullptr && lane == 0 && (warp == 0 || warp >= 4);
 #define TR_START() do { if (tracing) tr_t = clock64(); } while (0)
 #define TR_ADD(i) do { if (tracing) { const long long t_ = clock64(); tr[i] += (unsigned long long)(t_ - tr_t); tr_t = t_; } } while (0)
+#define TR_COUNT(i, v) do { if (tracing) tr[i] += (v); } while (0)
+#else
+#define TR_START() do { } while (0)
+#define TR_ADD(i) do { } while (0)
+#define TR_COUNT(i, v) do { } while (0)
+#endif
 
     if (warp == 5) {
         // ================================ MMA issuer ================================
@@ -154,14 +138,14 @@ msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const int64_t* __restrict_
                     for (int ks = 0; ks < ksteps; ++ks)
                         mma_bf16(tmem, desc_advance(descA, (unsigned)((ks >> 2) * 16384 + (ks & 3) * 32)),
                                  desc_advance(descB[vs], (unsigned)(ks * 1024)), idesc, !(first && ks == 0));
-                    if (tracing) { const long long t_ = clock64(); tr[9] += (unsigned long long)(t_ - tr_t); tr_t = t_; }
+                    TR_ADD(9);
                     mma_commit(&bars.mma_done);
                     mma_commit(&bars.v_free[vs]);
                 }
                 __syncwarp();
                 first = false;
                 TR_ADD(3);
-                if (tracing) { tr[4] += ksteps; tr[5] += 1; }
+                TR_COUNT(4, ksteps); TR_COUNT(5, 1);
             }
             if (pl.flags & kLpTileEnd) {
                 if (elect_one()) mma_commit(&bars.out_ready);
@@ -250,30 +234,11 @@ msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const int64_t* __restrict_
                 if (l + 1 < L) load_level(pf, loc, attn, pair, LP, l + 1, P, qi >= 0);
                 else if (item_next < total_items) load_level(pf, loc, attn, pair2, LP, 0, P, qi2 >= 0);
                 const int H = lm.H[l], W = lm.W[l];
-                // ---- footprints (cuh:285-288, :33-84) and the bounding box of this query's corner pixels ----
-                int bx[kMaxP], by[kMaxP];
-                float lw[kMaxP], lh[kMaxP];
-                unsigned inside = 0;
-                int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -1, mxy = -1;
-#pragma unroll
-                for (int s = 0; s < kMaxP; ++s) {
-                    const float w_im = ls.x[s] * (float)W - 0.5f, h_im = ls.y[s] * (float)H - 0.5f;
-                    const bool in = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
-                    const float hf = floorf(h_im), wf = floorf(w_im);
-                    bx[s] = (int)wf; by[s] = (int)hf;
-                    lw[s] = w_im - wf; lh[s] = h_im - hf;
-                    if (in) {
-                        inside |= 1u << s;
-                        mnx = min(mnx, max(bx[s], 0)); mxx = max(mxx, min(bx[s] + 1, W - 1));
-                        mny = min(mny, max(by[s], 0)); mxy = max(mxy, min(by[s] + 1, H - 1));
-                    }
-                }
-                mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
-                mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+                // ---- footprints and the bounding box of the tile's corner pixels on this level ----
+                Footprints fp;
+                footprints_of(ls, H, W, fp);
                 int* bb = s_bb[u % 3];
-                if (lane == 0 && mxx >= 0) {
-                    atomicMin(&bb[0], mnx); atomicMin(&bb[1], mny); atomicMax(&bb[2], mxx); atomicMax(&bb[3], mxy);
-                }
+                bbox_merge(fp, H, W, lane, bb);
                 TR_ADD(0);
                 named_bar_sync(1, kFwdBuild);
                 TR_ADD(1);
@@ -296,26 +261,10 @@ msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const int64_t* __restrict_
                         n * S + lm.start[l] + w.y0 * W + w.x0, W, h);
                 if (w.nseg == 0) continue;
                 nseg_total += w.nseg;
-                // ---- this query's entries of the level: (C offset | segment << 16), coefficient ----
-                unsigned e_pk[4 * kMaxP];
-                unsigned e_cf[2 * kMaxP];        // coefficients, rounded to bf16, two per register
+                // ---- this query's entries of the level ----
+                SampleEntries en[kMaxP];
 #pragma unroll
-                for (int s = 0; s < kMaxP; ++s) {
-                    const float hw = 1.f - lw[s], hh = 1.f - lh[s];
-                    const float wk[4] = {hh * hw * ls.a[s], hh * lw[s] * ls.a[s], lh[s] * hw * ls.a[s], lh[s] * lw[s] * ls.a[s]};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int x = bx[s] + (c & 1), y = by[s] + (c >> 1);
-                        const bool ok = ((inside >> s) & 1u) && x >= 0 && x < W && y >= 0 && y < H;
-                        const int yrel = y - w.y0;
-                        const int k = (yrel & ((1 << w.rshift) - 1)) * w.bw + (x - w.x0);
-                        e_pk[4 * s + c] = ok ? (c_offset(row_base, q7, k) | ((unsigned)(yrel >> w.rshift) << 16)) : 0xffff0000u;
-                    }
-                    e_cf[2 * s + 0] = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(wk[0])) |
-                                      ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(wk[1])) << 16);
-                    e_cf[2 * s + 1] = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(wk[2])) |
-                                      ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(wk[3])) << 16);
-                }
+                for (int s = 0; s < kMaxP; ++s) sample_entries(fp, s, ls.a[s], w, H, W, row_base, q7, en[s]);
                 TR_ADD(2);
                 for (int sidx = 0; sidx <= w.nseg; ++sidx) {
                     if (sidx > 0) {
@@ -324,21 +273,19 @@ msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const int64_t* __restrict_
                         TR_ADD(3);
                         ++waited;
 #pragma unroll
-                        for (int e = 0; e < 4 * kMaxP; ++e)
-                            if ((e_pk[e] >> 16) == (unsigned)(sidx - 1)) sts_u16(cb + (e_pk[e] & 0xffffu), 0);
+                        for (int s = 0; s < kMaxP; ++s) {      // predicated, not branched: the rows of a warp's queries differ
+                            c_row_clear(cb, (en[s].segs & 0xffu) == (unsigned)(sidx - 1) ? en[s].off01 : 0xffffffffu);
+                            c_row_clear(cb, (en[s].segs >> 8) == (unsigned)(sidx - 1) ? en[s].off23 : 0xffffffffu);
+                        }
                         TR_ADD(8);
                         if (sidx == w.nseg) break;
                     }
+                    // read-modify-write: the row is private to this thread; samples that share a pixel follow each other
 #pragma unroll
-                    for (int e = 0; e < 4 * kMaxP; ++e)
-                        if ((e_pk[e] >> 16) == (unsigned)sidx) {
-                            const unsigned addr = cb + (e_pk[e] & 0xffffu);
-                            unsigned short old;
-                            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(old) : "r"(addr) : "memory");
-                            const float cf = __uint_as_float((e & 1) ? (e_cf[e >> 1] & 0xffff0000u) : (e_cf[e >> 1] << 16));
-                            const float sum = __uint_as_float((unsigned)old << 16) + cf;
-                            sts_u16(addr, __bfloat16_as_ushort(__float2bfloat16_rn(sum)));
-                        }
+                    for (int s = 0; s < kMaxP; ++s) {
+                        c_row_add(cb, (en[s].segs & 0xffu) == (unsigned)sidx ? en[s].off01 : 0xffffffffu, en[s].cf01);
+                        c_row_add(cb, (en[s].segs >> 8) == (unsigned)sidx ? en[s].off23 : 0xffffffffu, en[s].cf23);
+                    }
                     TR_ADD(9);
                     fence_proxy_async();
                     TR_ADD(10);
@@ -379,13 +326,16 @@ msda_tc_fwd_kernel(const __grid_constant__ Maps maps, const int64_t* __restrict_
         wend.bw = 8; wend.rows = 0; wend.rshift = 4; wend.nseg = 0; wend.x0 = 0; wend.y0 = 0;
         publish(kLpEnd, wend, 0, 0, 0);
     }
+#ifdef MSDA_TC_TRACE
     if (tracing && blockIdx.x < 64) {
         const int role = warp == 0 ? 0 : warp - 3;          // 0 build, 1 producer, 2 issuer
 #pragma unroll
         for (int i = 0; i < 12; ++i) trace[(blockIdx.x * 3 + role) * 12 + i] = tr[i];
     }
+#endif
 #undef TR_START
 #undef TR_ADD
+#undef TR_COUNT
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) tmem_free(tmem, 32);
@@ -517,7 +467,7 @@ cudaError_t tc_forward(const FwdArgs& a, cudaStream_t stream)
     unsigned long long* trace = nullptr;
     if (want_trace) { cudaMalloc((void**)&trace, 64 * 3 * 12 * 8); cudaMemset(trace, 0, 64 * 3 * 12 * 8); }
     if (e == cudaSuccess) {
-        tc::msda_tc_fwd_kernel<<<4 * sms, tc::kFwdThreads, tc::kFwdSmem, stream>>>(
+        tc::msda_tc_fwd_kernel<<<MSDA_TC_FWD_CTAS * sms, tc::kFwdThreads, tc::kFwdSmem, stream>>>(
             maps, a.shapes, a.lsi, (const float*)a.loc, (const float*)a.attn, (__nv_bfloat16*)a.out,
             a.N, a.S, a.M, a.L, a.Lq, a.P, 1, bad_list, bad_cap, trace);
         e = cudaGetLastError();

@@ -49,8 +49,10 @@ typedef enum {
                                        bilinear weight) to bf16 and accumulate with the mixed-precision FMA
                                        (fp32 accumulator) -- half the math instructions; inference option */
 
-#define MSDA_FLAG_NO_TC 4           /* msda_forward / msda_backward: keep the lane-group gather kernels where the
-                                       tensor-core (tcgen05) formulation would run -- A/B measurements, tests */
+#define MSDA_FLAG_TC 4              /* msda_forward: run the tensor-core (tcgen05 + TMA) formulation of the gather
+                                       (csrc/msda_tc_forward.cu: bf16, 32 channels per head, <= 4 levels, <= 4 points)
+                                       where it applies.  Exact for any input, parity-tested, but measured SLOWER than
+                                       the default lane-group gather on B200, so it is opt-in */
 
 /* ABI version of this header (bumped on any signature change). */
 int msda_abi_version(void);

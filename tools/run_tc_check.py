@@ -136,8 +136,8 @@ def main():
         vd, ld, ad, gd = vb.to(dev), loc.to(dev), attn.to(dev), gb.to(dev)
         if what in ("fwd", "all"):
             ref = msda_oracle.core_pytorch(vb.double(), shapes, loc.double(), attn.double())
-            o_tc = fwd_call(vd, st, ls, ld, ad, 0)
-            o_lg = fwd_call(vd, st, ls, ld, ad, _lib.FLAG_NO_TC)
+            o_tc = fwd_call(vd, st, ls, ld, ad, _lib.FLAG_TC)
+            o_lg = fwd_call(vd, st, ls, ld, ad, 0)
             torch.cuda.synchronize()
             e_tc, e_lg = nerr(o_tc, ref), nerr(o_lg, ref)
             good = e_tc[0] <= 2.0 ** -7 and e_tc[1] <= 4e-3
@@ -150,8 +150,8 @@ def main():
             a64 = attn.double().requires_grad_(True)
             msda_oracle.core_pytorch(v64, shapes, l64, a64).backward(gb.double())
             refs = (v64.grad, l64.grad, a64.grad)
-            g_tc = bwd_call(vd, st, ls, ld, ad, gd, 0)
-            g_lg = bwd_call(vd, st, ls, ld, ad, gd, _lib.FLAG_NO_TC)
+            g_tc = bwd_call(vd, st, ls, ld, ad, gd, _lib.FLAG_TC)
+            g_lg = bwd_call(vd, st, ls, ld, ad, gd, 0)
             torch.cuda.synchronize()
             for nm, x, y, r in zip(("grad_value", "grad_loc", "grad_attn"), g_tc, g_lg, refs):
                 e_tc, e_lg = nerr(x, r), nerr(y, r)
@@ -167,12 +167,12 @@ def main():
             vd, ld, ad = value.to(torch.bfloat16).to(dev), loc.to(dev), attn.to(dev)
             gd = gout.to(torch.bfloat16).to(dev)
             if what in ("fwd", "all"):
-                t_tc = time_ms(lambda: fwd_call(vd, st, ls, ld, ad, 0))
-                t_lg = time_ms(lambda: fwd_call(vd, st, ls, ld, ad, _lib.FLAG_NO_TC))
+                t_tc = time_ms(lambda: fwd_call(vd, st, ls, ld, ad, _lib.FLAG_TC))
+                t_lg = time_ms(lambda: fwd_call(vd, st, ls, ld, ad, 0))
                 print(f"time fwd bf16 batch 8 {dist:6s}: tc {t_tc:.3f} ms   lane-group {t_lg:.3f} ms", flush=True)
             if what in ("bwd", "all"):
-                t_tc = time_ms(lambda: bwd_call(vd, st, ls, ld, ad, gd, 0))
-                t_lg = time_ms(lambda: bwd_call(vd, st, ls, ld, ad, gd, _lib.FLAG_NO_TC))
+                t_tc = time_ms(lambda: bwd_call(vd, st, ls, ld, ad, gd, _lib.FLAG_TC))
+                t_lg = time_ms(lambda: bwd_call(vd, st, ls, ld, ad, gd, 0))
                 print(f"time bwd bf16 batch 8 {dist:6s}: tc {t_tc:.3f} ms   lane-group {t_lg:.3f} ms", flush=True)
     print("ALL OK" if ok else "SOME FAILED")
     return 0 if ok else 1

@@ -13,5 +13,5 @@ st = torch.as_tensor(c.COCO, dtype=torch.long, device=dev)
 ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
 vd, ld, ad = value.to(torch.bfloat16).to(dev), loc.to(dev), attn.to(dev)
 for _ in range(2):
-    c.fwd_call(vd, st, ls, ld, ad, 0)
+    c.fwd_call(vd, st, ls, ld, ad, c._lib.FLAG_TC)
     torch.cuda.synchronize()
