@@ -534,11 +534,25 @@ def train_step_extras(torch, dev, world, dist, n_frames=4, iters=5):
         opt.step()
         return loss
 
+    def params_agree():
+        """after data-parallel steps every rank must hold the same parameters.  Compares the
+        element-wise MIN and MAX over ranks of every parameter (one flat fp32 vector); on one GPU trivially true."""
+        flat = torch.cat([p.detach().float().flatten() for p in model.parameters()])
+        if world == 1:
+            return True, 0.0
+        lo, hi = flat.clone(), flat.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        return bool(torch.equal(lo, hi)), float((hi - lo).abs().max().item())
+
     ms = _reduce_max(torch, dist, world, dev, _time_events(torch, step, iters, 2))
     reducer.remove()
+    same, spread = params_agree()
+    assert same, f"parameters differ across ranks after the eager data-parallel steps (max spread {spread:.3e})"
     out = {"frames_per_gpu": n_frames, "eager_ms_per_step": ms, "eager_frames_per_s": n_frames * world / ms * 1e3,
            "gradient_bytes": reducer.gradient_bytes, "dtype": "bf16",
-           "collective": "bucketed all-reduce (NCCL)" if world > 1 else "none (1 GPU)"}
+           "collective": "bucketed all-reduce (NCCL)" if world > 1 else "none (1 GPU)",
+           "params_equal_across_ranks_after_eager_steps": same}
     try:       # the same step with forward + backward replayed from a CUDA graph (host-launch bound otherwise)
         loss_fn = lambda: model(srcs, masks, poss, dsrcs, dmasks, dposs, query)[0].float().square().mean()
         graphed = data_parallel.GraphedTrainStep(model, opt, loss_fn)
@@ -546,9 +560,14 @@ def train_step_extras(torch, dev, world, dist, n_frames=4, iters=5):
         out["ms_per_step"] = ms
         out["frames_per_s"] = n_frames * world / ms * 1e3
         out["mode"] = "CUDA graph (fwd+bwd) + flat-buffer all-reduce + AdamW"
+        same, spread = params_agree()
+        out["params_equal_across_ranks_after_graphed_steps"] = same
+        out["params_max_spread_after_graphed_steps"] = spread
     except Exception as exc:      # report, do not hide
         out["graph_error"] = repr(exc)[:200]
         out["ms_per_step"], out["frames_per_s"] = out["eager_ms_per_step"], out["eager_frames_per_s"]
+    assert out.get("params_equal_across_ranks_after_graphed_steps", True), \
+        f"parameters differ across ranks after the graphed data-parallel steps: {out}"
     return out
 
 
@@ -656,6 +675,64 @@ def run_b200(args):
     d2h = sum(t.numel() * t.element_size() for t in pinned_out)
     del pipe
 
+    # ---- what bounds the end-to-end number: the host<->device copy ceiling of this box -----------
+    # The same bytes, nothing else: every rank copies its step's inputs in and its results out with plain pinned
+    # cudaMemcpyAsync on two streams, all ranks at once (the 8 GPUs of a box share the host's memory system).
+    dev_in = [torch.empty_like(t, device=dev) for t in host]
+    dev_out = [torch.empty_like(t, device=dev) for t in pinned_out]
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copy_step():
+        with torch.cuda.stream(s_in):
+            for d_, h_ in zip(dev_in, host):
+                d_.copy_(h_, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for h_, d_ in zip(pinned_out, dev_out):
+                h_.copy_(d_, non_blocking=True)
+
+    copy_step()
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    s_in.wait_stream(torch.cuda.current_stream(dev))
+    s_out.wait_stream(torch.cuda.current_stream(dev))
+    for _ in range(e2e_steps):
+        copy_step()
+    torch.cuda.current_stream(dev).wait_stream(s_in)
+    torch.cuda.current_stream(dev).wait_stream(s_out)
+    c1.record()
+    barrier()
+    t = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    copy_ms = float(t.item()) / e2e_steps
+    copy_limit_qps = n * s * world / (copy_ms * 1e-3)
+    e2e_limit = {"value": copy_limit_qps, "unit": UNIT, "ms_per_step": copy_ms,
+                 "h2d_gbytes_per_s_all_ranks": h2d * world / copy_ms / 1e6,
+                 "d2h_gbytes_per_s_all_ranks": d2h * world / copy_ms / 1e6,
+                 "frac_of_limit": e2e_qps / copy_limit_qps,
+                 "what": "the step's input and output bytes moved by plain pinned cudaMemcpyAsync on two streams, all "
+                         "ranks at once, no kernels: the ceiling of any host-buffer API on this box"}
+    del dev_in, dev_out
+
+    # ---- the other storage type of the op (bf16 values when the line is fp32 and vice versa): device-resident --
+    other = {}
+    try:
+        odt, oname, oe = (torch.bfloat16, "bf16", 2) if args.dtype == "f32" else (torch.float32, "f32", 4)
+        v2, g2 = value.to(odt), gout.to(odt)
+        f_ms = _time_events(torch, lambda: MSDA.ms_deform_attn_forward(v2, st, ls, loc, attn, 64), 10, 3)
+        b_ms = _time_events(torch, lambda: MSDA.ms_deform_attn_backward(v2, st, ls, loc, attn, g2, 64), 10, 3)
+        f_ms = _reduce_max(torch, dist, world, dev, f_ms)
+        b_ms = _reduce_max(torch, dist, world, dev, b_ms)
+        fb, bb = algorithmic_bytes(n, oe)
+        pk, _ = peaks()
+        other = {"dtype": oname, "fwd_ms": f_ms, "bwd_ms": b_ms, "value": n * s * world / ((f_ms + b_ms) * 1e-3),
+                 "unit": UNIT, "roofline_frac_fwd": fb / (f_ms * 1e-3) / 1e9 / pk,
+                 "roofline_frac_bwd": bb / (b_ms * 1e-3) / 1e9 / pk}
+        del v2, g2
+    except Exception as exc:
+        other = {"error": repr(exc)[:200]}
+
     # ---- roofline of the dominant kernel (the backward) ----------------------------------------
     peak, peak_src = peaks()
     fwd_bytes, bwd_bytes = algorithmic_bytes(n, e_v)
@@ -705,7 +782,7 @@ def run_b200(args):
                        "l2": "inputs (%d MB per step) larger than L2" % ((fwd_bytes + bwd_bytes) // (2 << 20)),
                        "parallelism": f"dp{world} (frames sharded, no data-path collective)"},
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "host_cores_bound_near_gpu": bound_cores,
+                    "steps": e2e_steps, "host_cores_bound_near_gpu": bound_cores, "limit": e2e_limit,
                     "api": "dfvod_b200.host_pipeline.HostPipelinedMSDA.forward_backward (pinned host tensors)"},
             "gpu_launches": args.steps * (2 if e_v == 4 else 3),
             "clocks": clocks.summary(),
@@ -713,6 +790,7 @@ def run_b200(args):
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
             "per_step_ms": {"fwd_median": fwd_med, "bwd_median": bwd_med, "fwd_min": fwd_all[0],
                             "bwd_min": bwd_all[0], "fwd_max": fwd_all[-1], "bwd_max": bwd_all[-1]},
+            "op_other_dtype": other,
             "cpu_baseline": cpu_baseline}
     line.update(extras)
     print(json.dumps(line), flush=True)

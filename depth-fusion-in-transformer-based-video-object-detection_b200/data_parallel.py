@@ -64,6 +64,7 @@ class GradientAllReducer:
                       for bucket in self.buckets]
         self._pending = [len(bucket) for bucket in self.buckets]
         self._work = [None] * len(self.buckets)
+        self._launched = 0            # buckets 0 .. _launched-1 have been sent this step
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
 
     def _launch(self, b):
@@ -80,15 +81,23 @@ class GradientAllReducer:
 
     def _on_grad(self, param):
         b = self._bucket_of[id(param)]
+        if self._pending[b] <= 0:
+            raise RuntimeError("GradientAllReducer: a second backward() reached a parameter before finish(); "
+                               "call finish() once per backward pass")
         self._pending[b] -= 1
-        if self._pending[b] == 0:
-            self._launch(b)
+        # Collectives must be issued in the SAME order on every rank (the set of unused parameters, and with it the
+        # order in which buckets complete, may differ between ranks): strictly by bucket index, a bucket only once
+        # every earlier bucket has been sent -- what DDP's reducer does.
+        while self._launched < len(self.buckets) and self._pending[self._launched] == 0:
+            self._launch(self._launched)
+            self._launched += 1
 
     def finish(self):
-        """Complete the step: buckets whose hooks never all fired (unused parameters) are sent now."""
-        for b in range(len(self.buckets)):
-            if self._pending[b] > 0:
-                self._launch(b)
+        """Complete the step: the remaining buckets (those waiting for an earlier one, and those whose hooks never
+        all fired because of unused parameters) are sent now, in index order."""
+        while self._launched < len(self.buckets):
+            self._launch(self._launched)
+            self._launched += 1
         for b, bucket in enumerate(self.buckets):
             if self._work[b] is not None:
                 self._work[b].wait()
@@ -103,6 +112,7 @@ class GradientAllReducer:
                 p.grad.copy_(flat[offset:offset + n].view_as(p))
                 offset += n
             self._pending[b] = len(bucket)
+        self._launched = 0
 
     def remove(self):
         for h in self._hooks:

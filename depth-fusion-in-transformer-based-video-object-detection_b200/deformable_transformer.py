@@ -81,8 +81,11 @@ def _shape_tensors(shapes, device):
     if hit is None:
         if len(_SHAPE_TENSORS) >= 64:
             _SHAPE_TENSORS.clear()
-        st = torch.as_tensor(shapes, dtype=torch.long, device=device)
-        hit = (st, torch.cat((st.new_zeros((1,)), st.prod(1).cumsum(0)[:-1])))
+        # built outside inference mode: an inference tensor cached here by a first call under torch.inference_mode()
+        # could not be saved for backward by a later training step
+        with torch.inference_mode(False):
+            st = torch.as_tensor(shapes, dtype=torch.long, device=device)
+            hit = (st, torch.cat((st.new_zeros((1,)), st.prod(1).cumsum(0)[:-1])))
         _SHAPE_TENSORS[key] = hit
     return hit
 

@@ -148,7 +148,8 @@ class ZeroMaskedRowsFunction(Function):
     """In place: rows of ``value`` [N, S, C] whose ``mask`` [N, S] entry is True become zero."""
 
     @staticmethod
-    def forward(ctx, value, mask):
+    def forward(ctx, value, mask, exclusive=False):
+        ctx.exclusive = bool(exclusive)
         if not value.is_contiguous():
             raise RuntimeError("zero_masked_rows_: value must be contiguous")
         mask8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else (mask != 0).to(torch.uint8)
@@ -168,25 +169,29 @@ class ZeroMaskedRowsFunction(Function):
     @once_differentiable
     def backward(ctx, grad):
         (mask8,) = ctx.saved_tensors
-        # `value` feeds only the deformable-attention op, whose backward allocates this gradient
-        # fresh: zero its masked rows in place instead of copying the whole tensor
-        if not grad.is_contiguous() or grad.data_ptr() % 16:
+        # Autograd forbids mutating an incoming gradient: the same buffer may feed another consumer of `value`, a
+        # tensor hook or retain_grad.  So the rows are zeroed in a COPY -- unless the call site vouched that `value`
+        # feeds only the deformable-attention op (whose backward allocates this gradient fresh) by passing
+        # exclusive=True to zero_masked_rows_: then the 180 MB copy per layer is skipped.
+        if not ctx.exclusive or not grad.is_contiguous() or grad.data_ptr() % 16:
             grad = grad.contiguous().clone()
         c = grad.shape[-1]
         code = _lib.load().msda_layer_zero_masked_rows(
             _DTYPES[grad.dtype], grad.data_ptr(), mask8.data_ptr(), grad.numel() // c, c,
             torch.cuda.current_stream().cuda_stream)
         _lib.check(code, "msda_layer_zero_masked_rows")
-        return grad, None
+        return grad, None, None
 
 
-def zero_masked_rows_(value, mask):
-    """``value.masked_fill(mask[..., None], 0)`` for a freshly produced ``value`` (modified in place)."""
+def zero_masked_rows_(value, mask, exclusive=False):
+    """``value.masked_fill(mask[..., None], 0)`` for a freshly produced ``value`` (modified in place).
+    ``exclusive=True``: the caller guarantees that the result has exactly one consumer whose backward hands over a
+    freshly allocated gradient (the deformable-attention op); the backward then zeroes that gradient in place."""
     c = value.shape[-1]
     if value.is_cuda and value.dtype in _DTYPES and value.is_contiguous() and (c * value.element_size()) % 16 == 0 \
             and value.data_ptr() % 16 == 0:
         with torch.cuda.device(value.device):
-            return ZeroMaskedRowsFunction.apply(value, mask)
+            return ZeroMaskedRowsFunction.apply(value, mask, exclusive)
     return value.masked_fill(mask[..., None], float(0))
 
 
@@ -212,8 +217,16 @@ class LinearFunction(Function):
 
     @staticmethod
     def forward(ctx, x2, weight, bias):              # x2 [rows, in] -> fresh [rows, out] (never a view)
-        ctx.save_for_backward(x2, weight)
-        return torch.addmm(bias, x2, weight.t())
+        # under torch.autocast the GEMM runs in the autocast dtype like F.linear does; the operands are saved as
+        # they were used, so that the backward (which runs outside autocast) multiplies matching dtypes
+        if torch.is_autocast_enabled():
+            adt = torch.get_autocast_gpu_dtype()
+            x2, weight_c, bias_c = x2.to(adt), weight.to(adt), bias.to(adt)
+        else:
+            weight_c, bias_c = weight, bias
+        ctx.save_for_backward(x2, weight_c)
+        ctx.param_dtypes = (weight.dtype, bias.dtype)
+        return torch.addmm(bias_c, x2, weight_c.t())
 
     @staticmethod
     @once_differentiable
@@ -221,9 +234,11 @@ class LinearFunction(Function):
         x2, weight = ctx.saved_tensors
         if not g2.is_contiguous():
             g2 = g2.contiguous()
+        if g2.dtype != weight.dtype:
+            g2 = g2.to(weight.dtype)
         dx = g2 @ weight if ctx.needs_input_grad[0] else None
-        dw = g2.t() @ x2 if ctx.needs_input_grad[1] else None
-        db = column_sum(g2) if ctx.needs_input_grad[2] else None
+        dw = (g2.t() @ x2).to(ctx.param_dtypes[0]) if ctx.needs_input_grad[1] else None
+        db = column_sum(g2).to(ctx.param_dtypes[1]) if ctx.needs_input_grad[2] else None
         return dx, dw, db
 
 

@@ -157,7 +157,8 @@ class MSDeformAttn(nn.Module):
         else:
             value = linear(self.value_proj, input_flatten.reshape(N * Len_in, -1))
             if input_padding_mask is not None:
-                value = zero_masked_rows_(value, input_padding_mask.reshape(-1))
+                # `value` is consumed by the deformable-attention op below and by nothing else
+                value = zero_masked_rows_(value, input_padding_mask.reshape(-1), exclusive=True)
             value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(
@@ -165,8 +166,7 @@ class MSDeformAttn(nn.Module):
 
         if self.fused and value.is_cuda:
             # [ offsets | logits ] from one GEMM; parameters stay separate for checkpoint compatibility
-            weight = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
-            bias = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+            weight, bias = self._raw_projection_params()
             raw = linear_wb(query, weight, bias)
             if raw.dtype != value.dtype and value.dtype == torch.float32:
                 raw = raw.float()
@@ -192,6 +192,27 @@ class MSDeformAttn(nn.Module):
             value.contiguous(), input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
             attention.contiguous(), self.im2col_step)
         return linear(self.output_proj, output) if project_output else output
+
+
+def _raw_projection_params(self):
+    """[sampling_offsets | attention_weights] weight and bias as one matrix for the single projection GEMM of the fused
+    path.  Training: concatenated inside autograd every call (the gradients must reach the two parameters).
+    Inference: concatenated once and reused until a parameter changes (in-place update, .to(), load_state_dict) --
+    two launches and a 300 KB copy per layer call otherwise."""
+    params = (self.sampling_offsets.weight, self.attention_weights.weight, self.sampling_offsets.bias,
+              self.attention_weights.bias)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return torch.cat(params[:2], 0), torch.cat(params[2:], 0)
+    key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in params)
+    cache = getattr(self, "_raw_cache", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            cache = (key, torch.cat(params[:2], 0), torch.cat(params[2:], 0))
+        self._raw_cache = cache
+    return cache[1], cache[2]
+
+
+MSDeformAttn._raw_projection_params = _raw_projection_params
 
 
 def project_values(modules, input_flatten, input_padding_mask=None):

@@ -201,3 +201,36 @@ def test_decoder_batched_value_projection_matches_per_layer_projection():
         hs_nograd, _ = dec(tgt, refs, mem, st, ls, vr, qpos, mask)
     err = float((hs_nograd - hs_grad.detach()).abs().max() / hs_grad.detach().abs().max())
     assert err <= 1e-5, err
+
+
+def test_odd_raw_row_length_does_not_take_the_fused_kernels():
+    """d_model 96 / 3 heads / 1 level / 3 points gives M*L*P = 9, so the [offsets | logits] rows of the
+    projection are 27 elements long and every odd row starts 4 bytes off the 8-byte boundary the fused kernels' paired
+    loads need.  Such shapes must route through the unfused sequence (no misaligned-address fault) and agree with it."""
+    import torch
+    from dfvod_b200.ops.modules import MSDeformAttn
+    torch.manual_seed(5)
+    dev = torch.device("cuda:0")
+    shapes = [(11, 13)]
+    s = 11 * 13
+    st = torch.as_tensor(shapes, dtype=torch.long, device=dev)
+    ls = torch.zeros(1, dtype=torch.long, device=dev)
+    mod = MSDeformAttn(96, 1, 3, 3).to(dev)
+    with torch.no_grad():
+        for p in mod.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    query = torch.randn(2, s, 96, device=dev)
+    feat = torch.randn(2, s, 96, device=dev)
+    ys, xs = torch.meshgrid(torch.linspace(0.05, 0.95, 11, device=dev), torch.linspace(0.05, 0.95, 13, device=dev), indexing="ij")
+    ref = torch.stack([xs.reshape(-1), ys.reshape(-1)], -1)[None, :, None, :].expand(2, s, 1, 2).contiguous()
+    outs = []
+    for fused in (True, False):
+        mod.fused = fused
+        q = query.clone().requires_grad_(True)
+        f = feat.clone().requires_grad_(True)
+        out = mod(q, ref, f, st, ls, None)
+        out.square().sum().backward()
+        torch.cuda.synchronize()
+        outs.append((out.detach(), q.grad, f.grad))
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)

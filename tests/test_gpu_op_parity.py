@@ -190,10 +190,11 @@ def test_reference_check_forward_double_and_float():
     assert torch.allclose(out, ref, rtol=1e-2, atol=1e-3)             # test.py:56
 
 
-@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025])
+@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025, 2048, 3096])
 def test_reference_gradcheck(channels):
-    """models/ops/test.py:63-78 (fp64 gradcheck on all three differentiable inputs).  The
-    reference list also has 2048 and 3096, which only exercise its D>1024 kernel variants."""
+    """models/ops/test.py:63-78, the reference's full channel list (:85): fp64 gradcheck on all three
+    differentiable inputs.  2048 and 3096 exercise the reference's D > 1024 kernel variants; here they run the
+    shape-generic kernels like every other fp64 case."""
     torch.manual_seed(3)
     shapes, value, loc, attn = _reference_recipe(channels)
     st, ls = util.shapes_tensors(shapes, DEV)
@@ -287,3 +288,35 @@ def test_autograd_function_contract():
     got = (out.detach(), v.grad, l.grad, a.grad)
     assert_close(tuple(t.double().cpu().numpy() for t in got), ref, F32_TOL, F32_TOL, "autograd")
     assert st.grad is None and ls.grad is None
+
+
+# ------------------------------------------------------------------ INTEGRATION.md Option A
+def test_option_a_module_alias_serves_the_reference_call_sites():
+    """INTEGRATION.md Option A: the repo's module registered under the reference's extension name, then used exactly
+    as the reference's autograd function uses it -- ``import MultiScaleDeformableAttention as MSDA`` and the two
+    POSITIONAL calls of models/ops/functions/ms_deform_attn_func.py:25-26 (forward) and :35-36 (backward, which
+    unpacks a 3-list)."""
+    import sys
+    import dfvod_b200
+    saved = sys.modules.get("MultiScaleDeformableAttention")
+    sys.modules["MultiScaleDeformableAttention"] = dfvod_b200.MultiScaleDeformableAttention
+    try:
+        import MultiScaleDeformableAttention as REF_MSDA          # what func.py:18 does
+        shapes = [(9, 11), (5, 6)]
+        value, loc, attn, gout = util.make_inputs(shapes, 2, 8, 32, 40, 4, seed=21)
+        st, ls = util.shapes_tensors(shapes, DEV)
+        v, l, a, g = value.to(DEV), loc.to(DEV), attn.to(DEV), gout.to(DEV)
+        im2col_step = 64
+        output = REF_MSDA.ms_deform_attn_forward(v, st, ls, l, a, im2col_step)                    # func.py:25-26
+        grad_value, grad_sampling_loc, grad_attn_weight = \
+            REF_MSDA.ms_deform_attn_backward(v, st, ls, l, a, g, im2col_step)                      # func.py:35-36
+        ref_out, ref_gv, ref_gl, ref_ga = msda_oracle.core_pytorch_fwd_bwd(
+            value.double(), shapes, loc.double(), attn.double(), gout.double())
+        for x, r in ((output, ref_out), (grad_value, ref_gv), (grad_sampling_loc, ref_gl), (grad_attn_weight, ref_ga)):
+            emax, el2 = util.nerr(x.detach().double().cpu().numpy().reshape(-1), r.detach().numpy().reshape(-1))
+            assert emax <= 1e-5 and el2 <= 1e-5
+    finally:
+        if saved is None:
+            del sys.modules["MultiScaleDeformableAttention"]
+        else:
+            sys.modules["MultiScaleDeformableAttention"] = saved
