@@ -26,37 +26,6 @@ _DTYPES = {torch.float32: _lib.DTYPE_F32, torch.float64: _lib.DTYPE_F64,
 
 # test hook: route through the shape-generic kernels
 _FORCE_GENERIC = False
-# 16-bit forward through the paired value layout (csrc/msda_paired.cu).  Measured on B200 at the
-# COCO-scale encoder shape (profiles/ncu_paired_r1.txt): the plain bf16 gather runs at 95 % of the L1
-# data pipe; the paired layout halves the lines per sample (data pipe 62 %) but the kernel then
-# becomes instruction-issue bound (83 % issue-active: bf16 unpack + FFMA), and with the re-layout
-# pass the two paths tie (0.48 ms).  So it stays OPT-IN: True = use it where supported.
-PAIRED_FORWARD = False
-# With the paired layout: round the per-corner weights to bf16 and accumulate with the mixed-precision
-# FMA (FHFMA.BF16, fp32 accumulator) -- half the math instructions of the issue-bound paired kernel.
-PAIRED_BF16_WEIGHTS = False
-
-
-def paired_flags(dtype):
-    return _lib.FLAG_BF16_WEIGHTS if (PAIRED_BF16_WEIGHTS and dtype == torch.bfloat16) else 0
-
-
-def use_paired_forward(dtype, d, s, lq, nl, p):
-    if not PAIRED_FORWARD or dtype not in (torch.bfloat16, torch.float16):
-        return False
-    return bool(_lib.load().msda_paired_supported(_DTYPES[dtype], int(d))) and nl <= 32 and p <= 64 and s > 0
-
-
-def pack_value_pairs(value):
-    """value [N,S,M,D] (16-bit, contiguous) -> paired tensor [N,S+1,M,2,D] (include/msda_b200.h)."""
-    n, s, m, d = value.shape
-    pairs = torch.empty((n, s + 1, m, 2, d), dtype=value.dtype, device=value.device)
-    code = _lib.load().msda_pack_value_pairs(_DTYPES[value.dtype], value.data_ptr(), n, s, m, d, pairs.data_ptr(),
-                                             torch.cuda.current_stream().cuda_stream)
-    _lib.check(code, "msda_pack_value_pairs")
-    return pairs
-
-
 def _check_inputs(named, im2col_step):
     value = named[0][1]
     if not value.is_cuda:
@@ -114,14 +83,6 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     lib = _lib.load()
     with torch.cuda.device(value.device):
         output = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
-        if not _FORCE_GENERIC and use_paired_forward(value.dtype, d, s, lq, nl, p):
-            pairs = pack_value_pairs(value)
-            code = lib.msda_forward_paired(
-                _DTYPES[value.dtype], pairs.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-                sampling_loc.data_ptr(), attn_weight.data_ptr(), n, s, m, d, nl, lq, p, output.data_ptr(),
-                paired_flags(value.dtype), torch.cuda.current_stream().cuda_stream)
-            _lib.check(code, "ms_deform_attn_forward (paired layout)")
-            return output
         code = lib.msda_forward(
             _DTYPES[value.dtype], value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), n, s, m, d, nl, lq, p, output.data_ptr(),

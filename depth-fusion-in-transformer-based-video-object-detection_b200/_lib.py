@@ -10,10 +10,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MSDA_B200_LIB selects another build of the same ABI (A/B kernel experiments); default: in-tree
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_HERE, "libmsda_b200.so")
 
-ABI_VERSION = 16
+ABI_VERSION = 17
 DTYPE_F32, DTYPE_F64, DTYPE_BF16, DTYPE_F16 = 0, 1, 2, 3
 FLAG_FORCE_GENERIC = 1
-FLAG_BF16_WEIGHTS = 2
 FLAG_TC = 4
 
 _lib = None
@@ -54,16 +53,6 @@ def load():
     lib.msda_fused_forward_strided.argtypes = [c_int, c_int, c_vp, c_i64] + fused_common[1:] + [c_vp, c_vp]
     lib.msda_fused_backward.restype = c_int
     lib.msda_fused_backward.argtypes = [c_int, c_int, c_vp] + fused_common + [c_vp, c_vp, c_vp, c_fp, c_vp, c_vp]
-    lib.msda_paired_supported.restype = c_int
-    lib.msda_paired_supported.argtypes = [c_int, c_int]
-    lib.msda_paired_value_elems.restype = c_i64
-    lib.msda_paired_value_elems.argtypes = [c_int] * 4
-    lib.msda_pack_value_pairs.restype = c_int
-    lib.msda_pack_value_pairs.argtypes = [c_int, c_vp] + [c_int] * 4 + [c_vp, c_vp]
-    lib.msda_forward_paired.restype = c_int
-    lib.msda_forward_paired.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 7 + [c_vp, c_int, c_vp]
-    lib.msda_fused_forward_paired.restype = c_int
-    lib.msda_fused_forward_paired.argtypes = [c_int, c_int] + fused_common + [c_vp, c_int, c_vp]
     c_f = ctypes.c_float
     lib.msda_layer_add_layernorm_supported.restype = c_int
     lib.msda_layer_add_layernorm_supported.argtypes = [c_int, c_int]

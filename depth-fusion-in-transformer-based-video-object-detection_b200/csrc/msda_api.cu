@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 16; }
+extern "C" int msda_abi_version(void) { return 17; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -195,59 +195,6 @@ extern "C" int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t*
 {
     if (rows < 0 || channels < 0) return (int)cudaErrorInvalidValue;
     return (int)msda::zero_masked_rows(dtype, data, mask, (long long)rows, channels, (cudaStream_t)stream);
-}
-
-// ---- paired value layout (16-bit forward) ------------------------------------------------------
-extern "C" int msda_paired_supported(int dtype, int channels) { return msda::paired_supported(dtype, channels) ? 1 : 0; }
-
-extern "C" int64_t msda_paired_value_elems(int batch, int spatial_size, int num_heads, int channels)
-{
-    return (int64_t)batch * (spatial_size + 1) * num_heads * 2 * channels;
-}
-
-extern "C" int msda_pack_value_pairs(int dtype, const void* value, int batch, int spatial_size, int num_heads,
-                                     int channels, void* value_pairs, void* stream)
-{
-    if (bad_dims(batch, spatial_size, num_heads, channels, 0, 0, 0)) return (int)cudaErrorInvalidValue;
-    return (int)msda::pack_value_pairs(dtype, value, value_pairs, batch, spatial_size, num_heads, channels,
-                                       (cudaStream_t)stream);
-}
-
-extern "C" int msda_forward_paired(int dtype, const void* value_pairs, const int64_t* spatial_shapes,
-                                   const int64_t* level_start_index, const void* sampling_loc,
-                                   const void* attn_weight, int batch, int spatial_size, int num_heads,
-                                   int channels, int num_levels, int num_query, int num_point, void* output,
-                                   int flags, void* stream)
-{
-    if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point) || num_levels == 0 ||
-        num_point == 0)
-        return (int)cudaErrorInvalidValue;
-    msda::FwdArgs a;
-    a.dtype = dtype;
-    a.value = value_pairs; a.shapes = spatial_shapes; a.lsi = level_start_index;
-    a.loc = sampling_loc; a.attn = attn_weight; a.out = output;
-    a.N = batch; a.S = spatial_size; a.M = num_heads; a.D = channels;
-    a.L = num_levels; a.Lq = num_query; a.P = num_point;
-    a.force_generic = flags;                    // forward_paired reads the flag bits from here
-    return (int)msda::forward_paired(a, (cudaStream_t)stream);
-}
-
-extern "C" int msda_fused_forward_paired(int dtype, int raw_dtype, const void* value_pairs,
-                                         const int64_t* spatial_shapes, const int64_t* level_start_index,
-                                         const float* reference_points, int ref_dim,
-                                         const void* sampling_offsets_raw, int64_t offsets_query_stride,
-                                         const void* attention_logits_raw, int64_t logits_query_stride, int batch,
-                                         int spatial_size, int num_heads, int channels, int num_levels,
-                                         int num_query, int num_point, void* output, int flags, void* stream)
-{
-    if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
-        return (int)cudaErrorInvalidValue;
-    msda::FusedArgs a = make_fused(dtype, raw_dtype, value_pairs, spatial_shapes, level_start_index, reference_points,
-                                   ref_dim, sampling_offsets_raw, offsets_query_stride, attention_logits_raw,
-                                   logits_query_stride, batch, spatial_size, num_heads, channels, num_levels,
-                                   num_query, num_point);
-    a.out = output;
-    return (int)msda::fused_forward_paired(a, flags, (cudaStream_t)stream);
 }
 
 extern "C" int msda_layer_colsum_blocks(int dtype, int64_t rows, int channels)

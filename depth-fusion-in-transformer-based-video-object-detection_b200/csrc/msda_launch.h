@@ -77,13 +77,6 @@ cudaError_t forward(const FwdArgs& a, cudaStream_t stream);
 bool tc_forward_supported(const FwdArgs& a);
 cudaError_t tc_forward(const FwdArgs& a, cudaStream_t stream);
 
-// Paired value layout (msda_paired.cu): pairs[n, r, m, 0|1, :] = value[n, r-1 | r, m, :], r = 0..S.
-// In forward_paired / fused_forward_paired the `value` member points at that tensor.
-bool paired_supported(int dtype, int D);
-cudaError_t pack_value_pairs(int dtype, const void* value, void* pairs, int N, int S, int M, int D,
-                             cudaStream_t stream);
-cudaError_t forward_paired(const FwdArgs& a, cudaStream_t stream);
-cudaError_t fused_forward_paired(const FusedArgs& a, int flags, cudaStream_t stream);
 cudaError_t backward(const BwdArgs& a, cudaStream_t stream);
 
 // Layer epilogues (layer_epilogue.cu):  y = LayerNorm(residual + act(branch)) * gamma + beta,

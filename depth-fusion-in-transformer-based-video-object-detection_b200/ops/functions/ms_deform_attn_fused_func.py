@@ -86,10 +86,6 @@ class MSDeformAttnFusedFunction(Function):
             if ld:
                 code = lib.msda_fused_forward_strided(_DTYPES[value.dtype], _DTYPES[raw.dtype], value.data_ptr(), ld,
                                                       *common, stream)
-            elif value.dtype == torch.bfloat16 and _msda.use_paired_forward(value.dtype, d, s, lq, nl, p):
-                pairs = _msda.pack_value_pairs(value)           # 2 lines per sample instead of 4
-                code = lib.msda_fused_forward_paired(_DTYPES[value.dtype], _DTYPES[raw.dtype], pairs.data_ptr(),
-                                                     *common, _msda.paired_flags(value.dtype), stream)
             else:
                 code = lib.msda_fused_forward(_DTYPES[value.dtype], _DTYPES[raw.dtype], value.data_ptr(),
                                               *common, stream)

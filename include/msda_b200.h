@@ -45,10 +45,6 @@ typedef enum {
 
 /* flags */
 #define MSDA_FLAG_FORCE_GENERIC 1   /* route through the shape-generic kernels (testing) */
-#define MSDA_FLAG_BF16_WEIGHTS 2    /* paired BF16 forward only: round the per-corner weights (attention weight x
-                                       bilinear weight) to bf16 and accumulate with the mixed-precision FMA
-                                       (fp32 accumulator) -- half the math instructions; inference option */
-
 #define MSDA_FLAG_TC 4              /* msda_forward: run the tensor-core (tcgen05 + TMA) formulation of the gather
                                        (csrc/msda_tc_forward.cu: bf16, 32 channels per head, <= 4 levels, <= 4 points)
                                        where it applies.  Exact for any input, parity-tested, but measured SLOWER than
@@ -139,36 +135,6 @@ int msda_fused_backward(int dtype, int raw_dtype,
                         int num_levels, int num_query, int num_point,
                         void* grad_value, void* grad_offsets_raw, void* grad_logits_raw,
                         float* grad_reference_points, void* grad_value_accum_f32, void* stream);
-
-/* ---------------------------------------------------------------------------------------------
- * Paired value layout for the 16-bit forward (no counterpart in the reference; an internal
- * re-layout the Python wrappers apply when the gather dominates, i.e. encoder-sized query sets).
- *     value_pairs[n, r, m, 0, :] = value[n, r-1, m, :]   (zeros for r = 0)        r = 0 .. spatial_size
- *     value_pairs[n, r, m, 1, :] = value[n, r,   m, :]   (zeros for r = spatial_size)
- * One (pixel pair, head) record is one 128-byte line for bf16 / channels = 32, so a bilinear sample
- * touches 2 lines instead of 4.  msda_pack_value_pairs writes all msda_paired_value_elems(...)
- * elements of value_pairs; msda_forward_paired / msda_fused_forward_paired are msda_forward /
- * msda_fused_forward reading that layout (same results up to fp32 summation order).
- * Supported: BF16 / F16 (fused: BF16), channels 16 / 32 / 64 (msda_paired_supported).
- */
-int msda_paired_supported(int dtype, int channels);
-int64_t msda_paired_value_elems(int batch, int spatial_size, int num_heads, int channels);
-int msda_pack_value_pairs(int dtype, const void* value, int batch, int spatial_size, int num_heads,
-                          int channels, void* value_pairs, void* stream);
-int msda_forward_paired(int dtype,
-                        const void* value_pairs, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                        const void* sampling_loc, const void* attn_weight,
-                        int batch, int spatial_size, int num_heads, int channels,
-                        int num_levels, int num_query, int num_point,
-                        void* output, int flags, void* stream);
-int msda_fused_forward_paired(int dtype, int raw_dtype,
-                              const void* value_pairs, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                              const float* reference_points, int ref_dim,
-                              const void* sampling_offsets_raw, int64_t offsets_query_stride,
-                              const void* attention_logits_raw, int64_t logits_query_stride,
-                              int batch, int spatial_size, int num_heads, int channels,
-                              int num_levels, int num_query, int num_point,
-                              void* output, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layer epilogues around the deformable attention (no counterpart symbol in the reference, which
