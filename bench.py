@@ -184,6 +184,19 @@ def traffic_from_profile(kind, dtype="f32"):
         return None
 
 
+def profile_build_matches():
+    """True when profiles/ncu_summary.json was captured from the gather-kernel sources this library is built from
+    (tools/build_hash.py), False when the sources changed since, None when unknown."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import build_hash
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            stamp = json.load(f).get("gather_kernels_build", {}).get("sha256_16")
+        return None if stamp is None else stamp == build_hash.gather_kernels_hash()
+    except Exception:
+        return None
+
+
 def limiter_from_profile(kind, dtype="f32"):
     """The on-chip unit that bounds the kernel, from the committed ncu capture:
     the gather kernels are not HBM-bound -- the forward saturates the L1 data pipe (128 B/clk/SM),
@@ -742,6 +755,7 @@ def run_b200(args):
                                           + (" and bf16 cast" if e_v == 2 else "") + ")",
                 "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
                 "traffic": traffic_from_profile("backward", args.dtype), "peak_source": peak_src,
+                "traffic_capture_is_of_this_build": profile_build_matches(),
                 "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": bwd_ms,
                 "limiter": limiter_from_profile("backward", args.dtype)}
     roofline_fwd = {"bound": "hbm", "kernel": "msda_fwd_fast_kernel", "achieved": achieved_fwd, "peak": peak,

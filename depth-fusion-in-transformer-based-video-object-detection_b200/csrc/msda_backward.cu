@@ -153,7 +153,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                                                  // (footprints) and again after the reduce-scatter (gradients)
     constexpr int FCH = (kChunk + CH - 1) / CH;  // passes of the fused op (host guarantees L*P <= kChunk)
     constexpr int U = MSDA_BWD_UNROLL;
-    static_assert(G >= 1 && G <= 16 && (G & (G - 1)) == 0, "fast backward needs 1..16 lanes per head");
+    static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "fast backward needs 1..32 lanes per head");
     static_assert(CH % G == 0 && CH % U == 0, "pass size must split evenly over the lanes and the unroll");
 
     __shared__ int s_meta[3 * kMaxLevelsFast];
@@ -733,12 +733,13 @@ static cudaError_t run_bwd_16or32(const BwdArgs& a, cudaStream_t stream)
         bool done = false;
         if (fast_shape_ok(a)) {
             done = true;
-            switch (a.D) {   // G = D/4 lanes per head must be a power of two <= 16
+            switch (a.D) {   // G = D/4 lanes per head must be a power of two <= 32
                 case 4:   err = launch_bwd_fast<VT, 4>(a, accum, stream); break;
                 case 8:   err = launch_bwd_fast<VT, 8>(a, accum, stream); break;
                 case 16:  err = launch_bwd_fast<VT, 16>(a, accum, stream); break;
                 case 32:  err = launch_bwd_fast<VT, 32>(a, accum, stream); break;
                 case 64:  err = launch_bwd_fast<VT, 64>(a, accum, stream); break;
+                case 128: err = launch_bwd_fast<VT, 128>(a, accum, stream); break;     // one (query, head) per warp
                 default: done = false;
             }
         }

@@ -41,19 +41,22 @@ def test_fp32_matches_reference_class(name):
         out, gin, gpar = module_cases.run_case(name, gold, "cuda", torch.float32)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+    # BASELINE.json's fp32 tolerance, 1e-5 (normalised max and relative L2 against the reference class in fp64), for
+    # the output AND every gradient.  Measured on B200 (tools/measure_module_errors.py, round 2): outputs <= 1.0e-6,
+    # input gradients <= 1.9e-6, parameter gradients <= 4.6e-6 over all cases.
     emax, el2 = nerr(out, gold["out"])
-    assert emax <= 2e-5 and el2 <= 2e-5, f"out: {emax:.2e} {el2:.2e}"
+    assert emax <= 1e-5 and el2 <= 1e-5, f"out: {emax:.2e} {el2:.2e}"
     for k, g in gin.items():
         if gold["grad_in." + k].shape == () or g is None:
             continue
         emax, el2 = nerr(g, gold["grad_in." + k])
-        assert emax <= 1e-4 and el2 <= 1e-4, f"{k}: {emax:.2e} {el2:.2e}"
+        assert emax <= 1e-5 and el2 <= 1e-5, f"{k}: {emax:.2e} {el2:.2e}"
     for k, g in gpar.items():
         ref = gold.get("grad_param." + k)
         if ref is None or ref.shape == () or g is None:
             continue
         emax, el2 = nerr(g, ref)
-        assert emax <= 1e-4 and el2 <= 1e-4, f"{k}: {emax:.2e} {el2:.2e}"
+        assert emax <= 1e-5 and el2 <= 1e-5, f"{k}: {emax:.2e} {el2:.2e}"
 
 
 def test_bf16_production_width_layer_matches_reference_class():

@@ -93,7 +93,8 @@ RANDOM_CASES = [
     ([(13, 21), (7, 11)], 3, 4, 64, 65, 4, (-0.1, 1.1)),            # D=64
     ([(9, 9)], 1, 16, 16, 33, 8, (-0.5, 1.5)),                      # D=16, P=8
     ([(8, 8), (4, 4), (2, 2)], 1, 5, 8, 31, 3, (0.0, 1.0)),         # D=8, odd P, odd M
-    ([(7, 5)], 2, 2, 128, 17, 2, (0.0, 1.0)),                       # D=128: fast fwd, generic bwd (fp32)
+    ([(7, 5)], 2, 2, 128, 17, 2, (0.0, 1.0)),                       # D=128: one (query, head) per warp, both ways
+    ([(9, 12), (5, 6)], 2, 3, 128, 70, 4, (-0.1, 1.1)),             # D=128, 2 levels x 4 points (shared-pixel merge)
     ([(6, 6), (3, 3)], 1, 3, 30, 10, 2, (-0.1, 1.1)),               # D=30: generic both ways
     ([(5, 5)] * 5, 1, 2, 32, 9, 4, (0.0, 1.0)),                     # L*P = 20 > one 16-sample chunk
     ([(1, 1), (1, 7), (7, 1)], 1, 2, 32, 11, 4, (-0.3, 1.3)),       # degenerate 1-pixel-wide maps
