@@ -728,6 +728,38 @@ def run_b200(args):
                          "ranks at once, no kernels: the ceiling of any host-buffer API on this box"}
     del dev_in, dev_out
 
+    # ---- the same end-to-end call with bf16 values / outputs / value gradients (locations, weights fp32) ----------
+    e2e_bf16 = None
+    if args.dtype == "f32":
+        try:
+            bft = torch.bfloat16
+            host16 = [value_h.to(bft).pin_memory(), loc_h.pin_memory(), attn_h.pin_memory(), gout_h.to(bft).pin_memory()]
+            out16 = [torch.empty((n, s, M * D), dtype=bft).pin_memory(), torch.empty(value_h.shape, dtype=bft).pin_memory(),
+                     torch.empty_like(loc_h).pin_memory(), torch.empty_like(attn_h).pin_memory()]
+            pipe16 = HostPipelinedMSDA(dev, st.cpu(), ls.cpu(), M, D, P, s, dtype=bft, chunk_frames=2, depth=3)
+            for _ in range(2):
+                pipe16.forward_backward(*host16, *out16)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(e2e_steps):
+                pipe16.forward_backward(*host16, *out16)
+            b1.record()
+            barrier()
+            t = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            h16 = sum(x.numel() * x.element_size() for x in host16)
+            d16 = sum(x.numel() * x.element_size() for x in out16)
+            q16 = n * s * world * e2e_steps / (float(t.item()) * 1e-3)
+            # the copy ceiling scales with the bytes: the measured fp32 ceiling (bytes per second) applied to these bytes
+            lim16 = copy_limit_qps * (h2d + d2h) / (h16 + d16)
+            e2e_bf16 = {"value": q16, "unit": UNIT, "h2d_bytes_per_step": h16, "d2h_bytes_per_step": d16,
+                        "steps": e2e_steps, "limit_from_measured_copy_rate": lim16, "frac_of_limit": q16 / lim16}
+            del pipe16, host16, out16
+        except Exception as exc:
+            e2e_bf16 = {"error": repr(exc)[:200]}
+
     # ---- the other storage type of the op (bf16 values when the line is fp32 and vice versa): device-resident --
     other = {}
     try:
@@ -804,7 +836,7 @@ def run_b200(args):
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
             "per_step_ms": {"fwd_median": fwd_med, "bwd_median": bwd_med, "fwd_min": fwd_all[0],
                             "bwd_min": bwd_all[0], "fwd_max": fwd_all[-1], "bwd_max": bwd_all[-1]},
-            "op_other_dtype": other,
+            "op_other_dtype": other, "e2e_bf16": e2e_bf16,
             "cpu_baseline": cpu_baseline}
     line.update(extras)
     print(json.dumps(line), flush=True)
