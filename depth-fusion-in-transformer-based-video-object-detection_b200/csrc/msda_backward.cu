@@ -28,6 +28,7 @@
 //   * grad_loc / grad_attn are written for every sample (zeros for samples outside the map),
 //     so they need no zero-fill pass; only grad_value is memset.
 // Generic kernel: any D / dtype (fp64 for gradcheck): one warp per pair, lanes stride channels.
+#include <type_traits>
 #include "msda_common.cuh"
 #include "msda_launch.h"
 
@@ -141,8 +142,11 @@ __global__ void __launch_bounds__(BwdWarps<32 / (D / 4)>::value * 32, MSDA_BWD_M
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const SampleSrc src, float* __restrict__ gv_accum, const GradDst dst,
-                     int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs)
+                     int S, int M, int L, int Lq, int P, int p_magic, long long total_pairs,
+                     const unsigned char* __restrict__ red_levels)
 {
+    // red_levels (optional): per pair, bit l set = this kernel issues the grad_value reductions of level l; clear =
+    // another kernel accumulates that level (msda_tc_backward.cu).  nullptr = every level.
     constexpr int EPL = 4;                       // channels per lane: one red.v4.f32 per corner
     using SliceT = Slice<VT, EPL>;
     constexpr int G = D / EPL;
@@ -203,6 +207,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         ap = static_cast<const float*>(src.attn) + pair * LP;
     }
 
+    const unsigned red_mask = red_levels != nullptr ? (unsigned)red_levels[pair] : 0xffffffffu;
     float g[EPL];
     SliceT::unpack(SliceT::load_stream(grad_out + pair * D + sub * EPL), g);
     if (!active) {
@@ -428,7 +433,10 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     float* q00 = gbase + (long long)geo[u].x * MD;
                     const long long row = (long long)geo[u].y * MD;
                     float* const qk[4] = {q00, q00 + MD, q00 + row, q00 + row + MD};
-                    if constexpr (DEDUP) {
+                    const bool do_red = (red_mask >> div_by_points(s0 + j0 + u, p_magic)) & 1u;
+                    if (!do_red) {
+                        // this (pair, level) is accumulated elsewhere
+                    } else if constexpr (DEDUP) {
                         const float4 cf = s_coef[warp][grp][j0 + u];       // merged coefficient; 0 = row issued elsewhere / no-op
                         const float ck[4] = {cf.x, cf.y, cf.z, cf.w};
 #pragma unroll
@@ -650,7 +658,8 @@ msda_cast_accum_kernel(const float* __restrict__ src, VT* __restrict__ dst, long
 // launchers
 // ------------------------------------------------------------------------------------------
 template <typename VT, int D>
-static cudaError_t launch_bwd_fast(const BwdArgs& a, float* accum, cudaStream_t stream)
+static cudaError_t launch_bwd_fast(const BwdArgs& a, float* accum, cudaStream_t stream,
+                                   const unsigned char* red_levels = nullptr)
 {
     constexpr int G = D / 4;
     constexpr int PAIRS = 32 / G;
@@ -670,7 +679,7 @@ static cudaError_t launch_bwd_fast(const BwdArgs& a, float* accum, cudaStream_t 
     dst.loc = a.grad_loc; dst.attn = a.grad_attn; dst.ref = nullptr;
     msda_bwd_fast_kernel<VT, D, false, float><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
         (const VT*)a.grad_out, (const VT*)a.value, a.shapes, a.lsi, src, accum, dst,
-        a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+        a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs, red_levels);
     return cudaGetLastError();
 }
 
@@ -696,7 +705,7 @@ static cudaError_t launch_bwd_fused(const FusedArgs& a, float* accum, cudaStream
     dst.loc = a.grad_offsets; dst.attn = a.grad_logits; dst.ref = a.grad_ref;
     msda_bwd_fast_kernel<VT, D, true, RT><<<(unsigned)blocks, WARPS * 32, 0, stream>>>(
         (const VT*)a.grad_out, (const VT*)a.value, a.shapes, a.lsi, src, accum, dst,
-        a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs);
+        a.S, a.M, a.L, a.Lq, a.P, p_magic, total_pairs, nullptr);
     return cudaGetLastError();
 }
 
@@ -729,6 +738,25 @@ static cudaError_t run_bwd_16or32(const BwdArgs& a, cudaStream_t stream)
     cudaError_t err = cudaMemsetAsync(accum, 0, count * sizeof(float), stream);
     if (err != cudaSuccess) return err;
     const long long total_pairs = (long long)a.N * a.Lq * a.M;
+    if constexpr (std::is_same<VT, __nv_bfloat16>::value) {
+        if (!a.no_tc && total_pairs > 0 && fast_shape_ok(a) && tc_backward_supported(a)) {
+            // opt-in: grad_value of every (tile, level) whose window fits is accumulated on the tensor cores
+            // (msda_tc_backward.cu); the lane-group kernel keeps grad_loc / grad_attn and the levels left over
+            unsigned char* red_levels = nullptr;
+            err = cudaMallocAsync((void**)&red_levels, (size_t)total_pairs, stream);
+            if (err != cudaSuccess) return err;
+            err = tc_backward_dv(a, red_levels, stream);
+            if (err == cudaSuccess) err = launch_bwd_fast<VT, 32>(a, accum, stream, red_levels);
+            const cudaError_t e2 = cudaFreeAsync(red_levels, stream);
+            if (err != cudaSuccess) return err;
+            if (e2 != cudaSuccess) return e2;
+            long long blocks = (long long)((count / 8 + 255) / 256);
+            if (blocks < 1) blocks = 1;
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            msda_cast_accum_kernel<VT><<<(unsigned)blocks, 256, 0, stream>>>(accum, (VT*)a.grad_value, (long long)count);
+            return cudaGetLastError();
+        }
+    }
     if (total_pairs > 0 && a.D > 0) {
         bool done = false;
         if (fast_shape_ok(a)) {

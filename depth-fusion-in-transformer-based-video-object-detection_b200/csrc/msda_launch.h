@@ -76,6 +76,10 @@ cudaError_t forward(const FwdArgs& a, cudaStream_t stream);
 // <= 4 points.  forward() / backward() route to it when it applies.
 bool tc_forward_supported(const FwdArgs& a);
 cudaError_t tc_forward(const FwdArgs& a, cudaStream_t stream);
+bool tc_backward_supported(const BwdArgs& a);
+// grad_value of every (tile, level) whose window fits -> a.grad_value_accum (zeroed by the caller);
+// red_levels[pair] = mask of the levels left to msda_bwd_fast_kernel's reductions
+cudaError_t tc_backward_dv(const BwdArgs& a, unsigned char* red_levels, cudaStream_t stream);
 
 cudaError_t backward(const BwdArgs& a, cudaStream_t stream);
 

@@ -64,3 +64,26 @@ def test_tc_flag_is_ignored_where_the_formulation_does_not_apply():
         torch.cuda.synchronize()
         emax, _ = tc.nerr(out, ref)
         assert emax <= (1e-5 if dtype == torch.float32 else 2.0 ** -7)
+
+
+@pytest.mark.parametrize("case", tc.CASES, ids=[c[0] for c in tc.CASES])
+def test_tc_backward_grad_value_matches_oracle(case):
+    """``msda_backward`` with MSDA_FLAG_TC: grad_value of every (tile, level) whose window fits is accumulated by
+    msda_tc_dv_kernel (C^T . G on tcgen05, one bulk tensor reduction per window row), the rest and grad_loc / grad_attn
+    by the lane-group kernel.  grad_value against the fp64 oracle within the bf16 bound; grad_loc / grad_attn must be
+    BIT-IDENTICAL to the default path (the same kernel computes them)."""
+    name, shapes, n, m, p, dist, seed, lq = case
+    dev = torch.device("cuda:0")
+    value, loc, attn, gout, lsi = tc.make_case(shapes, n, m, p, dist, seed, lq)
+    st = torch.as_tensor(shapes, dtype=torch.long, device=dev)
+    ls = torch.as_tensor(lsi, dtype=torch.long, device=dev)
+    vb, gb = value.to(torch.bfloat16), gout.to(torch.bfloat16)
+    v64 = vb.double().requires_grad_(True)
+    msda_oracle.core_pytorch(v64, shapes, loc.double(), attn.double()).backward(gb.double())
+    vd, ld, ad, gd = vb.to(dev), loc.to(dev), attn.to(dev), gb.to(dev)
+    gv_tc, gl_tc, ga_tc = tc.bwd_call(vd, st, ls, ld, ad, gd, _lib.FLAG_TC)
+    gv_lg, gl_lg, ga_lg = tc.bwd_call(vd, st, ls, ld, ad, gd, 0)
+    torch.cuda.synchronize()
+    emax, el2 = tc.nerr(gv_tc, v64.grad)
+    assert emax <= 2.0 ** -7 and el2 <= 4e-3, f"{name}: grad_value {emax:.2e} {el2:.2e}"
+    assert torch.equal(gl_tc, gl_lg) and torch.equal(ga_tc, ga_lg)

@@ -18,6 +18,6 @@ for _ in range(3):
     if what == "fwd":
         c.fwd_call(vd, st, ls, ld, ad, c._lib.FLAG_TC)
     else:
-        c.bwd_call(vd, st, ls, ld, ad, gd, 0)
+        c.bwd_call(vd, st, ls, ld, ad, gd, c._lib.FLAG_TC)
     torch.cuda.synchronize()
 print("done")
