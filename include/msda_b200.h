@@ -45,10 +45,14 @@ typedef enum {
 
 /* flags */
 #define MSDA_FLAG_FORCE_GENERIC 1   /* route through the shape-generic kernels (testing) */
-#define MSDA_FLAG_TC 4              /* msda_forward: run the tensor-core (tcgen05 + TMA) formulation of the gather
-                                       (csrc/msda_tc_forward.cu: bf16, 32 channels per head, <= 4 levels, <= 4 points)
-                                       where it applies.  Exact for any input, parity-tested, but measured SLOWER than
-                                       the default lane-group gather on B200, so it is opt-in */
+#define MSDA_FLAG_TC 4              /* msda_forward / msda_backward: run the tensor-core (tcgen05 + TMA) formulation where
+                                       it applies (bf16 values, 32 channels per head, <= 4 levels, <= 4 points, at least
+                                       2048 queries): csrc/msda_tc_forward.cu computes the output as C . V_window per
+                                       128-query tile, csrc/msda_tc_backward.cu accumulates grad_value as C^T . G with one
+                                       bulk tensor reduction per window row (grad_sampling_loc / grad_attn_weight stay
+                                       with the default kernel).  Exact for any input and parity-tested, but measured
+                                       SLOWER than the default lane-group kernels on B200:
+                                       opt-in, for experiments */
 
 /* ABI version of this header (bumped on any signature change). */
 int msda_abi_version(void);
