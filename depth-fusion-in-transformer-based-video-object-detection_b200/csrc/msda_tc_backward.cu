@@ -361,7 +361,8 @@ bool tc_backward_supported(const BwdArgs& a)
 {
     return a.dtype == kBF16 && a.D == tc::kD && a.L >= 1 && a.L <= tc::kMaxL && a.P >= 1 && a.P <= tc::kMaxP &&
            !a.force_generic && (long long)a.N * a.S < (1ll << 31) && (long long)a.N * a.Lq >= 2048 &&
-           (long long)a.N * a.Lq * a.M < (1ll << 30) && a.grad_value_accum != nullptr &&
+           (long long)a.N * a.Lq * a.M < (1ll << 30) && (long long)a.N * a.M * ((long long)a.Lq / 5 + a.L + 2) < (1ll << 30) &&
+           a.grad_value_accum != nullptr &&
            ((size_t)a.grad_value_accum % 16) == 0 && ((size_t)a.grad_out % 16) == 0;
 }
 
