@@ -10,10 +10,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MSDA_B200_LIB selects another build of the same ABI (A/B kernel experiments); default: in-tree
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_HERE, "libmsda_b200.so")
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 DTYPE_F32, DTYPE_F64, DTYPE_BF16, DTYPE_F16 = 0, 1, 2, 3
 FLAG_FORCE_GENERIC = 1
 FLAG_TC = 4
+FLAG_VALUE_HEAD_MAJOR = 8
 
 _lib = None
 
@@ -53,6 +54,12 @@ def load():
     lib.msda_fused_forward_strided.argtypes = [c_int, c_int, c_vp, c_i64] + fused_common[1:] + [c_vp, c_vp]
     lib.msda_fused_backward.restype = c_int
     lib.msda_fused_backward.argtypes = [c_int, c_int, c_vp] + fused_common + [c_vp, c_vp, c_vp, c_fp, c_vp, c_vp]
+    lib.msda_fused_forward_head_major.restype = c_int
+    lib.msda_fused_forward_head_major.argtypes = [c_int, c_int] + fused_common + [c_vp, c_vp]
+    lib.msda_layer_value_proj_head_major_supported.restype = c_int
+    lib.msda_layer_value_proj_head_major_supported.argtypes = [c_int, c_int, c_int]
+    lib.msda_layer_value_proj_head_major.restype = c_int
+    lib.msda_layer_value_proj_head_major.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]
     c_f = ctypes.c_float
     lib.msda_layer_add_layernorm_supported.restype = c_int
     lib.msda_layer_add_layernorm_supported.argtypes = [c_int, c_int]

@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 17; }
+extern "C" int msda_abi_version(void) { return 18; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -30,11 +30,13 @@ extern "C" int msda_forward(int dtype, const void* value, const int64_t* spatial
     a.L = num_levels; a.Lq = num_query; a.P = num_point;
     a.force_generic = (flags & MSDA_FLAG_FORCE_GENERIC) ? 1 : 0;
     a.no_tc = (flags & MSDA_FLAG_TC) ? 0 : 1;
+    a.head_major = (flags & MSDA_FLAG_VALUE_HEAD_MAJOR) ? 1 : 0;
     if (num_levels == 0 || num_point == 0) {   // empty sum: output is all zeros
         const size_t esz = dtype == MSDA_DTYPE_F64 ? 8 : (dtype == MSDA_DTYPE_F32 ? 4 : 2);
         return (int)cudaMemsetAsync(output, 0, (size_t)batch * num_query * num_heads * channels * esz,
                                     (cudaStream_t)stream);
     }
+    if (a.head_major) return (int)msda::forward_hm(a, (cudaStream_t)stream);
     return (int)msda::forward(a, (cudaStream_t)stream);
 }
 
@@ -300,6 +302,37 @@ extern "C" int msda_layer_group_norm_tokens(int dtype, const void* x, const void
     return (int)msda::group_norm_tokens(dtype, x, channel_bias, gamma, beta, y, partial_scratch, batch,
                                         (long long)tokens_per_item, channels, groups, slabs, eps,
                                         (long long)item_stride, (cudaStream_t)stream);
+}
+
+extern "C" int msda_fused_forward_head_major(int dtype, int raw_dtype, const void* value_hm, const int64_t* spatial_shapes,
+                                             const int64_t* level_start_index, const float* reference_points, int ref_dim,
+                                             const void* sampling_offsets_raw, int64_t offsets_query_stride,
+                                             const void* attention_logits_raw, int64_t logits_query_stride, int batch,
+                                             int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                                             int num_point, void* output, void* stream)
+{
+    if (bad_dims(batch, spatial_size, num_heads, channels, num_levels, num_query, num_point))
+        return (int)cudaErrorInvalidValue;
+    msda::FusedArgs a = make_fused(dtype, raw_dtype, value_hm, spatial_shapes, level_start_index, reference_points,
+                                   ref_dim, sampling_offsets_raw, offsets_query_stride, attention_logits_raw,
+                                   logits_query_stride, batch, spatial_size, num_heads, channels, num_levels,
+                                   num_query, num_point);
+    a.out = output;
+    return (int)msda::fused_forward_hm(a, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_value_proj_head_major_supported(int dtype, int d_model, int num_heads)
+{
+    return msda::value_proj_hm_supported(dtype, d_model, num_heads) ? 1 : 0;
+}
+
+extern "C" int msda_layer_value_proj_head_major(int dtype, const void* x, const void* weight, const void* bias,
+                                                const unsigned char* padding_mask, int64_t rows, int tokens_per_frame,
+                                                int d_model, int num_heads, void* value_hm, void* stream)
+{
+    if (rows < 0 || !msda::value_proj_hm_supported(dtype, d_model, num_heads)) return (int)cudaErrorInvalidValue;
+    return (int)msda::value_proj_hm(dtype, x, weight, bias, padding_mask, value_hm, (long long)rows, tokens_per_frame,
+                                    (cudaStream_t)stream);
 }
 
 extern "C" int msda_layer_proj_layernorm_supported(int dtype, int d_in, int d_out)

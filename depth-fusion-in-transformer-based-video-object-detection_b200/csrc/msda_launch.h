@@ -18,6 +18,7 @@ struct FwdArgs {
     int N, S, M, D, L, Lq, P;
     int force_generic;        // tests: route through the generic kernel
     int no_tc;                // 0: take the tensor-core formulation (msda_tc_forward.cu) where it applies (opt-in)
+    int head_major;           // value is [N, M, S, D] (msda_forward_hm.cu: bf16, D = 32) instead of [N, S, M, D]
 };
 
 struct BwdArgs {
@@ -71,6 +72,14 @@ cudaError_t fused_forward(const FusedArgs& a, cudaStream_t stream);
 cudaError_t fused_backward(const FusedArgs& a, cudaStream_t stream);
 
 cudaError_t forward(const FwdArgs& a, cudaStream_t stream);
+// head-major value layout [N, M, S, 32] (bf16): msda_forward_hm.cu
+bool forward_hm_supported(int dtype, int D, int L, int P);
+cudaError_t forward_hm(const FwdArgs& a, cudaStream_t stream);
+cudaError_t fused_forward_hm(const FusedArgs& a, cudaStream_t stream);
+// value_proj on tcgen05 with a head-major epilogue (value_proj_hm.cu): x [rows, 256] bf16 -> out_hm [N, 8, S, 32]
+bool value_proj_hm_supported(int dtype, int d_model, int n_heads);
+cudaError_t value_proj_hm(int dtype, const void* x, const void* w, const void* b, const unsigned char* mask, void* out_hm,
+                          long long rows, int S, cudaStream_t stream);
 
 // Tensor-core formulation (msda_tc_forward.cu / msda_tc_backward.cu): bf16 values, 32 channels per head, <= 4 levels,
 // <= 4 points.  forward() / backward() route to it when it applies.

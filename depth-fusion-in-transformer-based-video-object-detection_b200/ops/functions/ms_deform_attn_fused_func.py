@@ -128,3 +128,70 @@ class MSDeformAttnFusedFunction(Function):
         if grad_ref is not None and grad_ref.dtype != ctx.ref_dtype:
             grad_ref = grad_ref.to(ctx.ref_dtype)
         return grad_value, None, None, grad_ref, grad_raw, None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Inference with a HEAD-MAJOR value tensor (csrc/value_proj_hm.cu + csrc/msda_forward_hm.cu): the value projection runs
+# as an own tcgen05 GEMM whose epilogue adds the bias, zeroes the padding rows and writes [N, M, S, D] -- the layout in
+# which the x-neighbours of a bilinear footprint are adjacent (3 instead of 4 L1 lines per sample in the gather).
+# No autograd: callers use it only when no gradient is needed.
+# ------------------------------------------------------------------------------------------------------------------
+def head_major_supported(value_proj, input_flatten, raw, ref_dim, n_heads, n_levels, n_points):
+    """bf16 CUDA inference at d_model 256 / 8 heads of 32 with a raw projection the fused kernels accept."""
+    w = value_proj.weight
+    if not (input_flatten.is_cuda and raw.is_cuda) or input_flatten.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        return False
+    if value_proj.bias is None or raw.dtype not in _DTYPES or input_flatten.dim() != 3 or input_flatten.size(0) == 0:
+        return False
+    lib = _lib.load()
+    d_model = w.shape[0]
+    if w.shape[1] != d_model or d_model % n_heads != 0:
+        return False
+    if not lib.msda_layer_value_proj_head_major_supported(_lib.DTYPE_BF16, int(d_model), int(n_heads)):
+        return False
+    s = input_flatten.size(1)
+    return bool(lib.msda_fused_supported(_lib.DTYPE_BF16, _DTYPES[raw.dtype], int(ref_dim), int(s), int(n_heads),
+                                         int(d_model // n_heads), int(n_levels), int(n_points)))
+
+
+def value_proj_head_major(value_proj, input_flatten, padding_mask, n_heads):
+    """``value_proj(input_flatten)`` with masked rows zeroed (reference ms_deform_attn.py:94-96) -> [N, M, S, D]."""
+    n, s, c = input_flatten.shape
+    x = _aligned(input_flatten.contiguous())
+    w = _aligned(value_proj.weight.detach().contiguous())
+    b = value_proj.bias.detach().contiguous()
+    mask8 = None
+    if padding_mask is not None:
+        mask8 = padding_mask.reshape(-1).contiguous()
+        mask8 = mask8.view(torch.uint8) if mask8.dtype == torch.bool else (mask8 != 0).to(torch.uint8)
+    with torch.cuda.device(x.device):
+        out = torch.empty((n, n_heads, s, c // n_heads), dtype=x.dtype, device=x.device)
+        code = _lib.load().msda_layer_value_proj_head_major(
+            _lib.DTYPE_BF16, x.data_ptr(), w.data_ptr(), b.data_ptr(), mask8.data_ptr() if mask8 is not None else None,
+            n * s, s, c, n_heads, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(code, "msda_layer_value_proj_head_major")
+    return out
+
+
+def fused_forward_head_major(value_hm, spatial_shapes, level_start_index, reference_points, raw, n_points):
+    """The fused layer forward (softmax, location arithmetic, gather, head reduction) on a head-major value tensor
+    [N, M, S, D] -> [N, Lq, M*D].  Inference only."""
+    n, m, s, d = value_hm.shape
+    nl = spatial_shapes.size(0)
+    lq = raw.size(1)
+    p = int(n_points)
+    mlp = m * nl * p
+    if raw.size(-1) != 3 * mlp or raw.size(0) != n:
+        raise RuntimeError(f"raw must be [N, Lq, 3*M*L*P={3 * mlp}], got {tuple(raw.shape)}")
+    raw = _aligned(raw.contiguous())
+    ref = _aligned(reference_points.detach().to(torch.float32).contiguous())
+    with torch.cuda.device(value_hm.device):
+        out = torch.empty((n, lq, m * d), dtype=value_hm.dtype, device=value_hm.device)
+        esz = raw.element_size()
+        code = _lib.load().msda_fused_forward_head_major(
+            _DTYPES[value_hm.dtype], _DTYPES[raw.dtype], value_hm.data_ptr(), spatial_shapes.contiguous().data_ptr(),
+            level_start_index.contiguous().data_ptr(), ref.data_ptr(), ref.size(-1), raw.data_ptr(), 3 * mlp,
+            raw.data_ptr() + 2 * mlp * esz, 3 * mlp, n, s, m, d, nl, lq, p, out.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
+    _lib.check(code, "msda_fused_forward_head_major")
+    return out

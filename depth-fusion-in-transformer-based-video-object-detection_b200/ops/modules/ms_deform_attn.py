@@ -27,7 +27,13 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported, linear, linear_wb, zero_masked_rows_
+from ..functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported, linear, linear_wb,
+                         zero_masked_rows_, head_major_supported, value_proj_head_major, fused_forward_head_major)
+
+# bf16 inference: own value-projection GEMM with a head-major epilogue + the head-major fused gather (see forward).
+# Opt-in: measured on B200 (tools/run_hm_layer.py, 6-layer encoder, batch 8) the route is slower than the library GEMM +
+# reference-layout gather (5.25 vs 4.62 ms) -- see DESIGN.md section 3.11.
+HEAD_MAJOR_INFERENCE = False
 
 
 def _is_power_of_2(n):
@@ -149,6 +155,26 @@ class MSDeformAttn(nn.Module):
         N, Len_q, _ = query.shape
         N, Len_in, _ = input_flatten.shape
         assert _total_pixels(input_spatial_shapes) == Len_in
+
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError(
+                'Last dim of reference_points must be 2 or 4, but get {} instead.'.format(reference_points.shape[-1]))
+
+        # bf16 inference at d_model 256 / 8 heads: value_proj as an own tcgen05 GEMM whose epilogue adds the bias, zeroes
+        # the padding rows and writes the HEAD-MAJOR layout the gather likes best (3 instead of 4 L1 lines per sample);
+        # the fused forward kernel then reads that layout.  Opt-in (HEAD_MAJOR_INFERENCE).
+        if (self.fused and HEAD_MAJOR_INFERENCE and precomputed_value is None and input_flatten.is_cuda
+                and input_flatten.dtype == torch.bfloat16
+                and not (torch.is_grad_enabled() and (query.requires_grad or input_flatten.requires_grad
+                                                      or self.value_proj.weight.requires_grad))):
+            weight, bias = self._raw_projection_params()
+            raw = linear_wb(query, weight, bias)
+            if head_major_supported(self.value_proj, input_flatten, raw, reference_points.shape[-1], self.n_heads,
+                                    self.n_levels, self.n_points):
+                value_hm = value_proj_head_major(self.value_proj, input_flatten, input_padding_mask, self.n_heads)
+                output = fused_forward_head_major(value_hm, input_spatial_shapes, input_level_start_index,
+                                                  reference_points, raw, self.n_points)
+                return linear(self.output_proj, output) if project_output else output
 
         # 2-d in, 2-d out: the projection result is a fresh tensor (not a view), so the padding rows
         # can be zeroed in place without autograd having to copy slices back

@@ -54,6 +54,11 @@ typedef enum {
                                        SLOWER than the default lane-group kernels on B200:
                                        opt-in, for experiments */
 
+#define MSDA_FLAG_VALUE_HEAD_MAJOR 8 /* msda_forward: `value` is laid out [N, M, S, D] (all pixels of a head contiguous)
+                                       instead of the reference's [N, S, M, D].  BF16, D = 32 only (else an error).
+                                       The x-neighbours of a bilinear footprint are then adjacent in memory: 3 instead
+                                       of 4 L1 lines per sample (csrc/msda_forward_hm.cu) */
+
 /* ABI version of this header (bumped on any signature change). */
 int msda_abi_version(void);
 
@@ -113,6 +118,23 @@ int msda_fused_forward(int dtype, int raw_dtype,
                        int batch, int spatial_size, int num_heads, int channels,
                        int num_levels, int num_query, int num_point,
                        void* output, void* stream);
+
+/* Head-major variants for inference (round 2).  value_hm is laid out [N, M, S, D]: all pixels of a head contiguous, so
+ * the x-neighbours of a bilinear footprint are adjacent in memory (3 instead of 4 L1 lines per sample).  BF16, D = 32.
+ * msda_layer_value_proj_head_major computes  value = x @ W^T + b  (reference modules/ms_deform_attn.py:94), zeroes the
+ * rows of padding_mask (:95-96; one byte per row, may be NULL) and writes that layout directly from the GEMM epilogue
+ * (tcgen05, d_model 256, 8 heads); msda_fused_forward_head_major is msda_fused_forward reading it. */
+int msda_fused_forward_head_major(int dtype, int raw_dtype,
+                                  const void* value_hm, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                  const float* reference_points, int ref_dim,
+                                  const void* sampling_offsets_raw, int64_t offsets_query_stride,
+                                  const void* attention_logits_raw, int64_t logits_query_stride,
+                                  int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                                  int num_query, int num_point, void* output, void* stream);
+int msda_layer_value_proj_head_major_supported(int dtype, int d_model, int num_heads);
+int msda_layer_value_proj_head_major(int dtype, const void* x, const void* weight, const void* bias,
+                                     const unsigned char* padding_mask, int64_t rows, int tokens_per_frame,
+                                     int d_model, int num_heads, void* value_hm, void* stream);
 
 /* msda_fused_forward reading `value` with a pixel stride: pixel r of item n starts at
  * value[(n * spatial_size + r) * value_pixel_stride] (elements; >= num_heads * channels, a multiple of the 16-byte
