@@ -13,18 +13,23 @@
 //
 // Fast kernel (same lane mapping as the forward: a group of G lanes owns a pair, each lane a
 // 16-byte channel slice):
-//   * footprints are computed once per sample by one lane and shared through smem;
+//   * phase 1: one lane per sample computes the footprint ONCE and parks everything phase 2 needs in shared memory,
+//     already masked for corners outside the map: the four row offsets (clamped to a harmless in-range row), the
+//     grad_value coefficient of each row, and the coefficients that turn the four corner dot products
+//     t_k = <grad_output, value_k> into grad_attn and the two grad_loc partials
+//         pa = sum_k ca_k t_k      ca = (hh*hw, hh*lw, lh*hw, lh*lw)
+//         px = sum_k cx_k t_k      cx = a * (-hh, +hh, -lh, +lh)
+//         py = sum_k cy_k t_k      cy = a * (-hw, -lw, +hw, +lw)
+//     (the same sums as cuh:113-158, with the channel sum taken first);
+//   * phase 2, per sample and lane: 4 unconditional loads, 8 packed FMAs for the dots, 6 for the three outputs, three
+//     8-lane butterflies, 4 predicated reductions -- ~80 instructions where the round-1 kernel needed 164 (64-bit
+//     address arithmetic per corner, zero-filled predicated loads, branches around every reduction);
 //   * grad_value uses ONE 16-byte vector reduction (red.global.add.v4.f32 -> REDG.E.ADD.F32x4)
 //     per lane per corner instead of 4 scalar atomics, always into an fp32 buffer.  A lane
 //     always owns 4 channels here (16-bit values are read with 8-byte loads) so that the 8 lanes
 //     of a group cover one whole 128-byte fp32 row per instruction: measured on B200, the
 //     SM->L2 reduction path costs ~5.5 cycles per (instruction, row) whether the row is written
 //     whole or in halves (tools/microbench_red.cu), and it is what bounds this kernel;
-//   * the three per-sample dot products stay in registers; after a 16-sample chunk the 48
-//     partials per lane are combined across the group with a shuffle reduce-scatter
-//     (24+12+6 shuffles for G=8 instead of 144 for a per-value butterfly) that leaves every
-//     lane holding the finished gradients of its own samples, which it stores directly.
-//     No shared-memory reduction, no block barrier;
 //   * grad_loc / grad_attn are written for every sample (zeros for samples outside the map),
 //     so they need no zero-fill pass; only grad_value is memset.
 // Generic kernel: any D / dtype (fp64 for gradcheck): one warp per pair, lanes stride channels.
@@ -45,23 +50,6 @@ template <int PAIRS> struct BwdWarps { static constexpr int value = PAIRS >= 16 
 #ifndef MSDA_CTA_PER_HEAD      // see msda_forward.cu
 #define MSDA_CTA_PER_HEAD 1
 #endif
-
-// After the call lane `sub` of each G-lane group holds, in v[0 .. N*2*OFF/G... ) -- precisely
-// v[0 .. N/(2*OFF)) -- the group-wide sums of original elements [sub*len, (sub+1)*len).
-template <int N, int OFF>
-__device__ __forceinline__ void reduce_scatter(float* v, int sub)
-{
-    if constexpr (OFF >= 1) {
-        const bool upper = (sub & OFF) != 0;
-#pragma unroll
-        for (int i = 0; i < N / 2; ++i) {
-            const float send = upper ? v[i] : v[i + N / 2];
-            const float keep = upper ? v[i + N / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-        }
-        reduce_scatter<N / 2, OFF / 2>(v, sub);
-    }
-}
 
 // Where the per-sample gradients go.  Plain: grad_sampling_loc / grad_attn_weight.  Fused:
 // gradients w.r.t. the raw projection outputs (through the location arithmetic and the softmax)
@@ -84,18 +72,6 @@ struct GradDst {
 #ifndef MSDA_BWD_CHUNK
 #define MSDA_BWD_CHUNK 8
 #endif
-// samples gathered together per lane (2 spills at the 64-register budget)
-#ifndef MSDA_BWD_UNROLL
-#define MSDA_BWD_UNROLL 1
-#endif
-
-// 1: reduce each sample's three dot products across the group right away (3 butterflies per
-// sample) instead of keeping 3*CH partials per lane for one reduce-scatter per pass: more shuffles,
-// 24 fewer registers.
-#ifndef MSDA_BWD_IMMEDIATE
-#define MSDA_BWD_IMMEDIATE 1
-#endif
-
 // 1: before the reductions leave the SM, merge the corner rows that several samples of one (query, head, level)
 // share.  Every sample of a pair scatters coefficient * grad_output[pair] -- the SAME row -- so two samples that
 // touch the same pixel need one reduction of the summed coefficient, not two.  With the encoder's geometry (points
@@ -114,13 +90,6 @@ struct GradDst {
 // reg_pick / reg_put (selects over a static index) so that they stay in registers.
 #ifndef MSDA_BWD_FUSED_ROLLED
 #define MSDA_BWD_FUSED_ROLLED 1
-#endif
-// 1: the per-channel arithmetic of phase 2 runs on channel PAIRS with Blackwell's packed fp32 instructions
-// (fma / mul / add / sub .f32x2 -> FFMA2 / FMUL2 / FADD2; nvcc emits them only from inline PTX).  Each half is an
-// ordinary IEEE operation, so only the order of the per-sample channel sums changes (two partial sums instead of one
-// chain).  The fused backward is issue-bound after the pass loop was rolled (77 % issue-active, ncu r1l).
-#ifndef MSDA_BWD_F32X2
-#define MSDA_BWD_F32X2 1
 #endif
 template <int K>
 __device__ __forceinline__ float reg_pick(const float (&a)[K], int idx)
@@ -156,15 +125,17 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     constexpr int SPL = CH / G;                  // samples a lane owns per pass: j = sub*SPL + i, in phase 1
                                                  // (footprints) and again after the reduce-scatter (gradients)
     constexpr int FCH = (kChunk + CH - 1) / CH;  // passes of the fused op (host guarantees L*P <= kChunk)
-    constexpr int U = MSDA_BWD_UNROLL;
     static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "fast backward needs 1..32 lanes per head");
-    static_assert(CH % G == 0 && CH % U == 0, "pass size must split evenly over the lanes and the unroll");
+    static_assert(CH % G == 0, "pass size must split evenly over the lanes");
 
+    // per-sample records of a pass (+1 record: the groups of a warp start in distinct banks)
     __shared__ int s_meta[3 * kMaxLevelsFast];
-    __shared__ __align__(16) int4   s_geo[WARPS][PAIRS][CH + 1];   // pix00, rowstep, ok, -
-    __shared__ __align__(16) float4 s_frac[WARPS][PAIRS][CH + 1];  // lw, lh, a, -
+    // record of a sample, 5 x 16 bytes: [0] byte offset (pixel * M*D * sizeof(VT)) of each corner row (corner outside the map -> 0),
+    // [1] grad_value coefficient of each row (0 = no reduction), [2..4] corner dots -> grad_attn, grad_loc.x / W,
+    // grad_loc.y / H
+    constexpr int kRec = 5;
+    __shared__ __align__(16) uint4 s_rec[WARPS][PAIRS][CH * kRec + 1];
     constexpr bool DEDUP = MSDA_BWD_DEDUP && SPL == 1;
-    __shared__ __align__(16) float4 s_coef[DEDUP ? WARPS : 1][DEDUP ? PAIRS : 1][DEDUP ? CH + 1 : 1];   // merged corner coefficients
 
     if (threadIdx.x < L) {
         s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
@@ -193,8 +164,11 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     const int LP = L * P;
     const int MD = M * D;
     const long long head_off = (n * S * M + m) * (long long)D + sub * EPL;
-    const VT* vbase = value + head_off;
-    float* gbase = gv_accum + head_off;
+    // this lane's slice of pixel 0 of its (frame, head), as opaque addresses: a corner address is then one 64-bit add
+    // (two instructions) of the 32-bit BYTE offset parked in shared memory -- scaled by 4 / sizeof(VT) for grad_value
+    const unsigned long long vaddr = opaque_addr(value + head_off);
+    const unsigned long long gaddr = opaque_addr(gv_accum + head_off);
+    constexpr int kGradShift = sizeof(VT) == 4 ? 0 : 1;
     const float* lp = nullptr;
     const float* ap = nullptr;
     const RT* op = nullptr;
@@ -214,6 +188,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 #pragma unroll
         for (int c = 0; c < EPL; ++c) g[c] = 0.f;     // clamped duplicate pair contributes nothing
     }
+    F2 G01, G23;
+    G01.x = g[0]; G01.y = g[1]; G23.x = g[2]; G23.y = g[3];
 
     // fused: softmax over the pair's L*P logits; this lane keeps the numerators of its own samples
     float prob[FCH * SPL];
@@ -252,7 +228,6 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         const int s0 = c * CH;
         if (FUSED && s0 >= LP) break;
         const int cnt = min(CH, LP - s0);
-        const int cntu = (cnt + U - 1) / U * U;
         // ---- phase 1: footprints of this lane's own samples ------------------------------------
         float a_own[SPL];
 #pragma unroll
@@ -279,17 +254,17 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                 fr = make_float4(f.lw, f.lh, a, 0.f);
                 a_own[i] = a;
             }
-            s_geo[warp][grp][j] = geo;                 // samples past cnt: ok = 0 -> no loads, no reductions
-            s_frac[warp][grp][j] = fr;
+            // coefficient of each corner row in grad_value: bilinear weight x attention weight (cuh:113-116); every
+            // coefficient set is zero for corners outside the map (and for samples past cnt: ok = 0)
+            const float lw = fr.x, lh = fr.y, hw = 1.f - fr.x, hh = 1.f - fr.y, a = fr.z;
+            const bool k0 = geo.z & 1, k1 = geo.z & 2, k2 = geo.z & 4, k3 = geo.z & 8;
+            const float4 ca = make_float4(k0 ? hh * hw : 0.f, k1 ? hh * lw : 0.f, k2 ? lh * hw : 0.f, k3 ? lh * lw : 0.f);
+            const int my_level = div_by_points(s0 + j, p_magic);
+            float4 ck = make_float4(ca.x * a, ca.y * a, ca.z * a, ca.w * a);
             if constexpr (DEDUP) {
-                // coefficient of each corner row in grad_value: bilinear weight x attention weight (cuh:113-116);
-                // zero for corners outside the map
-                const float hw = 1.f - fr.x, hh = 1.f - fr.y;
-                const float own[4] = {(geo.z & 1) ? hh * hw * fr.z : 0.f, (geo.z & 2) ? hh * fr.x * fr.z : 0.f,
-                                      (geo.z & 4) ? fr.y * hw * fr.z : 0.f, (geo.z & 8) ? fr.y * fr.x * fr.z : 0.f};
+                const float own[4] = {ck.x, ck.y, ck.z, ck.w};
                 float merged[4] = {own[0], own[1], own[2], own[3]};
                 int dup = 0;
-                const int my_level = div_by_points(s0 + j, p_magic);
                 const int W = geo.y;
                 // corner mask / coefficient vector of a neighbour, moved by (dx, dy) pixels into MY corner frame:
                 // my corner (cx, cy) is their corner (cx - dx, cy - dy).  Bits / slots: 0 (0,0) 1 (1,0) 2 (0,1) 3 (1,1).
@@ -324,152 +299,83 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                         const float x0 = dx == 0 ? hc[0] : (dx < 0 ? hc[1] : 0.f), x1 = dx == 0 ? hc[1] : (dx > 0 ? hc[0] : 0.f);
                         const float x2 = dx == 0 ? hc[2] : (dx < 0 ? hc[3] : 0.f), x3 = dx == 0 ? hc[3] : (dx > 0 ? hc[2] : 0.f);
                         // only into corners that exist: a slot outside the map must not pass anything on
-                        merged[0] = (geo.z & 1) ? own[0] + (dy == 0 ? x0 : (dy < 0 ? x2 : 0.f)) : 0.f;
-                        merged[1] = (geo.z & 2) ? own[1] + (dy == 0 ? x1 : (dy < 0 ? x3 : 0.f)) : 0.f;
-                        merged[2] = (geo.z & 4) ? own[2] + (dy == 0 ? x2 : (dy > 0 ? x0 : 0.f)) : 0.f;
-                        merged[3] = (geo.z & 8) ? own[3] + (dy == 0 ? x3 : (dy > 0 ? x1 : 0.f)) : 0.f;
+                        merged[0] = k0 ? own[0] + (dy == 0 ? x0 : (dy < 0 ? x2 : 0.f)) : 0.f;
+                        merged[1] = k1 ? own[1] + (dy == 0 ? x1 : (dy < 0 ? x3 : 0.f)) : 0.f;
+                        merged[2] = k2 ? own[2] + (dy == 0 ? x2 : (dy > 0 ? x0 : 0.f)) : 0.f;
+                        merged[3] = k3 ? own[3] + (dy == 0 ? x3 : (dy > 0 ? x1 : 0.f)) : 0.f;
                     }
                 }
                 // a row is mine to issue if the corner lies in the map and no lower sample owns its pixel
                 const int mine = geo.z & ~dup;
-                s_coef[warp][grp][j] = make_float4((mine & 1) ? merged[0] : 0.f, (mine & 2) ? merged[1] : 0.f,
-                                                   (mine & 4) ? merged[2] : 0.f, (mine & 8) ? merged[3] : 0.f);
+                ck = make_float4((mine & 1) ? merged[0] : 0.f, (mine & 2) ? merged[1] : 0.f,
+                                 (mine & 4) ? merged[2] : 0.f, (mine & 8) ? merged[3] : 0.f);
             }
+            if (!((red_mask >> my_level) & 1u)) ck = make_float4(0.f, 0.f, 0.f, 0.f);   // level accumulated elsewhere
+            const unsigned MDu = (unsigned)MD * (unsigned)sizeof(VT);   // bytes between neighbouring pixels
+            uint4* rec = &s_rec[warp][grp][j * kRec];
+            rec[0] = make_uint4(k0 ? (unsigned)geo.x * MDu : 0u, k1 ? (unsigned)(geo.x + 1) * MDu : 0u,
+                                k2 ? (unsigned)(geo.x + geo.y) * MDu : 0u, k3 ? (unsigned)(geo.x + geo.y + 1) * MDu : 0u);
+            const float ahh = a * hh, alh = a * lh, ahw = a * hw, alw = a * lw;
+            reinterpret_cast<float4*>(rec)[1] = ck;
+            reinterpret_cast<float4*>(rec)[2] = ca;
+            reinterpret_cast<float4*>(rec)[3] = make_float4(k0 ? -ahh : 0.f, k1 ? ahh : 0.f, k2 ? -alh : 0.f, k3 ? alh : 0.f);
+            reinterpret_cast<float4*>(rec)[4] = make_float4(k0 ? -ahw : 0.f, k1 ? -alw : 0.f, k2 ? ahw : 0.f, k3 ? alw : 0.f);
         }
         __syncwarp();
 
-        // ---- phase 2: per-sample gather, dot products, vector reductions into grad_value -----
-#if MSDA_BWD_IMMEDIATE
+        // ---- phase 2: per-sample gather, corner dots, vector reductions into grad_value ----------
         float part[3 * SPL];
 #pragma unroll
         for (int i = 0; i < 3 * SPL; ++i) part[i] = 0.f;
-#else
-        float part[3 * CH];
-#pragma unroll
-        for (int i = 0; i < 3 * CH; ++i) part[i] = 0.f;
-#endif
 
 #pragma unroll
-        for (int j0 = 0; j0 < CH; j0 += U) {
-            if (j0 < cntu) {
-                int4 geo[U];
-                float4 fr[U];
-                typename SliceT::raw_t raw[U][4];
+        for (int j0 = 0; j0 < CH; ++j0) {
+            if (j0 < cnt) {
+                const uint4* rec = &s_rec[warp][grp][j0 * kRec];
+                const uint4 o = rec[0];
+                const unsigned ok[4] = {o.x, o.y, o.z, o.w};
+                typename SliceT::raw_t raw[4];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    geo[u] = s_geo[warp][grp][j0 + u];
-                    fr[u] = s_frac[warp][grp][j0 + u];
-                    const VT* p00 = vbase + (long long)geo[u].x * MD;
-                    const long long row = (long long)geo[u].y * MD;
-                    raw[u][0] = (geo[u].z & 1) ? SliceT::load(p00) : SliceT::zero();
-                    raw[u][1] = (geo[u].z & 2) ? SliceT::load(p00 + MD) : SliceT::zero();
-                    raw[u][2] = (geo[u].z & 4) ? SliceT::load(p00 + row) : SliceT::zero();
-                    raw[u][3] = (geo[u].z & 8) ? SliceT::load(p00 + row + MD) : SliceT::zero();
+                for (int k = 0; k < 4; ++k)
+                    raw[k] = SliceT::load(reinterpret_cast<const VT*>(vaddr + ok[k]));
+                const float4 ca = reinterpret_cast<const float4*>(rec)[2], cx = reinterpret_cast<const float4*>(rec)[3],
+                             cy = reinterpret_cast<const float4*>(rec)[4];
+                float t[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float v[EPL];
+                    SliceT::unpack(raw[k], v);
+                    F2 V01, V23;
+                    V01.x = v[0]; V01.y = v[1]; V23.x = v[2]; V23.y = v[3];
+                    const F2 d = fma2(G23, V23, mul2(G01, V01));      // this lane's 4 channels of <grad_output, value_k>
+                    t[k] = d.x + d.y;
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float lw = fr[u].x, lh = fr[u].y, a = fr[u].z;
-                    const float hw = 1.f - lw, hh = 1.f - lh;
-                    const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-                    float v1[EPL], v2[EPL], v3[EPL], v4[EPL], tg[EPL];
-                    SliceT::unpack(raw[u][0], v1);
-                    SliceT::unpack(raw[u][1], v2);
-                    SliceT::unpack(raw[u][2], v3);
-                    SliceT::unpack(raw[u][3], v4);
-                    float px = 0.f, py = 0.f, pa = 0.f;
-#if MSDA_BWD_F32X2
-                    {
-                        const F2 W1 = f2_dup(w1), W2 = f2_dup(w2), W3 = f2_dup(w3), W4 = f2_dup(w4);
-                        const F2 HH = f2_dup(hh), LH = f2_dup(lh), HW = f2_dup(hw), LW = f2_dup(lw), A2 = f2_dup(a);
-                        F2 pa2 = f2_dup(0.f), px2 = f2_dup(0.f), py2 = f2_dup(0.f);
-#pragma unroll
-                        for (int ch = 0; ch < EPL; ch += 2) {
-                            F2 V1, V2, V3, V4, G;
-                            V1.x = v1[ch]; V1.y = v1[ch + 1];
-                            V2.x = v2[ch]; V2.y = v2[ch + 1];
-                            V3.x = v3[ch]; V3.y = v3[ch + 1];
-                            V4.x = v4[ch]; V4.y = v4[ch + 1];
-                            G.x = g[ch]; G.y = g[ch + 1];
-                            const F2 TG = mul2(A2, G);                                          // cuh:113
-                            tg[ch] = TG.x;
-                            tg[ch + 1] = TG.y;
-                            const F2 val = fma2(W4, V4, fma2(W3, V3, fma2(W2, V2, mul2(W1, V1))));
-                            const F2 dx = fma2(LH, sub2(V4, V3), mul2(HH, sub2(V2, V1)));       // cuh:119-151 (grad_w_weight)
-                            const F2 dy = fma2(LW, sub2(V4, V2), mul2(HW, sub2(V3, V1)));       // (grad_h_weight)
-                            pa2 = fma2(G, val, pa2);
-                            px2 = fma2(TG, dx, px2);
-                            py2 = fma2(TG, dy, py2);
-                        }
-                        pa = pa2.x + pa2.y;
-                        px = px2.x + px2.y;
-                        py = py2.x + py2.y;
-                    }
-#else
-#pragma unroll
-                    for (int ch = 0; ch < EPL; ++ch) {
-                        tg[ch] = a * g[ch];                                        // cuh:113
-                        const float val = w1 * v1[ch] + w2 * v2[ch] + w3 * v3[ch] + w4 * v4[ch];
-                        const float dx = hh * (v2[ch] - v1[ch]) + lh * (v4[ch] - v3[ch]);   // cuh:119-151 (grad_w_weight)
-                        const float dy = hw * (v3[ch] - v1[ch]) + lw * (v4[ch] - v2[ch]);   // (grad_h_weight)
-                        pa = fmaf(g[ch], val, pa);
-                        px = fmaf(tg[ch], dx, px);
-                        py = fmaf(tg[ch], dy, py);
-                    }
-#endif
-#if MSDA_BWD_IMMEDIATE
-                    px = group_sum<G>(px);
-                    py = group_sum<G>(py);
-                    pa = group_sum<G>(pa);
-                    if ((j0 + u) / SPL == sub) {
-                        part[3 * ((j0 + u) % SPL) + 0] = px;
-                        part[3 * ((j0 + u) % SPL) + 1] = py;
-                        part[3 * ((j0 + u) % SPL) + 2] = pa;
-                    }
-#else
-                    part[3 * (j0 + u) + 0] = px;
-                    part[3 * (j0 + u) + 1] = py;
-                    part[3 * (j0 + u) + 2] = pa;
-#endif
-                    float* q00 = gbase + (long long)geo[u].x * MD;
-                    const long long row = (long long)geo[u].y * MD;
-                    float* const qk[4] = {q00, q00 + MD, q00 + row, q00 + row + MD};
-                    const bool do_red = (red_mask >> div_by_points(s0 + j0 + u, p_magic)) & 1u;
-                    if (!do_red) {
-                        // this (pair, level) is accumulated elsewhere
-                    } else if constexpr (DEDUP) {
-                        const float4 cf = s_coef[warp][grp][j0 + u];       // merged coefficient; 0 = row issued elsewhere / no-op
-                        const float ck[4] = {cf.x, cf.y, cf.z, cf.w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-#if MSDA_BWD_F32X2
-                            if (ck[k] != 0.f) {
-                                F2 g01, g23;
-                                g01.x = g[0]; g01.y = g[1]; g23.x = g[2]; g23.y = g[3];
-                                const F2 c2 = f2_dup(ck[k]);
-                                const F2 lo = mul2(c2, g01), hi = mul2(c2, g23);     // the same IEEE products, two per instruction
-                                red_add_f32x4(qk[k], lo.x, lo.y, hi.x, hi.y);
-                            }
-#else
-                            if (ck[k] != 0.f) red_add_f32x4(qk[k], ck[k] * g[0], ck[k] * g[1], ck[k] * g[2], ck[k] * g[3]);
-#endif
-                        }
-                    } else {
-                        const float wk[4] = {w1, w2, w3, w4};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (geo[u].z & (1 << k))
-                                red_add_f32x4(qk[k], wk[k] * tg[0], wk[k] * tg[1], wk[k] * tg[2], wk[k] * tg[3]);
-                        }
-                    }
+                F2 T01, T23;
+                T01.x = t[0]; T01.y = t[1]; T23.x = t[2]; T23.y = t[3];
+                auto combine = [&](const float4& cf) -> float {
+                    F2 C01, C23;
+                    C01.x = cf.x; C01.y = cf.y; C23.x = cf.z; C23.y = cf.w;
+                    const F2 r = fma2(C23, T23, mul2(C01, T01));
+                    return r.x + r.y;
+                };
+                const float px = group_sum<G>(combine(cx));           // cuh:119-151 (grad_w_weight * top_grad_value)
+                const float py = group_sum<G>(combine(cy));           // (grad_h_weight)
+                const float pa = group_sum<G>(combine(ca));           // cuh:156
+                if (j0 / SPL == sub) {
+                    part[3 * (j0 % SPL) + 0] = px;
+                    part[3 * (j0 % SPL) + 1] = py;
+                    part[3 * (j0 % SPL) + 2] = pa;
                 }
+                const float4 cf = reinterpret_cast<const float4*>(rec)[1];   // 0 = row outside the map / issued by another sample
+                const float ck[4] = {cf.x, cf.y, cf.z, cf.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    red_scaled_f32x4_if(reinterpret_cast<float*>(gaddr + ((unsigned long long)ok[k] << kGradShift)), ck[k], G01, G23);
             }
         }
         __syncwarp();
 
         // ---- phase 3: combine the group's partials; each lane finishes its own SPL samples ----
-#if !MSDA_BWD_IMMEDIATE
-        reduce_scatter<3 * CH, G / 2>(part, sub);
-#endif
         if constexpr (!FUSED) {
             float* grad_loc = static_cast<float*>(dst.loc);
             float* grad_attn = static_cast<float*>(dst.attn);
@@ -725,7 +631,7 @@ static cudaError_t launch_bwd_generic(const BwdArgs& a, typename Traits<VT>::acc
 static bool fast_shape_ok(const BwdArgs& a)
 {
     return !a.force_generic && a.L <= kMaxLevelsFast && a.P <= 64 && (long long)a.L * a.P * a.P < 65536 &&
-           (long long)a.S * a.M * a.D < (1ll << 31);
+           (long long)a.S * a.M * a.D < (1ll << 30);      // 32-bit byte offsets inside one frame
 }
 
 template <typename VT>

@@ -299,4 +299,28 @@ __device__ __forceinline__ F2 sub2(F2 a, F2 b)
     return f2_from(d);
 }
 
+
+// An address the compiler cannot re-derive from the kernel parameters (it would otherwise rebuild base + offset with
+// 64-bit shifts and carries at every use instead of keeping the pointer in a register pair).
+__device__ __forceinline__ unsigned long long opaque_addr(const void* p)
+{
+    unsigned long long a = reinterpret_cast<unsigned long long>(p);
+    asm volatile("" : "+l"(a));
+    return a;
+}
+// red.global.add.v4.f32 of coef * (g01, g23), issued only when coef != 0.  One asm block: the two packed products stay
+// outside the predicate, so ptxas emits a predicated REDG instead of a branch around a multiply-and-reduce block.
+__device__ __forceinline__ void red_scaled_f32x4_if(float* p, float coef, F2 g01, F2 g23)
+{
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b64 c2, lo, hi;\n\t.reg .f32 a, b, c, d;\n\t"
+                 "mov.b64 c2, {%1, %1};\n\t"
+                 "mul.rn.f32x2 lo, c2, %2;\n\t"
+                 "mul.rn.f32x2 hi, c2, %3;\n\t"
+                 "mov.b64 {a, b}, lo;\n\t"
+                 "mov.b64 {c, d}, hi;\n\t"
+                 "setp.neu.f32 q, %1, 0f00000000;\n\t"
+                 "@q red.global.add.v4.f32 [%0], {a, b, c, d};\n\t}"
+                 :: "l"(p), "f"(coef), "l"(f2_bits(g01)), "l"(f2_bits(g23)) : "memory");
+}
+
 }  // namespace msda
