@@ -1,3 +1,11 @@
+// EXPERIMENT, NOT BUILT (kept as the record of a measured negative result; see DESIGN.md section 3.2 and
+// profiles/r2_bwd_cta_merge.txt).  msda_backward.cu with the grad_value rows of a CTA (32 neighbouring queries of one head)
+// merged per pixel in shared memory before they leave the SM: hash table keyed by pixel (atomicCAS), per-slot linked lists
+// (atomicExch), one red.global.add.v4.f32 per distinct pixel and pass.  Parity: the 111 tests of test_gpu_op_parity /
+// test_gpu_fused / test_gpu_tc_forward pass.  Measured on B200, fp32 batch 8: reduction rows 69 M -> 22 M (request path
+// 84 % -> 23 % busy) but 2.29 ms instead of 1.57 ms -- the merge moves every row through shared memory once more, and the
+// L1 data pipe (128 B/clk/SM, shared by global loads, shared-memory traffic and shuffles) goes to 88 % busy with 440 M
+// shared-memory wavefronts.
 // Backward multi-scale deformable attention for sm_100a.
 //
 //   grad_value[n, pix, m, :] += w_corner * A * g            (scatter over the 4 corners)
@@ -39,16 +47,14 @@
 
 namespace msda {
 
-template <int PAIRS> struct BwdWarps { static constexpr int value = PAIRS >= 16 ? 2 : (PAIRS >= 8 ? 4 : 8); };
+// warps per CTA: at most 32 queries of a head per CTA (the merge tables are sized by queries x samples per pass)
+template <int PAIRS> struct BwdWarps { static constexpr int value = PAIRS >= 32 ? 1 : (PAIRS >= 16 ? 2 : (PAIRS >= 8 ? 4 : 8)); };
 
 // resident CTAs per SM the register allocation must allow.  Measured on B200 (tools/ab_variants.sh,
 // fp32 / bf16 backward, batch 8): 2 x 8 warps at 128 registers 1.90 / 1.88 ms; 3 x 8 warps at 80
 // registers 1.74 / 1.76 ms; 4 x 8 warps at 64 registers (immediate reduction, no spills) 1.70 / 1.75 ms.
 #ifndef MSDA_BWD_MINBLOCKS
 #define MSDA_BWD_MINBLOCKS 4
-#endif
-#ifndef MSDA_CTA_PER_HEAD      // see msda_forward.cu
-#define MSDA_CTA_PER_HEAD 1
 #endif
 
 // Where the per-sample gradients go.  Plain: grad_sampling_loc / grad_attn_weight.  Fused:
@@ -72,19 +78,17 @@ struct GradDst {
 #ifndef MSDA_BWD_CHUNK
 #define MSDA_BWD_CHUNK 8
 #endif
-// 1: before the reductions leave the SM, merge the corner rows that several samples of one (query, head, level)
-// share.  Every sample of a pair scatters coefficient * grad_output[pair] -- the SAME row -- so samples that touch the
-// same pixel need one reduction of the summed coefficient.  With the encoder's geometry (points a pixel apart along the
-// head's direction) 17 % of the corner rows are such duplicates (28 % at initialisation, where the offsets are exact
-// integers and half the bilinear weights are exactly zero -- zero-coefficient rows are dropped as well).  The kernel is
-// bound by the SM -> L2 reduction path (5.5 cycles per row), so rows saved are time saved; the price is 7 shuffles and
-// ~50 ALU instructions per lane, pass and point distance in phase 1.  Only for one sample per lane per pass (head
-// width >= 32).  Merging ACROSS queries needs the rows themselves moved between lanes: measured, it costs more L1
-// data-pipe wavefronts than the reduction rows it saves (tools/experiments/msda_backward_cta_merge.cu).
-#ifndef MSDA_BWD_DEDUP
-#define MSDA_BWD_DEDUP 1
-#endif
-
+// grad_value rows are merged ACROSS THE CTA before they leave the SM.  A CTA owns Q neighbouring queries of one head; their
+// samples of a level land on heavily overlapping pixels (bench distribution, Q = 32: 3.6 corner rows per distinct pixel
+// and pass; 5 at initialisation), and the SM -> L2 reduction path (5.5 cycles per 128-byte row, tools/microbench_red.cu)
+// is what bounded the round-1 kernel.  Per pass:
+//   * phase 1: the lane that owns a sample files each of its corner rows under the row's pixel in a shared-memory hash
+//     table (open addressing, atomicCAS on the key; a slot's rows form a linked list, atomicExch on its head); a slot's
+//     first row also appends the slot to a dense list.  Only integer shared-memory atomics -- fp32 atomics on shared
+//     memory are a CAS loop on sm_100a and cost as much as the global reduction they would replace;
+//   * phase C, after a block barrier: each lane group takes slots off the dense list, sums coefficient x grad_output row
+//     over the slot's rows (the CTA's grad_output rows sit in shared memory) and issues ONE red.global.add.v4.f32 per
+//     lane for the pixel; the group then clears the slot for the next pass.
 // 1: the fused kernel's passes run as a real loop instead of FCH unrolled copies.  Unrolled, the D = 32 bf16 kernel is
 // 4832 instructions (77 KB of SASS) that every warp walks end to end, and ncu shows 14 % of its stall samples waiting for
 // instructions (`no_instructions`, profiles/ncu_r1k.json); the per-pass register arrays are then indexed through
@@ -92,6 +96,9 @@ struct GradDst {
 #ifndef MSDA_BWD_FUSED_ROLLED
 #define MSDA_BWD_FUSED_ROLLED 1
 #endif
+template <int V> struct Log2 { static constexpr int value = 1 + Log2<V / 2>::value; };
+template <> struct Log2<1> { static constexpr int value = 0; };
+
 template <int K>
 __device__ __forceinline__ float reg_pick(const float (&a)[K], int idx)
 {
@@ -129,47 +136,64 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "fast backward needs 1..32 lanes per head");
     static_assert(CH % G == 0, "pass size must split evenly over the lanes");
 
+    constexpr int Q = WARPS * PAIRS;             // queries (of one head) per CTA
+    constexpr int E = Q * CH * 4;                // corner rows of a pass
+    constexpr int T = 2 * E;                     // hash slots: load factor <= 0.5
+    constexpr int kLogT = Log2<T>::value;
+    constexpr int kLogRowsPerQuery = Log2<CH * 4>::value;
+    constexpr unsigned kEmpty = 0xffffffffu;
+    constexpr unsigned short kEnd = 0xffffu;
+    static_assert(E <= 0xffff, "row ids are 16-bit");
+
     // per-sample records of a pass (+1 record: the groups of a warp start in distinct banks)
     __shared__ int s_meta[3 * kMaxLevelsFast];
-    // record of a sample, 5 x 16 bytes: [0] byte offset (pixel * M*D * sizeof(VT)) of each corner row (corner outside the map -> 0),
-    // [1] grad_value coefficient of each row (0 = no reduction), [2..4] corner dots -> grad_attn, grad_loc.x / W,
-    // grad_loc.y / H
-    constexpr int kRec = 5;
+    // record of a sample, 4 x 16 bytes: [0] byte offset (pixel * M*D * sizeof(VT)) of each corner row (corner outside the
+    // map -> 0), [1..3] corner dots -> grad_attn, grad_loc.x / W, grad_loc.y / H
+    constexpr int kRec = 4;
     __shared__ __align__(16) uint4 s_rec[WARPS][PAIRS][CH * kRec + 1];
-    constexpr bool DEDUP = MSDA_BWD_DEDUP && SPL == 1;
+    // the merge tables (see the top of the file)
+    __shared__ unsigned s_key[T];                // pixel of the slot: (frame - first frame of the CTA) * S + pixel
+    __shared__ int s_head[T];                    // newest row of the slot, -1 = none
+    __shared__ unsigned short s_next[E];         // next row of the same slot
+    __shared__ unsigned short s_list[E];         // slots in use
+    __shared__ float s_coef[E];                  // grad_value coefficient of a row
+    __shared__ int s_nslots[2];                  // per pass parity
+    __shared__ __align__(16) float4 s_g[Q][G];   // grad_output rows of the CTA's queries
 
     if (threadIdx.x < L) {
         s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
         s_meta[3 * threadIdx.x + 1] = (int)shapes[2 * threadIdx.x + 1];
         s_meta[3 * threadIdx.x + 2] = (int)lsi[threadIdx.x];
     }
-    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += WARPS * 32) {
+        s_key[i] = kEmpty;
+        s_head[i] = -1;
+    }
+    if (threadIdx.x < 2) s_nslots[threadIdx.x] = 0;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, sub = lane % G;
-#if MSDA_CTA_PER_HEAD
+    const int qloc = warp * PAIRS + grp;         // this group's query inside the CTA
+    // a CTA owns Q consecutive queries of ONE head: neighbouring queries of a head sample overlapping pixels (L1 reuse
+    // for the gather, shared rows for the merge)
     const int m = (int)(blockIdx.x % M);
     const long long nq_total = total_pairs / M;
-    const long long nq_raw = ((long long)(blockIdx.x / M) * WARPS + warp) * PAIRS + grp;
+    const long long nq_first = (long long)(blockIdx.x / M) * Q;
+    const long long nq_raw = nq_first + qloc;
     const bool active = nq_raw < nq_total;
     const long long nq = active ? nq_raw : nq_total - 1;
     const long long pair = nq * M + m;
-#else
-    const long long pair_raw = ((long long)blockIdx.x * WARPS + warp) * PAIRS + grp;
-    const bool active = pair_raw < total_pairs;
-    const long long pair = active ? pair_raw : total_pairs - 1;
-    const int m = (int)(pair % M);
-    const long long nq = pair / M;
-#endif
     const long long n = nq / Lq;
+    const long long n_first = nq_first / Lq;      // first frame the CTA touches
     const int LP = L * P;
     const int MD = M * D;
     const long long head_off = (n * S * M + m) * (long long)D + sub * EPL;
     // this lane's slice of pixel 0 of its (frame, head), as opaque addresses: a corner address is then one 64-bit add
     // (two instructions) of the 32-bit BYTE offset parked in shared memory -- scaled by 4 / sizeof(VT) for grad_value
     const unsigned long long vaddr = opaque_addr(value + head_off);
-    const unsigned long long gaddr = opaque_addr(gv_accum + head_off);
-    constexpr int kGradShift = sizeof(VT) == 4 ? 0 : 1;
+    // phase C: this lane's channels of pixel 0 of the CTA's FIRST frame; a slot's key is the pixel offset from there
+    const unsigned long long gaddr = opaque_addr(gv_accum + (n_first * S * M + m) * (long long)D + sub * EPL);
+    const unsigned key_frame = (unsigned)(n - n_first) * (unsigned)S;
     const float* lp = nullptr;
     const float* ap = nullptr;
     const RT* op = nullptr;
@@ -191,6 +215,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     }
     F2 G01, G23;
     G01.x = g[0]; G01.y = g[1]; G23.x = g[2]; G23.y = g[3];
+    s_g[qloc][sub] = make_float4(g[0], g[1], g[2], g[3]);
+    __syncthreads();                              // level metadata, empty merge tables, grad_output rows
 
     // fused: softmax over the pair's L*P logits; this lane keeps the numerators of its own samples
     float prob[FCH * SPL];
@@ -261,69 +287,44 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             const bool k0 = geo.z & 1, k1 = geo.z & 2, k2 = geo.z & 4, k3 = geo.z & 8;
             const float4 ca = make_float4(k0 ? hh * hw : 0.f, k1 ? hh * lw : 0.f, k2 ? lh * hw : 0.f, k3 ? lh * lw : 0.f);
             const int my_level = div_by_points(s0 + j, p_magic);
-            float4 ck = make_float4(ca.x * a, ca.y * a, ca.z * a, ca.w * a);
-            if constexpr (DEDUP) {
-                const float own[4] = {ck.x, ck.y, ck.z, ck.w};
-                float merged[4] = {own[0], own[1], own[2], own[3]};
-                int dup = 0;
-                const int W = geo.y;
-                // corner mask / coefficient vector of a neighbour, moved by (dx, dy) pixels into MY corner frame:
-                // my corner (cx, cy) is their corner (cx - dx, cy - dy).  Bits / slots: 0 (0,0) 1 (1,0) 2 (0,1) 3 (1,1).
-                auto decode = [&](int delta, int& dx, int& dy) -> bool {       // delta = their corner 00 - mine
-                    dy = delta > 1 ? 1 : (delta < -1 ? -1 : 0);
-                    dx = delta - dy * W;
-                    return W > 2 && dx >= -1 && dx <= 1;
-                };
-                auto shift_mask = [](int m, int dx, int dy) -> int {
-                    m = dx == 0 ? m : (dx > 0 ? (m & 5) << 1 : (m & 10) >> 1);
-                    return dy == 0 ? m : (dy > 0 ? (m & 3) << 2 : (m & 12) >> 2);
-                };
-                // Every pair of points of the level is compared: a pixel belongs to the LOWEST sample that touches it.  I
-                // collect the coefficients of every higher sample for the pixels we share, and skip the rows whose pixel a
-                // lower sample has (it collects mine).
-                auto gather = [&](const float (&hc)[4], int dx, int dy) {
-                    // x move, then y move, of the neighbour's coefficient vector into my corner frame
-                    const float x0 = dx == 0 ? hc[0] : (dx < 0 ? hc[1] : 0.f), x1 = dx == 0 ? hc[1] : (dx > 0 ? hc[0] : 0.f);
-                    const float x2 = dx == 0 ? hc[2] : (dx < 0 ? hc[3] : 0.f), x3 = dx == 0 ? hc[3] : (dx > 0 ? hc[2] : 0.f);
-                    // only into corners that exist: a slot outside the map must not take anything
-                    if (k0) merged[0] += dy == 0 ? x0 : (dy < 0 ? x2 : 0.f);
-                    if (k1) merged[1] += dy == 0 ? x1 : (dy < 0 ? x3 : 0.f);
-                    if (k2) merged[2] += dy == 0 ? x2 : (dy > 0 ? x0 : 0.f);
-                    if (k3) merged[3] += dy == 0 ? x3 : (dy > 0 ? x1 : 0.f);
-                };
-                const int span = min(P, G);
-                for (int d = 1; d < span; ++d) {
-                    const int lo_pix = __shfl_up_sync(0xffffffffu, geo.x, d, G);
-                    const int lo_ok = __shfl_up_sync(0xffffffffu, geo.z, d, G);
-                    const int hi_pix = __shfl_down_sync(0xffffffffu, geo.x, d, G);
-                    float hc[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) hc[k] = __shfl_down_sync(0xffffffffu, own[k], d, G);
-                    int dx, dy;
-                    if (sub >= d && div_by_points(s0 + j - d, p_magic) == my_level && decode(lo_pix - geo.x, dx, dy))
-                        dup |= shift_mask(lo_ok, dx, dy);
-                    if (sub + d < G && div_by_points(s0 + j + d, p_magic) == my_level && decode(hi_pix - geo.x, dx, dy))
-                        gather(hc, dx, dy);
-                }
-                // a row is mine to issue if the corner lies in the map and no lower sample owns its pixel
-                const int mine = geo.z & ~dup;
-                ck = make_float4((mine & 1) ? merged[0] : 0.f, (mine & 2) ? merged[1] : 0.f,
-                                 (mine & 4) ? merged[2] : 0.f, (mine & 8) ? merged[3] : 0.f);
-            }
-            if (!((red_mask >> my_level) & 1u)) ck = make_float4(0.f, 0.f, 0.f, 0.f);   // level accumulated elsewhere
+            // grad_value coefficient of each corner row: bilinear weight x attention weight (cuh:113-116)
+            const float ck[4] = {ca.x * a, ca.y * a, ca.z * a, ca.w * a};
+            const int pixk[4] = {geo.x, geo.x + 1, geo.x + geo.y, geo.x + geo.y + 1};
             const unsigned MDu = (unsigned)MD * (unsigned)sizeof(VT);   // bytes between neighbouring pixels
+            if (active && ((red_mask >> my_level) & 1u)) {
+                // file the rows under their pixels (zero-coefficient rows -- corners outside the map, exact-zero
+                // bilinear weights -- are dropped)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (ck[k] != 0.f) {
+                        const unsigned key = key_frame + (unsigned)pixk[k];
+                        unsigned h = (key * 0x9E3779B1u) >> (32 - kLogT);
+                        while (true) {
+                            const unsigned prev = atomicCAS(&s_key[h], kEmpty, key);
+                            if (prev == kEmpty) {
+                                s_list[atomicAdd(&s_nslots[c & 1], 1)] = (unsigned short)h;
+                                break;
+                            }
+                            if (prev == key) break;
+                            h = (h + 1) & (T - 1);
+                        }
+                        const int e = ((qloc * CH + j) << 2) + k;
+                        s_coef[e] = ck[k];
+                        s_next[e] = (unsigned short)atomicExch(&s_head[h], e);
+                    }
+                }
+            }
             uint4* rec = &s_rec[warp][grp][j * kRec];
-            rec[0] = make_uint4(k0 ? (unsigned)geo.x * MDu : 0u, k1 ? (unsigned)(geo.x + 1) * MDu : 0u,
-                                k2 ? (unsigned)(geo.x + geo.y) * MDu : 0u, k3 ? (unsigned)(geo.x + geo.y + 1) * MDu : 0u);
+            rec[0] = make_uint4(k0 ? (unsigned)pixk[0] * MDu : 0u, k1 ? (unsigned)pixk[1] * MDu : 0u,
+                                k2 ? (unsigned)pixk[2] * MDu : 0u, k3 ? (unsigned)pixk[3] * MDu : 0u);
             const float ahh = a * hh, alh = a * lh, ahw = a * hw, alw = a * lw;
-            reinterpret_cast<float4*>(rec)[1] = ck;
-            reinterpret_cast<float4*>(rec)[2] = ca;
-            reinterpret_cast<float4*>(rec)[3] = make_float4(k0 ? -ahh : 0.f, k1 ? ahh : 0.f, k2 ? -alh : 0.f, k3 ? alh : 0.f);
-            reinterpret_cast<float4*>(rec)[4] = make_float4(k0 ? -ahw : 0.f, k1 ? -alw : 0.f, k2 ? ahw : 0.f, k3 ? alw : 0.f);
+            reinterpret_cast<float4*>(rec)[1] = ca;
+            reinterpret_cast<float4*>(rec)[2] = make_float4(k0 ? -ahh : 0.f, k1 ? ahh : 0.f, k2 ? -alh : 0.f, k3 ? alh : 0.f);
+            reinterpret_cast<float4*>(rec)[3] = make_float4(k0 ? -ahw : 0.f, k1 ? -alw : 0.f, k2 ? ahw : 0.f, k3 ? alw : 0.f);
         }
         __syncwarp();
 
-        // ---- phase 2: per-sample gather, corner dots, vector reductions into grad_value ----------
+        // ---- phase 2: per-sample gather, corner dots -> grad_loc / grad_attn partials -------------
         float part[3 * SPL];
 #pragma unroll
         for (int i = 0; i < 3 * SPL; ++i) part[i] = 0.f;
@@ -338,8 +339,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     raw[k] = SliceT::load(reinterpret_cast<const VT*>(vaddr + ok[k]));
-                const float4 ca = reinterpret_cast<const float4*>(rec)[2], cx = reinterpret_cast<const float4*>(rec)[3],
-                             cy = reinterpret_cast<const float4*>(rec)[4];
+                const float4 ca = reinterpret_cast<const float4*>(rec)[1], cx = reinterpret_cast<const float4*>(rec)[2],
+                             cy = reinterpret_cast<const float4*>(rec)[3];
                 float t[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -366,11 +367,6 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     part[3 * (j0 % SPL) + 1] = py;
                     part[3 * (j0 % SPL) + 2] = pa;
                 }
-                const float4 cf = reinterpret_cast<const float4*>(rec)[1];   // 0 = row outside the map / issued by another sample
-                const float ck[4] = {cf.x, cf.y, cf.z, cf.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    red_scaled_f32x4_if(reinterpret_cast<float*>(gaddr + ((unsigned long long)ok[k] << kGradShift)), ck[k], G01, G23);
             }
         }
         __syncwarp();
@@ -402,6 +398,38 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                 reg_put(own_a, c * SPL + i, a_own[i]);
             }
         }
+
+        // ---- phase C: one reduction row per distinct pixel the CTA touched in this pass -----------
+        __syncthreads();                              // every row of the pass is filed
+        {
+            const int n_slots = s_nslots[c & 1];
+            if (threadIdx.x == 0) s_nslots[(c + 1) & 1] = 0;      // the next pass counts here (after the barrier below)
+            const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (grp * G);
+            const unsigned long long row_bytes = (unsigned long long)MD * 4ull;
+            for (int i = qloc; i < n_slots; i += Q) {
+                const int h = s_list[i];
+                const unsigned key = s_key[h];
+                int e = s_head[h];
+                F2 a01 = f2_dup(0.f), a23 = f2_dup(0.f);
+                while (e >= 0) {
+                    const F2 cf = f2_dup(s_coef[e]);
+                    const float4 gq = s_g[e >> kLogRowsPerQuery][sub];
+                    F2 q01, q23;
+                    q01.x = gq.x; q01.y = gq.y; q23.x = gq.z; q23.y = gq.w;
+                    a01 = fma2(cf, q01, a01);
+                    a23 = fma2(cf, q23, a23);
+                    const unsigned short nx = s_next[e];
+                    e = nx == kEnd ? -1 : (int)nx;
+                }
+                red_add_f32x4(reinterpret_cast<float*>(gaddr + key * row_bytes), a01.x, a01.y, a23.x, a23.y);
+                __syncwarp(gmask);                    // the whole group has read the slot
+                if (sub == 0) {
+                    s_key[h] = kEmpty;
+                    s_head[h] = -1;
+                }
+            }
+        }
+        __syncthreads();                              // tables are empty again
     }
 
     if constexpr (FUSED) {
@@ -571,12 +599,8 @@ static cudaError_t launch_bwd_fast(const BwdArgs& a, float* accum, cudaStream_t 
     constexpr int PAIRS = 32 / G;
     constexpr int WARPS = BwdWarps<PAIRS>::value;
     const long long total_pairs = (long long)a.N * a.Lq * a.M;
-#if MSDA_CTA_PER_HEAD
     const long long nq_total = (long long)a.N * a.Lq;
     const long long blocks = ((nq_total + WARPS * PAIRS - 1) / (WARPS * PAIRS)) * a.M;
-#else
-    const long long blocks = (total_pairs + WARPS * PAIRS - 1) / (WARPS * PAIRS);
-#endif
     if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
     const int p_magic = (65536 + a.P - 1) / a.P;
     SampleSrc src;
@@ -596,12 +620,8 @@ static cudaError_t launch_bwd_fused(const FusedArgs& a, float* accum, cudaStream
     constexpr int PAIRS = 32 / G;
     constexpr int WARPS = BwdWarps<PAIRS>::value;
     const long long total_pairs = (long long)a.N * a.Lq * a.M;
-#if MSDA_CTA_PER_HEAD
     const long long nq_total = (long long)a.N * a.Lq;
     const long long blocks = ((nq_total + WARPS * PAIRS - 1) / (WARPS * PAIRS)) * a.M;
-#else
-    const long long blocks = (total_pairs + WARPS * PAIRS - 1) / (WARPS * PAIRS);
-#endif
     if (blocks > 0x7fffffffll) return cudaErrorInvalidConfiguration;
     const int p_magic = (65536 + a.P - 1) / a.P;
     SampleSrc src;
@@ -631,7 +651,8 @@ static cudaError_t launch_bwd_generic(const BwdArgs& a, typename Traits<VT>::acc
 static bool fast_shape_ok(const BwdArgs& a)
 {
     return !a.force_generic && a.L <= kMaxLevelsFast && a.P <= 64 && (long long)a.L * a.P * a.P < 65536 &&
-           (long long)a.S * a.M * a.D < (1ll << 30);      // 32-bit byte offsets inside one frame
+           (long long)a.S * a.M * a.D < (1ll << 30) &&    // 32-bit byte offsets inside one frame
+           (long long)a.S < (1ll << 25);                   // merge keys: (frame of the CTA) * S + pixel in 32 bits
 }
 
 template <typename VT>
