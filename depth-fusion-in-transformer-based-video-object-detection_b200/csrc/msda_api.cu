@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 18; }
+extern "C" int msda_abi_version(void) { return 19; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -378,4 +378,17 @@ extern "C" int msda_layer_tf32_split(const float* x, int64_t rows, int cols, flo
 {
     if (rows < 0 || cols < 0) return (int)cudaErrorInvalidValue;
     return (int)msda::tf32_split(x, out, (long long)rows, cols, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_linear_tf32x3_supported(int out_features, int in_features)
+{
+    return msda::linear_tf32x3_supported(out_features, in_features) ? 1 : 0;
+}
+
+extern "C" int msda_layer_linear_tf32x3(const float* x, const float* weight_hi, const float* weight_lo, const float* bias,
+                                        int64_t rows, int out_features, int in_features, int relu, float* y, void* stream)
+{
+    if (rows < 0) return (int)cudaErrorInvalidValue;
+    return (int)msda::linear_tf32x3(x, weight_hi, weight_lo, bias, (long long)rows, out_features, in_features, relu, y,
+                                    (cudaStream_t)stream);
 }

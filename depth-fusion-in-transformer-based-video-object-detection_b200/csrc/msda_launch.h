@@ -169,6 +169,10 @@ bool norm_act_supported(int dtype, int C);
 cudaError_t norm_act_forward(int dtype, const void* x, const void* gamma, const void* beta, void* y, long long rows,
                              int C, float eps, int act, cudaStream_t stream);
 cudaError_t tf32_split(const float* x, float* out, long long rows, int cols, cudaStream_t stream);
+// y = x W^T + b (+ ReLU) in fp32 with the three-term TF32 split evaluated inside one tcgen05 kernel (linear_tf32x3.cu)
+bool linear_tf32x3_supported(int n, int k);
+cudaError_t linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, const float* bias, long long rows, int n,
+                          int k, int relu, float* y, cudaStream_t stream);
 cudaError_t sine_coordinates(const unsigned char* mask, float* y_embed, float* x_embed, int N, int H, int W,
                              int normalize, float scale, cudaStream_t stream);
 cudaError_t sine_position_tokens(int dtype, const float* y_embed, const float* x_embed, const float* dim_t,

@@ -249,7 +249,9 @@ class LinearFunction(Function):
 #              concatenated reduction [lo | hi | hi] x [hi | lo | hi] (fp32 accumulation; the dropped x_lo W_lo^T term and
 #              the rounding of the *_lo operands are O(2^-22)).  fp32-grade results (tests/test_gpu_layer_epilogue.py:
 #              8e-7 normalised against fp64, IEEE SGEMM 7e-7, one TF32 GEMM 3e-4) at a third of the TF32 rate instead of
-#              the SGEMM rate; the left operand is written by one kernel (msda_layer_tf32_split).
+#              the SGEMM rate.  One tcgen05 kernel per layer (csrc/linear_tf32x3.cu: the activation tile is split in shared
+#              memory, bias / ReLU in the epilogue); shapes it does not take fall back to the split pass
+#              (msda_layer_tf32_split) + one library TF32 GEMM over the concatenated reduction.
 FP32_GEMM_MODE = "library"
 TF32X3_MIN_ROWS = 1024              # below this the split pass + the longer reduction cost more than the SGEMM
 
@@ -283,8 +285,56 @@ def _tf32x3_wanted(x, weight):
             and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)))
 
 
-def linear_tf32x3(x, weight, bias):
+_TF32_WEIGHT_SPLITS = {}            # (data_ptr, version, shape) -> (weight_hi, weight_lo); weights are static in inference
+
+
+def _tf32_weight_split(weight):
+    """weight -> (hi, lo): hi = weight rounded to TF32's 10 mantissa bits (nearest, ties away), lo = weight - hi (exact)."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
+    hit = _TF32_WEIGHT_SPLITS.get(key)
+    if hit is None:
+        w = weight.detach().contiguous()
+        hi = ((w.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+        if len(_TF32_WEIGHT_SPLITS) >= 512:
+            _TF32_WEIGHT_SPLITS.clear()
+        hit = _TF32_WEIGHT_SPLITS[key] = (hi, w - hi)
+    return hit
+
+
+def linear_tf32x3_kernel_supported(x, weight):
+    """The one-kernel route (csrc/linear_tf32x3.cu): the activation tile is split in shared memory."""
+    n, k = weight.shape
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.shape[-1] == k
+            and bool(_lib.load().msda_layer_linear_tf32x3_supported(n, k)))
+
+
+def _tf32x3_kernel_wins(n, k):
+    """Measured on B200 at 8 x 22223 rows (tools/run_tf32x3.py), one kernel vs split pass + library GEMM, in ms:
+    256 <- 256: 0.164 / 0.260, 384 <- 256: 0.322 / 0.319, 1024 <- 256: 0.579 / 0.495, 256 <- 1024: 0.505 / 0.935.  The kernel
+    splits the activation tile once per 256 output columns, so wide outputs of a short reduction are the library's."""
+    return n <= 256 or k >= 512
+
+
+def linear_tf32x3(x, weight, bias, relu=False, route=None):
+    """route: None = the faster of the two for the shape, "kernel" / "library" to force one (tests, measurements)."""
     k = x.shape[-1]
+    use_kernel = linear_tf32x3_kernel_supported(x, weight) and route != "library" and (
+        route == "kernel" or _tf32x3_kernel_wins(weight.shape[0], k))
+    if use_kernel:
+        x2 = x.reshape(-1, k)
+        if not x2.is_contiguous() or x2.data_ptr() % 16 != 0:
+            x2 = x2.contiguous()
+        w_hi, w_lo = _tf32_weight_split(weight)
+        b = None if bias is None else bias.detach().contiguous()
+        y = torch.empty((x2.shape[0], weight.shape[0]), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            code = _lib.load().msda_layer_linear_tf32x3(x2.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(),
+                                                        None if b is None else b.data_ptr(), x2.shape[0],
+                                                        weight.shape[0], k, 1 if relu else 0, y.data_ptr(),
+                                                        torch.cuda.current_stream().cuda_stream)
+        _lib.check(code, "msda_layer_linear_tf32x3")
+        return y.view(*x.shape[:-1], weight.shape[0])
+    # shapes the kernel does not take: the same split as ONE library TF32 GEMM over the concatenated reduction
     a = _tf32_split(x.reshape(-1, k).contiguous())                       # [rows, 3k] = [lo | hi | hi]
     w = _tf32_split(weight.detach().contiguous())
     w = torch.cat([w[:, k:2 * k], w[:, :k], w[:, 2 * k:]], 1)            # [n, 3k]    = [hi | lo | hi]
@@ -294,6 +344,8 @@ def linear_tf32x3(x, weight, bias):
         y = torch.mm(a, w.t()) if bias is None else torch.addmm(bias.detach(), a, w.t())
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+    if relu:
+        y = torch.relu_(y)
     return y.view(*x.shape[:-1], weight.shape[0])
 
 
@@ -339,7 +391,7 @@ class LinearReLUFunction(Function):
 def linear_relu(linear, x):
     """``relu(linear(x))``; epilogue-fused on CUDA for 16-bit / fp32 dense inputs."""
     if _tf32x3_wanted(x, linear.weight):
-        return torch.relu_(linear_tf32x3(x, linear.weight, linear.bias))
+        return linear_tf32x3(x, linear.weight, linear.bias, relu=True)
     if x.is_cuda and linear.bias is not None and x.dtype == linear.weight.dtype and x.dtype in _DTYPES:
         return LinearReLUFunction.apply(x, linear.weight, linear.bias)
     return F.relu(linear(x))

@@ -259,6 +259,17 @@ int msda_layer_zero_masked_rows(int dtype, void* data, const uint8_t* mask, int6
  * selects it.  cols % 4 == 0; x and out 16-byte aligned. */
 int msda_layer_tf32_split(const float* x, int64_t rows, int cols, float* out, void* stream);
 
+/* The same FP32-grade product as ONE kernel: y [rows, out_features] = x [rows, in_features] weight^T + bias (then ReLU when
+ * relu != 0), FP32 in and out -- an nn.Linear of the reference's FP32 model
+ * (/root/reference/models/ops/modules/ms_deform_attn.py:94-116, deformable_transformer_single.py:544-548) on the tcgen05
+ * tensor cores.  weight_hi [out, in] = weight rounded to TF32 (10 mantissa bits, nearest), weight_lo = weight - weight_hi
+ * (the caller splits the static weight once); the activation tile is split in shared memory inside the kernel, so no
+ * [lo | hi | hi] copy of x ever reaches HBM.  bias may be NULL.  out_features % 32 == 0, in_features % 32 == 0, 16-byte
+ * aligned buffers (..._supported answers for a shape). */
+int msda_layer_linear_tf32x3_supported(int out_features, int in_features);
+int msda_layer_linear_tf32x3(const float* x, const float* weight_hi, const float* weight_lo, const float* bias,
+                             int64_t rows, int out_features, int in_features, int relu, float* y, void* stream);
+
 /* Cumulative coordinates of the sine position embedding (PositionEmbeddingSine.forward,
  * /root/reference/models/position_encoding.py:39-46): padding_mask [batch, height, width] bytes (non-zero = padding),
  * y_embed / x_embed [batch, height, width] FP32 = cumsum of the valid pixels down the rows / along the columns and,

@@ -393,6 +393,41 @@ def test_tf32x3_linear_is_fp32_grade():
     assert torch.backends.cuda.matmul.allow_tf32 == prev          # the switch is restored
 
 
+@pytest.mark.parametrize("rows,n,k,relu,has_bias", [
+    (20000, 256, 256, False, True),      # value_proj / output_proj
+    (1001, 384, 256, False, True),       # [offsets | logits]: a second column tile of 128, ragged rows
+    (4097, 1024, 256, True, True),       # linear1 + ReLU
+    (333, 256, 1024, False, True),       # linear2: 32 K blocks
+    (128, 32, 32, False, False),         # smallest shape, no bias
+    (1, 64, 96, True, False),
+])
+def test_tf32x3_kernel_matches_fp64(rows, n, k, relu, has_bias):
+    """csrc/linear_tf32x3.cu (the split of the activation tile happens in shared memory) against fp64: the same
+    fp32-grade bound as the split-pass route, for every tile shape the layers use."""
+    from dfvod_b200.ops.functions import layer_epilogue_func as L
+    torch.manual_seed(rows + n)
+    x = torch.randn(rows, k, device=DEV) * 3
+    w = torch.randn(n, k, device=DEV) / 16
+    b = torch.randn(n, device=DEV) if has_bias else None
+    assert L.linear_tf32x3_kernel_supported(x, w)
+    ref = F.linear(x.double(), w.double(), None if b is None else b.double())
+    if relu:
+        ref = ref.relu()
+    got = L.linear_tf32x3(x, w, b, relu=relu, route="kernel")
+    torch.cuda.synchronize()
+    assert got.shape == (rows, n) and got.dtype == torch.float32
+    err = nerr(got, ref)
+    # the main accumulator takes K / 8 truncating tensor-core additions (like one TF32 GEMM): measured 5.7e-7 at K = 256,
+    # 3.0e-6 at K = 1024; the IEEE SGEMM itself is 7e-7 at K = 256
+    assert err <= 2e-6 * max(1.0, k / 512.0), err
+    assert nerr(L.linear_tf32x3(x, w, b, relu=relu, route="library"), ref) <= 2e-6 * max(1.0, k / 512.0)
+    # a 3-d input with a weight the kernel does not take (K % 32 != 0) falls back to the split pass
+    x3 = torch.randn(4, 300, 40, device=DEV)
+    w3 = torch.randn(64, 40, device=DEV)
+    assert not L.linear_tf32x3_kernel_supported(x3, w3)
+    assert nerr(L.linear_tf32x3(x3, w3, None), F.linear(x3.double(), w3.double())) <= 2e-6
+
+
 def test_tf32x3_mode_routes_the_layer_gemms():
     """set_fp32_gemm_mode('tf32x3'): the fp32 transformer gives the library-SGEMM result within the fp32 parity
     tolerance (1e-5 normalised); gradients-needed calls and 16-bit inputs keep the library path."""
@@ -416,7 +451,7 @@ def test_tf32x3_mode_routes_the_layer_gemms():
             L.TF32X3_MIN_ROWS = 1
             calls = []
             original = L.linear_tf32x3
-            L.linear_tf32x3 = lambda *a: (calls.append(1), original(*a))[1]
+            L.linear_tf32x3 = lambda *a, **kw: (calls.append(1), original(*a, **kw))[1]
             try:
                 got = model(srcs, masks, poss, None, None, None, query)[0]
             finally:
