@@ -6,7 +6,7 @@
 // models/deformable_transformer_single.py:544-548 is an IEEE SGEMM there); on B200 the SIMT SGEMM is 40 of the 45 ms of a
 // 6-layer fp32 encoder.  This kernel evaluates the product with the error-compensated three-term TF32 split
 //
-//     x = x_hi + x_lo,  W = W_hi + W_lo      (*_hi = the operand rounded to TF32's 10 mantissa bits, *_lo = the exact rest)
+//     x = x_hi + x_lo,  W = W_hi + W_lo      (*_hi = the operand on TF32's 10 mantissa bits, *_lo = the exact rest)
 //     x W^T ~= x_lo W_hi^T + x_hi W_lo^T + x_hi W_hi^T          (fp32 accumulation in tensor memory)
 //
 // whose dropped term and operand roundings are O(2^-22) -- fp32-grade results (tests/test_gpu_layer_epilogue.py) at a
@@ -18,8 +18,8 @@
 // One CTA per SM, persistent over (row tile, column tile) pairs, 128 x 256 output tile, K in blocks of 32 fp32 (one
 // 128-byte SWIZZLE_128B row).  Warp roles (10 warps):
 //   0-3  epilogue   tcgen05.ld of the finished accumulator (lane = output row), + bias, ReLU, fp32 stores
-//   4-7  converter  x tile in shared memory -> x_hi (in place) and x_lo (second tile, same swizzled layout: the split is
-//                   elementwise, so it never has to know the layout), then fence.proxy.async
+//   4-7  converter  x tile in shared memory -> x_lo (second tile, same swizzled layout: the split is elementwise, so it
+//                   never has to know the layout), then fence.proxy.async; x_hi is the x tile as the tensor core reads it
 //   8    MMA issuer 4 K-steps x 3 terms of tcgen05.mma kind::tf32 per K block; TWO accumulators in TMEM (see there)
 //   9    TMA producer  x tile, W_hi tile, W_lo tile per K block, two stages of 96 KB
 #include <cuda.h>
@@ -101,6 +101,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             unsigned kiter = 0;
             for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int m0 = (int)(t / tiles_n) * kLtBM, n0 = (int)(t % tiles_n) * kLtBN;
+                // x is the only HBM stream (W stays in L2): bring the NEXT tile's rows as far as L2 while this tile computes
+                const long long tn = t + gridDim.x;
+                if (tn < tiles && tn / tiles_n != t / tiles_n) {
+                    for (int kb = 0; kb < kblocks; ++kb) tma_prefetch_l2_2d(&tm_x, kb * kLtBK, (int)(tn / tiles_n) * kLtBM);
+                }
                 for (int kb = 0; kb < kblocks; ++kb, ++kiter) {
                     const int s = kiter % kLtStages;
                     if (kiter >= kLtStages) mbar_wait(&bars->empty[s], ((kiter / kLtStages) - 1) & 1);
@@ -129,20 +134,28 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             if (it >= 1) mbar_wait(&bars->acc_free, (it - 1) & 1);               // the epilogue has drained the accumulators
             for (int kb = 0; kb < kblocks; ++kb, ++kiter) {
                 const int s = kiter % kLtStages;
-                mbar_wait(&bars->full[s], (kiter / kLtStages) & 1);              // W tiles landed
-                mbar_wait(&bars->conv[s], (kiter / kLtStages) & 1);              // x split in place
+                unsigned char* st = smem + s * kLtStageBytes;
+                const unsigned long long d_xh = make_desc_sw128(st), d_xl = make_desc_sw128(st + kLtABytes);
+                const unsigned long long d_wh = make_desc_sw128(st + 2 * kLtABytes),
+                                         d_wl = make_desc_sw128(st + 2 * kLtABytes + kLtBBytes);
+                mbar_wait(&bars->full[s], (kiter / kLtStages) & 1);              // x and W tiles landed
                 tcgen05_fence_after();
+                // the two terms with x_hi need nothing from the converter: the tensor core reads the top 19 bits of the
+                // fp32 words TMA wrote (x_hi = x truncated to TF32), so they go first and cover the converter's latency
                 if (elect_one()) {
-                    unsigned char* st = smem + s * kLtStageBytes;
-                    const unsigned long long d_xh = make_desc_sw128(st), d_xl = make_desc_sw128(st + kLtABytes);
-                    const unsigned long long d_wh = make_desc_sw128(st + 2 * kLtABytes),
-                                             d_wl = make_desc_sw128(st + 2 * kLtABytes + kLtBBytes);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {                                // K = 8 per instruction: 32 bytes of the row
-                        mma_tf32(acc_small, desc_advance(d_xl, j * 32), desc_advance(d_wh, j * 32), idesc, (kb | j) != 0);
-                        mma_tf32(acc_small, desc_advance(d_xh, j * 32), desc_advance(d_wl, j * 32), idesc, true);
+                        mma_tf32(acc_small, desc_advance(d_xh, j * 32), desc_advance(d_wl, j * 32), idesc, (kb | j) != 0);
                         mma_tf32(acc_big, desc_advance(d_xh, j * 32), desc_advance(d_wh, j * 32), idesc, (kb | j) != 0);
                     }
+                }
+                __syncwarp();
+                mbar_wait(&bars->conv[s], (kiter / kLtStages) & 1);              // x_lo written
+                tcgen05_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        mma_tf32(acc_small, desc_advance(d_xl, j * 32), desc_advance(d_wh, j * 32), idesc, true);
                     mma_commit(&bars->empty[s]);                                 // stage free once these MMAs have read it
                     if (kb == kblocks - 1) mma_commit(&bars->acc_full);
                 }
@@ -157,23 +170,20 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             for (int kb = 0; kb < kblocks; ++kb, ++kiter) {
                 const int s = kiter % kLtStages;
                 mbar_wait(&bars->full[s], (kiter / kLtStages) & 1);
-                uint4* xh = reinterpret_cast<uint4*>(smem + s * kLtStageBytes);
+                const uint4* xh = reinterpret_cast<const uint4*>(smem + s * kLtStageBytes);
                 uint4* xl = reinterpret_cast<uint4*>(smem + s * kLtStageBytes + kLtABytes);
+                // x_hi is what the tensor core sees of x: the word with its 13 low mantissa bits cleared (the x tile is not
+                // rewritten).  x_lo = x - x_hi is exact in fp32 (at most 13 significant bits); it is rounded to nearest on
+                // TF32's 10 mantissa bits here, so that the tensor core's own truncation of it is a no-op.
+                auto lo = [](unsigned v) -> unsigned {
+                    const float l = __uint_as_float(v) - __uint_as_float(v & 0xffffe000u);
+                    return (__float_as_uint(l) + 0x1000u) & 0xffffe000u;
+                };
 #pragma unroll
                 for (int i = 0; i < kLtABytes / 16 / kLtConvThreads; ++i) {
                     const int idx = i * kLtConvThreads + ct;                     // consecutive lanes, consecutive chunks
                     const uint4 v = xh[idx];
-                    // round to nearest on 10 mantissa bits (ties away): add half an ulp to the bit pattern, clear 13 bits
-                    uint4 h;
-                    h.x = (v.x + 0x1000u) & 0xffffe000u; h.y = (v.y + 0x1000u) & 0xffffe000u;
-                    h.z = (v.z + 0x1000u) & 0xffffe000u; h.w = (v.w + 0x1000u) & 0xffffe000u;
-                    uint4 l;
-                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-                    xh[idx] = h;
-                    xl[idx] = l;
+                    xl[idx] = make_uint4(lo(v.x), lo(v.y), lo(v.z), lo(v.w));
                 }
                 fence_proxy_async();                 // generic-proxy writes -> tensor-core (async proxy) reads
                 mbar_arrive(&bars->conv[s]);
