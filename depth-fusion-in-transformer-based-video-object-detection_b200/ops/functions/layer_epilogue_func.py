@@ -285,20 +285,20 @@ def _tf32x3_wanted(x, weight):
             and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)))
 
 
-_TF32_WEIGHT_SPLITS = {}            # (data_ptr, version, shape) -> (weight_hi, weight_lo); weights are static in inference
-
-
 def _tf32_weight_split(weight):
-    """weight -> (hi, lo): hi = weight rounded to TF32's 10 mantissa bits (nearest, ties away), lo = weight - hi (exact)."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
-    hit = _TF32_WEIGHT_SPLITS.get(key)
-    if hit is None:
+    """weight -> (hi, lo): hi = weight rounded to TF32's 10 mantissa bits (nearest, ties away), lo = weight - hi (exact).
+    Cached ON the weight tensor (weights are static in inference) together with the version counter it was made from:
+    the cache dies with the tensor, and an in-place update (optimizer step, load_state_dict) invalidates it."""
+    hit = getattr(weight, "_dfvod_tf32_split", None)
+    if hit is None or hit[0] != weight._version or hit[1].device != weight.device:
         w = weight.detach().contiguous()
         hi = ((w.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
-        if len(_TF32_WEIGHT_SPLITS) >= 512:
-            _TF32_WEIGHT_SPLITS.clear()
-        hit = _TF32_WEIGHT_SPLITS[key] = (hi, w - hi)
-    return hit
+        hit = (weight._version, hi, w - hi)
+        try:
+            weight._dfvod_tf32_split = hit
+        except (AttributeError, RuntimeError):      # a tensor that takes no attributes: split every call
+            pass
+    return hit[1], hit[2]
 
 
 def linear_tf32x3_kernel_supported(x, weight):

@@ -166,9 +166,10 @@ CASES.update({
 })
 
 
-def run_case(name, gold, device, dtype=torch.float64):
+def run_case(name, gold, device, dtype=torch.float64, forward_only=False):
     """Instantiate, load the reference state_dict (strict), run forward + backward.
-    Returns (out, {input grads}, {param grads}) as CPU float64 numpy."""
+    Returns (out, {input grads}, {param grads}) as CPU float64 numpy; forward_only: the output of an inference pass
+    (no gradients anywhere), as CPU float64 numpy."""
     case = CASES[name]
     module = case["build"]().to(dtype)
     state = {k[len("state."):]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("state.")}
@@ -183,9 +184,12 @@ def run_case(name, gold, device, dtype=torch.float64):
             # fp32 inputs of the fp64 cases (valid ratios) stay fp32; wide cases are stored as fp32 throughout
             t = t.to(dtype) if (t.dtype == torch.float64 or name in WIDE) else t
         name_in = k[len("in."):]
-        if name_in in case["wrt"]:
+        if name_in in case["wrt"] and not forward_only:
             t = t.requires_grad_(True)
         tensors[name_in] = t
+    if forward_only:
+        with torch.no_grad():
+            return case["call"](module, tensors).double().cpu().numpy()
     out = case["call"](module, tensors)
     gout = torch.from_numpy(gold["gout"]).to(device=device, dtype=out.dtype)
     params = dict(module.named_parameters())

@@ -59,6 +59,27 @@ def test_fp32_matches_reference_class(name):
         assert emax <= 1e-5 and el2 <= 1e-5, f"{k}: {emax:.2e} {el2:.2e}"
 
 
+@pytest.mark.parametrize("name", sorted(module_cases.CASES))
+def test_fp32_inference_with_tensor_core_gemms_matches_reference_class(name):
+    """set_fp32_gemm_mode("tf32x3"): every nn.Linear of an fp32 inference pass runs as the three-term TF32 product
+    (csrc/linear_tf32x3.cu where the shape allows, the split pass + library GEMM otherwise) -- same 1e-5 bound against the
+    reference class in fp64 as the IEEE path."""
+    from dfvod_b200.ops.functions import layer_epilogue_func as L
+    gold = load_golden(name)
+    prev_tf32, prev_rows = torch.backends.cuda.matmul.allow_tf32, L.TF32X3_MIN_ROWS
+    torch.backends.cuda.matmul.allow_tf32 = False
+    L.set_fp32_gemm_mode("tf32x3")
+    L.TF32X3_MIN_ROWS = 1
+    try:
+        out = module_cases.run_case(name, gold, "cuda", torch.float32, forward_only=True)
+    finally:
+        L.set_fp32_gemm_mode("library")
+        L.TF32X3_MIN_ROWS = prev_rows
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+    emax, el2 = nerr(out, gold["out"])
+    assert emax <= 1e-5 and el2 <= 1e-5, f"out: {emax:.2e} {el2:.2e}"
+
+
 def test_bf16_production_width_layer_matches_reference_class():
     """d_model 256 / 8 heads of 32 / 4 points in bf16: the fused bf16 deformable-attention kernels,
     the fused residual + LayerNorm (+ next query) kernels and the ReLU-epilogue GEMM inside the
