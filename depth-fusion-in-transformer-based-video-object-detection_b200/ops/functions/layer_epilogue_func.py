@@ -243,17 +243,19 @@ class LinearFunction(Function):
 
 
 # How the fp32 projections of an inference pass are evaluated (the gather kernels are not affected):
-#   "library"  whatever torch.backends.cuda.matmul says (IEEE SGEMM unless the caller allowed TF32) -- the default;
-#   "tf32x3"   error-compensated split on the tensor cores: x = x_hi + x_lo, W = W_hi + W_lo with the *_hi parts exactly
-#              TF32-representable, y = x_lo W_hi^T + x_hi W_lo^T + x_hi W_hi^T as ONE TF32 library GEMM over the
-#              concatenated reduction [lo | hi | hi] x [hi | lo | hi] (fp32 accumulation; the dropped x_lo W_lo^T term and
-#              the rounding of the *_lo operands are O(2^-22)).  fp32-grade results (tests/test_gpu_layer_epilogue.py:
-#              8e-7 normalised against fp64, IEEE SGEMM 7e-7, one TF32 GEMM 3e-4) at a third of the TF32 rate instead of
-#              the SGEMM rate.  One tcgen05 kernel per layer (csrc/linear_tf32x3.cu: the activation tile is split in shared
-#              memory, bias / ReLU in the epilogue); shapes it does not take fall back to the split pass
-#              (msda_layer_tf32_split) + one library TF32 GEMM over the concatenated reduction.
-FP32_GEMM_MODE = "library"
-TF32X3_MIN_ROWS = 1024              # below this the split pass + the longer reduction cost more than the SGEMM
+#   "tf32x3"   (default) error-compensated split on the tensor cores: x = x_hi + x_lo, W = W_hi + W_lo with the *_hi parts
+#              on TF32's 10 mantissa bits, y = x_lo W_hi^T + x_hi W_lo^T + x_hi W_hi^T with fp32 accumulation; the dropped
+#              x_lo W_lo^T term and the rounding of the *_lo operands are O(2^-22).  fp32-grade results
+#              (tests/test_gpu_layer_epilogue.py: 6.9e-7 normalised against fp64 at K = 256, the IEEE SGEMM 7.2e-7, one TF32
+#              GEMM 3e-4; every fp32 golden of tests/test_gpu_modules.py holds its 1e-5 with it) at a third of the TF32
+#              tensor rate instead of the SIMT SGEMM rate: 6-layer fp32 encoder 45.7 -> 12.6 ms.  One tcgen05 kernel per
+#              layer (csrc/linear_tf32x3.cu: the activation tile is split in shared memory, bias / ReLU in the epilogue);
+#              shapes it does not take fall back to the split pass (msda_layer_tf32_split) + one library TF32 GEMM over
+#              the concatenated reduction.  Only without gradients and from TF32X3_MIN_ROWS rows up.
+#   "library"  whatever torch.backends.cuda.matmul says (IEEE SGEMM unless the caller allowed TF32): the reference's own
+#              arithmetic, bit for bit what F.linear gives.
+FP32_GEMM_MODE = "tf32x3"
+TF32X3_MIN_ROWS = 1024              # below this the SGEMM is as fast
 
 
 def set_fp32_gemm_mode(mode):

@@ -182,9 +182,16 @@ def test_linear_custom_backward(dtype):
     assert torch.equal(got[0], x.grad) and torch.equal(got[1], lin.weight.grad)
     tol = 1e-5 if dtype == torch.float32 else 2.0 ** -7
     assert nerr(got[2], lin.bias.grad.double()) <= tol
-    # no autograd: plain module call
+    # no autograd: the plain module call -- bit for bit in "library" mode; fp32 inference defaults to the fp32-grade
+    # tensor-core product (set_fp32_gemm_mode, 2052 rows >= TF32X3_MIN_ROWS), equal within the SGEMM's own error
+    from dfvod_b200.ops.functions import layer_epilogue_func as L
     with torch.no_grad():
-        assert torch.equal(linear(lin, x), ref_out)
+        prev = L.set_fp32_gemm_mode("library")
+        try:
+            assert torch.equal(linear(lin, x), ref_out)
+        finally:
+            L.set_fp32_gemm_mode(prev)
+        assert nerr(linear(lin, x), ref_out.double()) <= (2e-6 if dtype == torch.float32 else 0.0)
 
 
 @pytest.mark.parametrize("rows,f,with_pos", [(1000, 1024, True), (128, 64, False), (37, 256, True), (5000, 512, False)])
@@ -430,7 +437,8 @@ def test_tf32x3_kernel_matches_fp64(rows, n, k, relu, has_bias):
 
 def test_tf32x3_mode_routes_the_layer_gemms():
     """set_fp32_gemm_mode('tf32x3'): the fp32 transformer gives the library-SGEMM result within the fp32 parity
-    tolerance (1e-5 normalised); gradients-needed calls and 16-bit inputs keep the library path."""
+    tolerance (1e-5 normalised); gradients-needed calls and 16-bit inputs keep the library path.  "tf32x3" is the
+    package default; "library" restores the IEEE SGEMMs."""
     from dfvod_b200.deformable_transformer import DeformableTransformer
     from dfvod_b200.ops.functions import layer_epilogue_func as L
     torch.manual_seed(7)
@@ -444,6 +452,8 @@ def test_tf32x3_mode_routes_the_layer_gemms():
     prev_tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     prev_rows = L.TF32X3_MIN_ROWS
+    prev_mode = L.set_fp32_gemm_mode("library")
+    assert prev_mode == "tf32x3"                                   # the package default
     try:
         with torch.no_grad():
             want = model(srcs, masks, poss, None, None, None, query)[0]
@@ -464,7 +474,7 @@ def test_tf32x3_mode_routes_the_layer_gemms():
         with pytest.raises(ValueError):
             L.set_fp32_gemm_mode("fp8")
     finally:
-        L.set_fp32_gemm_mode("library")
+        L.set_fp32_gemm_mode(prev_mode)
         L.TF32X3_MIN_ROWS = prev_rows
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 

@@ -61,19 +61,19 @@ def test_fp32_matches_reference_class(name):
 
 @pytest.mark.parametrize("name", sorted(module_cases.CASES))
 def test_fp32_inference_with_tensor_core_gemms_matches_reference_class(name):
-    """set_fp32_gemm_mode("tf32x3"): every nn.Linear of an fp32 inference pass runs as the three-term TF32 product
+    """set_fp32_gemm_mode("tf32x3") (the default), forced on for every row count: every nn.Linear of an fp32 inference pass runs as the three-term TF32 product
     (csrc/linear_tf32x3.cu where the shape allows, the split pass + library GEMM otherwise) -- same 1e-5 bound against the
     reference class in fp64 as the IEEE path."""
     from dfvod_b200.ops.functions import layer_epilogue_func as L
     gold = load_golden(name)
     prev_tf32, prev_rows = torch.backends.cuda.matmul.allow_tf32, L.TF32X3_MIN_ROWS
     torch.backends.cuda.matmul.allow_tf32 = False
-    L.set_fp32_gemm_mode("tf32x3")
+    prev_mode = L.set_fp32_gemm_mode("tf32x3")
     L.TF32X3_MIN_ROWS = 1
     try:
         out = module_cases.run_case(name, gold, "cuda", torch.float32, forward_only=True)
     finally:
-        L.set_fp32_gemm_mode("library")
+        L.set_fp32_gemm_mode(prev_mode)
         L.TF32X3_MIN_ROWS = prev_rows
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
     emax, el2 = nerr(out, gold["out"])

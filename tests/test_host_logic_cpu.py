@@ -190,4 +190,4 @@ def test_tf32_split_definition_and_three_term_product():
     want = x.double() @ w.double().t() - lo.double() @ wlo.double().t()
     scale = (x.double().abs() @ w.double().abs().t()).max()
     assert float((got - want).abs().max() / scale) <= 1e-6        # fp32 accumulation of exact terms (on the host)
-    assert L.FP32_GEMM_MODE == "library" and not L._tf32x3_wanted(x, w)   # host tensors never take the split path
+    assert L.FP32_GEMM_MODE == "tf32x3" and not L._tf32x3_wanted(x, w)   # host tensors never take the split path
