@@ -73,29 +73,6 @@ __device__ __forceinline__ void mma_tf32(unsigned tmem_d, unsigned long long des
 // two ROW tiles of the same column tile in lockstep, each loads HALF of every W tile and multicasts it into both CTAs'
 // shared memory: 48 KB per K block and CTA.  A stage is released by the MMAs of BOTH CTAs (multicast tcgen05.commit on
 // the `empty` barrier of each).
-__device__ __forceinline__ unsigned cluster_ctarank()
-{
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tensor_map, int c0, int c1,
-                                                      unsigned long long* bar, unsigned short cta_mask)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        :: "r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ void mma_commit_multicast(unsigned long long* bar, unsigned short cta_mask)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
-}
-
 __global__ void __cluster_dims__(kLtCluster, 1, 1) __launch_bounds__(kLtThreads, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                      const __grid_constant__ CUtensorMap tm_wl, const __grid_constant__ CUtensorMap tm_y,

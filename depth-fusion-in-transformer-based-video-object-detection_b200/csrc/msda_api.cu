@@ -7,7 +7,7 @@ static bool bad_dims(int N, int S, int M, int D, int L, int Lq, int P)
     return N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0;
 }
 
-extern "C" int msda_abi_version(void) { return 19; }
+extern "C" int msda_abi_version(void) { return 20; }
 
 extern "C" const char* msda_error_string(int code)
 {
@@ -378,6 +378,19 @@ extern "C" int msda_layer_tf32_split(const float* x, int64_t rows, int cols, flo
 {
     if (rows < 0 || cols < 0) return (int)cudaErrorInvalidValue;
     return (int)msda::tf32_split(x, out, (long long)rows, cols, (cudaStream_t)stream);
+}
+
+extern "C" int msda_layer_linear_bf16_supported(int out_features, int in_features)
+{
+    return msda::linear_bf16_supported(out_features, in_features) ? 1 : 0;
+}
+
+extern "C" int msda_layer_linear_bf16(const void* x, const void* weight, const void* bias, const uint8_t* zero_rows,
+                                      int64_t rows, int out_features, int in_features, int relu, void* y, void* stream)
+{
+    if (rows < 0) return (int)cudaErrorInvalidValue;
+    return (int)msda::linear_bf16(x, weight, bias, zero_rows, (long long)rows, out_features, in_features, relu, y,
+                                  (cudaStream_t)stream);
 }
 
 extern "C" int msda_layer_linear_tf32x3_supported(int out_features, int in_features)

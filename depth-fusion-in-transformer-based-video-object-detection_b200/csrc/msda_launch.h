@@ -170,6 +170,10 @@ cudaError_t norm_act_forward(int dtype, const void* x, const void* gamma, const 
                              int C, float eps, int act, cudaStream_t stream);
 cudaError_t tf32_split(const float* x, float* out, long long rows, int cols, cudaStream_t stream);
 // y = x W^T + b (+ ReLU) in fp32 with the three-term TF32 split evaluated inside one tcgen05 kernel (linear_tf32x3.cu)
+// y = x W^T + b (+ ReLU, + rows zeroed by a mask) in bf16: TMA / tcgen05 / TMEM kernel of linear_bf16.cu
+bool linear_bf16_supported(int n, int k);
+cudaError_t linear_bf16(const void* x, const void* w, const void* bias, const unsigned char* row_mask, long long rows, int n,
+                        int k, int relu, void* y, cudaStream_t stream);
 bool linear_tf32x3_supported(int n, int k);
 cudaError_t linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, const float* bias, long long rows, int n,
                           int k, int relu, float* y, cudaStream_t stream);

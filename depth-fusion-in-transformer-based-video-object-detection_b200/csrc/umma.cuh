@@ -182,6 +182,41 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tensor_map)
     asm volatile("prefetch.tensormap [%0];" :: "l"(tensor_map) : "memory");
 }
 
+// ---- thread-block clusters: rank, cluster barrier, TMA multicast, tcgen05.commit onto every CTA's barrier ----
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tensor_map, int c0, int c1,
+                                                      unsigned long long* bar, unsigned short cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        :: "r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void mma_commit_multicast(unsigned long long* bar, unsigned short cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
+// one 2-D box shared -> global (bulk group); rows / columns past the end of the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const void* tensor_map, const void* smem_src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(tensor_map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the bulk groups committed so far have READ their shared-memory source (it may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- generic-proxy writes -> async-proxy (tensor core) reads ----
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

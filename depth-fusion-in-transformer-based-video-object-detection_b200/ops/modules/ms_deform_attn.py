@@ -27,7 +27,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported, linear, linear_wb,
+from ..functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported, linear, linear_wb, linear_zero_rows,
                          zero_masked_rows_, head_major_supported, value_proj_head_major, fused_forward_head_major)
 
 # bf16 inference: own value-projection GEMM with a head-major epilogue + the head-major fused gather (see forward).
@@ -181,10 +181,9 @@ class MSDeformAttn(nn.Module):
         if precomputed_value is not None:
             value = precomputed_value
         else:
-            value = linear(self.value_proj, input_flatten.reshape(N * Len_in, -1))
-            if input_padding_mask is not None:
-                # `value` is consumed by the deformable-attention op below and by nothing else
-                value = zero_masked_rows_(value, input_padding_mask.reshape(-1), exclusive=True)
+            # `value` is consumed by the deformable-attention op below and by nothing else
+            value = linear_zero_rows(self.value_proj, input_flatten.reshape(N * Len_in, -1),
+                                     None if input_padding_mask is None else input_padding_mask.reshape(-1))
             value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(

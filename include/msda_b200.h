@@ -267,6 +267,16 @@ int msda_layer_tf32_split(const float* x, int64_t rows, int cols, float* out, vo
  * [lo | hi | hi] copy of x ever reaches HBM.  bias may be NULL.  out_features % 32 == 0, in_features % 32 == 0, 16-byte
  * aligned buffers (..._supported answers for a shape). */
 int msda_layer_linear_tf32x3_supported(int out_features, int in_features);
+
+/* BF16 nn.Linear of an inference pass as one TMA / tcgen05 kernel: y [rows, out_features] = x [rows, in_features] weight^T
+ * + bias, then ReLU when relu != 0, then rows whose zero_rows byte is non-zero overwritten with zeros -- value_proj with
+ * its masked_fill(padding_mask, 0) (/root/reference/models/ops/modules/ms_deform_attn.py:94-96), the
+ * [sampling_offsets | attention_weights] projection (:98-100), linear1 + ReLU
+ * (deformable_transformer_single.py:544-548).  bias and zero_rows may be NULL.  out_features % 64 == 0,
+ * in_features % 64 == 0, 16-byte aligned buffers (..._supported answers for a shape). */
+int msda_layer_linear_bf16_supported(int out_features, int in_features);
+int msda_layer_linear_bf16(const void* x, const void* weight, const void* bias, const uint8_t* zero_rows,
+                           int64_t rows, int out_features, int in_features, int relu, void* y, void* stream);
 int msda_layer_linear_tf32x3(const float* x, const float* weight_hi, const float* weight_lo, const float* bias,
                              int64_t rows, int out_features, int in_features, int relu, float* y, void* stream);
 

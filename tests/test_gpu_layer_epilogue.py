@@ -191,7 +191,9 @@ def test_linear_custom_backward(dtype):
             assert torch.equal(linear(lin, x), ref_out)
         finally:
             L.set_fp32_gemm_mode(prev)
-        assert nerr(linear(lin, x), ref_out.double()) <= (2e-6 if dtype == torch.float32 else 0.0)
+        # bf16 inference takes csrc/linear_bf16.cu from BF16_KERNEL_MIN_ROWS rows up: same fp32 accumulation, another
+        # summation order, so a result can land on the neighbouring bf16 value
+        assert nerr(linear(lin, x), ref_out.double()) <= (2e-6 if dtype == torch.float32 else 2.0 ** -7)
 
 
 @pytest.mark.parametrize("rows,f,with_pos", [(1000, 1024, True), (128, 64, False), (37, 256, True), (5000, 512, False)])
@@ -433,6 +435,70 @@ def test_tf32x3_kernel_matches_fp64(rows, n, k, relu, has_bias):
     w3 = torch.randn(64, 40, device=DEV)
     assert not L.linear_tf32x3_kernel_supported(x3, w3)
     assert nerr(L.linear_tf32x3(x3, w3, None), F.linear(x3.double(), w3.double())) <= 2e-6
+
+
+@pytest.mark.parametrize("rows,n,k,relu,has_bias,masked", [
+    (20000, 256, 256, False, True, True),    # value_proj with its padding mask
+    (1001, 384, 256, False, True, False),    # [offsets | logits]: a second column tile of 128, ragged rows
+    (4097, 1024, 256, True, True, False),    # linear1 + ReLU
+    (333, 256, 1024, False, True, False),    # linear2: 16 K blocks
+    (128, 64, 64, False, False, False),      # smallest shape, no bias
+    (1, 128, 192, True, False, True),
+])
+def test_bf16_linear_kernel_matches_fp64(rows, n, k, relu, has_bias, masked):
+    """csrc/linear_bf16.cu against the fp64 product of the same bf16 operands: one bf16 rounding of an fp32-accumulated
+    result (2^-8 of the output range), bias / ReLU / zeroed rows in the epilogue."""
+    from dfvod_b200.ops.functions import layer_epilogue_func as L
+    torch.manual_seed(rows + n)
+    x = (torch.randn(rows, k, device=DEV) * 3).bfloat16()
+    w = (torch.randn(n, k, device=DEV) / 16).bfloat16()
+    b = torch.randn(n, device=DEV).bfloat16() if has_bias else None
+    mask = (torch.rand(rows, device=DEV) < 0.3) if masked else None
+    ref = F.linear(x.double(), w.double(), None if b is None else b.double())
+    if relu:
+        ref = ref.relu()
+    if mask is not None:
+        ref = ref.masked_fill(mask[:, None], 0.0)
+    got = L.linear_bf16(x, w, b, relu=relu, zero_rows=mask)
+    torch.cuda.synchronize()
+    assert got.shape == (rows, n) and got.dtype == torch.bfloat16
+    assert nerr(got, ref) <= 2.0 ** -8
+    if mask is not None:
+        assert not bool(got[mask].any())
+
+
+def test_bf16_linear_routes():
+    """linear / linear_relu / linear_zero_rows pick the kernel for bf16 inference from BF16_KERNEL_MIN_ROWS rows up and
+    keep the library GEMM (and the custom autograd function) when gradients flow."""
+    from dfvod_b200.ops.functions import layer_epilogue_func as L
+    from dfvod_b200.ops.functions import linear_relu, linear_zero_rows
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(256, 384).to(DEV).bfloat16()
+    x = torch.randn(3000, 256, device=DEV).bfloat16()
+    mask = torch.rand(3000, device=DEV) < 0.2
+    calls = []
+    original, prev_rows = L.linear_bf16, L.BF16_KERNEL_MIN_ROWS
+    L.linear_bf16 = lambda *a, **kw: (calls.append(kw), original(*a, **kw))[1]
+    L.BF16_KERNEL_MIN_ROWS = 1024
+    try:
+        with torch.no_grad():
+            y = linear(lin, x)
+            yr = linear_relu(lin, x)
+            ym = linear_zero_rows(lin, x, mask)
+            assert len(calls) == 3 and calls[1].get("relu") and calls[2].get("zero_rows") is mask
+            ref = lin(x)
+            assert nerr(y, ref.double()) <= 2.0 ** -7 and nerr(yr, ref.relu().double()) <= 2.0 ** -7
+            assert nerr(ym, ref.masked_fill(mask[:, None], 0).double()) <= 2.0 ** -7 and not bool(ym[mask].any())
+            linear(lin, x[:100])                                   # few rows: library
+            assert len(calls) == 3
+        xg = x.clone().requires_grad_(True)
+        out = linear_zero_rows(lin, xg, mask)                     # gradients flow: library GEMM + row-zeroing function
+        assert len(calls) == 3
+        out.float().sum().backward()
+        assert xg.grad is not None and not bool(xg.grad[mask].any())
+    finally:
+        L.linear_bf16 = original
+        L.BF16_KERNEL_MIN_ROWS = prev_rows
 
 
 def test_tf32x3_mode_routes_the_layer_gemms():
