@@ -53,6 +53,17 @@ constexpr int kSmemH = kFfnTM * 128;              // 16384 per buffer
 constexpr int kSmemStat = 2 * kFfnSplit * kFfnTM * 4;   // partial row statistics (sum, sum of squares)
 constexpr int kSmemBars = 256;
 constexpr int kFfnSmem = kSmemX + 2 * kSmemW1 + 2 * kSmemW2 + 2 * kSmemH + kSmemStat + kSmemBars;
+// CTAs of a cluster that work on neighbouring row tiles in lockstep and share every weight chunk: each loads 1 / C of a
+// W1 / W2 chunk and multicasts it into all of them (TMA multicast).  The kernel streams 1 MB of weights per 128-row tile
+// out of L2 -- 1.64 GB per call at the encoder's 8 x 22 223 rows, 9 TB/s (profiles/ncu_r1e_ffn.json: tensor pipe 52-57 %
+// active) -- and a cluster of two halves that.  MEASURED (round 2, same box, alternating runs, tools/run_ffn.py):
+// 0.1896 ms with clusters of two against 0.1815 ms without: the L2 -> SM traffic is not what holds this kernel, and the
+// lockstep of two CTAs costs 4 %.  Default 1 (no clusters); 2 stays as a build option (parity-tested).
+#ifndef MSDA_FFN_CLUSTER
+#define MSDA_FFN_CLUSTER 1
+#endif
+constexpr int kFfnCluster = MSDA_FFN_CLUSTER;
+static_assert(kFfnCluster == 1 || kFfnCluster == 2, "W1 chunks are split by K block pairs, W2 chunks by row halves");
 static_assert(kFfnSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 
 #ifdef MSDA_FFN_TRACE
@@ -64,6 +75,9 @@ __device__ long long g_ffn_trace[2][40][8];
 
 struct FfnBars {
     unsigned long long x, xcopied, xy_free, stage_full, stage_free, w1[2], w2[2], g1[2], g2[2], hfull[2];
+    // cluster-wide versions of g1 / g2 / xcopied (one arrival per CTA, multicast tcgen05.commit): a weight buffer may be
+    // refilled -- the refill lands in EVERY CTA of the cluster -- once its readers in every CTA are done
+    unsigned long long f1[2], f2[2], xc_all;
     unsigned tmem_base;
 };
 
@@ -76,7 +90,7 @@ __device__ __forceinline__ unsigned chunk_parity(unsigned it, int c, int NC)
     return (it * nb + (unsigned)(c >> 1)) & 1u;
 }
 
-__global__ void __launch_bounds__(kFfnThreads, 1)
+__global__ void __cluster_dims__(kFfnCluster, 1, 1) __launch_bounds__(kFfnThreads, 1)
 ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2,
                      const __nv_bfloat16* __restrict__ b1, const __nv_bfloat16* __restrict__ b2,
@@ -94,7 +108,12 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NC = F / kFfnCH;
-    const long long tiles = (rows + kFfnTM - 1) / kFfnTM;
+    // work unit of a cluster: kFfnCluster consecutive row tiles; CTA `rank` takes tile unit * C + rank (past the last
+    // tile: TMA reads zeros, nothing is stored)
+    const long long units = ((rows + kFfnTM - 1) / kFfnTM + kFfnCluster - 1) / kFfnCluster;
+    const unsigned rank = kFfnCluster > 1 ? cluster_ctarank() : 0u;
+    const long long first = blockIdx.x / kFfnCluster, stride = gridDim.x / kFfnCluster;
+    constexpr unsigned short kAll = (unsigned short)((1u << kFfnCluster) - 1u);
 
     if (warp == 0) tmem_alloc(&bars->tmem_base, 512);
     if (tid == kFfnEpiThreads) {
@@ -107,12 +126,15 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             mbar_init(&bars->w1[i], 1); mbar_init(&bars->w2[i], 1);
             mbar_init(&bars->g1[i], 1); mbar_init(&bars->g2[i], 1);
             mbar_init(&bars->hfull[i], kFfnEpiThreads);
+            mbar_init(&bars->f1[i], kFfnCluster); mbar_init(&bars->f2[i], kFfnCluster);
         }
+        mbar_init(&bars->xc_all, kFfnCluster);
         fence_mbar_init();
         tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2);
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (kFfnCluster > 1) cluster_sync_all();       // every CTA's barriers exist before anything arrives on them
     tcgen05_fence_after();
     const unsigned tmem = bars->tmem_base;
     const unsigned tmem_y = tmem;                  // columns [0, 256)
@@ -125,7 +147,7 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const unsigned idesc2 = make_idesc_bf16(kFfnTM, kFfnC);
         const unsigned long long dW1 = make_desc_sw128(sW1), dW2 = make_desc_sw128(sW2), dH = make_desc_sw128(sH);
         unsigned it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        for (long long unit = first; unit < units; unit += stride, ++it) {
             // GEMM1(buf): Hacc[buf] = X (TMEM) @ W1buf[buf]^T
             auto gemm1 = [&](int buf) {
                 tcgen05_fence_after();
@@ -137,6 +159,7 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                             mma_bf16_ts(tmem_h + buf * kFfnCH, tmem_x + (kb * 4 + j) * 8,
                                         desc_advance(dW1, buf * kSmemW1 + kb * kFfnCH * 128 + j * 32), idesc1, (kb | j) != 0);
                     mma_commit(&bars->g1[buf]);
+                    if (kFfnCluster > 1) mma_commit_multicast(&bars->f1[buf], kAll);
                 }
                 __syncwarp();
             };
@@ -150,6 +173,7 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     for (int j = 0; j < 4; ++j)
                         tmem_cp_128x256b(tmem_x + (kb * 4 + j) * 8, desc_advance(dW2, kb * kFfnTM * 128 + j * 32));
                 mma_commit(&bars->xcopied);                                  // the W2 buffers may be refilled
+                if (kFfnCluster > 1) mma_commit_multicast(&bars->xc_all, kAll);
             }
             __syncwarp();
             mbar_wait(&bars->w1[0], chunk_parity(it, 0, NC));
@@ -174,6 +198,7 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                         mma_bf16(tmem_y, desc_advance(dH, b * kSmemH + j * 32), desc_advance(dW2, b * kSmemW2 + j * 32),
                                  idesc2, (c | j) != 0);
                     mma_commit(&bars->g2[b]);
+                    if (kFfnCluster > 1) mma_commit_multicast(&bars->f2[b], kAll);
                 }
                 __syncwarp();
                 FFN_TRACE(0, c, 5);
@@ -182,24 +207,38 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     } else if (warp == kFfnEpiWarps + 1) {
         // ======================================= TMA producer =======================================
         unsigned it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        for (long long unit = first; unit < units; unit += stride, ++it) {
+            const long long tile = unit * kFfnCluster + rank;
+            // a chunk of W1 is 4 K blocks of [64 rows x 128 B], a chunk of W2 one box of [256 rows x 128 B]: CTA `rank`
+            // loads K blocks 2 rank, 2 rank + 1 and rows [128 rank, 128 rank + 128) and multicasts them to the cluster
             auto load_w1 = [&](int c, int buf) {
                 if (elect_one()) {
                     mbar_expect_tx(&bars->w1[buf], kSmemW1);
+                    if (kFfnCluster > 1) {
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb)
-                        tma_load_2d(sW1 + buf * kSmemW1 + kb * kFfnCH * 128, &tm_w1, kb * 64, c * kFfnCH, &bars->w1[buf]);
+                        for (int kb = 2 * (int)rank; kb < 2 * (int)rank + 2; ++kb)
+                            tma_load_2d_multicast(sW1 + buf * kSmemW1 + kb * kFfnCH * 128, &tm_w1, kb * 64, c * kFfnCH,
+                                                  &bars->w1[buf], kAll);
+                    } else {
+#pragma unroll
+                        for (int kb = 0; kb < 4; ++kb)
+                            tma_load_2d(sW1 + buf * kSmemW1 + kb * kFfnCH * 128, &tm_w1, kb * 64, c * kFfnCH, &bars->w1[buf]);
+                    }
                 }
                 __syncwarp();
             };
             auto load_w2 = [&](int c, int buf) {
                 if (elect_one()) {
                     mbar_expect_tx(&bars->w2[buf], kSmemW2);
-                    tma_load_2d(sW2 + buf * kSmemW2, &tm_w2, c * kFfnCH, 0, &bars->w2[buf]);
+                    if (kFfnCluster > 1)
+                        tma_load_2d_multicast(sW2 + buf * kSmemW2 + rank * (kSmemW2 / kFfnCluster), &tm_w2, c * kFfnCH,
+                                              (int)rank * (kFfnC / kFfnCluster), &bars->w2[buf], kAll);
+                    else
+                        tma_load_2d(sW2 + buf * kSmemW2, &tm_w2, c * kFfnCH, 0, &bars->w2[buf]);
                 }
                 __syncwarp();
             };
-            // every MMA of the previous tile has completed: W1 / W2 buffers are free
+            // every MMA of MY previous tile has completed: the W2 buffers may take my X tile
             if (it > 0) mbar_wait(&bars->g2[(NC - 1) & 1], chunk_parity(it - 1, NC - 1, NC));
             if (elect_one()) {
                 mbar_expect_tx(&bars->x, kSmemX);
@@ -208,18 +247,24 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     tma_load_2d(sW2 + kb * kFfnTM * 128, &tm_x, kb * 64, (int)(tile * kFfnTM), &bars->x);
             }
             __syncwarp();
+            if (kFfnCluster > 1 && it > 0) {
+                // the W1 buffers of EVERY CTA are free: the last GEMM1 on each buffer, cluster-wide
+                if (NC > 1) mbar_wait(&bars->f1[(NC - 2) & 1], chunk_parity(it - 1, NC - 2, NC));
+                mbar_wait(&bars->f1[(NC - 1) & 1], chunk_parity(it - 1, NC - 1, NC));
+            }
             load_w1(0, 0);
             if (NC > 1) load_w1(1, 1);
             mbar_wait(&bars->xcopied, it & 1);       // X has been copied into tensor memory
+            if (kFfnCluster > 1) mbar_wait(&bars->xc_all, it & 1);   // ... in every CTA: their W2 buffers held their X tiles
             load_w2(0, 0);
             for (int c = 0; c < NC; ++c) {
                 const int b = c & 1;
-                if (c + 2 < NC) {                // W1 buffer b is free once GEMM1(c) has completed
-                    mbar_wait(&bars->g1[b], chunk_parity(it, c, NC));
+                if (c + 2 < NC) {                // W1 buffer b is free once GEMM1(c) has completed (in every CTA)
+                    mbar_wait(kFfnCluster > 1 ? &bars->f1[b] : &bars->g1[b], chunk_parity(it, c, NC));
                     load_w1(c + 2, b);
                 }
-                if (c + 1 < NC) {                // W2 buffer b^1 is free once GEMM2(c-1) has completed
-                    if (c >= 1) mbar_wait(&bars->g2[b ^ 1], chunk_parity(it, c - 1, NC));
+                if (c + 1 < NC) {                // W2 buffer b^1 is free once GEMM2(c-1) has completed (in every CTA)
+                    if (c >= 1) mbar_wait(kFfnCluster > 1 ? &bars->f2[b ^ 1] : &bars->g2[b ^ 1], chunk_parity(it, c - 1, NC));
                     load_w2(c + 1, b ^ 1);
                 }
             }
@@ -230,7 +275,7 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int hsel = warp >> 2;                    // which 1/SPLIT of the columns this warp handles
         const unsigned lane_base = (unsigned)((warp & 3) * 32) << 16;
         unsigned it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        for (long long unit = first; unit < units; unit += stride, ++it) {
             for (int c = 0; c < NC; ++c) {
                 const int b = c & 1;
                 constexpr int kCols1 = kFfnCH / kFfnSplit;         // Hacc columns per thread: 32 or 16
@@ -313,8 +358,8 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         constexpr int kRowsPerSweep = kFfnStoreThreads >> 5;     // rows covered by one sweep of the store warps
         constexpr int kSweeps = kFfnTM / kRowsPerSweep;
         unsigned it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            const long long row0 = tile * kFfnTM;
+        for (long long unit = first; unit < units; unit += stride, ++it) {
+            const long long row0 = (unit * kFfnCluster + rank) * kFfnTM;
             mbar_wait(&bars->stage_full, it & 1);
 #pragma unroll 1
             for (int batch = 0; batch < kSweeps / 8; ++batch) {
@@ -363,6 +408,7 @@ ffn_layernorm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (kFfnCluster > 1) cluster_sync_all();       // no CTA leaves while a peer may still write its shared memory / barriers
     if (warp == 0) tmem_free(tmem, 512);
 }
 
@@ -424,11 +470,12 @@ cudaError_t ffn_layernorm_forward(const FfnArgs& a, cudaStream_t stream)
     alignas(64) CUtensorMap tm_x, tm_w1, tm_w2;
     if (!make_map(&tm_x, a.x, (unsigned long long)a.rows, kFfnC, kFfnTM) ||
         !make_map(&tm_w1, a.w1, (unsigned long long)a.F, kFfnC, kFfnCH) ||
-        !make_map(&tm_w2, a.w2, kFfnC, (unsigned long long)a.F, kFfnC))
+        !make_map(&tm_w2, a.w2, kFfnC, (unsigned long long)a.F, kFfnC / kFfnCluster))
         return cudaErrorNotSupported;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (a.rows + kFfnTM - 1) / kFfnTM;
-    const int grid = (int)(tiles < sms ? tiles : sms);
+    const long long units = (tiles + kFfnCluster - 1) / kFfnCluster, clusters = sms / kFfnCluster;
+    const int grid = (int)(units < clusters ? units : clusters) * kFfnCluster;
     using bf = __nv_bfloat16;
     ffn_layernorm_kernel<<<grid, kFfnThreads, kFfnSmem, stream>>>(
         tm_x, tm_w1, tm_w2, (const bf*)a.b1, (const bf*)a.b2, (const bf*)a.gamma, (const bf*)a.beta,
