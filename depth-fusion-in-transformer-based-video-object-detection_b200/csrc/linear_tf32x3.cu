@@ -305,7 +305,7 @@ bool linear_tf32x3_supported(int n, int k)
 cudaError_t linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, const float* bias, long long rows, int n,
                           int k, int relu, float* y, cudaStream_t stream)
 {
-    if (!linear_tf32x3_supported(n, k) || rows < 0 || rows >= (1ll << 31)) return cudaErrorInvalidValue;
+    if (!linear_tf32x3_supported(n, k) || rows < 0 || rows >= (1ll << 31) - 1024) return cudaErrorInvalidValue;   // row coordinates are int
     if (rows == 0) return cudaSuccess;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo) |
          reinterpret_cast<uintptr_t>(y)) % 16 != 0)

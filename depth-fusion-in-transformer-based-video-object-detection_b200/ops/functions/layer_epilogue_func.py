@@ -296,10 +296,12 @@ def _tf32_weight_split(weight):
         w = weight.detach().contiguous()
         hi = ((w.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
         hit = (weight._version, hi, w - hi)
-        try:
-            weight._dfvod_tf32_split = hit
-        except (AttributeError, RuntimeError):      # a tensor that takes no attributes: split every call
-            pass
+        # (tensors made during a CUDA-graph capture live in the graph's private pool: never cache those)
+        if not (weight.is_cuda and torch.cuda.is_current_stream_capturing()):
+            try:
+                weight._dfvod_tf32_split = hit
+            except (AttributeError, RuntimeError):      # a tensor that takes no attributes: split every call
+                pass
     return hit[1], hit[2]
 
 

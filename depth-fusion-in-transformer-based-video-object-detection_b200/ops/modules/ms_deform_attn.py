@@ -233,7 +233,9 @@ def _raw_projection_params(self):
     if cache is None or cache[0] != key:
         with torch.no_grad():
             cache = (key, torch.cat(params[:2], 0), torch.cat(params[2:], 0))
-        self._raw_cache = cache
+        # tensors made during a CUDA-graph capture live in the graph's private pool: never cache those
+        if not (params[0].is_cuda and torch.cuda.is_current_stream_capturing()):
+            self._raw_cache = cache
     return cache[1], cache[2]
 
 
