@@ -89,6 +89,18 @@ struct GradDst {
 // 4832 instructions (77 KB of SASS) that every warp walks end to end, and ncu shows 14 % of its stall samples waiting for
 // instructions (`no_instructions`, profiles/ncu_r1k.json); the per-pass register arrays are then indexed through
 // reg_pick / reg_put (selects over a static index) so that they stay in registers.
+// 1: phase 1 parks the three coefficient vectors (ca, cx, cy: 48 bytes per sample) that turn the corner dots into the
+// sample's gradients; 0: it parks (lw, lh, a, corner mask) -- 16 bytes -- and phase 2 rebuilds the combination (about 15
+// more instructions per sample, 2 shared-memory wavefronts fewer: the L1 data pipe is the busier unit, ncu r2c).
+#ifndef MSDA_BWD_COEF_RECORDS
+#define MSDA_BWD_COEF_RECORDS 0
+#endif
+// 1 (plain op, 8 lanes per head): the three per-sample sums of FOUR samples are reduced across the group together by a
+// reduce-scatter -- 12 shuffles per 4 samples instead of 36 -- which leaves lanes 2s, 2s+1 holding the finished sums of
+// sample s of the batch; the even lane stores them.  Shuffles cross the same L1 data pipe as loads and reductions.
+#ifndef MSDA_BWD_BATCHED_REDUCE
+#define MSDA_BWD_BATCHED_REDUCE 1
+#endif
 #ifndef MSDA_BWD_FUSED_ROLLED
 #define MSDA_BWD_FUSED_ROLLED 1
 #endif
@@ -134,8 +146,9 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     // record of a sample, 5 x 16 bytes: [0] byte offset (pixel * M*D * sizeof(VT)) of each corner row (corner outside the map -> 0),
     // [1] grad_value coefficient of each row (0 = no reduction), [2..4] corner dots -> grad_attn, grad_loc.x / W,
     // grad_loc.y / H
-    constexpr int kRec = 5;
+    constexpr int kRec = MSDA_BWD_COEF_RECORDS ? 5 : 3;
     __shared__ __align__(16) uint4 s_rec[WARPS][PAIRS][CH * kRec + 1];
+    constexpr bool BATCHED = MSDA_BWD_BATCHED_REDUCE && !FUSED && G == 8 && CH == 8;
     constexpr bool DEDUP = MSDA_BWD_DEDUP && SPL == 1;
 
     if (threadIdx.x < L) {
@@ -315,11 +328,15 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             uint4* rec = &s_rec[warp][grp][j * kRec];
             rec[0] = make_uint4(k0 ? (unsigned)geo.x * MDu : 0u, k1 ? (unsigned)(geo.x + 1) * MDu : 0u,
                                 k2 ? (unsigned)(geo.x + geo.y) * MDu : 0u, k3 ? (unsigned)(geo.x + geo.y + 1) * MDu : 0u);
-            const float ahh = a * hh, alh = a * lh, ahw = a * hw, alw = a * lw;
             reinterpret_cast<float4*>(rec)[1] = ck;
+#if MSDA_BWD_COEF_RECORDS
+            const float ahh = a * hh, alh = a * lh, ahw = a * hw, alw = a * lw;
             reinterpret_cast<float4*>(rec)[2] = ca;
             reinterpret_cast<float4*>(rec)[3] = make_float4(k0 ? -ahh : 0.f, k1 ? ahh : 0.f, k2 ? -alh : 0.f, k3 ? alh : 0.f);
             reinterpret_cast<float4*>(rec)[4] = make_float4(k0 ? -ahw : 0.f, k1 ? -alw : 0.f, k2 ? ahw : 0.f, k3 ? alw : 0.f);
+#else
+            reinterpret_cast<float4*>(rec)[2] = make_float4(lw, lh, a, __int_as_float(geo.z));
+#endif
         }
         __syncwarp();
 
@@ -327,6 +344,9 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         float part[3 * SPL];
 #pragma unroll
         for (int i = 0; i < 3 * SPL; ++i) part[i] = 0.f;
+        float acc12[BATCHED ? 12 : 1];                // BATCHED: this lane's partial (px, py, pa) of the batch's 4 samples
+#pragma unroll
+        for (int i = 0; i < (BATCHED ? 12 : 1); ++i) acc12[i] = 0.f;
 
 #pragma unroll
         for (int j0 = 0; j0 < CH; ++j0) {
@@ -338,8 +358,6 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     raw[k] = SliceT::load(reinterpret_cast<const VT*>(vaddr + ok[k]));
-                const float4 ca = reinterpret_cast<const float4*>(rec)[2], cx = reinterpret_cast<const float4*>(rec)[3],
-                             cy = reinterpret_cast<const float4*>(rec)[4];
                 float t[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -350,21 +368,44 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     const F2 d = fma2(G23, V23, mul2(G01, V01));      // this lane's 4 channels of <grad_output, value_k>
                     t[k] = d.x + d.y;
                 }
-                F2 T01, T23;
-                T01.x = t[0]; T01.y = t[1]; T23.x = t[2]; T23.y = t[3];
-                auto combine = [&](const float4& cf) -> float {
-                    F2 C01, C23;
-                    C01.x = cf.x; C01.y = cf.y; C23.x = cf.z; C23.y = cf.w;
-                    const F2 r = fma2(C23, T23, mul2(C01, T01));
-                    return r.x + r.y;
-                };
-                const float px = group_sum<G>(combine(cx));           // cuh:119-151 (grad_w_weight * top_grad_value)
-                const float py = group_sum<G>(combine(cy));           // (grad_h_weight)
-                const float pa = group_sum<G>(combine(ca));           // cuh:156
-                if (j0 / SPL == sub) {
-                    part[3 * (j0 % SPL) + 0] = px;
-                    part[3 * (j0 % SPL) + 1] = py;
-                    part[3 * (j0 % SPL) + 2] = pa;
+                float lx, ly, la;                                     // this lane's share of the sample's three sums
+#if MSDA_BWD_COEF_RECORDS
+                {
+                    const float4 ca = reinterpret_cast<const float4*>(rec)[2], cx = reinterpret_cast<const float4*>(rec)[3],
+                                 cy = reinterpret_cast<const float4*>(rec)[4];
+                    F2 T01, T23;
+                    T01.x = t[0]; T01.y = t[1]; T23.x = t[2]; T23.y = t[3];
+                    auto combine = [&](const float4& cf) -> float {
+                        F2 C01, C23;
+                        C01.x = cf.x; C01.y = cf.y; C23.x = cf.z; C23.y = cf.w;
+                        const F2 r = fma2(C23, T23, mul2(C01, T01));
+                        return r.x + r.y;
+                    };
+                    lx = combine(cx); ly = combine(cy); la = combine(ca);
+                }
+#else
+                {
+                    const float4 fr = reinterpret_cast<const float4*>(rec)[2];        // lw, lh, a, corner mask
+                    const unsigned okm = __float_as_uint(fr.w);
+                    const float t0 = (okm & 1u) ? t[0] : 0.f, t1 = (okm & 2u) ? t[1] : 0.f;
+                    const float t2 = (okm & 4u) ? t[2] : 0.f, t3 = (okm & 8u) ? t[3] : 0.f;
+                    const float lw = fr.x, lh = fr.y, hw = 1.f - fr.x, hh = 1.f - fr.y;
+                    lx = fr.z * fmaf(lh, t3 - t2, hh * (t1 - t0));                    // cuh:119-151 (grad_w_weight * top_grad_value)
+                    ly = fr.z * fmaf(lw, t3 - t1, hw * (t2 - t0));                    // (grad_h_weight)
+                    la = fmaf(lh, fmaf(lw, t3, hw * t2), hh * fmaf(lw, t1, hw * t0)); // cuh:156
+                }
+#endif
+                if constexpr (BATCHED) {
+                    acc12[3 * (j0 & 3) + 0] = lx;
+                    acc12[3 * (j0 & 3) + 1] = ly;
+                    acc12[3 * (j0 & 3) + 2] = la;
+                } else {
+                    const float px = group_sum<G>(lx), py = group_sum<G>(ly), pa = group_sum<G>(la);
+                    if (j0 / SPL == sub) {
+                        part[3 * (j0 % SPL) + 0] = px;
+                        part[3 * (j0 % SPL) + 1] = py;
+                        part[3 * (j0 % SPL) + 2] = pa;
+                    }
                 }
                 const float4 cf = reinterpret_cast<const float4*>(rec)[1];   // 0 = row outside the map / issued by another sample
                 const float ck[4] = {cf.x, cf.y, cf.z, cf.w};
@@ -372,11 +413,49 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                 for (int k = 0; k < 4; ++k)
                     red_scaled_f32x4_if(reinterpret_cast<float*>(gaddr + ((unsigned long long)ok[k] << kGradShift)), ck[k], G01, G23);
             }
+            if constexpr (BATCHED) {
+                if ((j0 & 3) == 3 && j0 - 3 < cnt) {
+                    // reduce-scatter of the batch's 12 partial sums over the 8 lanes: after the three steps lanes 2s, 2s+1
+                    // hold the finished (px, py, pa) of sample s of the batch in acc12[0..2]
+                    {
+                        const bool up = (sub & 4) != 0;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            const float send = up ? acc12[i] : acc12[i + 6], keep = up ? acc12[i + 6] : acc12[i];
+                            acc12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                    }
+                    {
+                        const bool up = (sub & 2) != 0;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const float send = up ? acc12[i] : acc12[i + 3], keep = up ? acc12[i + 3] : acc12[i];
+                            acc12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) acc12[i] += __shfl_xor_sync(0xffffffffu, acc12[i], 1);
+                    const int j = (j0 - 3) + (sub >> 1);               // the sample whose sums this lane pair holds
+                    if (active && (sub & 1) == 0 && j < cnt) {
+                        const int s = s0 + j;
+                        const int l = div_by_points(s, p_magic);
+                        const float Hf = (float)s_meta[3 * l], Wf = (float)s_meta[3 * l + 1];
+                        float* grad_loc = static_cast<float*>(dst.loc);
+                        float* grad_attn = static_cast<float*>(dst.attn);
+                        *reinterpret_cast<float2*>(grad_loc + (pair * LP + s) * 2) = make_float2(Wf * acc12[0], Hf * acc12[1]);   // cuh:157-158
+                        grad_attn[pair * LP + s] = acc12[2];                                                                   // cuh:156
+                    }
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) acc12[i] = 0.f;
+                }
+            }
         }
         __syncwarp();
 
         // ---- phase 3: combine the group's partials; each lane finishes its own SPL samples ----
-        if constexpr (!FUSED) {
+        if constexpr (BATCHED) {
+            // already stored by the lanes that held the sums
+        } else if constexpr (!FUSED) {
             float* grad_loc = static_cast<float*>(dst.loc);
             float* grad_attn = static_cast<float*>(dst.attn);
             if (active) {
