@@ -13,17 +13,17 @@
 //
 // Fast kernel (same lane mapping as the forward: a group of G lanes owns a pair, each lane a
 // 16-byte channel slice):
-//   * phase 1: one lane per sample computes the footprint ONCE and parks everything phase 2 needs in shared memory,
-//     already masked for corners outside the map: the four row offsets (clamped to a harmless in-range row), the
-//     grad_value coefficient of each row, and the coefficients that turn the four corner dot products
-//     t_k = <grad_output, value_k> into grad_attn and the two grad_loc partials
-//         pa = sum_k ca_k t_k      ca = (hh*hw, hh*lw, lh*hw, lh*lw)
-//         px = sum_k cx_k t_k      cx = a * (-hh, +hh, -lh, +lh)
-//         py = sum_k cy_k t_k      cy = a * (-hw, -lw, +hw, +lw)
-//     (the same sums as cuh:113-158, with the channel sum taken first);
-//   * phase 2, per sample and lane: 4 unconditional loads, 8 packed FMAs for the dots, 6 for the three outputs, three
-//     8-lane butterflies, 4 predicated reductions -- ~80 instructions where the round-1 kernel needed 164 (64-bit
-//     address arithmetic per corner, zero-filled predicated loads, branches around every reduction);
+//   * phase 1: one lane per sample computes the footprint ONCE and parks what phase 2 needs in shared memory (48 bytes per
+//     sample): the four corner-row byte offsets (corners outside the map clamped to a harmless in-range row), the
+//     grad_value coefficient of each row, and (lw, lh, a, corner mask);
+//   * phase 2, per sample and lane: 4 unconditional loads, 8 packed FMAs for the corner dot products
+//     t_k = <grad_output, value_k>, which give all three gradients of the sample (the sums of cuh:113-158 with the
+//     channel sum taken first):
+//         grad_attn   = sum_k ca_k t_k      ca = (hh*hw, hh*lw, lh*hw, lh*lw)
+//         grad_loc.x ~ a * (hh (t1 - t0) + lh (t3 - t2)),   grad_loc.y ~ a * (hw (t2 - t0) + lw (t3 - t1))
+//     then the cross-lane sums (a reduce-scatter over four samples at a time for the plain op) and 4 predicated
+//     reductions -- ~100 instructions where the round-1 kernel needed 164 (64-bit address arithmetic per corner,
+//     zero-filled predicated loads, branches around every reduction);
 //   * grad_value uses ONE 16-byte vector reduction (red.global.add.v4.f32 -> REDG.E.ADD.F32x4)
 //     per lane per corner instead of 4 scalar atomics, always into an fp32 buffer.  A lane
 //     always owns 4 channels here (16-bit values are read with 8-byte loads) so that the 8 lanes
