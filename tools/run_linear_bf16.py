@@ -17,7 +17,7 @@ def t(fn, iters=20):
 
 
 for n, k, relu, masked in ((256, 256, False, False), (256, 256, False, True), (384, 256, False, False), (1024, 256, True, False),
-                           (256, 1024, False, False)):
+                           (256, 1024, False, False), (1536, 256, False, True)):
     torch.manual_seed(0)
     x = torch.randn(rows, k, device=dev).bfloat16()
     w = (torch.randn(n, k, device=dev) / 16).bfloat16()
