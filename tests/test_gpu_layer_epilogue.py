@@ -501,6 +501,39 @@ def test_bf16_linear_routes():
         L.BF16_KERNEL_MIN_ROWS = prev_rows
 
 
+@pytest.mark.parametrize("rows", [1, 127, 129, 1000])
+def test_linear_kernels_write_only_their_rows(rows):
+    """The two GEMM kernels store whole 32-row boxes by TMA; the tensor map clips them at `rows`.  Outputs placed in the
+    middle of a sentinel-filled buffer: nothing before the first or after the last row may change (C ABI called
+    directly, ragged row counts around the 128-row tile)."""
+    from dfvod_b200 import _lib
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(rows)
+    n, k, pad = 128, 64, 160
+    # bf16
+    x = torch.randn(rows, k, device=DEV).bfloat16()
+    w = torch.randn(n, k, device=DEV).bfloat16()
+    big = torch.full((pad + rows + pad, n), 7.0, device=DEV, dtype=torch.bfloat16)
+    y = big[pad:pad + rows]
+    _lib.check(lib.msda_layer_linear_bf16(x.data_ptr(), w.data_ptr(), None, None, rows, n, k, 0, y.data_ptr(), stream), "bf16")
+    torch.cuda.synchronize()
+    assert bool((big[:pad] == 7.0).all()) and bool((big[pad + rows:] == 7.0).all())
+    assert nerr(y, F.linear(x.double(), w.double())) <= 2.0 ** -8
+    # fp32-grade
+    x32 = torch.randn(rows, k, device=DEV)
+    w32 = torch.randn(n, k, device=DEV)
+    hi = ((w32.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+    lo = w32 - hi
+    big32 = torch.full((pad + rows + pad, n), 7.0, device=DEV)
+    y32 = big32[pad:pad + rows]
+    _lib.check(lib.msda_layer_linear_tf32x3(x32.data_ptr(), hi.data_ptr(), lo.data_ptr(), None, rows, n, k, 0,
+                                            y32.data_ptr(), stream), "tf32x3")
+    torch.cuda.synchronize()
+    assert bool((big32[:pad] == 7.0).all()) and bool((big32[pad + rows:] == 7.0).all())
+    assert nerr(y32, F.linear(x32.double(), w32.double())) <= 2e-6
+
+
 def test_tf32x3_mode_routes_the_layer_gemms():
     """set_fp32_gemm_mode('tf32x3'): the fp32 transformer gives the library-SGEMM result within the fp32 parity
     tolerance (1e-5 normalised); gradients-needed calls and 16-bit inputs keep the library path.  "tf32x3" is the
