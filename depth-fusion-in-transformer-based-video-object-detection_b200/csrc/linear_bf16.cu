@@ -25,7 +25,10 @@ constexpr int kLbBM = 128;                 // output rows per tile (TMEM lanes)
 constexpr int kLbBN = 256;                 // output columns per tile (TMEM columns of one accumulator)
 constexpr int kLbBK = 64;                  // bf16 per K block = 128 bytes = one swizzle row
 constexpr int kLbStages = 4;
-constexpr int kLbCluster = 2;
+#ifndef MSDA_LINEAR_BF16_CLUSTER
+#define MSDA_LINEAR_BF16_CLUSTER 2
+#endif
+constexpr int kLbCluster = MSDA_LINEAR_BF16_CLUSTER;   // CTAs that share every weight tile (TMA multicast); 1 = none
 constexpr int kLbABytes = kLbBM * 128;     // 16 KB
 constexpr int kLbBBytes = kLbBN * 128;     // 32 KB
 constexpr int kLbStageBytes = kLbABytes + kLbBBytes;

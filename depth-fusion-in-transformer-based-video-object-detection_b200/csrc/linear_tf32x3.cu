@@ -76,7 +76,7 @@ __device__ __forceinline__ void mma_tf32(unsigned tmem_d, unsigned long long des
 __global__ void __cluster_dims__(kLtCluster, 1, 1) __launch_bounds__(kLtThreads, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                      const __grid_constant__ CUtensorMap tm_wl, const __grid_constant__ CUtensorMap tm_y,
-                     const float* __restrict__ bias, long long rows, int N, int K, int relu)
+                     const float* __restrict__ bias, long long rows, int N, int K, int relu, int bn)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* s_out = smem + kLtStages * kLtStageBytes;            // [8 epilogue warps][kLtOutBytes], 1024-byte aligned
@@ -85,7 +85,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long tiles_m = (rows + kLtBM - 1) / kLtBM;
-    const int tiles_n = (N + kLtBN - 1) / kLtBN;
+    // bn: column tile width chosen by the host (<= kLtBN, a multiple of 32 that splits N evenly: 384 -> 2 x 192)
+    const int tiles_n = (N + bn - 1) / bn;
     // work unit of a cluster: kLtCluster consecutive row tiles x one column tile; CTA `rank` takes row tile group * C + rank
     // (past the last row tile: TMA reads zeros, the epilogue stores nothing)
     const long long tiles = ((tiles_m + kLtCluster - 1) / kLtCluster) * tiles_n;
@@ -116,15 +117,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         // ======================================= TMA producer =======================================
         if (elect_one()) {
             unsigned kiter = 0;
-            constexpr int kSlice = kLtBN / kLtCluster, kSliceBytes = kLtBBytes / kLtCluster;
+            const int kSlice = bn / kLtCluster, kSliceBytes = kSlice * 128;
             for (long long t = first; t < tiles; t += stride) {
-                const int m0 = (int)((t / tiles_n) * kLtCluster + rank) * kLtBM, n0 = (int)(t % tiles_n) * kLtBN;
+                const int m0 = (int)((t / tiles_n) * kLtCluster + rank) * kLtBM, n0 = (int)(t % tiles_n) * bn;
                 for (int kb = 0; kb < kblocks; ++kb, ++kiter) {
                     const int s = kiter % kLtStages;
                     // both CTAs are done with the stage: my slices land in the peer's shared memory too
                     if (kiter >= kLtStages) mbar_wait(&bars->empty[s], ((kiter / kLtStages) - 1) & 1);
                     unsigned char* st = smem + s * kLtStageBytes;
-                    mbar_expect_tx(&bars->full[s], kLtABytes + 2 * kLtBBytes);      // my x tile + every CTA's W slices
+                    mbar_expect_tx(&bars->full[s], kLtABytes + 2 * bn * 128);       // my x tile + every CTA's W slices
                     tma_load_2d(st, &tm_x, kb * kLtBK, m0, &bars->full[s]);
                     tma_load_2d_multicast(st + 2 * kLtABytes + rank * kSliceBytes, &tm_wh, kb * kLtBK,
                                           n0 + (int)rank * kSlice, &bars->full[s], kAll);
@@ -138,8 +139,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         // ======================================= MMA issuer =======================================
         unsigned kiter = 0, it = 0;
         for (long long t = first; t < tiles; t += stride, ++it) {
-            const int n0 = (int)(t % tiles_n) * kLtBN;
-            const int n_cur = min(kLtBN, N - n0);
+            const int n0 = (int)(t % tiles_n) * bn;
+            const int n_cur = min(bn, N - n0);
             const unsigned idesc = make_idesc_tf32(kLtBM, n_cur);
             // Two accumulators: the hi x hi products and the two correction terms.  The tensor core truncates when it adds
             // into the accumulator, about half an ulp of the RUNNING SUM per instruction and always towards zero; 96
@@ -213,8 +214,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         unsigned it = 0;
         for (long long t = first; t < tiles; t += stride, ++it) {
             const long long m0 = ((t / tiles_n) * kLtCluster + rank) * kLtBM;
-            const int n0 = (int)(t % tiles_n) * kLtBN;
-            const int n_cur = min(kLtBN, N - n0);
+            const int n0 = (int)(t % tiles_n) * bn;
+            const int n_cur = min(bn, N - n0);
             // bias slice of the tile (the previous tile's readers are past their last read: barrier below)
             named_bar_sync(1, kLtEpiThreads);
             for (int i = et; i < kLtBN; i += kLtEpiThreads) s_bias[i] = (bias != nullptr && i < n_cur) ? bias[n0 + i] : 0.f;
@@ -318,18 +319,22 @@ cudaError_t linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, 
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
+    // column tile width: as few tiles as 256 columns allow, of equal width (a multiple of 32; each CTA of the cluster
+    // loads bn / 2 weight rows, a multiple of the 8-row swizzle group)
+    const int tiles_n = (n + kLtBN - 1) / kLtBN;
+    const int bn = ((n + tiles_n - 1) / tiles_n + 31) / 32 * 32;
     alignas(64) CUtensorMap tm_x, tm_wh, tm_wl, tm_y;
     if (!lt_make_map(&tm_x, x, (unsigned long long)rows, (unsigned long long)k, kLtBM) ||
-        !lt_make_map(&tm_wh, w_hi, (unsigned long long)n, (unsigned long long)k, kLtBN / kLtCluster) ||
-        !lt_make_map(&tm_wl, w_lo, (unsigned long long)n, (unsigned long long)k, kLtBN / kLtCluster) ||
+        !lt_make_map(&tm_wh, w_hi, (unsigned long long)n, (unsigned long long)k, bn / kLtCluster) ||
+        !lt_make_map(&tm_wl, w_lo, (unsigned long long)n, (unsigned long long)k, bn / kLtCluster) ||
         !lt_make_map(&tm_y, y, (unsigned long long)rows, (unsigned long long)n, 32))
         return cudaErrorNotSupported;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles_m = (rows + kLtBM - 1) / kLtBM;
-    const long long units = ((tiles_m + kLtCluster - 1) / kLtCluster) * ((n + kLtBN - 1) / kLtBN);
+    const long long units = ((tiles_m + kLtCluster - 1) / kLtCluster) * ((n + bn - 1) / bn);
     const long long clusters = sms / kLtCluster;
     const int grid = (int)(units < clusters ? units : clusters) * kLtCluster;
-    linear_tf32x3_kernel<<<grid, kLtThreads, kLtSmem, stream>>>(tm_x, tm_wh, tm_wl, tm_y, bias, rows, n, k, relu);
+    linear_tf32x3_kernel<<<grid, kLtThreads, kLtSmem, stream>>>(tm_x, tm_wh, tm_wl, tm_y, bias, rows, n, k, relu, bn);
     return cudaGetLastError();
 }
 
