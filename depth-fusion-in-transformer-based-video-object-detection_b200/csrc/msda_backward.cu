@@ -143,6 +143,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 
     // per-sample records of a pass (+1 record: the groups of a warp start in distinct banks)
     __shared__ int s_meta[3 * kMaxLevelsFast];
+    __shared__ float s_inv[FUSED ? 2 * kMaxLevelsFast : 2];       // fused: 1 / H, 1 / W per level
     // record of a sample, 5 x 16 bytes: [0] byte offset (pixel * M*D * sizeof(VT)) of each corner row (corner outside the map -> 0),
     // [1] grad_value coefficient of each row (0 = no reduction), [2..4] corner dots -> grad_attn, grad_loc.x / W,
     // grad_loc.y / H
@@ -155,6 +156,10 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
         s_meta[3 * threadIdx.x + 1] = (int)shapes[2 * threadIdx.x + 1];
         s_meta[3 * threadIdx.x + 2] = (int)lsi[threadIdx.x];
+        if constexpr (FUSED) {
+            s_inv[2 * threadIdx.x + 0] = 1.f / (float)shapes[2 * threadIdx.x];
+            s_inv[2 * threadIdx.x + 1] = 1.f / (float)shapes[2 * threadIdx.x + 1];
+        }
     }
     __syncthreads();
 
@@ -225,8 +230,9 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             prob[k] = prob[k] == -INFINITY ? 0.f : expf(prob[k] - mx);
             sum += prob[k];
         }
-        inv_sum = group_sum<G>(sum);
+        inv_sum = 1.f / group_sum<G>(sum);            // one division per lane; the samples multiply
     }
+    const float half_inv_p = 0.5f / (float)P;
     // fused: finished per-sample gradients of this lane's own samples, kept until the softmax
     // backward can be applied (it needs sum_j a_j * g_a_j over the whole pair)
     float fin_x[FCH * SPL], fin_y[FCH * SPL], fin_a[FCH * SPL], own_a[FCH * SPL];
@@ -257,8 +263,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                 float a;
                 if constexpr (FUSED) {
                     xy = fused_location(load_raw2<RT>(op + 2 * s), src.ref + (nq * L + l) * src.ref_dim, src.ref_dim,
-                                        s_meta[3 * l], s_meta[3 * l + 1], P);
-                    a = reg_pick(prob, c * SPL + i) / inv_sum;
+                                        s_inv[2 * l], s_inv[2 * l + 1], half_inv_p);
+                    a = reg_pick(prob, c * SPL + i) * inv_sum;
                 } else {
                     xy = ldg_stream_f32x2(lp + 2 * s);
                     a = ldg_stream_f32(ap + s);
@@ -516,16 +522,16 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     const float glogit = a * (fin_a[k] - dot);
                     float gox, goy, gwx = 0.f, gwy = 0.f;
                     if (src.ref_dim == 2) {
-                        gox = glx / Wf;
-                        goy = gly / Hf;
+                        gox = glx * s_inv[2 * l + 1];
+                        goy = gly * s_inv[2 * l];
                     } else {
                         const float4 r = *reinterpret_cast<const float4*>(src.ref + (nq * L + l) * 4);
-                        gox = glx * (r.z * 0.5f / (float)P);
-                        goy = gly * (r.w * 0.5f / (float)P);
+                        gox = glx * (r.z * half_inv_p);
+                        goy = gly * (r.w * half_inv_p);
                         if (dst.ref != nullptr) {
                             const float2 off = load_raw2<RT>(op + 2 * s);
-                            gwx = glx * (off.x / (float)P * 0.5f);
-                            gwy = gly * (off.y / (float)P * 0.5f);
+                            gwx = glx * (off.x * half_inv_p);
+                            gwy = gly * (off.y * half_inv_p);
                         }
                     }
                     store_raw2<RT>(gop + 2 * s, gox, goy);

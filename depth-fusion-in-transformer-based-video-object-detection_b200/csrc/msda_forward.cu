@@ -70,6 +70,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     constexpr int FCH = (msda::kChunk + kChunk - 1) / kChunk;   // passes of the fused op (L*P <= msda::kChunk)
 
     __shared__ int s_meta[3 * kMaxLevelsFast];
+    __shared__ float s_inv[FUSED ? 2 * kMaxLevelsFast : 2];       // fused: 1 / H, 1 / W per level
     __shared__ __align__(16) int4   s_pix[WARPS][PAIRS][kChunk + 1];   // +1 record: group stride 272 B, so the groups of a warp hit distinct banks
     __shared__ __align__(16) float4 s_wgt[WARPS][PAIRS][kChunk + 1];
 
@@ -77,6 +78,10 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
         s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
         s_meta[3 * threadIdx.x + 1] = (int)shapes[2 * threadIdx.x + 1];
         s_meta[3 * threadIdx.x + 2] = (int)lsi[threadIdx.x];
+        if constexpr (FUSED) {
+            s_inv[2 * threadIdx.x + 0] = 1.f / (float)shapes[2 * threadIdx.x];
+            s_inv[2 * threadIdx.x + 1] = 1.f / (float)shapes[2 * threadIdx.x + 1];
+        }
     }
     __syncthreads();
 
@@ -138,8 +143,9 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
             prob[i] = prob[i] == -INFINITY ? 0.f : expf(prob[i] - mx);
             sum += prob[i];
         }
-        inv_sum = group_sum<G>(sum);
+        inv_sum = 1.f / group_sum<G>(sum);            // one division per lane; the samples multiply
     }
+    const float half_inv_p = 0.5f / (float)P;
 
 #pragma unroll
     for (int c = 0; c < (FUSED ? FCH : 1 << 30); ++c) {
@@ -161,8 +167,8 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
                 float a;
                 if constexpr (FUSED) {
                     xy = fused_location(load_raw2<RT>(op + 2 * s), src.ref + (nq * L + l) * src.ref_dim, src.ref_dim,
-                                        s_meta[3 * l], s_meta[3 * l + 1], P);
-                    a = prob[c * K + k] / inv_sum;       // softmax: exp(x - max) / sum
+                                        s_inv[2 * l], s_inv[2 * l + 1], half_inv_p);
+                    a = prob[c * K + k] * inv_sum;       // softmax: exp(x - max) / sum
                 } else {
                     xy = ldg_stream_f32x2(lp + 2 * s);
                     a = ldg_stream_f32(ap + s);

@@ -31,6 +31,7 @@ msda_fwd_hm_kernel(const __nv_bfloat16* __restrict__ value_hm, const int64_t* __
                    int S, int M, int L, int Lq, int P, int p_magic, long long nq_total)
 {
     __shared__ int s_meta[3 * kMaxLevelsFast];
+    __shared__ float s_inv[FUSED ? 2 * kMaxLevelsFast : 2];       // fused: 1 / H, 1 / W per level
     // per sample: [column 0 | column 1], each {pix row0, pix row1, weight row0, weight row1}
     __shared__ __align__(16) uint4 s_rec[kHmWarps][kHmPairs][kHmChunk + 1][2];
 
@@ -38,6 +39,10 @@ msda_fwd_hm_kernel(const __nv_bfloat16* __restrict__ value_hm, const int64_t* __
         s_meta[3 * threadIdx.x + 0] = (int)shapes[2 * threadIdx.x];
         s_meta[3 * threadIdx.x + 1] = (int)shapes[2 * threadIdx.x + 1];
         s_meta[3 * threadIdx.x + 2] = (int)lsi[threadIdx.x];
+        if constexpr (FUSED) {
+            s_inv[2 * threadIdx.x + 0] = 1.f / (float)shapes[2 * threadIdx.x];
+            s_inv[2 * threadIdx.x + 1] = 1.f / (float)shapes[2 * threadIdx.x + 1];
+        }
     }
     __syncthreads();
 
@@ -87,8 +92,9 @@ msda_fwd_hm_kernel(const __nv_bfloat16* __restrict__ value_hm, const int64_t* __
             prob[k] = prob[k] == -INFINITY ? 0.f : expf(prob[k] - mx);
             sum += prob[k];
         }
-        inv_sum = group_sum<kHmG>(sum);
+        inv_sum = 1.f / group_sum<kHmG>(sum);
     }
+    const float half_inv_p = 0.5f / (float)P;
 
     for (int s0 = 0; s0 < LP; s0 += kHmChunk) {
         const int cnt = min(kHmChunk, LP - s0);
@@ -106,8 +112,8 @@ msda_fwd_hm_kernel(const __nv_bfloat16* __restrict__ value_hm, const int64_t* __
                 float a;
                 if constexpr (FUSED) {
                     xy = fused_location(load_raw2<RT>(op + 2 * s), src.ref + (nq * L + l) * src.ref_dim, src.ref_dim,
-                                        s_meta[3 * l], s_meta[3 * l + 1], P);
-                    a = prob[k] / inv_sum;
+                                        s_inv[2 * l], s_inv[2 * l + 1], half_inv_p);
+                    a = prob[k] * inv_sum;
                 } else {
                     xy = ldg_stream_f32x2(lp + 2 * s);
                     a = ldg_stream_f32(ap + s);
