@@ -282,7 +282,9 @@ def _tf32_split(t):
 
 
 def _tf32x3_wanted(x, weight):
+    # (under torch.autocast an fp32 nn.Linear is the caller's request for a 16-bit GEMM: F.linear honours it)
     return (FP32_GEMM_MODE == "tf32x3" and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and not torch.is_autocast_enabled()
             and x.numel() // max(x.shape[-1], 1) >= TF32X3_MIN_ROWS
             and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)))
 

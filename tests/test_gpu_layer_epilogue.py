@@ -570,6 +570,11 @@ def test_tf32x3_mode_routes_the_layer_gemms():
         xg = torch.randn(2048, 64, device=DEV, requires_grad=True)
         lin = torch.nn.Linear(64, 64).to(DEV)
         assert not L._tf32x3_wanted(xg, lin.weight) and not L._tf32x3_wanted(xg.detach().bfloat16(), lin.weight)
+        with torch.no_grad():
+            assert L._tf32x3_wanted(xg.detach(), lin.weight)
+            with torch.autocast("cuda", dtype=torch.bfloat16):       # the caller asked for 16-bit GEMMs
+                assert not L._tf32x3_wanted(xg.detach(), lin.weight)
+                assert L.linear(lin, xg.detach()).dtype == torch.bfloat16
         with pytest.raises(ValueError):
             L.set_fp32_gemm_mode("fp8")
     finally:
