@@ -327,6 +327,13 @@ def encoder_extras(torch, dev, world, dist, n_frames=8, iters=10):
         out["encoder_fp32_ms"] = ms
         out["encoder_fp32_fps"] = n_frames * world / ms * 1e3
         out["encoder_fp32_gemm_mode"] = "tf32x3 (dfvod_b200.ops.functions.set_fp32_gemm_mode default)"
+        try:                                       # the same fp32 encoder replayed from one CUDA graph, like the bf16 lines
+            ms = _reduce_max(torch, dist, world, dev,
+                             _graph_time(torch, lambda: model.encoder(src, st, ls, vr, pos, None), 3))
+            out["encoder_fp32_graph_ms"] = ms
+            out["encoder_fp32_graph_fps"] = n_frames * world / ms * 1e3
+        except Exception as exc:
+            out["encoder_fp32_graph_error"] = repr(exc)[:160]
         # the same encoder with the library's IEEE SGEMMs (set_fp32_gemm_mode("library"): the reference's own arithmetic)
         prev_mode = set_fp32_gemm_mode("library")
         try:

@@ -15,15 +15,15 @@
 // of the activation tile happens in SHARED MEMORY between the TMA load and the MMA; W_hi / W_lo are split once on the
 // host side of the C ABI (weights are static during inference).
 //
-// One CTA per SM, clusters of two, persistent over (row tile, column tile) pairs, 128 x 256 output tile per CTA, K in blocks of 32 fp32 (one
-// 128-byte SWIZZLE_128B row).  Warp roles (14 warps):
+// One CTA per SM, clusters of two, persistent over (row tile, column tile) pairs, 128 x 256 output tile per CTA, K in blocks of 16 fp32
+// (64-byte SWIZZLE_64B rows).  Warp roles (14 warps):
 //   0-3, 10-13  epilogue   tcgen05.ld of the finished accumulators (lane = output row), + bias, ReLU, staged 32 x 32 and written
 //                   with TMA stores
 //   4-7  converter  x tile in shared memory -> x_lo (second tile, same swizzled layout: the split is elementwise, so it
 //                   never has to know the layout), then fence.proxy.async; x_hi is the x tile as the tensor core reads it
-//   8    MMA issuer 4 K-steps x 3 terms of tcgen05.mma kind::tf32 per K block; TWO accumulators in TMEM (see there)
-//   9    TMA producer  x tile and this CTA's half of the W_hi / W_lo tiles (multicast to the cluster) per K block, two
-//                      stages of 96 KB
+//   8    MMA issuer 2 K-steps x 3 terms of tcgen05.mma kind::tf32 per K block; TWO accumulators in TMEM (see there)
+//   9    TMA producer  x tile and this CTA's half of the W_hi / W_lo tiles (multicast to the cluster) per K block, four
+//                      stages of 48 KB
 #include <cuda.h>
 
 #include "msda_common.cuh"
@@ -36,11 +36,20 @@ using namespace umma;
 
 constexpr int kLtBM = 128;                 // output rows per tile (TMEM lanes)
 constexpr int kLtBN = 256;                 // output columns per tile (TMEM columns of one accumulator)
-constexpr int kLtBK = 32;                  // fp32 per K block = 128 bytes = one swizzle row
-constexpr int kLtStages = 2;
+// K block: 16 fp32 = 64-byte SWIZZLE_64B rows, four stages of 48 KB (default), or 32 fp32 = one 128-byte SWIZZLE_128B row,
+// two stages of 96 KB (-DMSDA_TF32_BK=32).  The same bytes in flight in finer grains: measured at 8 x 22 223 rows, BK 32 |
+// BK 16, ms: 256 <- 256: 0.122 | 0.116; 384 <- 256: 0.190 | 0.175; 1024 <- 256: 0.412 | 0.417; 256 <- 1024: 0.380 | 0.370.
+#ifndef MSDA_TF32_BK
+#define MSDA_TF32_BK 16
+#endif
+constexpr int kLtBK = MSDA_TF32_BK;
+constexpr int kLtRowBytes = kLtBK * 4;     // bytes of a K block row = swizzle span
+constexpr int kLtKSteps = kLtBK / 8;       // tcgen05.mma kind::tf32 takes K = 8 per instruction
+constexpr int kLtStages = kLtBK == 32 ? 2 : 4;
+static_assert(kLtBK == 32 || kLtBK == 16, "K block = one SWIZZLE_128B or SWIZZLE_64B row");
 constexpr int kLtCluster = 2;              // CTAs that share every W tile (TMA multicast)
-constexpr int kLtABytes = kLtBM * 128;     // 16 KB
-constexpr int kLtBBytes = kLtBN * 128;     // 32 KB
+constexpr int kLtABytes = kLtBM * kLtRowBytes;     // 16 KB
+constexpr int kLtBBytes = kLtBN * kLtRowBytes;     // 32 KB
 constexpr int kLtStageBytes = 2 * kLtABytes + 2 * kLtBBytes;      // x_hi | x_lo | W_hi | W_lo = 96 KB
 constexpr int kLtEpiThreads = 256, kLtConvThreads = 128;      // epilogue: warps 0-3 and 10-13 (two per TMEM lane quadrant)
 constexpr int kLtThreads = kLtEpiThreads + kLtConvThreads + 64;
@@ -57,6 +66,20 @@ struct LtBars {
 __device__ __forceinline__ unsigned make_idesc_tf32(int m, int n)
 {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+// shared-memory matrix descriptor of a K-major operand tile whose rows are one swizzle span (128 or 64 bytes): 8-row groups
+// of 8 x span bytes
+__device__ __forceinline__ unsigned long long lt_desc(const void* smem_ptr)
+{
+    if constexpr (kLtBK == 32) return make_desc_sw128(smem_ptr);
+    const unsigned addr = smem_u32(smem_ptr);
+    unsigned long long d = 0;
+    d |= (unsigned long long)((addr & 0x3FFFF) >> 4);            // start address
+    d |= (unsigned long long)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (unsigned long long)(512 >> 4) << 32;                   // stride between 8-row groups: 8 x 64 bytes
+    d |= (unsigned long long)1 << 46;                            // descriptor version (sm_100)
+    d |= (unsigned long long)4 << 61;                            // layout: SWIZZLE_64B
+    return d;
 }
 __device__ __forceinline__ void mma_tf32(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b,
                                          unsigned idesc, bool accumulate)
@@ -117,7 +140,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         // ======================================= TMA producer =======================================
         if (elect_one()) {
             unsigned kiter = 0;
-            const int kSlice = bn / kLtCluster, kSliceBytes = kSlice * 128;
+            const int kSlice = bn / kLtCluster, kSliceBytes = kSlice * kLtRowBytes;
             for (long long t = first; t < tiles; t += stride) {
                 const int m0 = (int)((t / tiles_n) * kLtCluster + rank) * kLtBM, n0 = (int)(t % tiles_n) * bn;
                 for (int kb = 0; kb < kblocks; ++kb, ++kiter) {
@@ -125,7 +148,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     // both CTAs are done with the stage: my slices land in the peer's shared memory too
                     if (kiter >= kLtStages) mbar_wait(&bars->empty[s], ((kiter / kLtStages) - 1) & 1);
                     unsigned char* st = smem + s * kLtStageBytes;
-                    mbar_expect_tx(&bars->full[s], kLtABytes + 2 * bn * 128);       // my x tile + every CTA's W slices
+                    mbar_expect_tx(&bars->full[s], kLtABytes + 2 * bn * kLtRowBytes);   // my x tile + every CTA's W slices
                     tma_load_2d(st, &tm_x, kb * kLtBK, m0, &bars->full[s]);
                     tma_load_2d_multicast(st + 2 * kLtABytes + rank * kSliceBytes, &tm_wh, kb * kLtBK,
                                           n0 + (int)rank * kSlice, &bars->full[s], kAll);
@@ -152,16 +175,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             for (int kb = 0; kb < kblocks; ++kb, ++kiter) {
                 const int s = kiter % kLtStages;
                 unsigned char* st = smem + s * kLtStageBytes;
-                const unsigned long long d_xh = make_desc_sw128(st), d_xl = make_desc_sw128(st + kLtABytes);
-                const unsigned long long d_wh = make_desc_sw128(st + 2 * kLtABytes),
-                                         d_wl = make_desc_sw128(st + 2 * kLtABytes + kLtBBytes);
+                const unsigned long long d_xh = lt_desc(st), d_xl = lt_desc(st + kLtABytes);
+                const unsigned long long d_wh = lt_desc(st + 2 * kLtABytes), d_wl = lt_desc(st + 2 * kLtABytes + kLtBBytes);
                 mbar_wait(&bars->full[s], (kiter / kLtStages) & 1);              // x and W tiles landed
                 tcgen05_fence_after();
                 // the two terms with x_hi need nothing from the converter: the tensor core reads the top 19 bits of the
                 // fp32 words TMA wrote (x_hi = x truncated to TF32), so they go first and cover the converter's latency
                 if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {                                // K = 8 per instruction: 32 bytes of the row
+                    for (int j = 0; j < kLtKSteps; ++j) {                        // K = 8 per instruction: 32 bytes of the row
                         mma_tf32(acc_small, desc_advance(d_xh, j * 32), desc_advance(d_wl, j * 32), idesc, (kb | j) != 0);
                         mma_tf32(acc_big, desc_advance(d_xh, j * 32), desc_advance(d_wh, j * 32), idesc, (kb | j) != 0);
                     }
@@ -171,7 +193,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 tcgen05_fence_after();
                 if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < kLtKSteps; ++j)
                         mma_tf32(acc_small, desc_advance(d_xl, j * 32), desc_advance(d_wh, j * 32), idesc, true);
                     mma_commit_multicast(&bars->empty[s], kAll);                 // stage free (here and in the peer) once these MMAs have read it
                     if (kb == kblocks - 1) mma_commit(&bars->acc_full);
@@ -285,22 +307,24 @@ static LtEncodeTiledFn lt_encode_tiled_fn()
 
 // row-major fp32 matrix [n_rows, n_cols]; box = 32 columns (128 bytes, SWIZZLE_128B) x box_rows rows; rows past the end
 // read as zeros
-static bool lt_make_map(CUtensorMap* map, const void* base, unsigned long long n_rows, unsigned long long n_cols, int box_rows)
+static bool lt_make_map(CUtensorMap* map, const void* base, unsigned long long n_rows, unsigned long long n_cols, int box_rows,
+                        int box_cols = kLtBK)
 {
     LtEncodeTiledFn fn = lt_encode_tiled_fn();
     if (fn == nullptr) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)n_cols, n_rows};
     const cuuint64_t strides[1] = {(cuuint64_t)n_cols * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)kLtBK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool linear_tf32x3_supported(int n, int k)
 {
-    return n >= 32 && n % 32 == 0 && k >= kLtBK && k % kLtBK == 0;
+    return n >= 32 && n % 32 == 0 && k >= 32 && k % 32 == 0;
 }
 
 cudaError_t linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, const float* bias, long long rows, int n,
@@ -327,7 +351,7 @@ cudaError_t linear_tf32x3(const float* x, const float* w_hi, const float* w_lo, 
     if (!lt_make_map(&tm_x, x, (unsigned long long)rows, (unsigned long long)k, kLtBM) ||
         !lt_make_map(&tm_wh, w_hi, (unsigned long long)n, (unsigned long long)k, bn / kLtCluster) ||
         !lt_make_map(&tm_wl, w_lo, (unsigned long long)n, (unsigned long long)k, bn / kLtCluster) ||
-        !lt_make_map(&tm_y, y, (unsigned long long)rows, (unsigned long long)n, 32))
+        !lt_make_map(&tm_y, y, (unsigned long long)rows, (unsigned long long)n, 32, 32))
         return cudaErrorNotSupported;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles_m = (rows + kLtBM - 1) / kLtBM;

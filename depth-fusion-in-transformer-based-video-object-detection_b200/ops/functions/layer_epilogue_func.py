@@ -248,7 +248,7 @@ class LinearFunction(Function):
 #              x_lo W_lo^T term and the rounding of the *_lo operands are O(2^-22).  fp32-grade results
 #              (tests/test_gpu_layer_epilogue.py: 6.9e-7 normalised against fp64 at K = 256, the IEEE SGEMM 7.2e-7, one TF32
 #              GEMM 3e-4; every fp32 golden of tests/test_gpu_modules.py holds its 1e-5 with it) at a third of the TF32
-#              tensor rate instead of the SIMT SGEMM rate: 6-layer fp32 encoder 45.7 -> 12.6 ms.  One tcgen05 kernel per
+#              tensor rate instead of the SIMT SGEMM rate: 6-layer fp32 encoder 45.7 -> 12.2 ms.  One tcgen05 kernel per
 #              layer (csrc/linear_tf32x3.cu: the activation tile is split in shared memory, bias / ReLU in the epilogue);
 #              shapes it does not take fall back to the split pass (msda_layer_tf32_split) + one library TF32 GEMM over
 #              the concatenated reduction.  Only without gradients and from TF32X3_MIN_ROWS rows up.
