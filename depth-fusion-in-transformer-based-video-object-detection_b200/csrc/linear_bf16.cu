@@ -23,14 +23,23 @@ using namespace umma;
 
 constexpr int kLbBM = 128;                 // output rows per tile (TMEM lanes)
 constexpr int kLbBN = 256;                 // output columns per tile (TMEM columns of one accumulator)
-constexpr int kLbBK = 64;                  // bf16 per K block = 128 bytes = one swizzle row
-constexpr int kLbStages = 4;
+// K block: 64 bf16 = one 128-byte SWIZZLE_128B row, four stages of 48 KB (default), or 32 bf16 = 64-byte SWIZZLE_64B rows,
+// eight stages of 24 KB (-DMSDA_LINEAR_BF16_BK=32: what helped the TF32 kernel is slower here -- 38.2 -> 41.9 us at
+// 256 <- 256, 125 -> 131 us at 1024 <- 256)
+#ifndef MSDA_LINEAR_BF16_BK
+#define MSDA_LINEAR_BF16_BK 64
+#endif
+constexpr int kLbBK = MSDA_LINEAR_BF16_BK;
+constexpr int kLbRowBytes = kLbBK * 2;
+constexpr int kLbKSteps = kLbBK / 16;      // tcgen05.mma kind::f16 takes K = 16 per instruction
+constexpr int kLbStages = kLbBK == 64 ? 4 : 8;
+static_assert(kLbBK == 64 || kLbBK == 32, "K block = one SWIZZLE_128B or SWIZZLE_64B row");
 #ifndef MSDA_LINEAR_BF16_CLUSTER
 #define MSDA_LINEAR_BF16_CLUSTER 2
 #endif
 constexpr int kLbCluster = MSDA_LINEAR_BF16_CLUSTER;   // CTAs that share every weight tile (TMA multicast); 1 = none
-constexpr int kLbABytes = kLbBM * 128;     // 16 KB
-constexpr int kLbBBytes = kLbBN * 128;     // 32 KB
+constexpr int kLbABytes = kLbBM * kLbRowBytes;     // 16 KB
+constexpr int kLbBBytes = kLbBN * kLbRowBytes;     // 32 KB
 constexpr int kLbStageBytes = kLbABytes + kLbBBytes;
 constexpr int kLbEpiThreads = 256;
 constexpr int kLbThreads = kLbEpiThreads + 64;
@@ -42,6 +51,20 @@ struct LbBars {
     unsigned long long full[kLbStages], empty[kLbStages], acc_full[2], acc_free[2];
     unsigned tmem_base;
 };
+
+// shared-memory matrix descriptor of a K-major operand tile whose rows are one swizzle span (128 or 64 bytes)
+__device__ __forceinline__ unsigned long long lb_desc(const void* smem_ptr)
+{
+    if constexpr (kLbBK == 64) return make_desc_sw128(smem_ptr);
+    const unsigned addr = smem_u32(smem_ptr);
+    unsigned long long d = 0;
+    d |= (unsigned long long)((addr & 0x3FFFF) >> 4);            // start address
+    d |= (unsigned long long)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (unsigned long long)(512 >> 4) << 32;                   // stride between 8-row groups: 8 x 64 bytes
+    d |= (unsigned long long)1 << 46;                            // descriptor version (sm_100)
+    d |= (unsigned long long)4 << 61;                            // layout: SWIZZLE_64B
+    return d;
+}
 
 __global__ void __cluster_dims__(kLbCluster, 1, 1) __launch_bounds__(kLbThreads, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
@@ -85,7 +108,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // ======================================= TMA producer =======================================
         if (elect_one()) {
             unsigned kiter = 0;
-            const int slice = bn / kLbCluster, slice_bytes = slice * 128;
+            const int slice = bn / kLbCluster, slice_bytes = slice * kLbRowBytes;
             for (long long t = first; t < tiles; t += stride) {
                 const int m0 = (int)((t / tiles_n) * kLbCluster + rank) * kLbBM, n0 = (int)(t % tiles_n) * bn;
                 // (an L2 prefetch of the next unit's x rows was measured: 38.0 -> 40.9 us at 256 <- 256, 96 -> 120 us at
@@ -95,7 +118,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     // both CTAs are done with the stage: my slice lands in the peer's shared memory too
                     if (kiter >= kLbStages) mbar_wait(&bars->empty[s], ((kiter / kLbStages) - 1) & 1);
                     unsigned char* st = smem + s * kLbStageBytes;
-                    mbar_expect_tx(&bars->full[s], kLbABytes + bn * 128);           // my x tile + every CTA's W slice
+                    mbar_expect_tx(&bars->full[s], kLbABytes + bn * kLbRowBytes);   // my x tile + every CTA's W slice
                     tma_load_2d(st, &tm_x, kb * kLbBK, m0, &bars->full[s]);
                     tma_load_2d_multicast(st + kLbABytes + rank * slice_bytes, &tm_w, kb * kLbBK, n0 + (int)rank * slice,
                                           &bars->full[s], kAll);
@@ -119,9 +142,9 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 tcgen05_fence_after();
                 if (elect_one()) {
                     unsigned char* st = smem + s * kLbStageBytes;
-                    const unsigned long long d_x = make_desc_sw128(st), d_w = make_desc_sw128(st + kLbABytes);
+                    const unsigned long long d_x = lb_desc(st), d_w = lb_desc(st + kLbABytes);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)                                  // K = 16 per instruction: 32 bytes of the row
+                    for (int j = 0; j < kLbKSteps; ++j)                          // K = 16 per instruction: 32 bytes of the row
                         mma_bf16(acc, desc_advance(d_x, j * 32), desc_advance(d_w, j * 32), idesc, (kb | j) != 0);
                     mma_commit_multicast(&bars->empty[s], kAll);                 // stage free, here and in the peer
                     if (kb == kblocks - 1) mma_commit(&bars->acc_full[buf]);
@@ -210,22 +233,24 @@ static LbEncodeTiledFn lb_encode_tiled_fn()
 }
 
 // row-major bf16 matrix [n_rows, n_cols]; box = 64 columns (128 bytes, SWIZZLE_128B) x box_rows rows
-static bool lb_make_map(CUtensorMap* map, const void* base, unsigned long long n_rows, unsigned long long n_cols, int box_rows)
+static bool lb_make_map(CUtensorMap* map, const void* base, unsigned long long n_rows, unsigned long long n_cols, int box_rows,
+                        int box_cols = kLbBK)
 {
     LbEncodeTiledFn fn = lb_encode_tiled_fn();
     if (fn == nullptr) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)n_cols, n_rows};
     const cuuint64_t strides[1] = {(cuuint64_t)n_cols * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kLbBK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool linear_bf16_supported(int n, int k)
 {
-    return n >= 64 && n % 64 == 0 && k >= kLbBK && k % kLbBK == 0;
+    return n >= 64 && n % 64 == 0 && k >= 64 && k % 64 == 0;
 }
 
 cudaError_t linear_bf16(const void* x, const void* w, const void* bias, const unsigned char* row_mask, long long rows, int n,
@@ -250,7 +275,7 @@ cudaError_t linear_bf16(const void* x, const void* w, const void* bias, const un
     alignas(64) CUtensorMap tm_x, tm_w, tm_y;
     if (!lb_make_map(&tm_x, x, (unsigned long long)rows, (unsigned long long)k, kLbBM) ||
         !lb_make_map(&tm_w, w, (unsigned long long)n, (unsigned long long)k, bn / kLbCluster) ||
-        !lb_make_map(&tm_y, y, (unsigned long long)rows, (unsigned long long)n, 32))
+        !lb_make_map(&tm_y, y, (unsigned long long)rows, (unsigned long long)n, 32, 64))
         return cudaErrorNotSupported;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles_m = (rows + kLbBM - 1) / kLbBM;
