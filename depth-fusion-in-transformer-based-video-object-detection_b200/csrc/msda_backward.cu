@@ -101,6 +101,12 @@ struct GradDst {
 #ifndef MSDA_BWD_BATCHED_REDUCE
 #define MSDA_BWD_BATCHED_REDUCE 1
 #endif
+// ... and the same in the fused op, whose lanes then fetch their own samples' sums from the lanes that hold them.  Measured
+// (training step, alternating runs): 22.81 ms with it, 22.69 ms without -- the 12 partials cost the 64-register kernel
+// spills.  Off.
+#ifndef MSDA_BWD_BATCHED_FUSED
+#define MSDA_BWD_BATCHED_FUSED 0
+#endif
 #ifndef MSDA_BWD_FUSED_ROLLED
 #define MSDA_BWD_FUSED_ROLLED 1
 #endif
@@ -149,7 +155,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     // grad_loc.y / H
     constexpr int kRec = MSDA_BWD_COEF_RECORDS ? 5 : 3;
     __shared__ __align__(16) uint4 s_rec[WARPS][PAIRS][CH * kRec + 1];
-    constexpr bool BATCHED = MSDA_BWD_BATCHED_REDUCE && !FUSED && G == 8 && CH == 8;
+    constexpr bool BATCHED = MSDA_BWD_BATCHED_REDUCE && (!FUSED || MSDA_BWD_BATCHED_FUSED) && G == 8 && CH == 8 && SPL == 1;
     constexpr bool DEDUP = MSDA_BWD_DEDUP && SPL == 1;
 
     if (threadIdx.x < L) {
@@ -441,8 +447,17 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                     }
 #pragma unroll
                     for (int i = 0; i < 3; ++i) acc12[i] += __shfl_xor_sync(0xffffffffu, acc12[i], 1);
+                    if constexpr (FUSED) {
+                        // the fused op finishes a sample in the lane that owns it (softmax backward): lane 4b + s takes
+                        // the sums of sample s of batch b from lane 2s
+                        const int from = 2 * (sub & 3);
+                        const float fx = __shfl_sync(0xffffffffu, acc12[0], from, G);
+                        const float fy = __shfl_sync(0xffffffffu, acc12[1], from, G);
+                        const float fa = __shfl_sync(0xffffffffu, acc12[2], from, G);
+                        if ((sub >> 2) == (j0 >> 2)) { part[0] = fx; part[1] = fy; part[2] = fa; }
+                    }
                     const int j = (j0 - 3) + (sub >> 1);               // the sample whose sums this lane pair holds
-                    if (active && (sub & 1) == 0 && j < cnt) {
+                    if (!FUSED && active && (sub & 1) == 0 && j < cnt) {
                         const int s = s0 + j;
                         const int l = div_by_points(s, p_magic);
                         const float Hf = (float)s_meta[3 * l], Wf = (float)s_meta[3 * l + 1];
@@ -459,7 +474,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         __syncwarp();
 
         // ---- phase 3: combine the group's partials; each lane finishes its own SPL samples ----
-        if constexpr (BATCHED) {
+        if constexpr (BATCHED && !FUSED) {
             // already stored by the lanes that held the sums
         } else if constexpr (!FUSED) {
             float* grad_loc = static_cast<float*>(dst.loc);
